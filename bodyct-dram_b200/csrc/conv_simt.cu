@@ -1,0 +1,287 @@
+// CUDA-core fp32 implicit-GEMM convolution (k in {1,3}, pad k/2, stride 1) on channels-last volumes.
+// Role on the path: the bandwidth-bound first layer (Cin = 1, K = 27), the 1x1x1 heads (models.py:109,490) and any
+// channel count the tcgen05 kernel does not cover.  GEMM view: M = N*D*H*W voxels, N = Cout, K = taps*Cin with the K
+// index kk = tap*Cin + ci flattened so that tiny Cin does not waste the K tile.
+#include "common.cuh"
+
+namespace dram {
+
+constexpr int BM = 64, BN = 64, BK = 16, APAD = 4;
+
+struct VoxelCoord {
+  int n, z, y, x;
+  bool ok;
+};
+__device__ __forceinline__ VoxelCoord decode(long long m, long long M, int D, int H, int W) {
+  VoxelCoord v;
+  v.ok = m < M;
+  long long r = v.ok ? m : 0;
+  v.x = (int)(r % W); r /= W;
+  v.y = (int)(r % H); r /= H;
+  v.z = (int)(r % D);
+  v.n = (int)(r / D);
+  return v;
+}
+
+// value of the im2col matrix A[m][kk]
+template <int KS>
+__device__ __forceinline__ const float* a_ptr(const float* x, const VoxelCoord& v, int tap, int ci, int D, int H, int W,
+                                              int Cin) {
+  int z = v.z, y = v.y, xx = v.x;
+  if (KS == 3) {
+    z += tap / 9 - 1; y += (tap / 3) % 3 - 1; xx += tap % 3 - 1;
+    if (z < 0 || z >= D || y < 0 || y >= H || xx < 0 || xx >= W) return nullptr;
+  }
+  return x + ((((long long)v.n * D + z) * H + y) * W + xx) * Cin + ci;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256)
+k_conv_simt_fwd(const float* __restrict__ x, const float* __restrict__ pack, const float* __restrict__ bias,
+                float* __restrict__ y, int N, int D, int H, int W, int Cin, int Cout) {
+  __shared__ __align__(16) float As[BK][BM + APAD];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const long long M = (long long)N * D * H * W;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+  const int Ktot = KS * KS * KS * Cin;
+  const bool vecA = (Cin % 4 == 0), vecB = (Cout % 4 == 0);
+
+  const int a_row = tid >> 2, a_k4 = (tid & 3) * 4;
+  const VoxelCoord av = decode(m0 + a_row, M, D, H, W);
+  const int b_k = tid >> 4, b_n4 = (tid & 15) * 4;
+  const int tm = tid >> 4, tn = tid & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+    // ---- A tile (im2col gather)
+    float va[4] = {0.f, 0.f, 0.f, 0.f};
+    int kk = k0 + a_k4;
+    if (av.ok && kk < Ktot) {
+      if (vecA) {
+        const float* p = a_ptr<KS>(x, av, kk / Cin, kk % Cin, D, H, W, Cin);
+        if (p) {
+          float4 t = *reinterpret_cast<const float4*>(p);
+          va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (kk + j < Ktot) {
+            const float* p = a_ptr<KS>(x, av, (kk + j) / Cin, (kk + j) % Cin, D, H, W, Cin);
+            if (p) va[j] = *p;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[a_k4 + j][a_row] = va[j];
+    // ---- B tile
+    float vb[4] = {0.f, 0.f, 0.f, 0.f};
+    int bk = k0 + b_k, bc = co0 + b_n4;
+    if (bk < Ktot) {
+      const float* p = pack + (long long)bk * Cout + bc;
+      if (vecB && bc + 3 < Cout) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        vb[0] = t.x; vb[1] = t.y; vb[2] = t.z; vb[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (bc + j < Cout) vb[j] = p[j];
+      }
+    }
+    *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+      float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int c = co0 + tn * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + tm * 4 + i;
+    if (m >= M) continue;
+    float* q = y + m * Cout + c;
+    if (vecB && c + 3 < Cout) {
+      float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (bias) { o.x += bias[c]; o.y += bias[c + 1]; o.z += bias[c + 2]; o.w += bias[c + 3]; }
+      *reinterpret_cast<float4*>(q) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < Cout) q[j] = acc[i][j] + (bias ? bias[c + j] : 0.f);
+    }
+  }
+}
+
+// dpack[kk][co] += sum_{m in slab} A[m][kk] * dy[m][co]
+constexpr int WK = 64, WN = 64, WM = 16, kWgradSlab = 4096;
+
+template <int KS>
+__global__ void __launch_bounds__(256)
+k_conv_simt_wgrad(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dpack, int N, int D,
+                  int H, int W, int Cin, int Cout) {
+  __shared__ __align__(16) float As[WM][WK + APAD];
+  __shared__ __align__(16) float Bs[WM][WN];
+  const int tid = threadIdx.x;
+  const long long M = (long long)N * D * H * W;
+  const int Ktot = KS * KS * KS * Cin;
+  const int kk0 = blockIdx.x * WK, co0 = blockIdx.y * WN;
+  const bool vecA = (Cin % 4 == 0), vecB = (Cout % 4 == 0);
+  const int l_m = tid >> 4, l_4 = (tid & 15) * 4;
+  const int tk = tid >> 4, tn = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long slab = (long long)blockIdx.z * kWgradSlab; slab < M; slab += (long long)gridDim.z * kWgradSlab) {
+    long long end = slab + kWgradSlab < M ? slab + kWgradSlab : M;
+    for (long long mb = slab; mb < end; mb += WM) {
+      long long m = mb + l_m;
+      VoxelCoord v = decode(m, end, D, H, W);
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+      int kk = kk0 + l_4;
+      if (v.ok && kk < Ktot) {
+        if (vecA) {
+          const float* p = a_ptr<KS>(x, v, kk / Cin, kk % Cin, D, H, W, Cin);
+          if (p) { float4 t = *reinterpret_cast<const float4*>(p); va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (kk + j < Ktot) {
+              const float* p = a_ptr<KS>(x, v, (kk + j) / Cin, (kk + j) % Cin, D, H, W, Cin);
+              if (p) va[j] = *p;
+            }
+        }
+      }
+      int bc = co0 + l_4;
+      if (v.ok) {
+        const float* p = dy + m * Cout + bc;
+        if (vecB && bc + 3 < Cout) { float4 t = *reinterpret_cast<const float4*>(p); vb[0] = t.x; vb[1] = t.y; vb[2] = t.z; vb[3] = t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (bc + j < Cout) vb[j] = p[j];
+        }
+      }
+      *reinterpret_cast<float4*>(&As[l_m][l_4]) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(&Bs[l_m][l_4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+      __syncthreads();
+#pragma unroll
+      for (int mi = 0; mi < WM; ++mi) {
+        float4 a = *reinterpret_cast<const float4*>(&As[mi][tk * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[mi][tn * 4]);
+        float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kk = kk0 + tk * 4 + i;
+    if (kk >= Ktot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = co0 + tn * 4 + j;
+      if (c < Cout) atomicAdd(&dpack[(long long)kk * Cout + c], acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// w [Cout][Cin][T]  ->  mode 0: pack[t][ci][co]   mode 1: pack[t][co][ci] with flipped taps
+__global__ void k_pack_weight_f32(const float* __restrict__ w, float* __restrict__ pack, int Cout, int Cin, int T, int mode) {
+  long long total = (long long)Cout * Cin * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      int co = (int)(i % Cout); long long r = i / Cout;
+      int ci = (int)(r % Cin); int t = (int)(r / Cin);
+      pack[i] = w[((long long)co * Cin + ci) * T + t];
+    } else {
+      int ci = (int)(i % Cin); long long r = i / Cin;
+      int co = (int)(r % Cout); int t = (int)(r / Cout);
+      pack[i] = w[((long long)co * Cin + ci) * T + (T - 1 - t)];
+    }
+  }
+}
+__global__ void k_unpack_wgrad_f32(const float* __restrict__ pack, float* __restrict__ dw, int Cout, int Cin, int T) {
+  long long total = (long long)Cout * Cin * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % T); long long r = i / T;
+    int ci = (int)(r % Cin); int co = (int)(r / Cin);
+    dw[i] = pack[((long long)t * Cin + ci) * Cout + co];
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" {
+
+int dram_pack_weight_f32(const float* w, float* pack, int Cout, int Cin, int ksize, int mode, void* stream) {
+  DRAM_REQUIRE(w && pack && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3) && (mode == 0 || mode == 1), "pack_weight_f32: bad arguments");
+  int T = ksize * ksize * ksize;
+  k_pack_weight_f32<<<grid_for((long long)Cout * Cin * T, 256), 256, 0, (cudaStream_t)stream>>>(w, pack, Cout, Cin, T, mode);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_unpack_wgrad_f32(const float* pack, float* dw, int Cout, int Cin, int ksize, void* stream) {
+  DRAM_REQUIRE(pack && dw && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "unpack_wgrad_f32: bad arguments");
+  int T = ksize * ksize * ksize;
+  k_unpack_wgrad_f32<<<grid_for((long long)Cout * Cin * T, 256), 256, 0, (cudaStream_t)stream>>>(pack, dw, Cout, Cin, T);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_conv3d_simt_fwd(const float* x, const float* pack, const float* bias, float* y, int N, int D, int H, int W,
+                         int Cin, int Cout, int ksize, void* stream) {
+  DRAM_REQUIRE(x && pack && y && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_simt_fwd: bad arguments");
+  DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_simt_fwd: kernel size %d unsupported (1 or 3)", ksize);
+  long long M = (long long)N * D * H * W;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN));
+  if (ksize == 3) k_conv_simt_fwd<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, N, D, H, W, Cin, Cout);
+  else k_conv_simt_fwd<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, N, D, H, W, Cin, Cout);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack, int N, int D, int H, int W, int Cin, int Cout,
+                           int ksize, void* stream) {
+  DRAM_REQUIRE(x && dy && dpack && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_simt_wgrad: bad arguments");
+  DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_simt_wgrad: kernel size %d unsupported (1 or 3)", ksize);
+  long long M = (long long)N * D * H * W;
+  int Ktot = ksize * ksize * ksize * Cin;
+  long long slabs = (M + kWgradSlab - 1) / kWgradSlab;
+  long long tiles = (long long)((Ktot + WK - 1) / WK) * ((Cout + WN - 1) / WN);
+  long long want = ((long long)kNumSMs * 8 + tiles - 1) / tiles;       // >= 8 waves worth of CTAs
+  unsigned gz = (unsigned)(slabs < want ? slabs : want);
+  if (gz < 1) gz = 1;
+  dim3 grid((unsigned)((Ktot + WK - 1) / WK), (unsigned)((Cout + WN - 1) / WN), gz);
+  if (ksize == 3) k_conv_simt_wgrad<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, N, D, H, W, Cin, Cout);
+  else k_conv_simt_wgrad<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, N, D, H, W, Cin, Cout);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

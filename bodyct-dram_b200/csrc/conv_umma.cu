@@ -1,0 +1,709 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3-D convolution for sm_100a (nn.Conv3d k3 p1 / k1, parts.py:105-106,133,185-186).
+//
+// Forward / dgrad (k_conv_umma_fwd)
+//   GEMM view: D[m][co] = sum_{tap,ci} X[m + off(tap)][ci] * Wp[tap][co][ci];  M tile = 128 output voxels arranged as
+//   a (TW,TH,TD) box of the volume, N tile = BN output channels, K loop = taps x (Cin_pad/64) blocks.
+//   Per K block the producer warp issues ONE 5-D TMA box load per operand plane: the box is the output tile shifted by
+//   the tap offset, and TMA's out-of-bounds zero fill implements the pad=1 halo, so no im2col buffer and no bounds
+//   code exists anywhere.  The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which is
+//   exactly the canonical K-major UMMA operand layout.  A single elected thread issues tcgen05.mma (M=128, N=BN,
+//   K=16) into a double-buffered TMEM accumulator; four epilogue warps drain TMEM with tcgen05.ld and write fp32.
+//   dgrad is the same kernel run on dy with the flipped/transposed weight pack (dram_pack_weight_bf16 mode 1).
+//
+// Split-bf16 ("bf16x3"): each fp32 operand is carried as hi = bf16(x), lo = bf16(x - hi); the MMA warp issues
+//   hi*hi + hi*lo + lo*hi into the same fp32 accumulator (lo*lo ~ 2^-32 dropped).  This is what meets the 1e-3
+//   parity target through 14 train-mode BatchNorm layers; lo == NULL selects 1-pass bf16.
+//
+// Wgrad (k_conv_umma_wgrad)
+//   GEMM view: dW[(tap,ci)][co] = sum_m X[m + off(tap)][ci] * dY[m][co]: the reduction runs over voxels, so both
+//   operands are MN-major: a TMA box of 64 voxels x 64 channels IS the canonical MN-major SW128 atom column.  The M
+//   dimension of one MMA (128) is two 64-channel blocks that may belong to different taps (they are separate TMA boxes
+//   LBO bytes apart), N = Cout tile.  Voxel chunks are split across CTAs (split-K); partial tiles go to a workspace and
+//   a second kernel reduces them in a fixed order into the nn.Parameter layout [Cout][Cin][taps] (deterministic).
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace dram {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap (context error, GPU released) instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle, sm_100 version field = 1.
+//   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart, LBO unused (1).
+//   MN-major: K rows of 128 B (= 64 MN elements), 8-row groups SBO = 1024 B apart, 64-element MN blocks LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad
+constexpr int kFwdThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kATileBytes = 128 * 128;    // 128 voxel rows x 64 bf16
+
+struct FwdParams {
+  float* y;
+  const float* scale;
+  const float* shift;
+  int N, D, H, W, Cout, BN, kblocks_c, taps, pad;
+  int TW, TH, TD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles;
+  int passes, stages, stage_bytes, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), tfull0 = smem_u32(bars + 2 * S),
+                 tempty0 = smem_u32(bars + 2 * S + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool three = p.passes == 3;
+  const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t offAlo = kATileBytes, offBhi = three ? 2 * kATileBytes : kATileBytes,
+                 offBlo = offBhi + b_tile_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
+  const int kblocks = p.taps * p.kblocks_c;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
+      if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+      const uint32_t stage_tx = (three ? 2u : 1u) * ((uint32_t)kATileBytes + b_tile_bytes);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_ntiles;
+        int mt = tile / p.n_ntiles;
+        const int w0 = (mt % p.tiles_w) * p.TW; mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.TH; mt /= p.tiles_h;
+        const int d0 = (mt % p.tiles_d) * p.TD;
+        const int n = mt / p.tiles_d;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kd = p.taps == 1 ? 0 : tap / 9, kh = p.taps == 1 ? 0 : (tap / 3) % 3, kw = p.taps == 1 ? 0 : tap % 3;
+          for (int cb = 0; cb < p.kblocks_c; ++cb, ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes), fb = full0 + 8 * s;
+            mbar_expect_tx(fb, stage_tx);
+            tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+            tma_load_2d(sb + offBhi, &tmB_hi, fb, cb * 64, tap * p.Cout + nt * p.BN);
+            if (three) {
+              tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+              tma_load_2d(sb + offBlo, &tmB_lo, fb, cb * 64, tap * p.Cout + nt * p.BN);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.BN, 0, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t a_hi = umma_desc(sb, 16, 1024), b_hi = umma_desc(sb + offBhi, 16, 1024);
+          const uint64_t a_lo = umma_desc(sb + offAlo, 16, 1024), b_lo = umma_desc(sb + offBlo, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {               // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+            if (three) {
+              umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
+        }
+        umma_commit(tfull0 + 8 * acc);                 // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW, th = (row / p.TW) % p.TH, td = row / (p.TW * p.TH);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int nt = tile % p.n_ntiles;
+      int mt = tile / p.n_ntiles;
+      const int w = (mt % p.tiles_w) * p.TW + tw; mt /= p.tiles_w;
+      const int h = (mt % p.tiles_h) * p.TH + th; mt /= p.tiles_h;
+      const int d = (mt % p.tiles_d) * p.TD + td;
+      const int n = mt / p.tiles_d;
+      const bool valid = td < p.TD && w < p.W && h < p.H && d < p.D;
+      float* out = p.y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * p.Cout + nt * p.BN;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = nt * p.BN + c0 + j;
+              v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+constexpr int kWgKV = 64;                       // voxels per K chunk (one TMA box)
+constexpr int kWgBlkBytes = kWgKV * 128;        // one 64-voxel x 64-channel MN-major block
+
+struct WgParams {
+  float* ws;                                    // [slabs][n_mtiles][n_ntiles][128][BN]
+  int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles, n_ntiles, BN;
+  int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, chunks_per_slab;
+  int passes, stages, stage_bytes, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                  const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                  const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), tfull0 = smem_u32(bars + 2 * S),
+                 tempty0 = smem_u32(bars + 2 * S + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool three = p.passes == 3;
+  const int nb = p.BN / 64;                                            // 64-channel blocks of the N operand
+  const uint32_t a_bytes = 2u * kWgBlkBytes, b_bytes = (uint32_t)nb * kWgBlkBytes;
+  const uint32_t offAlo = a_bytes, offBhi = three ? 2 * a_bytes : a_bytes, offBlo = offBhi + b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_stride = p.tmem_cols / 2;
+  const int n_items = p.n_slabs * p.n_mtiles * p.n_ntiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmY_hi);
+      if (three) { tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_lo); }
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = item % p.n_ntiles;
+        const int mt = (item / p.n_ntiles) % p.n_mtiles;
+        const int slab = item / (p.n_ntiles * p.n_mtiles);
+        const int mb0 = 2 * mt, mb1 = 2 * mt + 1;
+        const bool has1 = mb1 < p.MB;
+        const uint32_t tx = (three ? 2u : 1u) * ((has1 ? 2u : 1u) * kWgBlkBytes + b_bytes);
+        int tapv[2] = {mb0 / p.CB, has1 ? mb1 / p.CB : 0}, cbv[2] = {mb0 % p.CB, has1 ? mb1 % p.CB : 0};
+        const int c_begin = slab * p.chunks_per_slab;
+        const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+          int t = ch;
+          const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
+          const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
+          const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
+          const int n0 = t * p.TN;
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes), fb = full0 + 8 * s;
+          mbar_expect_tx(fb, tx);
+          for (int j = 0; j < (has1 ? 2 : 1); ++j) {
+            const int tap = tapv[j];
+            const int kd = p.taps == 1 ? 0 : tap / 9, kh = p.taps == 1 ? 0 : (tap / 3) % 3, kw = p.taps == 1 ? 0 : tap % 3;
+            tma_load_5d(sb + j * kWgBlkBytes, &tmX_hi, fb, cbv[j] * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n0);
+            if (three)
+              tma_load_5d(sb + offAlo + j * kWgBlkBytes, &tmX_lo, fb, cbv[j] * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n0);
+          }
+          for (int j = 0; j < nb; ++j) {
+            tma_load_5d(sb + offBhi + j * kWgBlkBytes, &tmY_hi, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
+            if (three) tma_load_5d(sb + offBlo + j * kWgBlkBytes, &tmY_lo, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.BN, 1, 1);
+      uint32_t it = 0, tcount = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+        const int slab = item / (p.n_ntiles * p.n_mtiles);
+        const int c_begin = slab * p.chunks_per_slab;
+        const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)acc_stride;
+        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t a_hi = umma_desc(sb, kWgBlkBytes, 1024), b_hi = umma_desc(sb + offBhi, kWgBlkBytes, 1024);
+          const uint64_t a_lo = umma_desc(sb + offAlo, kWgBlkBytes, 1024), b_lo = umma_desc(sb + offBlo, kWgBlkBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kWgKV / 16; ++k) {        // 16 voxel rows (2048 B) per MMA
+            const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (ch > c_begin || k) ? 1u : 0u);
+            if (three) {
+              umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int mt = (item / p.n_ntiles) % p.n_mtiles;
+      const bool valid = (2 * mt + row / 64) < p.MB;
+      float* out = p.ws + ((long long)item * 128 + row) * p.BN;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)acc_stride;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// dw[co][ci][tap] = sum_slab ws[slab][mt][nt][row][n]   (fixed summation order => deterministic)
+__global__ void k_wgrad_reduce(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int taps, int CB,
+                               int n_mtiles, int n_ntiles, int BN, int n_slabs) {
+  const long long total = (long long)taps * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int ci = (int)(r % Cin), tap = (int)(r / Cin);
+    const int mb = tap * CB + ci / 64;
+    const int mt = mb >> 1, row = (mb & 1) * 64 + (ci & 63), nt = co / BN, n = co % BN;
+    float acc = 0.f;
+    for (int s = 0; s < n_slabs; ++s)
+      acc += ws[((((long long)s * n_mtiles + mt) * n_ntiles + nt) * 128 + row) * BN + n];
+    dw[((long long)co * Cin + ci) * taps + tap] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+// x fp32 [rows][C] -> hi/lo bf16 [rows][Cpad]; 8 channels (two float4 in, one 16-byte store per plane) per thread
+__global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             long long rows, int C, int Cpad) {
+  const int groups = Cpad / 8;
+  const long long total = rows * groups;
+  const bool vec = (C % 8 == 0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long r = i / groups;
+    float v[8];
+    const int c0 = g * 8;
+    if (vec && c0 + 8 <= C) {
+      const float4* p = reinterpret_cast<const float4*>(x + r * C + c0);
+      float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? x[r * C + c0 + j] : 0.f;
+    }
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __float2bfloat16_rn(v[j]);
+      l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + r * Cpad + c0) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * Cpad + c0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// w [Cout][Cin][T] -> mode 0: out[t][co][k = ci]  (rows = Cout, K = Cin  -> Kpad)
+//                     mode 1: out[t][ci][k = co]  (rows = Cin,  K = Cout -> Kpad), taps flipped
+__global__ void k_pack_weight_bf16(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                   int Cout, int Cin, int Kpad, int T, int mode) {
+  const int R = mode == 0 ? Cout : Cin, K = mode == 0 ? Cin : Cout;
+  const long long total = (long long)T * R * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    long long r = i / Kpad;
+    const int row = (int)(r % R), t = (int)(r / R);
+    float v = 0.f;
+    if (k < K) v = mode == 0 ? w[((long long)row * Cin + k) * T + t] : w[((long long)k * Cin + row) * T + (T - 1 - t)];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 5-D map over a channels-last bf16 volume [N][D][H][W][C]; box = (64 channels, bw, bh, bd, bn), 128-byte swizzle
+static int make_volume_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bw, int bh, int bd, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DRAM_E_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(volume %dx%dx%dx%dx%d box %dx%dx%dx%d) failed: %d", N, D, H, W, C, bn, bd, bh, bw, (int)r); return DRAM_E_CUDA; }
+  return DRAM_OK;
+}
+// 2-D map over packed weights [rows][K] bf16; box = (64, box_rows)
+static int make_weight_map(CUtensorMap* m, const void* base, long long rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DRAM_E_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %lldx%d box %d) failed: %d", rows, K, box_rows, (int)r); return DRAM_E_CUDA; }
+  return DRAM_OK;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// output tile (TW,TH,TD), TW*TH*TD <= 128, maximising the fraction of useful MMA rows
+static void pick_fwd_tile(int D, int H, int W, int& TW, int& TH, int& TD) {
+  double best = -1.0;
+  TW = TH = TD = 1;
+  for (int tw = 1; tw <= 128 && tw <= W; ++tw)
+    for (int th = 1; tw * th <= 128 && th <= H; ++th) {
+      int td = 128 / (tw * th);
+      if (td > D) td = D;
+      if (td < 1) continue;
+      double eff = ((double)W * H * D) / ((double)cdiv(W, tw) * cdiv(H, th) * cdiv(D, td) * 128.0);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && (tw > TW || (tw == TW && th > TH)))) { best = eff; TW = tw; TH = th; TD = td; }
+    }
+}
+// K chunk (TW,TH,TD,TN) with product exactly 64 (powers of two), minimising zero-filled rows
+static void pick_wgrad_chunk(int N, int D, int H, int W, int& TW, int& TH, int& TD, int& TN) {
+  double best = 1e300;
+  TW = 64; TH = TD = TN = 1;
+  for (int tw = 1; tw <= 64; tw *= 2)
+    for (int th = 1; tw * th <= 64; th *= 2)
+      for (int td = 1; tw * th * td <= 64; td *= 2) {
+        int tn = 64 / (tw * th * td);
+        double vol = (double)cdiv(W, tw) * tw * cdiv(H, th) * th * (double)cdiv(D, td) * td * cdiv(N, tn) * tn;
+        if (vol < best - 0.5 || (vol < best + 0.5 && tw > TW)) { best = vol; TW = tw; TH = th; TD = td; TN = tn; }
+      }
+}
+static int pick_bn(int Cout) {
+  const int cand[6] = {128, 96, 64, 48, 32, 16};
+  for (int i = 0; i < 6; ++i)
+    if (Cout % cand[i] == 0) return cand[i];
+  return 0;
+}
+static int pow2_cols(int c) { int v = 32; while (v < c) v *= 2; return v; }
+
+constexpr int kSmemBudget = 200 * 1024;
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" {
+
+int dram_split_bf16(const float* x, void* hi, void* lo, long long rows, int C, int Cpad, void* stream) {
+  DRAM_REQUIRE(x && hi && rows > 0 && C > 0 && Cpad >= C && Cpad % 8 == 0, "split_bf16: bad arguments (C=%d Cpad=%d)", C, Cpad);
+  k_split_bf16<<<grid_for(rows * (Cpad / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, C, Cpad);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo, int Cout, int Cin, int Kpad, int ksize, int mode,
+                          void* stream) {
+  DRAM_REQUIRE(w && w_hi && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3) && (mode == 0 || mode == 1), "pack_weight_bf16: bad arguments");
+  DRAM_REQUIRE(Kpad >= (mode == 0 ? Cin : Cout) && Kpad % 64 == 0, "pack_weight_bf16: Kpad=%d must be a multiple of 64 covering K", Kpad);
+  const int T = ksize * ksize * ksize;
+  long long total = (long long)T * (mode == 0 ? Cout : Cin) * Kpad;
+  k_pack_weight_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
+                                                                            Cout, Cin, Kpad, T, mode);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* scale,
+                         const float* shift, float* y, int N, int D, int H, int W, int Cin_pad, int Cout, int ksize,
+                         void* stream) {
+  DRAM_REQUIRE(x_hi && w_hi && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
+  DRAM_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "conv3d_umma_fwd: x_lo and w_lo must both be set (bf16x3) or both NULL (bf16)");
+  DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
+  DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
+  DRAM_REQUIRE(Cin_pad > 0 && Cin_pad % 64 == 0, "conv3d_umma_fwd: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  FwdParams p;
+  p.BN = pick_bn(Cout);
+  DRAM_REQUIRE(p.BN > 0, "conv3d_umma_fwd: Cout=%d must be a multiple of 16", Cout);
+  p.y = y; p.scale = scale; p.shift = shift;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
+  p.kblocks_c = Cin_pad / 64; p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
+  pick_fwd_tile(D, H, W, p.TW, p.TH, p.TD);
+  p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD);
+  p.n_mtiles = N * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.n_ntiles = Cout / p.BN;
+  p.passes = x_lo ? 3 : 1;
+  p.stage_bytes = (x_lo ? 2 : 1) * (kATileBytes + p.BN * 128);
+  p.stages = (kSmemBudget - 1024) / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_fwd: pipeline does not fit in shared memory");
+  p.tmem_cols = pow2_cols(2 * p.BN);
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  int rc;
+  if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, 1))) return rc;
+  if ((rc = make_weight_map(&tmB_hi, w_hi, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
+  if (x_lo) {
+    if ((rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, 1))) return rc;
+    if ((rc = make_weight_map(&tmB_lo, w_lo, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
+  } else {
+    tmA_lo = tmA_hi; tmB_lo = tmB_hi;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(k_conv_umma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  const long long tiles = (long long)p.n_mtiles * p.n_ntiles;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  k_conv_umma_fwd<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize, int passes) {
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
+  p.CB = Cin_pad / 64; p.MB = p.taps * p.CB; p.n_mtiles = cdiv(p.MB, 2);
+  p.BN = Cout_pad <= 256 ? Cout_pad : (Cout_pad % 256 == 0 ? 256 : (Cout_pad % 128 == 0 ? 128 : 64));
+  p.n_ntiles = Cout_pad / p.BN;
+  pick_wgrad_chunk(N, D, H, W, p.TW, p.TH, p.TD, p.TN);
+  p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD); p.tiles_n = cdiv(N, p.TN);
+  p.n_chunks = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  const int tiles = p.n_mtiles * p.n_ntiles;
+  int slabs = cdiv(2 * kNumSMs, tiles);                    // ~2 waves of work items
+  const int max_slabs = cdiv(p.n_chunks, 8);               // >= 8 chunks per item so the pipeline fills
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  p.chunks_per_slab = cdiv(p.n_chunks, slabs);
+  p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
+  p.passes = passes;
+  p.stage_bytes = (passes == 3 ? 2 : 1) * (2 * kWgBlkBytes + (p.BN / 64) * kWgBlkBytes);
+  p.stages = (kSmemBudget - 1024) / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  p.tmem_cols = pow2_cols(2 * p.BN);
+  return DRAM_OK;
+}
+
+size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin_pad <= 0 || Cin_pad % 64 || Cout_pad <= 0 || Cout_pad % 64 ||
+      (ksize != 1 && ksize != 3))
+    return 0;
+  WgParams p;
+  wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, 3);
+  return (size_t)p.n_slabs * p.n_mtiles * p.n_ntiles * 128 * p.BN * sizeof(float);
+}
+
+int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* dw,
+                           void* workspace, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad,
+                           int ksize, void* stream) {
+  DRAM_REQUIRE(dy_hi && x_hi && dw && workspace && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_wgrad: bad arguments");
+  DRAM_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv3d_umma_wgrad: dy_lo and x_lo must both be set or both NULL");
+  DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_wgrad: kernel size %d unsupported", ksize);
+  DRAM_REQUIRE(Cin > 0 && Cin_pad >= Cin && Cin_pad % 64 == 0 && Cout > 0 && Cout_pad >= Cout && Cout_pad % 64 == 0,
+               "conv3d_umma_wgrad: channel pads must be multiples of 64 (Cin %d/%d, Cout %d/%d)", Cin, Cin_pad, Cout, Cout_pad);
+  WgParams p;
+  wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, dy_lo ? 3 : 1);
+  DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_wgrad: pipeline does not fit in shared memory");
+  DRAM_REQUIRE(p.tmem_cols <= 512, "conv3d_umma_wgrad: accumulator does not fit in TMEM");
+  p.ws = (float*)workspace;
+  CUtensorMap tmX_hi, tmX_lo, tmY_hi, tmY_lo;
+  int rc;
+  if ((rc = make_volume_map(&tmX_hi, x_hi, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  if ((rc = make_volume_map(&tmY_hi, dy_hi, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  if (dy_lo) {
+    if ((rc = make_volume_map(&tmX_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+    if ((rc = make_volume_map(&tmY_lo, dy_lo, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  } else {
+    tmX_lo = tmX_hi; tmY_lo = tmY_hi;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(k_conv_umma_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  const int items = p.n_slabs * p.n_mtiles * p.n_ntiles;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_conv_umma_wgrad<<<grid, kFwdThreads, smem, st>>>(tmX_hi, tmX_lo, tmY_hi, tmY_lo, p);
+  DRAM_LAUNCH_CHECK();
+  k_wgrad_reduce<<<grid_for((long long)p.taps * Cin * Cout, 256), 256, 0, st>>>(p.ws, dw, Cout, Cin, p.taps, p.CB, p.n_mtiles,
+                                                                                p.n_ntiles, p.BN, p.n_slabs);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,653 @@
+// BatchNorm / ReLU / MaxPool / trilinear upsample+concat / resize kernels on channels-last fp32 volumes.
+// All of them are HBM-bound streaming kernels: float4 accesses along the contiguous channel dimension, grids sized
+// as multiples of the 148 SMs with grid-stride loops, per-block reductions finished with a few double atomics.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace dram {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void k_nc2cl(const float* __restrict__ src, float* __restrict__ dst, int C, long long S, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    long long s = r % S, n = r / S;
+    dst[i] = src[(n * C + c) * S + s];
+  }
+}
+__global__ void k_cl2nc(const float* __restrict__ src, float* __restrict__ dst, int C, long long S, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long s = i % S;
+    long long r = i / S;
+    int c = (int)(r % C);
+    long long n = r / C;
+    dst[i] = src[(n * S + s) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN statistics
+// y [rows][C].  Block = 256 threads arranged as (row lanes) x (channel groups of VEC).  Each block owns a contiguous
+// slab of rows (<= kRowsPerBlock so fp32 partials stay short), reduces across row lanes in shared memory and adds
+// its per-channel partial to the double accumulators.
+constexpr int kStatThreads = 256;
+constexpr int kRowsPerBlock = 2048;
+
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(kStatThreads)
+k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const float* __restrict__ scale,
+            const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+            double* __restrict__ sums, long long rows, int C) {
+  extern __shared__ float sm[];  // [2][kStatThreads][VEC]
+  const int groups = (C + VEC - 1) / VEC;             // channel groups per row
+  const int lanes = kStatThreads / groups > 0 ? kStatThreads / groups : 1;  // row lanes per pass
+  // when groups > kStatThreads each thread loops over several channel groups
+  for (int g0 = 0; g0 < groups; g0 += kStatThreads) {
+    const int g = g0 + (threadIdx.x % (groups < kStatThreads ? groups : kStatThreads));
+    const int lane = groups < kStatThreads ? threadIdx.x / groups : 0;
+    float a0[VEC], a1[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
+    const bool active = (g < groups) && (lane < lanes);
+    float sc[VEC], sh[VEC], mu[VEC], rs[VEC];
+    if (BWD && active) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        int c = g * VEC + v;
+        bool ok = c < C;
+        sc[v] = ok ? scale[c] : 0.f; sh[v] = ok ? shift[c] : 0.f; mu[v] = ok ? mean[c] : 0.f; rs[v] = ok ? rstd[c] : 0.f;
+      }
+    }
+    for (long long slab = (long long)blockIdx.x * kRowsPerBlock; slab < rows; slab += (long long)gridDim.x * kRowsPerBlock) {
+      long long end = slab + kRowsPerBlock < rows ? slab + kRowsPerBlock : rows;
+      if (active) {
+        for (long long r = slab + lane; r < end; r += lanes) {
+          const float* p = y + r * C + (long long)g * VEC;
+          float yv[VEC], dv[VEC];
+          if (VEC == 4) {
+            float4 t = *reinterpret_cast<const float4*>(p);
+            yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3 % VEC] = t.w;
+            if (BWD) {
+              float4 u = *reinterpret_cast<const float4*>(da + r * C + (long long)g * VEC);
+              dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3 % VEC] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              bool ok = g * VEC + v < C;
+              yv[v] = ok ? p[v] : 0.f;
+              if (BWD) dv[v] = ok ? da[r * C + (long long)g * VEC + v] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (!BWD) {
+              a0[v] += yv[v];
+              a1[v] += yv[v] * yv[v];
+            } else {
+              float dz = (yv[v] * sc[v] + sh[v] > 0.f) ? dv[v] : 0.f;
+              a0[v] += dz;
+              a1[v] += dz * (yv[v] - mu[v]) * rs[v];
+            }
+          }
+        }
+      }
+    }
+    // cross-lane reduction in shared memory
+    float* s0 = sm;
+    float* s1 = sm + kStatThreads * VEC;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      s0[threadIdx.x * VEC + v] = a0[v];
+      s1[threadIdx.x * VEC + v] = a1[v];
+    }
+    __syncthreads();
+    if (active && lane == 0) {
+      const int gl = groups < kStatThreads ? groups : kStatThreads;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        int c = g * VEC + v;
+        if (c < C) {
+          double t0 = 0.0, t1 = 0.0;
+          for (int l = 0; l < lanes; ++l) {
+            t0 += (double)s0[(l * gl + (threadIdx.x % gl)) * VEC + v];
+            t1 += (double)s1[(l * gl + (threadIdx.x % gl)) * VEC + v];
+          }
+          atomicAdd(&sums[c], t0);
+          atomicAdd(&sums[C + c], t1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_bn_finalize(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                              float eps, int n_updates, float* mean, float* rstd, float* scale, float* shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  float r = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = (float)m;
+  rstd[c] = r;
+  scale[c] = g * r;
+  shift[c] = b - (float)m * g * r;
+  if (running_mean) {
+    float unbiased = count > 1.0 ? (float)(var * count / (count - 1.0)) : (float)var;
+    float rm = running_mean[c], rv = running_var[c];
+    for (int i = 0; i < n_updates; ++i) {
+      rm = (1.f - momentum) * rm + momentum * (float)m;
+      rv = (1.f - momentum) * rv + momentum * unbiased;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+}
+
+__global__ void k_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                               float* scale, float* shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float r = 1.0f / sqrtf(rv[c] + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * r;
+  shift[c] = b - rm[c] * g * r;
+}
+
+// ------------------------------------------------------------------------------------------------ BN apply + ReLU (+pool)
+template <int VEC>
+__global__ void k_bn_relu_apply(const float* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, float* __restrict__ a, long long rows, int C) {
+  const int groups = C / VEC;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    if (VEC == 4) {
+      float4 t = reinterpret_cast<const float4*>(y)[i];
+      float4 sc = reinterpret_cast<const float4*>(scale)[g], sh = reinterpret_cast<const float4*>(shift)[g];
+      t.x = fmaxf(t.x * sc.x + sh.x, 0.f); t.y = fmaxf(t.y * sc.y + sh.y, 0.f);
+      t.z = fmaxf(t.z * sc.z + sh.z, 0.f); t.w = fmaxf(t.w * sc.w + sh.w, 0.f);
+      reinterpret_cast<float4*>(a)[i] = t;
+    } else {
+      a[i] = fmaxf(y[i] * scale[g] + shift[g], 0.f);
+    }
+  }
+}
+
+// one thread per (pool cell, channel group): writes the 8 activations of the cell and their max
+template <int VEC>
+__global__ void k_bn_relu_pool(const float* __restrict__ y, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float* __restrict__ a, float* __restrict__ pooled,
+                               int N, int D, int H, int W, int C) {
+  const int groups = C / VEC;
+  const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;   // cells incl. ragged tail
+  const int pd = D / 2, ph = H / 2, pw = W / 2;                       // pooled size (floor)
+  const long long total = (long long)N * cd * ch * cw * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    long long r = i / groups;
+    int x = (int)(r % cw); r /= cw;
+    int yy = (int)(r % ch); r /= ch;
+    int z = (int)(r % cd);
+    int n = (int)(r / cd);
+    float sc[VEC], sh[VEC], mx[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { sc[v] = scale[g * VEC + v]; sh[v] = shift[g * VEC + v]; mx[v] = -INFINITY; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int zz = 2 * z + (k >> 2), yv = 2 * yy + ((k >> 1) & 1), xv = 2 * x + (k & 1);
+      if (zz < D && yv < H && xv < W) {
+        long long off = ((((long long)n * D + zz) * H + yv) * W + xv) * C + (long long)g * VEC;
+        float t[VEC];
+        if (VEC == 4) {
+          float4 q = *reinterpret_cast<const float4*>(y + off);
+          t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3 % VEC] = q.w;
+        } else {
+          t[0] = y[off];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { t[v] = fmaxf(t[v] * sc[v] + sh[v], 0.f); mx[v] = fmaxf(mx[v], t[v]); }
+        if (VEC == 4) *reinterpret_cast<float4*>(a + off) = make_float4(t[0], t[1], t[2], t[3 % VEC]);
+        else a[off] = t[0];
+      }
+    }
+    if (z < pd && yy < ph && x < pw) {
+      long long po = ((((long long)n * pd + z) * ph + yy) * pw + x) * C + (long long)g * VEC;
+      if (VEC == 4) *reinterpret_cast<float4*>(pooled + po) = make_float4(mx[0], mx[1], mx[2], mx[3 % VEC]);
+      else pooled[po] = mx[0];
+    }
+  }
+}
+
+template <int VEC>
+__global__ void k_bn_relu_bwd_apply(const float* __restrict__ da, const float* __restrict__ y,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ sums, double count,
+                                    float* __restrict__ dy, long long rows, int C) {
+  const int groups = C / VEC;
+  const long long total = rows * groups;
+  const float inv = sums ? (float)(1.0 / count) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    float yv[VEC], dv[VEC], o[VEC];
+    if (VEC == 4) {
+      float4 t = reinterpret_cast<const float4*>(y)[i], u = reinterpret_cast<const float4*>(da)[i];
+      yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3 % VEC] = t.w;
+      dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3 % VEC] = u.w;
+    } else {
+      yv[0] = y[i]; dv[0] = da[i];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      int c = g * VEC + v;
+      float sc = scale[c];
+      float dz = (yv[v] * sc + shift[c] > 0.f) ? dv[v] : 0.f;
+      if (sums) {
+        float xh = (yv[v] - mean[c]) * rstd[c];
+        float gm = gamma ? gamma[c] : 1.f;
+        o[v] = gm * rstd[c] * (dz - (float)sums[c] * inv - xh * (float)sums[C + c] * inv);
+      } else {
+        o[v] = dz * sc;
+      }
+    }
+    if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1], o[2], o[3 % VEC]);
+    else dy[i] = o[0];
+  }
+}
+
+// MaxPool3d(2,2,0) backward: first maximum in (d,h,w) scan order receives the gradient (ATen semantics: val > max).
+template <int VEC>
+__global__ void k_maxpool2_bwd(const float* __restrict__ a, const float* __restrict__ dpooled, float* __restrict__ da,
+                               int N, int D, int H, int W, int C) {
+  const int groups = C / VEC;
+  const int pd = D / 2, ph = H / 2, pw = W / 2;
+  const long long total = (long long)N * pd * ph * pw * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    long long r = i / groups;
+    int x = (int)(r % pw); r /= pw;
+    int yy = (int)(r % ph); r /= ph;
+    int z = (int)(r % pd);
+    int n = (int)(r / pd);
+    float mx[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { mx[v] = -INFINITY; arg[v] = 0; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      long long off = ((((long long)n * D + 2 * z + (k >> 2)) * H + 2 * yy + ((k >> 1) & 1)) * W + 2 * x + (k & 1)) * C + (long long)g * VEC;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float t = a[off + v];
+        if (t > mx[v] || t != t) { mx[v] = t; arg[v] = k; }
+      }
+    }
+    long long po = ((((long long)n * pd + z) * ph + yy) * pw + x) * C + (long long)g * VEC;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      int k = arg[v];
+      long long off = ((((long long)n * D + 2 * z + (k >> 2)) * H + 2 * yy + ((k >> 1) & 1)) * W + 2 * x + (k & 1)) * C + (long long)g * VEC + v;
+      da[off] += dpooled[po + v];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resize / upsample+concat
+// dst[n][Z][Y][X][co + c] = trilinear(src)[c] for c < Csrc.  Generic in the destination channel stride so that the
+// same kernel writes the "up" half of the concat buffer.
+template <int VEC>
+__global__ void k_trilinear_fwd(const float* __restrict__ src, float* __restrict__ dst, int N, int d, int h, int w,
+                                int D, int H, int W, int C, int dstC, int dstOff, float sz, float sy, float sx) {
+  const int groups = C / VEC;
+  const long long total = (long long)N * D * H * W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    long long r = i / groups;
+    int X = (int)(r % W); r /= W;
+    int Y = (int)(r % H); r /= H;
+    int Z = (int)(r % D);
+    int n = (int)(r / D);
+    Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int zi = (k & 4) ? lz.i1 : lz.i0, yi = (k & 2) ? ly.i1 : ly.i0, xi = (k & 1) ? lx.i1 : lx.i0;
+      float wt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
+      const float* p = src + ((((long long)n * d + zi) * h + yi) * w + xi) * C + (long long)g * VEC;
+      if (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        acc[0] += wt * t.x; acc[1] += wt * t.y; acc[2] += wt * t.z; acc[3 % VEC] += wt * t.w;
+      } else {
+        acc[0] += wt * p[0];
+      }
+    }
+    float* q = dst + ((((long long)n * D + Z) * H + Y) * W + X) * dstC + dstOff + (long long)g * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(acc[0], acc[1], acc[2], acc[3 % VEC]);
+    else q[0] = acc[0];
+  }
+}
+
+// candidate destination range along one axis whose taps may touch source index i
+__device__ __forceinline__ void adj_range(int i, float scale, int out_size, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out_size - 1; return; }
+  float inv = 1.0f / scale;
+  lo = (int)floorf((float)(i - 1) * inv) - 1;
+  hi = (int)ceilf((float)(i + 1) * inv) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+// exact adjoint of k_trilinear_fwd in gather form: dsrc[n][z][y][x][c] = sum over dst voxels of weight * ddst
+template <int VEC>
+__global__ void k_trilinear_bwd(const float* __restrict__ ddst, float* __restrict__ dsrc, int N, int d, int h, int w,
+                                int D, int H, int W, int C, int dstC, int dstOff, float sz, float sy, float sx) {
+  const int groups = C / VEC;
+  const long long total = (long long)N * d * h * w * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    long long r = i / groups;
+    int x = (int)(r % w); r /= w;
+    int y = (int)(r % h); r /= h;
+    int z = (int)(r % d);
+    int n = (int)(r / d);
+    int zl, zh, yl, yh, xl, xh;
+    adj_range(z, sz, D, zl, zh); adj_range(y, sy, H, yl, yh); adj_range(x, sx, W, xl, xh);
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int Z = zl; Z <= zh; ++Z) {
+      Lerp lz = lerp_setup(Z, sz, d);
+      float wz = (lz.i0 == z ? lz.w0 : 0.f) + (lz.i1 == z ? lz.w1 : 0.f);
+      if (wz == 0.f) continue;
+      for (int Y = yl; Y <= yh; ++Y) {
+        Lerp ly = lerp_setup(Y, sy, h);
+        float wy = (ly.i0 == y ? ly.w0 : 0.f) + (ly.i1 == y ? ly.w1 : 0.f);
+        if (wy == 0.f) continue;
+        for (int X = xl; X <= xh; ++X) {
+          Lerp lx = lerp_setup(X, sx, w);
+          float wx = (lx.i0 == x ? lx.w0 : 0.f) + (lx.i1 == x ? lx.w1 : 0.f);
+          if (wx == 0.f) continue;
+          float wt = wz * wy * wx;
+          const float* p = ddst + ((((long long)n * D + Z) * H + Y) * W + X) * dstC + dstOff + (long long)g * VEC;
+          if (VEC == 4) {
+            float4 t = *reinterpret_cast<const float4*>(p);
+            acc[0] += wt * t.x; acc[1] += wt * t.y; acc[2] += wt * t.z; acc[3 % VEC] += wt * t.w;
+          } else {
+            acc[0] += wt * p[0];
+          }
+        }
+      }
+    }
+    float* q = dsrc + i * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(acc[0], acc[1], acc[2], acc[3 % VEC]);
+    else q[0] = acc[0];
+  }
+}
+
+// copy the (centre-cropped) skip tensor into / out of channels [C1, C1+C2) of the concat buffer
+template <int VEC, bool BWD>
+__global__ void k_concat_skip(const float* __restrict__ in, float* __restrict__ out, int N, int D, int H, int W,
+                              int Ds, int Hs, int Ws, int oz, int oy, int ox, int C1, int C2) {
+  // FWD: in = skip [N][Ds][Hs][Ws][C2], out = cat [N][D][H][W][C1+C2]
+  // BWD: in = dcat, out = dskip (every voxel of dskip is written; outside the crop -> 0)
+  const int groups = C2 / VEC;
+  const int Ct = C1 + C2;
+  if (!BWD) {
+    const long long total = (long long)N * D * H * W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      int g = (int)(i % groups);
+      long long r = i / groups;
+      int X = (int)(r % W); r /= W;
+      int Y = (int)(r % H); r /= H;
+      int Z = (int)(r % D);
+      int n = (int)(r / D);
+      const float* p = in + ((((long long)n * Ds + Z + oz) * Hs + Y + oy) * Ws + X + ox) * C2 + (long long)g * VEC;
+      float* q = out + ((((long long)n * D + Z) * H + Y) * W + X) * Ct + C1 + (long long)g * VEC;
+      if (VEC == 4) *reinterpret_cast<float4*>(q) = *reinterpret_cast<const float4*>(p);
+      else q[0] = p[0];
+    }
+  } else {
+    const long long total = (long long)N * Ds * Hs * Ws * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      int g = (int)(i % groups);
+      long long r = i / groups;
+      int X = (int)(r % Ws); r /= Ws;
+      int Y = (int)(r % Hs); r /= Hs;
+      int Z = (int)(r % Ds);
+      int n = (int)(r / Ds);
+      int z = Z - oz, y = Y - oy, x = X - ox;
+      bool inside = z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W;
+      float* q = out + i * VEC;
+      if (inside) {
+        const float* p = in + ((((long long)n * D + z) * H + y) * W + x) * Ct + C1 + (long long)g * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(q) = *reinterpret_cast<const float4*>(p);
+        else q[0] = p[0];
+      } else {
+        if (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else q[0] = 0.f;
+      }
+    }
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+#define VEC_DISPATCH(C, CALL4, CALL1) \
+  do { if ((C) % 4 == 0) { CALL4; } else { CALL1; } } while (0)
+
+extern "C" {
+
+int dram_version(void) { return 100; }
+int dram_sm_arch(void) { return 100; }
+const char* dram_last_error(void) { return dram::last_error(); }
+int dram_device_check(void) {
+  int dev = 0, major = 0;
+  DRAM_CUDA(cudaGetDevice(&dev));
+  DRAM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libdram_b200 is built for sm_100a only; current device has compute capability major %d", major);
+    return DRAM_E_ARCH;
+  }
+  return DRAM_OK;
+}
+
+int dram_ncdhw_to_ndhwc(const float* src, float* dst, int N, int C, long long S, void* stream) {
+  DRAM_REQUIRE(src && dst && N > 0 && C > 0 && S > 0, "ncdhw_to_ndhwc: bad arguments");
+  long long total = (long long)N * C * S;
+  k_nc2cl<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, C, S, total);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+int dram_ndhwc_to_ncdhw(const float* src, float* dst, int N, int C, long long S, void* stream) {
+  DRAM_REQUIRE(src && dst && N > 0 && C > 0 && S > 0, "ndhwc_to_ncdhw: bad arguments");
+  long long total = (long long)N * C * S;
+  k_cl2nc<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, C, S, total);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static int stat_grid(long long rows) {
+  long long slabs = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  long long cap = (long long)kNumSMs * 8;
+  return (int)(slabs < cap ? (slabs < 1 ? 1 : slabs) : cap);
+}
+
+int dram_bn_stats(const float* y, double* sums, long long rows, int C, void* stream) {
+  DRAM_REQUIRE(y && sums && rows > 0 && C > 0, "bn_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  if (C % 4 == 0)
+    k_bn_reduce<4, false><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
+  else
+    k_bn_reduce<1, false><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int n_updates, float* mean, float* rstd,
+                     float* scale, float* shift, int C, void* stream) {
+  DRAM_REQUIRE(sums && mean && rstd && scale && shift && C > 0 && count > 0, "bn_finalize: bad arguments");
+  DRAM_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must both be set");
+  k_bn_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, beta, running_mean, running_var,
+                                                                  momentum, eps, n_updates, mean, rstd, scale, shift, C);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, float* scale, float* shift, int C, void* stream) {
+  DRAM_REQUIRE(running_mean && running_var && scale && shift && C > 0, "bn_fold_eval: bad arguments");
+  k_bn_fold_eval<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, scale,
+                                                                   shift, C);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_relu_apply(const float* y, const float* scale, const float* shift, float* a, float* pooled, int N, int D,
+                       int H, int W, int C, void* stream) {
+  DRAM_REQUIRE(y && scale && shift && a && N > 0 && D > 0 && H > 0 && W > 0 && C > 0, "bn_relu_apply: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long rows = (long long)N * D * H * W;
+  if (!pooled) {
+    VEC_DISPATCH(C, (k_bn_relu_apply<4><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>(y, scale, shift, a, rows, C)),
+                 (k_bn_relu_apply<1><<<grid_for(rows * C, 256), 256, 0, st>>>(y, scale, shift, a, rows, C)));
+  } else {
+    DRAM_REQUIRE(D >= 2 && H >= 2 && W >= 2, "bn_relu_apply: pooling needs every spatial size >= 2");
+    long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+    VEC_DISPATCH(C, (k_bn_relu_pool<4><<<grid_for(cells * (C / 4), 256), 256, 0, st>>>(y, scale, shift, a, pooled, N, D, H, W, C)),
+                 (k_bn_relu_pool<1><<<grid_for(cells * C, 256), 256, 0, st>>>(y, scale, shift, a, pooled, N, D, H, W, C)));
+  }
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_relu_bwd_reduce(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
+                            const float* rstd, double* sums, long long rows, int C, void* stream) {
+  DRAM_REQUIRE(da && y && scale && shift && mean && rstd && sums && rows > 0 && C > 0, "bn_relu_bwd_reduce: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  if (C % 4 == 0)
+    k_bn_reduce<4, true><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
+        y, da, scale, shift, mean, rstd, sums, rows, C);
+  else
+    k_bn_reduce<1, true><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
+        y, da, scale, shift, mean, rstd, sums, rows, C);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_relu_bwd_apply(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
+                           const float* rstd, const float* gamma, const double* sums, double count, float* dy,
+                           long long rows, int C, void* stream) {
+  DRAM_REQUIRE(da && y && scale && shift && dy && rows > 0 && C > 0, "bn_relu_bwd_apply: bad arguments");
+  DRAM_REQUIRE(!sums || (mean && rstd && count > 0), "bn_relu_bwd_apply: training mode needs mean/rstd/count");
+  cudaStream_t st = (cudaStream_t)stream;
+  VEC_DISPATCH(C, (k_bn_relu_bwd_apply<4><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C)),
+               (k_bn_relu_bwd_apply<1><<<grid_for(rows * C, 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C)));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_maxpool2_bwd(const float* a, const float* dpooled, float* da, int N, int D, int H, int W, int C, void* stream) {
+  DRAM_REQUIRE(a && dpooled && da && N > 0 && D >= 2 && H >= 2 && W >= 2 && C > 0, "maxpool2_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long cells = (long long)N * (D / 2) * (H / 2) * (W / 2);
+  VEC_DISPATCH(C, (k_maxpool2_bwd<4><<<grid_for(cells * (C / 4), 256), 256, 0, st>>>(a, dpooled, da, N, D, H, W, C)),
+               (k_maxpool2_bwd<1><<<grid_for(cells * C, 256), 256, 0, st>>>(a, dpooled, da, N, D, H, W, C)));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static int launch_trilinear_fwd(const float* src, float* dst, int N, int d, int h, int w, int D, int H, int W, int C,
+                                int dstC, int dstOff, cudaStream_t st) {
+  float sz = ac_scale(d, D), sy = ac_scale(h, H), sx = ac_scale(w, W);
+  long long vox = (long long)N * D * H * W;
+  if (C % 4 == 0 && dstC % 4 == 0 && dstOff % 4 == 0)
+    k_trilinear_fwd<4><<<grid_for(vox * (C / 4), 256), 256, 0, st>>>(src, dst, N, d, h, w, D, H, W, C, dstC, dstOff, sz, sy, sx);
+  else
+    k_trilinear_fwd<1><<<grid_for(vox * C, 256), 256, 0, st>>>(src, dst, N, d, h, w, D, H, W, C, dstC, dstOff, sz, sy, sx);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+static int launch_trilinear_bwd(const float* ddst, float* dsrc, int N, int d, int h, int w, int D, int H, int W, int C,
+                                int dstC, int dstOff, cudaStream_t st) {
+  float sz = ac_scale(d, D), sy = ac_scale(h, H), sx = ac_scale(w, W);
+  long long vox = (long long)N * d * h * w;
+  if (C % 4 == 0 && dstC % 4 == 0 && dstOff % 4 == 0)
+    k_trilinear_bwd<4><<<grid_for(vox * (C / 4), 128), 128, 0, st>>>(ddst, dsrc, N, d, h, w, D, H, W, C, dstC, dstOff, sz, sy, sx);
+  else
+    k_trilinear_bwd<1><<<grid_for(vox * C, 128), 128, 0, st>>>(ddst, dsrc, N, d, h, w, D, H, W, C, dstC, dstOff, sz, sy, sx);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_trilinear_resize_fwd(const float* src, float* dst, int N, int d, int h, int w, int D, int H, int W, int C,
+                              void* stream) {
+  DRAM_REQUIRE(src && dst && N > 0 && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0 && C > 0, "trilinear_resize_fwd: bad arguments");
+  return launch_trilinear_fwd(src, dst, N, d, h, w, D, H, W, C, C, 0, (cudaStream_t)stream);
+}
+int dram_trilinear_resize_bwd(const float* ddst, float* dsrc, int N, int d, int h, int w, int D, int H, int W, int C,
+                              void* stream) {
+  DRAM_REQUIRE(ddst && dsrc && N > 0 && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0 && C > 0, "trilinear_resize_bwd: bad arguments");
+  return launch_trilinear_bwd(ddst, dsrc, N, d, h, w, D, H, W, C, C, 0, (cudaStream_t)stream);
+}
+
+static inline int ceil_half(int a) { return (a + 1) / 2; }  // int(np.ceil((b - a) / 2)) for b >= a
+
+int dram_upsample2x_concat_fwd(const float* x, const float* skip, float* cat, int N, int d, int h, int w, int C1,
+                               int Ds, int Hs, int Ws, int C2, void* stream) {
+  DRAM_REQUIRE(x && skip && cat && N > 0 && d > 0 && h > 0 && w > 0 && C1 > 0 && C2 > 0, "upsample2x_concat_fwd: bad arguments");
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_fwd: skip (%d,%d,%d) smaller than upsampled (%d,%d,%d)", Ds, Hs, Ws, D, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_trilinear_fwd(x, cat, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);
+  if (rc) return rc;
+  int oz = ceil_half(Ds - D), oy = ceil_half(Hs - H), ox = ceil_half(Ws - W);
+  long long vox = (long long)N * D * H * W;
+  if (C1 % 4 == 0 && C2 % 4 == 0)
+    k_concat_skip<4, false><<<grid_for(vox * (C2 / 4), 256), 256, 0, st>>>(skip, cat, N, D, H, W, Ds, Hs, Ws, oz, oy, ox, C1, C2);
+  else
+    k_concat_skip<1, false><<<grid_for(vox * C2, 256), 256, 0, st>>>(skip, cat, N, D, H, W, Ds, Hs, Ws, oz, oy, ox, C1, C2);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N, int d, int h, int w, int C1, int Ds,
+                               int Hs, int Ws, int C2, void* stream) {
+  DRAM_REQUIRE(dcat && dx && dskip && N > 0 && d > 0 && h > 0 && w > 0 && C1 > 0 && C2 > 0, "upsample2x_concat_bwd: bad arguments");
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_bwd: bad skip size");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_trilinear_bwd(dcat, dx, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);
+  if (rc) return rc;
+  int oz = ceil_half(Ds - D), oy = ceil_half(Hs - H), ox = ceil_half(Ws - W);
+  long long vox = (long long)N * Ds * Hs * Ws;
+  if (C1 % 4 == 0 && C2 % 4 == 0)
+    k_concat_skip<4, true><<<grid_for(vox * (C2 / 4), 256), 256, 0, st>>>(dcat, dskip, N, D, H, W, Ds, Hs, Ws, oz, oy, ox, C1, C2);
+  else
+    k_concat_skip<1, true><<<grid_for(vox * C2, 256), 256, 0, st>>>(dcat, dskip, N, D, H, W, Ds, Hs, Ws, oz, oy, ox, C1, C2);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

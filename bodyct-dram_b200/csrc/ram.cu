@@ -1,0 +1,280 @@
+// Dense regression-activation-map (RAM) head: channel reduce with the regression weights (models.py:109-110,145),
+// per-lobe masked pooling (models.py:37-49, metrics.py:160-165) and the inference epilogue that upsamples a chunk's
+// RAM to the lobe crop and pastes it into the scan-sized heat map under the lobe mask (job_runner.py:765-770,993-1004).
+// All kernels are HBM-bound: algorithmic bytes = one read of the features (C*4 B/voxel) + one write of the map.
+#include "common.cuh"
+
+namespace dram {
+
+// feat [rows][C] (C % 4 == 0, C <= 128*... ), w [O][C].  A group of G = C/4 lanes owns one row (float4 per lane),
+// 32/G rows per warp per iteration, shuffle-reduced inside the group.  Fully coalesced 512 B per warp load.
+template <int G>
+__global__ void __launch_bounds__(256)
+k_ram_reduce_fwd(const float* __restrict__ feat, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ ram, long long rows,
+                 int C, int O) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G, rsub = lane / G;
+  constexpr int RPW = 32 / G;                      // rows per warp-iteration
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool fused = scale != nullptr;
+  if (fused) { sc = reinterpret_cast<const float4*>(scale)[sub]; sh = reinterpret_cast<const float4*>(shift)[sub]; }
+  for (long long r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    long long r = r0 + rsub;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) t = __ldg(reinterpret_cast<const float4*>(feat + r * C) + sub);
+    if (fused) {
+      t.x = fmaxf(t.x * sc.x + sh.x, 0.f); t.y = fmaxf(t.y * sc.y + sh.y, 0.f);
+      t.z = fmaxf(t.z * sc.z + sh.z, 0.f); t.w = fmaxf(t.w * sc.w + sh.w, 0.f);
+    }
+    for (int o = 0; o < O; ++o) {
+      float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)o * C) + sub);
+      float p = t.x * wv.x + t.y * wv.y + t.z * wv.z + t.w * wv.w;
+#pragma unroll
+      for (int s = G / 2; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+      if (sub == 0 && r < rows) ram[r * O + o] = p + b[o];
+    }
+  }
+}
+
+// generic (any C): one thread per (row, o)
+__global__ void k_ram_reduce_fwd_generic(const float* __restrict__ feat, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, const float* __restrict__ w,
+                                         const float* __restrict__ b, float* __restrict__ ram, long long rows, int C, int O) {
+  long long total = rows * O;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / O;
+    int o = (int)(i % O);
+    float acc = b[o];
+    for (int c = 0; c < C; ++c) {
+      float t = feat[r * C + c];
+      if (scale) t = fmaxf(t * scale[c] + shift[c], 0.f);
+      acc = fmaf(t, w[(long long)o * C + c], acc);
+    }
+    ram[i] = acc;
+  }
+}
+
+// dfeat[m][c] = sum_o dram[m][o] w[o][c];  dwb[o*C+c] += sum_m dram[m][o] feat[m][c];  dwb[O*C+o] += sum_m dram[m][o]
+// One thread per channel c (blockDim = C rounded up), blocks stride over row slabs.
+constexpr int kRamSlab = 1024;
+__global__ void k_ram_reduce_bwd(const float* __restrict__ dram, const float* __restrict__ feat,
+                                 const float* __restrict__ w, float* __restrict__ dfeat, double* __restrict__ dwb,
+                                 long long rows, int C, int O) {
+  const int c = threadIdx.x % C;                    // blockDim.x is a multiple of C
+  const int rl = threadIdx.x / C, rlanes = blockDim.x / C;
+  extern __shared__ float red[];                    // [blockDim.x]
+  for (int o = 0; o < O; ++o) {
+    const float wv = w[(long long)o * C + c];
+    float accw = 0.f, accb = 0.f;
+    for (long long slab = (long long)blockIdx.x * kRamSlab; slab < rows; slab += (long long)gridDim.x * kRamSlab) {
+      long long end = slab + kRamSlab < rows ? slab + kRamSlab : rows;
+      for (long long r = slab + rl; r < end; r += rlanes) {
+        float g = dram[r * O + o];
+        float f = feat[r * C + c];
+        accw = fmaf(g, f, accw);
+        accb += g;
+        if (O == 1) dfeat[r * C + c] = g * wv;
+      }
+    }
+    red[threadIdx.x] = accw;
+    __syncthreads();
+    if (rl == 0) {
+      double t = 0.0;
+      for (int l = 0; l < rlanes; ++l) t += (double)red[l * C + c];
+      atomicAdd(&dwb[(long long)o * C + c], t);
+    }
+    __syncthreads();
+    if (c == 0) red[rl] = accb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int l = 0; l < rlanes; ++l) t += (double)red[l];
+      atomicAdd(&dwb[(long long)O * C + o], t);
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_ram_dfeat_multi(const float* __restrict__ dram, const float* __restrict__ w, float* __restrict__ dfeat,
+                                  long long rows, int C, int O) {
+  long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C;
+    int c = (int)(i % C);
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) acc = fmaf(dram[r * O + o], w[(long long)o * C + c], acc);
+    dfeat[i] = acc;
+  }
+}
+
+// masked pooling: per sample b: sum f(x)*m and sum m
+__global__ void __launch_bounds__(256)
+k_masked_pool_fwd(const float* __restrict__ x, const float* __restrict__ mask, double* __restrict__ out, long long V,
+                  int use_sigmoid, int mode_gt0) {
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * V;
+  const float* mb = mask + (long long)b * V;
+  float s = 0.f, cnt = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+    float m = mb[i];
+    if (mode_gt0) m = m > 0.f ? 1.f : 0.f;
+    float v = xb[i];
+    if (use_sigmoid) v = sigmoidf_(v);
+    s = fmaf(v, m, s);
+    cnt += m;
+  }
+  s = warp_sum(s);
+  cnt = warp_sum(cnt);
+  __shared__ float sh[2][8];
+  int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][wid] = s; sh[1][wid] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += (double)sh[0][i]; c += (double)sh[1][i]; }
+    atomicAdd(&out[2 * b], a);
+    atomicAdd(&out[2 * b + 1], c);
+  }
+}
+
+__global__ void k_masked_pool_bwd(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ g,
+                                  float* __restrict__ dx, long long V, int use_sigmoid, int mode_gt0) {
+  const int b = blockIdx.y;
+  const float gb = g[b];
+  const float* xb = x + (long long)b * V;
+  const float* mb = mask + (long long)b * V;
+  float* db = dx + (long long)b * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+    float m = mb[i];
+    if (mode_gt0) m = m > 0.f ? 1.f : 0.f;
+    float d = gb * m;
+    if (use_sigmoid) { float s = sigmoidf_(xb[i]); d *= s * (1.f - s); }
+    db[i] = d;
+  }
+}
+
+// inference epilogue: one thread per crop voxel, x fastest (coalesced mask read / heat write)
+__device__ __forceinline__ float atomic_max_pos(float* addr, float v) {  // v >= 0
+  return __int_as_float(atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v)));
+}
+__global__ void __launch_bounds__(256)
+k_ram_upsample_mask_scatter(const float* __restrict__ ram, const uint8_t* __restrict__ crop_mask, float* __restrict__ heat,
+                            float* maxval, int d, int h, int w, int cd, int ch, int cw, int SD, int SH, int SW, int oz,
+                            int oy, int ox, int act, float gain, float sz, float sy, float sx) {
+  const long long total = (long long)cd * ch * cw;
+  float local_max = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % cw);
+    long long r = i / cw;
+    int Y = (int)(r % ch);
+    int Z = (int)(r / ch);
+    const bool inside = crop_mask[i] != 0;
+    if (!inside && maxval == nullptr) continue;
+    Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int zi = (k & 4) ? lz.i1 : lz.i0, yi = (k & 2) ? ly.i1 : ly.i0, xi = (k & 1) ? lx.i1 : lx.i0;
+      float wt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
+      if (act == 1) acc += wt * sigmoidf_(__ldg(ram + ((long long)zi * h + yi) * w + xi));   // sigmoid BEFORE interpolation
+      else acc += wt * __ldg(ram + ((long long)zi * h + yi) * w + xi);
+    }
+    if (act == 2) acc = fmaxf(acc, 0.f);                                                         // relu AFTER interpolation
+    if (maxval) local_max = fmaxf(local_max, acc);
+    if (inside && heat) heat[((long long)(Z + oz) * SH + (Y + oy)) * SW + (X + ox)] = acc * gain;
+  }
+  if (maxval) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((threadIdx.x & 31) == 0 && local_max > 0.f) atomic_max_pos(maxval, local_max);
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" {
+
+int dram_ram_reduce_fwd(const float* feat, const float* scale, const float* shift, const float* w, const float* b,
+                        float* ram, long long rows, int C, int O, void* stream) {
+  DRAM_REQUIRE(feat && w && b && ram && rows > 0 && C > 0 && O > 0, "ram_reduce_fwd: bad arguments");
+  DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "ram_reduce_fwd: scale and shift must come together");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = C / 4;
+  if (C % 4 == 0 && (G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32)) {
+    long long warps = (rows + (32 / G) - 1) / (32 / G);
+    int grid = grid_for(warps * 32, 256, 16);
+    switch (G) {
+      case 1: k_ram_reduce_fwd<1><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+      case 2: k_ram_reduce_fwd<2><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+      case 4: k_ram_reduce_fwd<4><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+      case 8: k_ram_reduce_fwd<8><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+      case 16: k_ram_reduce_fwd<16><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+      default: k_ram_reduce_fwd<32><<<grid, 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O); break;
+    }
+  } else {
+    k_ram_reduce_fwd_generic<<<grid_for(rows * O, 256), 256, 0, st>>>(feat, scale, shift, w, b, ram, rows, C, O);
+  }
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_ram_reduce_bwd(const float* dram_, const float* feat, const float* w, float* dfeat, double* dwb, long long rows,
+                        int C, int O, void* stream) {
+  DRAM_REQUIRE(dram_ && feat && w && dfeat && dwb && rows > 0 && C > 0 && O > 0, "ram_reduce_bwd: bad arguments");
+  DRAM_REQUIRE(C <= 1024, "ram_reduce_bwd: C=%d > 1024 unsupported", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(dwb, 0, sizeof(double) * ((size_t)O * C + O), st));
+  int rl = 256 / C; if (rl < 1) rl = 1;
+  int block = rl * C;
+  long long slabs = (rows + kRamSlab - 1) / kRamSlab;
+  int grid = (int)(slabs < (long long)kNumSMs * 8 ? slabs : (long long)kNumSMs * 8);
+  k_ram_reduce_bwd<<<grid, block, block * sizeof(float), st>>>(dram_, feat, w, dfeat, dwb, rows, C, O);
+  DRAM_LAUNCH_CHECK();
+  if (O > 1) {
+    k_ram_dfeat_multi<<<grid_for(rows * C, 256), 256, 0, st>>>(dram_, w, dfeat, rows, C, O);
+    DRAM_LAUNCH_CHECK();
+  }
+  return DRAM_OK;
+}
+
+int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, long long V, int use_sigmoid,
+                         int mode_gt0, void* stream) {
+  DRAM_REQUIRE(x && mask && out && B > 0 && V > 0, "masked_pool_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * B, st));
+  int gx = grid_for(V, 256 * 8, 4);
+  k_masked_pool_fwd<<<dim3(gx, B), 256, 0, st>>>(x, mask, out, V, use_sigmoid, mode_gt0);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, float* dx, int B, long long V,
+                         int use_sigmoid, int mode_gt0, void* stream) {
+  DRAM_REQUIRE(x && mask && g && dx && B > 0 && V > 0, "masked_pool_bwd: bad arguments");
+  int gx = grid_for(V, 256 * 4, 4);
+  k_masked_pool_bwd<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, mask, g, dx, V, use_sigmoid, mode_gt0);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, float* heat, float* maxval, int d, int h,
+                                   int w, int cd, int ch, int cw, int SD, int SH, int SW, int oz, int oy, int ox, int act,
+                                   float gain, void* stream) {
+  DRAM_REQUIRE(ram && crop_mask && (heat || maxval), "ram_upsample_mask_scatter: bad pointers");
+  DRAM_REQUIRE(d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "ram_upsample_mask_scatter: bad sizes");
+  DRAM_REQUIRE(act >= 0 && act <= 2, "ram_upsample_mask_scatter: act %d unknown", act);
+  DRAM_REQUIRE(oz >= 0 && oy >= 0 && ox >= 0 && oz + cd <= SD && oy + ch <= SH && ox + cw <= SW,
+               "ram_upsample_mask_scatter: crop [%d+%d,%d+%d,%d+%d] outside scan [%d,%d,%d]", oz, cd, oy, ch, ox, cw, SD, SH, SW);
+  long long total = (long long)cd * ch * cw;
+  k_ram_upsample_mask_scatter<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      ram, crop_mask, heat, maxval, d, h, w, cd, ch, cw, SD, SH, SW, oz, oy, ox, act, gain, ac_scale(d, cd),
+      ac_scale(h, ch), ac_scale(w, cw));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C ABI (include/dram_b200.h).
+
+Volumes are torch tensors of LOGICAL shape [N, C, D, H, W] (the reference's layout at every nn.Module boundary) whose
+MEMORY is channels-last ([N][D][H][W][C], `torch.channels_last_3d`), the layout every kernel works in.  PyTorch is used
+for device memory and streams only; every op below is a call into libdram_b200.so and raises if that is impossible.
+"""
+import os
+
+import torch
+
+from . import lib as _lib
+
+CL = torch.channels_last_3d
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DramLibraryError(f"{name}: the DRAM B200 path needs CUDA tensors (got {type(t).__name__} on "
+                                    f"{getattr(t, 'device', '?')}); there is no CPU fallback")
+    if t.dtype != dtype:
+        raise _lib.DramLibraryError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def new_volume(N, C, D, H, W, device, dtype=torch.float32, zero=False):
+    buf = (torch.zeros if zero else torch.empty)((N, D, H, W, C), device=device, dtype=dtype)
+    return buf.permute(0, 4, 1, 2, 3)
+
+
+def is_cl(x):
+    return x.dim() == 5 and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def to_cl(x, name="input"):
+    """Return x (logical NCDHW) with channels-last memory; converts with our own kernel when needed."""
+    _req(x, name)
+    if x.dim() != 5:
+        raise _lib.DramLibraryError(f"{name}: expected a 5-d NCDHW tensor, got {tuple(x.shape)}")
+    if is_cl(x):
+        return x
+    x = x.contiguous()
+    N, C, D, H, W = x.shape
+    out = new_volume(N, C, D, H, W, x.device)
+    _lib.check(_L().dram_ncdhw_to_ndhwc(x.data_ptr(), out.data_ptr(), N, C, D * H * W, _stream()), "ncdhw_to_ndhwc")
+    return out
+
+
+def to_ncdhw(x):
+    """Channels-last volume -> standard contiguous NCDHW (only needed when a caller insists on that memory layout)."""
+    _req(x, "to_ncdhw")
+    if x.is_contiguous():
+        return x
+    N, C, D, H, W = x.shape
+    src = to_cl(x)
+    out = torch.empty((N, C, D, H, W), device=x.device, dtype=x.dtype)
+    _lib.check(_L().dram_ndhwc_to_ncdhw(src.data_ptr(), out.data_ptr(), N, C, D * H * W, _stream()), "ndhwc_to_ncdhw")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ configuration
+def conv_path():
+    """'umma' (tcgen05 tensor cores where the shape allows, default) or 'simt' (CUDA-core fp32 everywhere)."""
+    return os.environ.get("DRAM_CONV_PATH", "umma")
+
+
+def precision():
+    """'bf16x3' (split-bf16, parity mode, default) or 'bf16' (single pass, fast mode)."""
+    return os.environ.get("DRAM_PRECISION", "bf16x3")
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def umma_ok_fwd(Cin, Cout, ksize):
+    return conv_path() == "umma" and ksize in (1, 3) and Cin >= 16 and Cout % 16 == 0
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def pack_weight_f32(w, mode):
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+    pack = torch.empty(k ** 3 * Cin * Cout, device=w.device, dtype=torch.float32)
+    _lib.check(_L().dram_pack_weight_f32(w.data_ptr(), pack.data_ptr(), Cout, Cin, k, mode, _stream()), "pack_weight_f32")
+    return pack
+
+
+def conv_simt(x, pack, bias, Cout, ksize):
+    """x CL volume [N,Cin,D,H,W]; pack [taps][Cin][Cout] -> CL volume [N,Cout,D,H,W]"""
+    N, Cin, D, H, W = x.shape
+    y = new_volume(N, Cout, D, H, W, x.device)
+    _lib.check(_L().dram_conv3d_simt_fwd(x.data_ptr(), pack.data_ptr(), _p(bias), y.data_ptr(), N, D, H, W, Cin, Cout,
+                                         ksize, _stream()), "conv3d_simt_fwd")
+    return y
+
+
+def conv_simt_wgrad(x, dy, ksize):
+    """-> dw in nn.Parameter layout [Cout, Cin, k, k, k]"""
+    N, Cin, D, H, W = x.shape
+    Cout = dy.shape[1]
+    taps = ksize ** 3
+    dpack = torch.zeros(taps * Cin * Cout, device=x.device, dtype=torch.float32)
+    _lib.check(_L().dram_conv3d_simt_wgrad(x.data_ptr(), dy.data_ptr(), dpack.data_ptr(), N, D, H, W, Cin, Cout, ksize,
+                                           _stream()), "conv3d_simt_wgrad")
+    dw = torch.empty((Cout, Cin, ksize, ksize, ksize), device=x.device, dtype=torch.float32)
+    _lib.check(_L().dram_unpack_wgrad_f32(dpack.data_ptr(), dw.data_ptr(), Cout, Cin, ksize, _stream()), "unpack_wgrad_f32")
+    return dw
+
+
+class SplitPlanes:
+    """bf16 split planes of a CL volume: hi (+ lo in bf16x3 mode), channels zero-padded to a multiple of 64."""
+    __slots__ = ("hi", "lo", "shape", "Cpad")
+
+    def __init__(self, hi, lo, shape, Cpad):
+        self.hi, self.lo, self.shape, self.Cpad = hi, lo, shape, Cpad
+
+
+def split_bf16(x, three=None):
+    N, C, D, H, W = x.shape
+    three = (precision() == "bf16x3") if three is None else three
+    Cpad = _pad64(C)
+    rows = N * D * H * W
+    hi = torch.empty((rows, Cpad), device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty((rows, Cpad), device=x.device, dtype=torch.bfloat16) if three else None
+    _lib.check(_L().dram_split_bf16(x.data_ptr(), hi.data_ptr(), _p(lo), rows, C, Cpad, _stream()), "split_bf16")
+    return SplitPlanes(hi, lo, (N, C, D, H, W), Cpad)
+
+
+def pack_weight_bf16(w, mode, three=None):
+    """mode 0: [taps][Cout][pad64(Cin)]; mode 1 (dgrad): [taps][Cin][pad64(Cout)] -> (hi, lo|None, Kpad)"""
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+    three = (precision() == "bf16x3") if three is None else three
+    rows, K = (Cout, Cin) if mode == 0 else (Cin, Cout)
+    Kpad = _pad64(K)
+    hi = torch.empty((k ** 3 * rows, Kpad), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if three else None
+    _lib.check(_L().dram_pack_weight_bf16(w.data_ptr(), hi.data_ptr(), _p(lo), Cout, Cin, Kpad, k, mode, _stream()),
+               "pack_weight_bf16")
+    return hi, lo, Kpad
+
+
+def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None):
+    """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32."""
+    N, _, D, H, W = xs.shape
+    y = new_volume(N, Cout, D, H, W, xs.hi.device)
+    _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
+                                         y.data_ptr(), N, D, H, W, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
+    return y
+
+
+def conv_umma_wgrad(dys, xs, Cin, Cout, ksize):
+    """dys / xs: SplitPlanes of dy and of the layer input -> dw [Cout, Cin, k, k, k] fp32."""
+    N, _, D, H, W = xs.shape
+    nbytes = _L().dram_conv3d_umma_wgrad_workspace_bytes(N, D, H, W, xs.Cpad, dys.Cpad, ksize)
+    if nbytes == 0:
+        raise _lib.DramLibraryError("conv3d_umma_wgrad: unsupported shape")
+    ws = torch.empty(nbytes // 4, device=xs.hi.device, dtype=torch.float32)
+    dw = torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
+    _lib.check(_L().dram_conv3d_umma_wgrad(dys.hi.data_ptr(), _p(dys.lo), xs.hi.data_ptr(), _p(xs.lo), dw.data_ptr(),
+                                           ws.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize, _stream()),
+               "conv3d_umma_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------ BN / ReLU / pool
+def bn_stats(y):
+    N, C, D, H, W = y.shape
+    sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+    _lib.check(_L().dram_bn_stats(y.data_ptr(), sums.data_ptr(), N * D * H * W, C, _stream()), "bn_stats")
+    return sums
+
+
+def bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps, n_updates):
+    C = sums.numel() // 2
+    out = torch.empty((4, C), device=sums.device, dtype=torch.float32)     # mean, rstd, scale, shift
+    _lib.check(_L().dram_bn_finalize(sums.data_ptr(), float(count), _p(gamma), _p(beta), _p(running_mean),
+                                     _p(running_var), float(momentum), float(eps), int(n_updates), out[0].data_ptr(),
+                                     out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), C, _stream()), "bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_fold_eval(gamma, beta, running_mean, running_var, eps):
+    C = running_mean.numel()
+    out = torch.empty((2, C), device=running_mean.device, dtype=torch.float32)
+    _lib.check(_L().dram_bn_fold_eval(_p(gamma), _p(beta), running_mean.data_ptr(), running_var.data_ptr(), float(eps),
+                                      out[0].data_ptr(), out[1].data_ptr(), C, _stream()), "bn_fold_eval")
+    return out[0], out[1]
+
+
+def bn_relu_apply(y, scale, shift, pool=False):
+    N, C, D, H, W = y.shape
+    a = new_volume(N, C, D, H, W, y.device)
+    pooled = new_volume(N, C, D // 2, H // 2, W // 2, y.device) if pool else None
+    _lib.check(_L().dram_bn_relu_apply(y.data_ptr(), scale.data_ptr(), shift.data_ptr(), a.data_ptr(), _p(pooled), N, D,
+                                       H, W, C, _stream()), "bn_relu_apply")
+    return a, pooled
+
+
+def bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd):
+    N, C, D, H, W = y.shape
+    sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+    _lib.check(_L().dram_bn_relu_bwd_reduce(da.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                            mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), N * D * H * W, C,
+                                            _stream()), "bn_relu_bwd_reduce")
+    return sums
+
+
+def bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, sums, count):
+    N, C, D, H, W = y.shape
+    dy = new_volume(N, C, D, H, W, y.device)
+    _lib.check(_L().dram_bn_relu_bwd_apply(da.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(mean),
+                                           _p(rstd), _p(gamma), _p(sums), float(count), dy.data_ptr(), N * D * H * W, C,
+                                           _stream()), "bn_relu_bwd_apply")
+    return dy
+
+
+def maxpool2_bwd(a, dpooled, da):
+    N, C, D, H, W = a.shape
+    _lib.check(_L().dram_maxpool2_bwd(a.data_ptr(), dpooled.data_ptr(), da.data_ptr(), N, D, H, W, C, _stream()),
+               "maxpool2_bwd")
+    return da
+
+
+# ------------------------------------------------------------------------------------------------ decoder glue
+def upsample2x_concat(x, skip):
+    N, C1, d, h, w = x.shape
+    _, C2, Ds, Hs, Ws = skip.shape
+    cat = new_volume(N, C1 + C2, 2 * d, 2 * h, 2 * w, x.device)
+    _lib.check(_L().dram_upsample2x_concat_fwd(x.data_ptr(), skip.data_ptr(), cat.data_ptr(), N, d, h, w, C1, Ds, Hs, Ws,
+                                               C2, _stream()), "upsample2x_concat_fwd")
+    return cat
+
+
+def upsample2x_concat_bwd(dcat, x_shape, skip_shape):
+    N, C1, d, h, w = x_shape
+    _, C2, Ds, Hs, Ws = skip_shape
+    dx = new_volume(N, C1, d, h, w, dcat.device)
+    dskip = new_volume(N, C2, Ds, Hs, Ws, dcat.device)
+    _lib.check(_L().dram_upsample2x_concat_bwd(dcat.data_ptr(), dx.data_ptr(), dskip.data_ptr(), N, d, h, w, C1, Ds, Hs,
+                                               Ws, C2, _stream()), "upsample2x_concat_bwd")
+    return dx, dskip
+
+
+def trilinear_resize(x, size):
+    N, C, d, h, w = x.shape
+    D, H, W = size
+    out = new_volume(N, C, D, H, W, x.device)
+    _lib.check(_L().dram_trilinear_resize_fwd(x.data_ptr(), out.data_ptr(), N, d, h, w, D, H, W, C, _stream()),
+               "trilinear_resize_fwd")
+    return out
+
+
+def trilinear_resize_bwd(dout, src_size):
+    N, C, D, H, W = dout.shape
+    d, h, w = src_size
+    dx = new_volume(N, C, d, h, w, dout.device)
+    _lib.check(_L().dram_trilinear_resize_bwd(dout.data_ptr(), dx.data_ptr(), N, d, h, w, D, H, W, C, _stream()),
+               "trilinear_resize_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ RAM head
+def ram_reduce(feat, w, b, scale=None, shift=None):
+    """feat CL volume [N,C,D,H,W]; w [O,C]; b [O] -> CL volume [N,O,D,H,W]"""
+    N, C, D, H, W = feat.shape
+    O = w.shape[0]
+    ram = new_volume(N, O, D, H, W, feat.device)
+    _lib.check(_L().dram_ram_reduce_fwd(feat.data_ptr(), _p(scale), _p(shift), w.data_ptr(), b.data_ptr(), ram.data_ptr(),
+                                        N * D * H * W, C, O, _stream()), "ram_reduce_fwd")
+    return ram
+
+
+def ram_reduce_bwd(dram, feat, w):
+    N, C, D, H, W = feat.shape
+    O = w.shape[0]
+    dfeat = new_volume(N, C, D, H, W, feat.device)
+    dwb = torch.empty(O * C + O, device=feat.device, dtype=torch.float64)
+    _lib.check(_L().dram_ram_reduce_bwd(dram.data_ptr(), feat.data_ptr(), w.data_ptr(), dfeat.data_ptr(), dwb.data_ptr(),
+                                        N * D * H * W, C, O, _stream()), "ram_reduce_bwd")
+    return dfeat, dwb[:O * C].view(O, C).float(), dwb[O * C:].float()
+
+
+def masked_pool(x, mask, use_sigmoid=False, mode_gt0=False):
+    """x, mask: [B, V] contiguous fp32 -> double [B, 2] (sum f(x)*m, sum m)"""
+    B, V = x.shape
+    out = torch.empty((B, 2), device=x.device, dtype=torch.float64)
+    _lib.check(_L().dram_masked_pool_fwd(x.data_ptr(), mask.data_ptr(), out.data_ptr(), B, V, int(use_sigmoid),
+                                         int(mode_gt0), _stream()), "masked_pool_fwd")
+    return out
+
+
+def masked_pool_bwd(x, mask, g, use_sigmoid=False, mode_gt0=False):
+    B, V = x.shape
+    dx = torch.empty_like(x)
+    _lib.check(_L().dram_masked_pool_bwd(x.data_ptr(), mask.data_ptr(), g.data_ptr(), dx.data_ptr(), B, V,
+                                         int(use_sigmoid), int(mode_gt0), _stream()), "masked_pool_bwd")
+    return dx
+
+
+def ram_upsample_mask_scatter(ram, crop_mask, heat, offset, act, gain=1.0, maxval=None):
+    """ram [d,h,w] fp32; crop_mask [cd,ch,cw] uint8; heat [SD,SH,SW] fp32 (in place) or None."""
+    d, h, w = ram.shape
+    cd, ch, cw = crop_mask.shape
+    if crop_mask.dtype != torch.uint8 or not crop_mask.is_contiguous():
+        raise _lib.DramLibraryError("ram_upsample_mask_scatter: crop_mask must be a contiguous uint8 tensor")
+    SD, SH, SW = heat.shape if heat is not None else (cd, ch, cw)
+    oz, oy, ox = offset
+    _lib.check(_L().dram_ram_upsample_mask_scatter(ram.data_ptr(), crop_mask.data_ptr(), _p(heat), _p(maxval), d, h, w,
+                                                   cd, ch, cw, SD, SH, SW, oz, oy, ox, int(act), float(gain), _stream()),
+               "ram_upsample_mask_scatter")
+
+
+# ------------------------------------------------------------------------------------------------ PCM
+MERGE_FLAGS = {"sm": 0, "smrelu": 1, "scaled_dot_product": 2, "scaled_dot_product_relu": 3, "smscaled": 4}
+
+
+def pcm_num_offsets(connectivity, self_loop):
+    return _L().dram_pcm_num_offsets(int(connectivity), int(bool(self_loop)))
+
+
+def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags):
+    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk, att)"""
+    B, Cf, D, H, W = f.shape
+    F = tw.shape[0]
+    O = pcm_num_offsets(connectivity, self_loop)
+    V = D * H * W
+    qk = torch.empty((B * V, 2 * F), device=f.device, dtype=torch.float32)
+    att = torch.empty((B * V, O), device=f.device, dtype=torch.float32)
+    out = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
+    _lib.check(_L().dram_pcm_fwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), tb.data_ptr(), pw.data_ptr(), pb.data_ptr(),
+                                 qk.data_ptr(), att.data_ptr(), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
+                                 int(bool(self_loop)), int(flags), _stream()), "pcm_fwd")
+    return out, qk, att
+
+
+def pcm_bwd(f, cam, tw, pw, qk, att, dout, connectivity, self_loop, flags):
+    B, Cf, D, H, W = f.shape
+    F = tw.shape[0]
+    dd = torch.empty_like(att)
+    dqk = torch.empty_like(qk)
+    dcam = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
+    df = new_volume(B, Cf, D, H, W, f.device)
+    dparams = torch.empty(2 * F * (Cf + 1), device=f.device, dtype=torch.float64)
+    _lib.check(_L().dram_pcm_bwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), pw.data_ptr(), qk.data_ptr(), att.data_ptr(),
+                                 dout.data_ptr(), dd.data_ptr(), dqk.data_ptr(), dcam.data_ptr(), df.data_ptr(),
+                                 dparams.data_ptr(), B, D, H, W, Cf, F, int(connectivity), int(bool(self_loop)),
+                                 int(flags), _stream()), "pcm_bwd")
+    dp = dparams.float()
+    n = F * Cf
+    return dcam, df, dp[:n].view(F, Cf), dp[n:n + F], dp[n + F:2 * n + F].view(F, Cf), dp[2 * n + F:]

@@ -1,0 +1,174 @@
+/* dram_b200.h — C ABI of the B200-native DRAM hot path (libdram_b200.so).
+ *
+ * The reference (DIAGNijmegen/bodyct-dram) is pure Python and has NO FFI of its own: every device op on this path is a
+ * PyTorch/cuDNN/DGL library call made from dram/parts.py and dram/models.py.  Each entry point below therefore cites the
+ * reference call site (file:line under /root/reference/dram/) whose library call it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the PyTorch caching allocator in practice);
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it and returns;
+ *   - no allocation happens inside; scratch space is caller-provided (see the *_workspace_bytes queries);
+ *   - return value: 0 = ok, negative = error (DRAM_E_*); dram_last_error() gives a thread-local message;
+ *   - volumes are channels-last:  [N][D][H][W][C]  ("NDHWC"), fp32 unless a name says bf16;
+ *   - "bf16 split planes": a tensor x is carried as two bf16 tensors (hi, lo) with hi = bf16(x), lo = bf16(x - hi);
+ *     tensor-core convolutions accumulate hi*hi + hi*lo + lo*hi in fp32 (3 passes, ~2^-16 relative operand error).
+ */
+#ifndef DRAM_B200_H
+#define DRAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRAM_OK 0
+#define DRAM_E_INVALID (-1) /* bad argument / unsupported shape (no silent fallback) */
+#define DRAM_E_CUDA (-2)    /* CUDA runtime / driver error */
+#define DRAM_E_ARCH (-3)    /* device is not sm_100 */
+
+/* ------------------------------------------------------------------------------------------------ library */
+int dram_version(void);              /* 100*major + minor */
+int dram_sm_arch(void);              /* 100 — the only architecture this library is built for */
+const char* dram_last_error(void);   /* thread-local, never NULL */
+int dram_device_check(void);         /* DRAM_OK iff the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------ layout */
+/* [N][C][S] <-> [N][S][C] (S = D*H*W).  Boundary converters for nn.Module inputs with C > 1 (models.py:120). */
+int dram_ncdhw_to_ndhwc(const float* src, float* dst, int N, int C, long long S, void* stream);
+int dram_ndhwc_to_ncdhw(const float* src, float* dst, int N, int C, long long S, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ convolution
+ * nn.Conv3d(k in {1,3}, padding=k/2, stride 1, bias=False|True): parts.py:105-106,133,185-186; models.py:109-110,490.
+ *
+ * Weight packs (produced on device from the nn.Parameter [Cout][Cin][k][k][k], every step):
+ *   mode 0 (forward): pack[tap][ci][co] = w[co][ci][tap]
+ *   mode 1 (dgrad)  : pack[tap][co][ci] = w[co][ci][ntaps-1-tap]   (flipped taps, channels swapped)
+ * so that dgrad is the SAME kernel run on dy with the mode-1 pack. */
+int dram_pack_weight_f32(const float* w, float* pack, int Cout, int Cin, int ksize, int mode, void* stream);
+/* dw[co][ci][tap] = pack[tap][ci][co] (wgrad output -> nn.Parameter.grad layout) */
+int dram_unpack_wgrad_f32(const float* pack, float* dw, int Cout, int Cin, int ksize, void* stream);
+
+/* CUDA-core fp32 implicit GEMM: any Cin/Cout.  Used for Cin=1 (K=27, bandwidth-bound), the 1x1x1 heads and shapes
+ * the tcgen05 kernel does not cover.  y[n,d,h,w,co] = bias[co] + sum_{tap,ci} x[n,d+kd-p,..,ci] * pack[tap][ci][co] */
+int dram_conv3d_simt_fwd(const float* x, const float* pack, const float* bias /*nullable*/, float* y,
+                         int N, int D, int H, int W, int Cin, int Cout, int ksize, void* stream);
+/* dpack[tap][ci][co] = sum_m x[m+tap][ci] * dy[m][co]; dpack must be zeroed by the caller (atomic split-K). */
+int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack,
+                           int N, int D, int H, int W, int Cin, int Cout, int ksize, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit GEMM (sm_100a).  Operands are bf16 split planes, channels padded to a multiple of 64.
+ *   x_hi/x_lo : [N][D][H][W][Cin_pad] bf16          (x_lo may be NULL => single-pass bf16 "fast" mode)
+ *   w_hi/w_lo : [taps][Cout][Cin_pad] bf16 (K-major; mode as above, see dram_pack_weight_bf16)
+ *   y         : [N][D][H][W][Cout] fp32 raw accumulators; if scale/shift != NULL the epilogue applies
+ *               y = max(0, acc*scale[co] + shift[co])  (eval-mode folded BatchNorm + ReLU, parts.py:107-108)
+ * Cout must be a multiple of 16.  K loop = taps x Cin_pad/64 stages of {A 128x64, B BNx64} fed by TMA (5-D tensor map
+ * with zero fill for the padding halo), accumulators double-buffered in TMEM, persistent over output tiles. */
+int dram_split_bf16(const float* x, void* hi, void* lo /*nullable*/, long long rows, int C, int Cpad, void* stream);
+int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo /*nullable*/, int Cout, int Cin, int Cin_pad,
+                          int ksize, int mode, void* stream);
+int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                         const float* scale /*nullable*/, const float* shift /*nullable*/, float* y,
+                         int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, void* stream);
+/* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes
+ *   dy_hi/dy_lo : [N][D][H][W][Cout_pad]   x_hi/x_lo : [N][D][H][W][Cin_pad]   (pads are multiples of 64)
+ * partial sums over voxel ranges are written to `workspace` (dram_conv3d_umma_wgrad_workspace_bytes) and reduced
+ * deterministically into dw in nn.Parameter layout [Cout][Cin][taps]. */
+size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize);
+int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* dw,
+                           void* workspace, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad,
+                           int ksize, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ BatchNorm + ReLU (+ pool)
+ * nn.BatchNorm3d (eps 1e-5, momentum 0.1) + nn.ReLU: parts.py:19,50,107-108.  rows = N*D*H*W, y is [rows][C]. */
+int dram_bn_stats(const float* y, double* sums /*[2*C]: sum, sumsq; overwritten*/, long long rows, int C, void* stream);
+/* sums -> mean/rstd/scale/shift; running stats updated `n_updates` times (checkpointed blocks update twice per step,
+ * models.py:123-143).  `count` = rows (global rows under data parallelism, after the caller all-reduced `sums`). */
+int dram_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int n_updates, float* mean, float* rstd,
+                     float* scale, float* shift, int C, void* stream);
+/* eval mode: scale/shift from running statistics */
+int dram_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, float* scale, float* shift, int C, void* stream);
+/* a = max(0, y*scale + shift); if pooled != NULL also MaxPool3d(2,2,0) of a (parts.py:191,195), floor semantics */
+int dram_bn_relu_apply(const float* y, const float* scale, const float* shift, float* a, float* pooled /*nullable*/,
+                       int N, int D, int H, int W, int C, void* stream);
+/* backward, pass 1: dz = da * (y*scale+shift > 0); sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat */
+int dram_bn_relu_bwd_reduce(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
+                            const float* rstd, double* sums, long long rows, int C, void* stream);
+/* backward, pass 2 (training): dy = gamma*rstd*(dz - sum_dz/count - xhat*sum_dz_xhat/count);
+ * eval (sums == NULL): dy = dz*scale */
+int dram_bn_relu_bwd_apply(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
+                           const float* rstd, const float* gamma, const double* sums /*nullable*/, double count,
+                           float* dy, long long rows, int C, void* stream);
+/* MaxPool3d(2,2,0) backward: da[first argmax of each window] += dpooled (da is read-modify-write; windows are disjoint) */
+int dram_maxpool2_bwd(const float* a, const float* dpooled, float* da, int N, int D, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ decoder glue
+ * nn.Upsample(scale_factor=2, trilinear, align_corners=True) + crop_concat_5d: parts.py:149-153,37-46.
+ * cat[..., 0:C1] = up(x) ; cat[..., C1:C1+C2] = skip centre-cropped with ceil offsets.  x: [N][d][h][w][C1],
+ * skip: [N][Ds][Hs][Ws][C2], cat: [N][2d][2h][2w][C1+C2]. */
+int dram_upsample2x_concat_fwd(const float* x, const float* skip, float* cat, int N, int d, int h, int w, int C1,
+                               int Ds, int Hs, int Ws, int C2, void* stream);
+/* dx (gather form of the transposed interpolation, no atomics) and dskip (zero outside the crop) */
+int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N, int d, int h, int w, int C1,
+                               int Ds, int Hs, int Ws, int C2, void* stream);
+/* F.interpolate(size=..., trilinear, align_corners=True): models.py:146,514-518,588,591-592; job_runner.py:766,993.
+ * src [N][d][h][w][C] -> dst [N][D][H][W][C]; the backward is the exact adjoint, gather form. */
+int dram_trilinear_resize_fwd(const float* src, float* dst, int N, int d, int h, int w, int D, int H, int W, int C,
+                              void* stream);
+int dram_trilinear_resize_bwd(const float* ddst, float* dsrc, int N, int d, int h, int w, int D, int H, int W, int C,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------ RAM head
+ * top_layer = nn.Conv3d(64 -> out_ch, k=1) (models.py:109-110,145): the regression-weight channel reduce.
+ * Fused with the last BatchNorm+ReLU when scale/shift != NULL:  ram[m][o] = b[o] + sum_c relu(y*scale+shift)[c]*w[o][c] */
+int dram_ram_reduce_fwd(const float* feat, const float* scale /*nullable*/, const float* shift /*nullable*/,
+                        const float* w /*[O][C]*/, const float* b /*[O]*/, float* ram /*[rows][O]*/, long long rows,
+                        int C, int O, void* stream);
+/* dfeat[m][c] = sum_o dram[m][o]*w[o][c]; dwb[o*C+c] = sum_m dram[m][o]*feat[m][c]; dwb[O*C+o] = sum_m dram[m][o]
+ * (dwb: double[O*C+O], overwritten) */
+int dram_ram_reduce_bwd(const float* dram, const float* feat, const float* w, float* dfeat, double* dwb,
+                        long long rows, int C, int O, void* stream);
+/* pooling_dense_features / masked mean (models.py:37-49; metrics.py:160-165):
+ * out[b*2+0] = sum_v f(x[b][v]) * mask[b][v], out[b*2+1] = sum_v mask[b][v]; f = sigmoid if use_sigmoid.
+ * mode_gt0: use (mask > 0) instead of the mask value (metrics.py:162).  out: double[2*B], overwritten. */
+int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, long long V, int use_sigmoid,
+                         int mode_gt0, void* stream);
+/* dx[b][v] = g[b] * f'(x) * m[b][v]   (g already divided by the mask count by the caller) */
+int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, float* dx, int B, long long V,
+                         int use_sigmoid, int mode_gt0, void* stream);
+/* Inference epilogue (job_runner.py:765-770 / 993-1004): trilinear-upsample one chunk's RAM [d][h][w] to the lobe crop
+ * [cd][ch][cw] (align_corners=True), apply `act` (0 = identity, 1 = sigmoid, 2 = relu), multiply by `gain`
+ * (1/max for the max-normalised head) and write it into the scan-sized heat map at offset (oz,oy,ox) ONLY where
+ * crop_mask != 0 (bit-exact lobe masking).  If maxval != NULL, also atomically tracks max(act(value)) over the crop. */
+int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, float* heat, float* maxval /*nullable*/,
+                                   int d, int h, int w, int cd, int ch, int cw, int SD, int SH, int SW, int oz, int oy,
+                                   int ox, int act, float gain, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ PCM stencil attention
+ * PCM.forward via DGL update_all (models.py:322-411) on the voxel-grid graph of models.py:223-259, restated as an
+ * 18/6/26(+1)-point stencil attention on a [D][H][W] grid:
+ *   q = theta(f_x), k_o = phi(f_{x+o}); s_o = act(<q,k_o>) / T(x); a = softmax_o over in-grid neighbours;
+ *   out_x = sum_o a_o * cam_{x+o}                      (the affine G/r maps collapse to a scalar affine, applied by the host)
+ * f: [B][D][H][W][Cf] fp32, cam/out: [B][D][H][W].  theta/phi: [F][Cf] weights + [F] bias.
+ * flags bit0: relu on logits; bits1-2: temperature (0 none, 1 sqrt(degree) — models.py:274-277, 2 = 0.01);
+ * connectivity 1|2|3, self_loop 0|1. */
+int dram_pcm_num_offsets(int connectivity, int self_loop); /* O: 18 for (2, no self loop) */
+/* qk  [B][V][2F] (out): theta|phi projections;  att [B][V][O] (out): softmax weights, kept for the backward */
+int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
+                 const float* phi_b, float* qk, float* att, float* out, int B, int D, int H, int W, int Cf, int F,
+                 int connectivity, int self_loop, int flags, void* stream);
+/* dd_ws [B][V][O], dqk_ws [B][V][2F]: scratch.  dcam [B][V], df [B][V][Cf]: overwritten.
+ * dparams double[2*F*(Cf+1)] = dtheta_w, dtheta_b, dphi_w, dphi_b: overwritten. */
+int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
+                 const float* att, const float* dout, float* dd_ws, float* dqk_ws, float* dcam, float* df,
+                 double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAM_B200_H */
