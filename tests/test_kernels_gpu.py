@@ -1,0 +1,388 @@
+"""GPU parity tests, op level: every libdram_b200 kernel (called through the C ABI via dram_native.ops /
+dram_native.functional) against the matching torch fp32 CPU computation — the same library calls the reference makes
+(F.conv3d, F.batch_norm, F.max_pool3d, F.interpolate(trilinear, align_corners=True), ...) — or against the oracle.
+
+Tolerances (max-abs error relative to max |ref|):
+  fp32 CUDA-core kernels and elementwise kernels : 2e-5
+  split-bf16 (bf16x3) tensor-core convolutions   : 1e-4   (operand error ~2^-16; north_star bound is 1e-3)
+  single-pass bf16 tensor-core convolutions      : 2e-2   (fast mode, reported separately)
+  index / mask work                              : bit-exact
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close, cuda_cl
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 2e-5
+TOL_X3 = 1e-4
+TOL_BF16 = 2e-2
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+
+
+def ops():
+    from dram_native import ops as o
+    return o
+
+
+def DF():
+    from dram_native import functional as f
+    return f
+
+
+# ------------------------------------------------------------------------------------------------ library / layout
+def test_library_loads_on_device():
+    from dram_native import lib
+    L = lib.load()
+    assert L.dram_sm_arch() == 100
+    assert L.dram_device_check() == 0, L.dram_last_error()
+
+
+def test_errors_are_loud():
+    from dram_native import lib
+    o = ops()
+    with pytest.raises(lib.DramLibraryError):
+        o.to_cl(torch.zeros(1, 2, 4, 4, 4))                       # CPU tensor: no fallback
+    x = torch.zeros(1, 3, 4, 4, 4, device="cuda")
+    with pytest.raises(lib.DramLibraryError):                      # kernel size 5 unsupported
+        lib.check(lib.load().dram_conv3d_simt_fwd(x.data_ptr(), x.data_ptr(), 0, x.data_ptr(), 1, 4, 4, 4, 3, 3, 5, 0), "conv")
+
+
+def test_layout_round_trip():
+    o = ops()
+    x = torch.randn(2, 5, 3, 4, 6)
+    xc = o.to_cl(x.cuda())
+    assert o.is_cl(xc) and torch.equal(xc.cpu(), x)
+    assert torch.equal(xc.permute(0, 2, 3, 4, 1).contiguous().cpu(), x.permute(0, 2, 3, 4, 1).contiguous())
+    back = o.to_ncdhw(xc)
+    assert back.is_contiguous() and torch.equal(back.cpu(), x)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-core convolution
+@pytest.mark.parametrize("N,Cin,Cout,S,k,bias", [(2, 1, 32, (8, 9, 10), 3, False), (1, 5, 7, (6, 5, 7), 3, True),
+                                                 (2, 8, 16, (8, 8, 8), 3, False), (2, 12, 8, (5, 6, 7), 1, True),
+                                                 (1, 64, 1, (6, 6, 6), 1, True)])
+def test_conv_simt_forward(N, Cin, Cout, S, k, bias):
+    o = ops()
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, k, k, k) * 0.2
+    b = torch.randn(Cout) if bias else None
+    ref = F.conv3d(x, w, b, padding=k // 2)
+    pack = o.pack_weight_f32(w.cuda(), 0)
+    y = o.conv_simt(cuda_cl(x), pack, b.cuda() if bias else None, Cout, k)
+    assert_close(y, ref, TOL_F32, "conv_simt fwd")
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S,k", [(2, 1, 32, (8, 9, 10), 3), (2, 6, 10, (6, 5, 7), 3), (2, 12, 8, (5, 6, 7), 1)])
+def test_conv_simt_dgrad_wgrad(N, Cin, Cout, S, k):
+    o = ops()
+    x = torch.randn(N, Cin, *S, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, k) * 0.2).requires_grad_(True)
+    y = F.conv3d(x, w, None, padding=k // 2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dx = o.conv_simt(cuda_cl(dy), o.pack_weight_f32(w.detach().cuda(), 1), None, Cin, k)
+    dw = o.conv_simt_wgrad(cuda_cl(x.detach()), cuda_cl(dy), k)
+    assert_close(dx, x.grad, TOL_F32, "conv_simt dgrad")
+    assert_close(dw, w.grad, TOL_F32, "conv_simt wgrad")
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core convolution
+UMMA_CASES = [
+    # N, Cin, Cout, spatial, k
+    (1, 64, 64, (16, 16, 16), 3),      # tile (16,8,1), BN=64
+    (2, 32, 64, (8, 8, 16), 3),        # Cin padded 32 -> 64 (ds0.c1 shape class)
+    (1, 192, 64, (8, 8, 8), 3),        # 3 K blocks per tap (us2.c0 shape class)
+    (1, 64, 192, (8, 8, 8), 3),        # BN=96 (dgrad of us2.c0 shape class)
+    (2, 128, 256, (10, 10, 10), 3),    # ragged tile (5,5,5), 2 N tiles (bg shape class)
+    (1, 64, 32, (20, 20, 20), 3),      # BN=32 (dgrad of ds0.c1 shape class)
+    (1, 128, 16, (6, 7, 9), 1),        # 1x1x1, odd spatial sizes
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES)
+@pytest.mark.parametrize("three", [True, False])
+def test_conv_umma_forward(N, Cin, Cout, S, k, three):
+    o = ops()
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, k, k, k) * (2.0 / (Cin * k ** 3)) ** 0.5
+    ref = F.conv3d(x, w, None, padding=k // 2)
+    xs = o.split_bf16(cuda_cl(x), three)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, three)
+    y = o.conv_umma(xs, w_hi, w_lo, Cout, k)
+    assert_close(y, ref, TOL_X3 if three else TOL_BF16, "conv_umma fwd")
+
+
+def test_conv_umma_forward_folded_bn_relu():
+    o = ops()
+    N, Cin, Cout, S = 1, 64, 64, (8, 8, 8)
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, 3, 3, 3) * 0.03
+    scale, shift = torch.rand(Cout) + 0.5, torch.randn(Cout) * 0.1
+    ref = F.relu(F.conv3d(x, w, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    xs = o.split_bf16(cuda_cl(x), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    y = o.conv_umma(xs, w_hi, w_lo, Cout, 3, scale.cuda(), shift.cuda())
+    assert_close(y, ref, TOL_X3, "conv_umma fwd + folded BN/ReLU epilogue")
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES)
+def test_conv_umma_dgrad(N, Cin, Cout, S, k):
+    o = ops()
+    if Cin % 16:
+        pytest.skip("dgrad output channels must be a multiple of 16")
+    x = torch.randn(N, Cin, *S, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, k) * (2.0 / (Cin * k ** 3)) ** 0.5
+    y = F.conv3d(x, w, None, padding=k // 2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dys = o.split_bf16(cuda_cl(dy), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 1, True)
+    dx = o.conv_umma(dys, w_hi, w_lo, Cin, k)
+    assert_close(dx, x.grad, TOL_X3, "conv_umma dgrad")
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES + [(8, 256, 512, (10, 10, 10), 3), (3, 64, 64, (12, 20, 16), 3)])
+@pytest.mark.parametrize("three", [True, False])
+def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
+    o = ops()
+    x = torch.randn(N, Cin, *S)
+    w = (torch.randn(Cout, Cin, k, k, k) * 0.05).requires_grad_(True)
+    y = F.conv3d(x, w, None, padding=k // 2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dw = o.conv_umma_wgrad(o.split_bf16(cuda_cl(dy), three), o.split_bf16(cuda_cl(x), three), Cin, Cout, k)
+    assert_close(dw, w.grad, TOL_X3 if three else TOL_BF16, "conv_umma wgrad")
+
+
+def test_conv_umma_is_deterministic():
+    o = ops()
+    x, w = torch.randn(2, 64, 8, 8, 8), torch.randn(64, 64, 3, 3, 3) * 0.05
+    dy = torch.randn(2, 64, 8, 8, 8)
+    xs, dys = o.split_bf16(cuda_cl(x), True), o.split_bf16(cuda_cl(dy), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    a, b = o.conv_umma(xs, w_hi, w_lo, 64, 3), o.conv_umma(xs, w_hi, w_lo, 64, 3)
+    assert torch.equal(a, b)
+    g1, g2 = o.conv_umma_wgrad(dys, xs, 64, 64, 3), o.conv_umma_wgrad(dys, xs, 64, 64, 3)
+    assert torch.equal(g1, g2)
+
+
+# ------------------------------------------------------------------------------------------------ fused conv unit
+def _unit_reference(x, w, b, gamma, beta, rm, rv, training, pool):
+    y = F.conv3d(x, w, b, padding=w.shape[2] // 2)
+    z = F.relu(F.batch_norm(y, rm, rv, gamma, beta, training, 0.1, 1e-5))
+    return (z, F.max_pool3d(z, 2, 2, 0)) if pool else z
+
+
+@pytest.mark.parametrize("Cin,Cout,S,k,bias,pool,training", [
+    (1, 32, (8, 8, 8), 3, False, False, True),       # CUDA-core path (first layer)
+    (64, 64, (8, 8, 8), 3, False, True, True),       # tensor-core path + pool
+    (64, 64, (8, 8, 8), 3, False, True, False),      # eval mode
+    (6, 10, (7, 9, 5), 3, False, True, True),        # ragged pool (floor) on the CUDA-core path
+    (64, 8, (6, 6, 6), 1, True, False, True),        # 1x1x1 reshape head with conv bias (models.py:490)
+])
+def test_conv_bn_relu_unit(Cin, Cout, S, k, bias, pool, training):
+    N = 2
+    x = torch.randn(N, Cin, *S, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, k) * (2.0 / (Cin * k ** 3)) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout).requires_grad_(True) if bias else None
+    gamma, beta = (torch.rand(Cout) + 0.5).requires_grad_(True), (torch.randn(Cout) * 0.1).requires_grad_(True)
+    rm, rv = torch.randn(Cout) * 0.1, torch.rand(Cout) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = _unit_reference(x, w, b, gamma, beta, rm_ref, rv_ref, training, pool)
+    outs = ref if pool else (ref,)
+    gouts = [torch.randn_like(t) for t in outs]
+    torch.autograd.backward(outs, gouts)
+
+    xg = cuda_cl(x.detach()).requires_grad_(True)
+    wg = w.detach().cuda().requires_grad_(True)
+    bg = b.detach().cuda().requires_grad_(True) if bias else None
+    gg, beg = gamma.detach().cuda().requires_grad_(True), beta.detach().cuda().requires_grad_(True)
+    rmg, rvg = rm.cuda(), rv.cuda()
+    got = DF().ConvBnRelu.apply(xg, wg, bg, gg, beg, rmg, rvg, training, 0.1, 1e-5, 1, pool)
+    gots = got if pool else (got,)
+    for t, r, name in zip(gots, outs, ("a", "pooled")):
+        assert_close(t, r, TOL_X3, f"unit fwd {name}")
+    torch.autograd.backward(gots, [g.cuda() for g in gouts])
+    gs = (x.grad.abs().max() + 1e-12)
+    assert_close(xg.grad, x.grad, 2e-4, "unit dx")
+    assert_close(wg.grad, w.grad, 2e-4, "unit dw")
+    assert_close(gg.grad, gamma.grad, 2e-4, "unit dgamma")
+    assert_close(beg.grad, beta.grad, 2e-4, "unit dbeta")
+    if bias and not training:
+        assert_close(bg.grad, b.grad, 2e-4, "unit dbias")
+    if training:
+        assert_close(rmg, rm_ref, TOL_X3, "running_mean")
+        assert_close(rvg, rv_ref, TOL_X3, "running_var")
+
+
+def test_bn_running_stats_double_update():
+    """checkpointed blocks update the running statistics twice per step (models.py:123-143)."""
+    o = ops()
+    y = torch.randn(2, 8, 4, 4, 4)
+    rm, rv = torch.zeros(8), torch.ones(8)
+    for _ in range(2):
+        F.batch_norm(y, rm, rv, None, None, True, 0.1, 1e-5)
+    yg = cuda_cl(y)
+    rmg, rvg = torch.zeros(8, device="cuda"), torch.ones(8, device="cuda")
+    o.bn_finalize(o.bn_stats(yg), y.numel() // 8, None, None, rmg, rvg, 0.1, 1e-5, 2)
+    assert_close(rmg, rm, TOL_F32, "running_mean x2")
+    assert_close(rvg, rv, TOL_F32, "running_var x2")
+
+
+def test_maxpool_backward_first_max_on_ties():
+    """all-zero windows (common after ReLU) route the gradient to the first element like ATen."""
+    o = ops()
+    a = torch.zeros(1, 4, 4, 4, 4)
+    a[0, :, 1, 1, 1] = 2.0
+    a.requires_grad_(True)
+    p = F.max_pool3d(a, 2, 2, 0)
+    g = torch.randn_like(p)
+    p.backward(g)
+    da = torch.zeros(1, 4, 4, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    o.maxpool2_bwd(cuda_cl(a.detach()), cuda_cl(g), da)
+    assert torch.equal(da.cpu(), a.grad)
+
+
+# ------------------------------------------------------------------------------------------------ decoder glue / resize
+@pytest.mark.parametrize("C1,C2,s,skip", [(8, 4, (4, 5, 6), (8, 10, 12)), (16, 8, (3, 3, 3), (7, 6, 8)), (3, 5, (4, 4, 4), (8, 8, 8))])
+def test_upsample_concat(C1, C2, s, skip):
+    from oracle_import import O
+    x = torch.randn(2, C1, *s, requires_grad=True)
+    sk = torch.randn(2, C2, *skip, requires_grad=True)
+    up = F.interpolate(x, scale_factor=(2, 2, 2), mode="trilinear", align_corners=True)
+    ref = O.crop_concat(up, sk)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xg, skg = cuda_cl(x.detach()).requires_grad_(True), cuda_cl(sk.detach()).requires_grad_(True)
+    got = DF().UpsampleConcat.apply(xg, skg)
+    assert_close(got, ref, TOL_F32, "upsample+concat fwd")
+    got.backward(g.cuda())
+    assert_close(xg.grad, x.grad, TOL_F32, "upsample+concat dx")
+    assert torch.equal(skg.grad.cpu(), sk.grad), "skip gradient is a pure copy: bit-exact"
+
+
+@pytest.mark.parametrize("C,src,dst", [(1, (20, 20, 20), (16, 16, 16)), (1, (16, 16, 16), (20, 20, 20)), (8, (10, 12, 9), (16, 16, 16)),
+                                        (17, (5, 6, 7), (5, 6, 7)), (4, (6, 6, 6), (1, 13, 6))])
+def test_trilinear_resize(C, src, dst):
+    x = torch.randn(2, C, *src, requires_grad=True)
+    ref = F.interpolate(x, size=dst, mode="trilinear", align_corners=True)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xg = cuda_cl(x.detach()).requires_grad_(True)
+    got = DF().TrilinearResize.apply(xg, dst)
+    assert_close(got, ref, TOL_F32, "trilinear fwd")
+    got.backward(g.cuda())
+    assert_close(xg.grad, x.grad, TOL_F32, "trilinear bwd")
+
+
+# ------------------------------------------------------------------------------------------------ RAM head
+@pytest.mark.parametrize("C,O", [(64, 1), (8, 1), (64, 3), (6, 2)])
+def test_ram_reduce(C, O):
+    feat = torch.randn(2, C, 6, 7, 8, requires_grad=True)
+    w = (torch.randn(O, C, 1, 1, 1) * 0.2).requires_grad_(True)
+    b = torch.randn(O).requires_grad_(True)
+    ref = F.conv3d(feat, w, b)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    fg = cuda_cl(feat.detach()).requires_grad_(True)
+    wg, bg = w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    got = DF().RamReduce.apply(fg, wg, bg)
+    assert_close(got, ref, TOL_F32, "ram reduce fwd")
+    got.backward(cuda_cl(g))
+    assert_close(fg.grad, feat.grad, TOL_F32, "ram reduce dfeat")
+    assert_close(wg.grad, w.grad, TOL_F32, "ram reduce dw")
+    assert_close(bg.grad, b.grad, TOL_F32, "ram reduce db")
+
+
+def test_ram_reduce_fused_bn_relu():
+    o = ops()
+    y = torch.randn(2, 64, 5, 6, 7)
+    scale, shift = torch.rand(64) + 0.5, torch.randn(64) * 0.2
+    w, b = torch.randn(1, 64) * 0.2, torch.randn(1)
+    a = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    ref = F.conv3d(a, w.view(1, 64, 1, 1, 1), b)
+    got = o.ram_reduce(cuda_cl(y), w.cuda(), b.cuda(), scale.cuda(), shift.cuda())
+    assert_close(got, ref, TOL_F32, "fused BN+ReLU+RAM reduce")
+
+
+@pytest.mark.parametrize("use_sigmoid,gt0", [(False, False), (True, True)])
+def test_masked_mean(use_sigmoid, gt0):
+    from oracle_import import O
+    x = torch.randn(3, 1, 8, 9, 10, requires_grad=True)
+    lobes = O.ellipsoid_lobe(3, (8, 9, 10), seed=3)
+    fx = torch.sigmoid(x) if use_sigmoid else x
+    m = (lobes > 0).float() if gt0 else lobes
+    ref = (fx * m).reshape(3, -1).sum(-1) / m.reshape(3, -1).sum(-1)
+    g = torch.randn(3)
+    ref.backward(g)
+    xg = x.detach().cuda().requires_grad_(True)
+    mean, cnt = DF().MaskedMean.apply(xg, lobes.cuda(), use_sigmoid, gt0)
+    assert_close(mean, ref, TOL_F32, "masked mean")
+    assert torch.equal(cnt.cpu(), m.reshape(3, -1).sum(-1)), "mask count is exact"
+    mean.backward(g.cuda())
+    assert_close(xg.grad, x.grad, TOL_F32, "masked mean bwd")
+
+
+def test_pooling_dense_features_matches_oracle():
+    from oracle_import import O
+    import models
+    d = torch.randn(2, 1, 8, 8, 8)
+    lobes = O.ellipsoid_lobe(2, (8, 8, 8), seed=5)
+    got = models.pooling_dense_features(d.cuda(), lobes.cuda())
+    assert_close(got, O.masked_pool(d, lobes), TOL_F32, "pooling_dense_features")
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_ram_upsample_mask_scatter(act):
+    """inference epilogue: values within fp32 tolerance, lobe masking / indexing bit-exact."""
+    o = ops()
+    ram = torch.randn(1, 1, 8, 8, 8)
+    crop = (13, 9, 17)
+    mask = (torch.rand(*crop) > 0.4).to(torch.uint8)
+    scan_shape, off = (20, 16, 24), (3, 2, 5)
+    if act == 1:
+        up = F.interpolate(torch.sigmoid(ram), size=crop, mode="trilinear", align_corners=True)[0, 0]
+    else:
+        up = F.relu(F.interpolate(ram, size=crop, mode="trilinear", align_corners=True)[0, 0])
+    ref = torch.full(scan_shape, -7.0)
+    view = ref[off[0]:off[0] + crop[0], off[1]:off[1] + crop[1], off[2]:off[2] + crop[2]]
+    view[mask > 0] = up[mask > 0]
+    heat = torch.full(scan_shape, -7.0, device="cuda")
+    mx = torch.zeros(1, device="cuda")
+    o.ram_upsample_mask_scatter(ram[0, 0].cuda(), mask.cuda(), heat, off, act, 1.0, mx)
+    touched_ref = ref != -7.0
+    assert torch.equal((heat.cpu() != -7.0), touched_ref), "lobe mask / paste indices must be bit-exact"
+    assert_close(heat.cpu()[touched_ref], ref[touched_ref], TOL_F32, "scatter values")
+    assert abs(mx.item() - up.max().item()) <= 1e-5 * max(1.0, abs(up.max().item()))
+
+
+# ------------------------------------------------------------------------------------------------ PCM stencil attention
+@pytest.mark.parametrize("merge,self_loop,conn,grid", [("scaled_dot_product_relu", False, 2, (6, 7, 8)), ("sm", True, 1, (5, 5, 5)),
+                                                       ("scaled_dot_product", False, 3, (4, 6, 5)), ("smrelu", False, 2, (2, 1, 3))])
+def test_pcm_attention(merge, self_loop, conn, grid):
+    from oracle_import import O
+    import models
+    B, Cf, Fd = 2, 17, 8
+    torch.manual_seed(7)
+    pcm = models.PCM(grid, Cf, 1, Fd, 0, 8, 1, 3, merge, self_loop, connectivity=conn, p_enc_dim=0)
+    sd = {"attention_module." + k: v.detach().clone().requires_grad_(True) for k, v in pcm.state_dict().items()}
+    cam = torch.randn(B, 1, *grid, requires_grad=True)
+    f = torch.randn(B, Cf, *grid, requires_grad=True)
+    ref = O.pcm_forward(sd, cam, f, merge_type=merge, self_loop=self_loop, connectivity=conn)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    pcm = pcm.cuda()
+    camg, fg = cam.detach().cuda().requires_grad_(True), cuda_cl(f.detach()).requires_grad_(True)
+    got = pcm(camg, fg)
+    assert_close(got, ref, 5e-5, "pcm fwd")
+    got.backward(g.cuda())
+    assert_close(camg.grad, cam.grad, 1e-4, "pcm dcam")
+    assert_close(fg.grad, f.grad, 1e-4, "pcm df")
+    for name, p in pcm.named_parameters():
+        assert_close(p.grad, sd["attention_module." + name].grad, 2e-4, f"pcm d{name}")
