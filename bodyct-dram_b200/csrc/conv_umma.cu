@@ -167,7 +167,8 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
       if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
-      const uint32_t stage_tx = (three ? 2u : 1u) * ((uint32_t)kATileBytes + b_tile_bytes);
+      // bytes TMA will actually deliver: the A box has TW*TH*TD rows (<= 128), zero-filled halo included
+      const uint32_t stage_tx = (three ? 2u : 1u) * ((uint32_t)(p.TW * p.TH * p.TD) * 128u + b_tile_bytes);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;

@@ -17,20 +17,28 @@ def _cl_grad(g, like):
 
 
 class _WeightCache:
-    """Packed weights are rebuilt whenever the parameter changes (nn.Parameter._version bumps on optimizer.step)."""
+    """Packed weights live ON the parameter object (attribute `_dram_packs`) and are rebuilt whenever the parameter
+    changes (`_version` bumps on optimizer.step / load_state_dict).  Nothing is keyed on addresses: the caching
+    allocator reuses them across models."""
 
     def __init__(self):
-        self.store = {}
+        self.misses = 0
 
     def get(self, w, kind, builder):
-        key = (w.data_ptr(), kind, ops.precision())
-        hit = self.store.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == tuple(w.shape):
+        packs = getattr(w, "_dram_packs", None)
+        if packs is None:
+            packs = {}
+            try:
+                w._dram_packs = packs
+            except AttributeError:
+                pass
+        key = (kind, ops.precision())
+        hit = packs.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
             return hit[2]
+        self.misses += 1
         val = builder()
-        if len(self.store) > 256:
-            self.store.clear()
-        self.store[key] = (w._version, tuple(w.shape), val)
+        packs[key] = (w._version, w.data_ptr(), val)
         return val
 
 
@@ -83,7 +91,7 @@ class ConvBnRelu(torch.autograd.Function):
                                                        n_updates)
         else:
             scale, shift = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
-            mean = rstd = None
+            mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)      # only for dgamma/dbeta in eval mode
         a, pooled = ops.bn_relu_apply(y, scale, shift, pool)
         ctx.training, ctx.pool, ctx.count, ctx.has_bias = training, pool, count, bias is not None
         ctx.saved_in = saved_in if isinstance(saved_in, ops.SplitPlanes) else None
@@ -119,6 +127,9 @@ class ConvBnRelu(torch.autograd.Function):
         else:
             dy = ops.bn_relu_bwd_apply(da, y, scale, shift, None, None, gamma, None, 1.0)
             dgamma = dbeta = None
+            if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+                sums = ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd)
+                dbeta, dgamma = sums[:C].float(), sums[C:].float()
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
         dys = None
         if isinstance(saved_in, ops.SplitPlanes) or (ctx.needs_input_grad[0] and ops.umma_ok_fwd(Cout, Cin, k)):

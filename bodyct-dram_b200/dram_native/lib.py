@@ -40,6 +40,74 @@ class DramLibraryError(RuntimeError):
     pass
 
 
+# kernels launched per C-ABI call (for the bench's `gpu_launches` claim); memsets are not counted
+KERNELS_PER_CALL = {"dram_version": 0, "dram_sm_arch": 0, "dram_last_error": 0, "dram_device_check": 0,
+                    "dram_pcm_num_offsets": 0, "dram_conv3d_umma_wgrad_workspace_bytes": 0,
+                    "dram_upsample2x_concat_fwd": 2, "dram_upsample2x_concat_bwd": 2, "dram_conv3d_umma_wgrad": 2,
+                    "dram_pcm_fwd": 2, "dram_pcm_bwd": 3}
+
+
+class Profile:
+    """Launch accounting.  `enabled` additionally brackets every call with CUDA events on the launching stream."""
+
+    def __init__(self):
+        self.enabled = False
+        self.reset()
+
+    def reset(self):
+        self.launches = 0
+        self.calls = {}
+        self.records = []          # (name, note, start_event, end_event)
+        self.pending_note = None
+
+    def note(self, **kw):
+        """Attach algorithmic flops / bytes to the NEXT call (consumed by it)."""
+        self.pending_note = kw
+
+    def summary(self):
+        """-> {name: {"calls", "ms", "flops", "bytes"}} after a device synchronize."""
+        out = {}
+        for name, note, s, e in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+            if note:
+                d["flops"] += float(note.get("flops", 0.0))
+                d["bytes"] += float(note.get("bytes", 0.0))
+        return out
+
+
+PROFILE = Profile()
+
+
+def _instrument(name, fn):
+    nk = KERNELS_PER_CALL.get(name, 1)
+    if nk == 0:
+        return fn
+
+    def call(*args):
+        P = PROFILE
+        P.launches += nk
+        P.calls[name] = P.calls.get(name, 0) + 1
+        if P.enabled:
+            import torch
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            note, P.pending_note = P.pending_note, None
+            s.record()
+            rc = fn(*args)
+            e.record()
+            P.records.append((name, note, s, e))
+            return rc
+        P.pending_note = None
+        return fn(*args)
+
+    return call
+
+
+class _Lib:
+    pass
+
+
 _LIB = None
 
 
@@ -51,11 +119,14 @@ def load():
         raise DramLibraryError(
             f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the DRAM hot path.")
-    lib = ctypes.CDLL(LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    lib = _Lib()
     for name, (restype, argtypes) in parse_header().items():
-        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn = getattr(cdll, name)         # AttributeError if the .so lacks a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
+        setattr(lib, name, _instrument(name, fn))
+    lib.cdll = cdll
     _LIB = lib
     return lib
 

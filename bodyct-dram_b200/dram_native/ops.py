@@ -99,6 +99,7 @@ def conv_simt(x, pack, bias, Cout, ksize):
     """x CL volume [N,Cin,D,H,W]; pack [taps][Cin][Cout] -> CL volume [N,Cout,D,H,W]"""
     N, Cin, D, H, W = x.shape
     y = new_volume(N, Cout, D, H, W, x.device)
+    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, bytes=4.0 * N * D * H * W * (Cin + Cout))
     _lib.check(_L().dram_conv3d_simt_fwd(x.data_ptr(), pack.data_ptr(), _p(bias), y.data_ptr(), N, D, H, W, Cin, Cout,
                                          ksize, _stream()), "conv3d_simt_fwd")
     return y
@@ -151,8 +152,9 @@ def pack_weight_bf16(w, mode, three=None):
 
 def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None):
     """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32."""
-    N, _, D, H, W = xs.shape
+    N, Cin, D, H, W = xs.shape
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
+    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3)          # algorithmic (unpadded, 1 pass)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
                                          y.data_ptr(), N, D, H, W, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
     return y
@@ -166,6 +168,7 @@ def conv_umma_wgrad(dys, xs, Cin, Cout, ksize):
         raise _lib.DramLibraryError("conv3d_umma_wgrad: unsupported shape")
     ws = torch.empty(nbytes // 4, device=xs.hi.device, dtype=torch.float32)
     dw = torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
+    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3)
     _lib.check(_L().dram_conv3d_umma_wgrad(dys.hi.data_ptr(), _p(dys.lo), xs.hi.data_ptr(), _p(xs.lo), dw.data_ptr(),
                                            ws.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize, _stream()),
                "conv3d_umma_wgrad")
@@ -275,6 +278,7 @@ def ram_reduce(feat, w, b, scale=None, shift=None):
     N, C, D, H, W = feat.shape
     O = w.shape[0]
     ram = new_volume(N, O, D, H, W, feat.device)
+    _lib.PROFILE.note(bytes=4.0 * N * D * H * W * (C + O))                           # read features once, write the map
     _lib.check(_L().dram_ram_reduce_fwd(feat.data_ptr(), _p(scale), _p(shift), w.data_ptr(), b.data_ptr(), ram.data_ptr(),
                                         N * D * H * W, C, O, _stream()), "ram_reduce_fwd")
     return ram

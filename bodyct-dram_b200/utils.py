@@ -1,0 +1,116 @@
+"""Host-side helpers the job runners and entry points need, mirroring the names in the reference's `dram/utils.py`
+(Settings :42-69, get_callable_by_name :280-283, windowing :189-198, find_crops :244-254, binary_cam :226-242,
+expand_dims/squeeze_dims :127-140, IOU/Dice :437-446, AverageMeter :98-114).  Pure numpy/Python — no SimpleITK,
+skimage or OpenCV; the GPU versions of windowing / resampling / Otsu live in libdram_b200 (dram_native.ops)."""
+import importlib
+import importlib.util
+import math
+
+import numpy as np
+
+
+class Settings:
+    """Execute a settings .py file; every UPPERCASE name becomes an attribute (same contract as the reference)."""
+
+    def __init__(self, settings_module_path, settings_name="settings"):
+        self.settings_module_path = settings_module_path
+        spec = importlib.util.spec_from_file_location(settings_name, settings_module_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        self._explicit_settings = set()
+        for name in dir(mod):
+            if name.isupper():
+                setattr(self, name, getattr(mod, name))
+                self._explicit_settings.add(name)
+
+    def is_overridden(self, setting):
+        return setting in self._explicit_settings
+
+    def __str__(self):
+        return "\n".join(f"{k} = {getattr(self, k)!r}" for k in sorted(self._explicit_settings))
+
+
+def get_callable_by_name(dotted):
+    module_name, _, attr = dotted.rpartition('.')
+    return getattr(importlib.import_module(module_name), attr)
+
+
+class AverageMeter:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = 0.0
+        self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / max(self.count, 1)
+
+
+def expand_dims(t, expected_dim):
+    while t.dim() < expected_dim:
+        t = t.unsqueeze(0)
+    return t
+
+
+def squeeze_dims(t, expected_dim, squeeze_start_index=0):
+    while t.dim() > expected_dim:
+        t = t.squeeze(squeeze_start_index)
+    return t
+
+
+def windowing(image, from_span=(-1150, 350), to_span=(0, 255)):
+    lo, hi = (np.min(image), np.max(image)) if from_span is None else from_span
+    image = np.clip(image, a_min=lo, a_max=hi)
+    return ((image - lo) / float(hi - lo)) * (to_span[1] - to_span[0]) + to_span[0]
+
+
+def find_crops(mask, spacing, border):
+    """Bounding box of mask > 0, padded by ceil(border / spacing) voxels per axis and clipped to the volume."""
+    nz = np.nonzero(np.asarray(mask) > 0)
+    out = []
+    for ax, (size, sp) in enumerate(zip(mask.shape, spacing)):
+        pad = int(math.ceil(border / sp)) if border > 0 else 0
+        out.append(slice(max(0, int(nz[ax].min()) - pad), min(size, int(nz[ax].max()) + 1 + pad)))
+    return tuple(out)
+
+
+def otsu_threshold_from_histogram(hist, lo, hi):
+    """Otsu threshold of data summarised by a 256-bin histogram over [lo, hi] (bin centres, first maximum wins)."""
+    hist = np.asarray(hist, dtype=np.float64)
+    edges = np.linspace(lo, hi, 257)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    w1 = np.cumsum(hist)
+    w2 = np.cumsum(hist[::-1])[::-1]
+    m1 = np.cumsum(hist * centers) / np.maximum(w1, 1e-300)
+    m2 = (np.cumsum((hist * centers)[::-1]) / np.maximum(w2[::-1], 1e-300))[::-1]
+    return centers[:-1][int(np.argmax(w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2))]
+
+
+def binary_cam(cam_probs, scaler=1.0, from_span=(0, 1)):
+    """(mask, threshold in [0,1]) — window to uint8, Otsu on the 8-bit values (utils.py:226-242)."""
+    cam = np.asarray(cam_probs.detach().cpu().numpy() if hasattr(cam_probs, "detach") else cam_probs)
+    if cam.size == 0:
+        raise ValueError("empty array encountered! cam_probs.size == 0.")
+    w = windowing(cam, from_span=from_span).astype(np.uint8)
+    u = np.unique(w)
+    if len(u) < 2:
+        return np.ones_like(w).astype(bool), u[0] / 255.0
+    hist = np.bincount(w.ravel(), minlength=256)
+    lo, hi = float(u[0]), float(u[-1])
+    h256, _ = np.histogram(w, bins=256, range=(lo, hi))
+    th = min(otsu_threshold_from_histogram(h256, lo, hi) * scaler, 255.0)
+    return w >= th, th / 255.0
+
+
+def IOU(predict, target, smooth):
+    inter = np.sum(np.logical_and(predict, target))
+    return (inter + smooth) / (np.sum(np.logical_or(predict, target)) + smooth)
+
+
+def Dice(predict, target, smooth):
+    inter = np.sum(np.logical_and(predict, target))
+    return (2. * inter + smooth) / (predict.sum() + target.sum() + smooth)

@@ -384,5 +384,9 @@ def test_pcm_attention(merge, self_loop, conn, grid):
     got.backward(g.cuda())
     assert_close(camg.grad, cam.grad, 1e-4, "pcm dcam")
     assert_close(fg.grad, f.grad, 1e-4, "pcm df")
+    # softmax is shift invariant: without ReLU the phi-bias gradient is analytically 0 (the reference value is rounding
+    # noise), so parameter gradients are compared on the scale of the largest parameter gradient
+    scale = max(v.grad.abs().max().item() for k, v in sd.items())
     for name, p in pcm.named_parameters():
-        assert_close(p.grad, sd["attention_module." + name].grad, 2e-4, f"pcm d{name}")
+        ref = sd["attention_module." + name].grad
+        assert (p.grad.cpu() - ref).abs().max().item() <= 2e-4 * scale, f"pcm d{name}"
