@@ -1,0 +1,119 @@
+"""CPU tests of the host-side logic: module surface, settings, loss arithmetic (pure torch parts), error behaviour."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle_import import O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_state_dict_surface_matches_reference_fixtures():
+    import models
+    for fixture in ("dc3d_div8_16.pt", "dc3dat_div16_16.pt"):
+        g = torch.load(os.path.join(GOLDEN, fixture))
+        cfg = dict(g["cfg"])
+        cls = getattr(models, cfg.pop("method").split(".")[-1])
+        m = cls(**cfg)
+        own = m.state_dict()
+        assert list(own.keys()) == list(g["state_dict"].keys())
+        for k, v in g["state_dict"].items():
+            assert tuple(own[k].shape) == tuple(v.shape), k
+        m.load_state_dict(g["state_dict"])
+        assert m.trace_path is None and hasattr(m, "dummy") and hasattr(m, "top_layer")
+
+
+def test_full_config_parameter_count_and_init():
+    import models
+    from utils import Settings
+    s = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref.py"))
+    cfg = dict(s.MODEL)
+    assert cfg.pop("method") == "models.DC3D"
+    torch.manual_seed(0)
+    m = models.DC3D(**cfg)
+    m.init(models.HeNorm(mode="fan_in"))
+    assert sum(p.numel() for p in m.parameters()) == 16317921
+    w = m.ds_modules[1].conv_blocks[0][0].weight
+    assert abs(w.std().item() - (2.0 / (64 * 27)) ** 0.5) < 2e-3          # He normal, fan_in
+    assert torch.all(m.top_layer.bias == 0.01)
+    s2 = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    cfg2 = dict(s2.MODEL)
+    cfg2.pop("method")
+    m2 = models.DC3DATGeneric(**cfg2)
+    assert sum(p.numel() for p in m2.parameters()) == 16317921 + 1897
+    assert m2.attention_module.theta.weight.shape == (8, 17)
+
+
+def test_unsupported_options_raise_instead_of_falling_back():
+    import models
+    import parts
+    with pytest.raises(NotImplementedError):
+        parts.ConvBlock5d([4, 4], [4, 4], 0, 5, False, 2)                 # kernel size 5
+    with pytest.raises(NotImplementedError):
+        parts.ConvBlock5d([4, 4], [4, 4], 0, 3, False, 1, dropout=0.5)
+    with pytest.raises(NotImplementedError):
+        parts.normal_wrapper("ln", 8)
+    pcm = models.PCM((4, 4, 4), 17, 1, 8, 0, 8, 1, 3, "l2", False, p_enc_dim=0)
+    with pytest.raises(NotImplementedError):
+        pcm(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 17, 4, 4, 4))
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from dram_native import lib
+    import models
+    g = torch.load(os.path.join(GOLDEN, "dc3d_div8_16.pt"))
+    cfg = dict(g["cfg"])
+    cfg.pop("method")
+    m = models.DC3D(**cfg)
+    with pytest.raises(lib.DramLibraryError, match="no CPU fallback"):
+        m(g["images"], g["lobes"])
+
+
+def test_interval_targets_match_oracle():
+    import metrics
+    loss = metrics.IntRegRefineLoss(band_width=1e-2)
+    rub = torch.tensor([0.0, 0.0005, 0.02, 0.2, 0.45, 0.9, 0.3, 0.004], dtype=torch.float32)
+    ctss = ["0", "1", "2", "3", "4", "5", "0", "5"]
+    got = loss.get_labels(ctss, rub)
+    ref = O.interval_targets(ctss, rub, 1e-2)
+    assert torch.equal(got, ref)
+
+
+def test_boot_bce_matches_oracle_and_reference_structure():
+    import metrics
+    torch.manual_seed(0)
+    p = torch.rand(2, 1, 6, 6, 6).clamp(0.01, 0.99).requires_grad_(True)
+    voi = O.ellipsoid_lobe(2, (6, 6, 6), seed=1) > 0
+    t = ((torch.rand(2, 1, 6, 6, 6) > 0.6) & voi).float()
+    ref = O.boot_bce(p, t, voi, 0.1)
+    gref, = torch.autograd.grad(ref, p)
+    got = metrics.BootBinCrossEntropy(0.1)(p, t, voi)
+    ggot, = torch.autograd.grad(got, p)
+    assert abs(got.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert (ggot - gref).abs().max() <= 1e-6 * gref.abs().max()
+    only_out = metrics.BootBinCrossEntropy(0.1)(p, torch.zeros_like(t), torch.zeros_like(voi))
+    assert abs(only_out.item() - O.boot_bce(p, torch.zeros_like(t), torch.zeros_like(voi), 0.1).item()) < 1e-6
+
+
+def test_settings_files_expose_the_reference_names():
+    from utils import Settings
+    for name, method in (("st_dram_ref.py", "models.DC3D"), ("st_dram_ref_att.py", "models.DC3DATGeneric")):
+        s = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", name))
+        for key in ("MODEL", "INITIALIZER", "OPTIMIZER", "SCHEDULER", "LOSS_FUNC", "LOSS_FACTORS", "RESAMPLE_SIZE",
+                    "WINDOWING_MAX", "WINDOWING_MIN", "PAD_VALUE", "TRAIN_BATCH_SIZE", "JOB_RUNNER_CLS", "TEST_JOB_RUNNER_CLS"):
+            assert hasattr(s, key), key
+        assert s.MODEL["method"] == method and s.RESAMPLE_SIZE == (80, 80, 80) and s.LOSS_FACTORS[:2] == [2.0, 1.0]
+
+
+def test_utils_helpers():
+    import utils
+    a = np.random.RandomState(0).randint(-2048, 1000, size=(5, 6, 7)).astype(np.int16)
+    assert np.array_equal(utils.windowing(a), O.windowing(a))
+    mask = np.zeros((20, 30, 25), bool)
+    mask[5:9, 10:22, 3:20] = True
+    assert utils.find_crops(mask, (1.0, 0.7, 0.7), 5) == O.find_crops(mask, (1.0, 0.7, 0.7), 5)
+    v = np.random.RandomState(1).rand(4000)
+    assert abs(utils.binary_cam(v)[1] - O.binary_cam(v)) < 1e-12
