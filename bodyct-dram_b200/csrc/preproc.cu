@@ -1,0 +1,269 @@
+// Scan-level pre/post-processing around the chunk model: everything LesionSegTest.run does on the
+// host with numpy / SimpleITK / skimage between reading a scan and writing a lesion mask (job_runner.py:951-1015),
+// as HBM-bound kernels so that a full CT scan never leaves the GPU between upload and mask download.
+#include "common.cuh"
+
+namespace dram {
+
+// ------------------------------------------------------------------------------------------------ lobe bounding boxes
+// utils.find_crops (utils.py:244-254) for all labels at once: out[l][0..2] = min z,y,x; out[l][3..5] = max z,y,x (inclusive)
+__global__ void __launch_bounds__(256)
+k_label_bboxes(const uint8_t* __restrict__ labels, int D, int H, int W, int nlabels, int* __restrict__ out) {
+  __shared__ int smin[8][3], smax[8][3];                       // labels 1..7 supported per launch
+  for (int i = threadIdx.x; i < 8 * 3; i += blockDim.x) { (&smin[0][0])[i] = 0x7fffffff; (&smax[0][0])[i] = -1; }
+  __syncthreads();
+  const long long total = (long long)D * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int l = labels[i];
+    if (l >= 1 && l <= nlabels) {
+      int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
+      atomicMin(&smin[l][0], z); atomicMin(&smin[l][1], y); atomicMin(&smin[l][2], x);
+      atomicMax(&smax[l][0], z); atomicMax(&smax[l][1], y); atomicMax(&smax[l][2], x);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 3; i += blockDim.x) {
+    int l = i / 3, a = i % 3;
+    if (l >= 1 && l <= nlabels) {
+      if (smax[l][a] >= 0) { atomicMin(&out[l * 6 + a], smin[l][a]); atomicMax(&out[l * 6 + 3 + a], smax[l][a]); }
+    }
+  }
+}
+__global__ void k_bbox_init(int* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (i % 6) < 3 ? 0x7fffffff : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ ITK-style resampling
+// SimpleITK ResampleImageFilter with identity transform / same origin (utils.py:414-434): output index o maps to the
+// continuous input index o * (in/out) (no half-pixel shift); linear = 8-tap with neighbours clamped at the last
+// sample; nearest = round-half-up.  Restated from the published ITK semantics (SimpleITK 1.1.0 is not vendored).
+// A continuous index outside [-0.5, n - 0.5) is outside the ITK buffer: the output voxel takes the default value 0.
+struct Axis { int i0, i1; float w1; bool inside; };
+__device__ __forceinline__ Axis itk_axis(int o, float ratio, int n) {
+  float c = (float)o * ratio;
+  int i0 = (int)floorf(c);
+  Axis a;
+  a.inside = c < (float)n - 0.5f;
+  a.w1 = c - (float)i0;
+  a.i0 = min(max(i0, 0), n - 1);
+  a.i1 = min(i0 + 1, n - 1);
+  return a;
+}
+__device__ __forceinline__ int itk_nearest(int o, float ratio, int n, bool& inside) {
+  float c = (float)o * ratio;
+  inside = inside && (c < (float)n - 0.5f);
+  int i = (int)floorf(c + 0.5f);
+  return min(max(i, 0), n - 1);
+}
+
+// one lobe chunk: crop [cz..cz+cd) x ... of the scan, blank voxels outside `label` to pad_value, window to [0,1],
+// linear-resample to (d,h,w); mask = nearest-resampled (labels == label) as float {0,1}   (job_runner.py:961-984)
+__global__ void __launch_bounds__(256)
+k_lobe_chunk_preprocess(const short* __restrict__ scan, const uint8_t* __restrict__ labels, int SH, int SW, int label,
+                        int cz, int cy, int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value,
+                        float* __restrict__ img, float* __restrict__ msk, int d, int h, int w) {
+  const long long total = (long long)d * h * w;
+  const float rz = (float)cd / d, ry = (float)ch / h, rx = (float)cw / w;
+  const float span = win_hi - win_lo;              // numpy divides (utils.py:197), keep the same rounding
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % w), Y = (int)((i / w) % h), Z = (int)(i / ((long long)w * h));
+    Axis az = itk_axis(Z, rz, cd), ay = itk_axis(Y, ry, ch), ax = itk_axis(X, rx, cw);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int zi = ((k & 4) ? az.i1 : az.i0) + cz, yi = ((k & 2) ? ay.i1 : ay.i0) + cy, xi = ((k & 1) ? ax.i1 : ax.i0) + cx;
+      float wt = ((k & 4) ? az.w1 : 1.f - az.w1) * ((k & 2) ? ay.w1 : 1.f - ay.w1) * ((k & 1) ? ax.w1 : 1.f - ax.w1);
+      long long off = ((long long)zi * SH + yi) * SW + xi;
+      float v = (labels[off] == label) ? (float)scan[off] : pad_value;
+      v = fminf(fmaxf(v, win_lo), win_hi);
+      acc += wt * ((v - win_lo) / span);
+    }
+    bool in = az.inside && ay.inside && ax.inside;
+    img[i] = in ? acc : 0.f;
+    int zn = itk_nearest(Z, rz, cd, in) + cz, yn = itk_nearest(Y, ry, ch, in) + cy, xn = itk_nearest(X, rx, cw, in) + cx;
+    msk[i] = (in && labels[((long long)zn * SH + yn) * SW + xn] == label) ? 1.f : 0.f;
+  }
+}
+
+// generic volume resample (scan <-> working grid): T in {short, uint8, float}; linear (mode 0) or nearest (mode 1)
+template <typename T>
+__device__ __forceinline__ T cast_out(float v);
+template <> __device__ __forceinline__ float cast_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ short cast_out<short>(float v) { return (short)fminf(fmaxf(v, -32768.f), 32767.f); }        // trunc
+template <> __device__ __forceinline__ uint8_t cast_out<uint8_t>(float v) { return (uint8_t)fminf(fmaxf(v, 0.f), 255.f); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_itk_resample(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, float rz, float ry,
+               float rx, int mode) {
+  const long long total = (long long)D * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W), Y = (int)((i / W) % H), Z = (int)(i / ((long long)W * H));
+    if (mode == 1) {
+      bool in = true;
+      int zn = itk_nearest(Z, rz, d, in), yn = itk_nearest(Y, ry, h, in), xn = itk_nearest(X, rx, w, in);
+      dst[i] = in ? src[((long long)zn * h + yn) * w + xn] : (T)0;
+    } else {
+      Axis az = itk_axis(Z, rz, d), ay = itk_axis(Y, ry, h), ax = itk_axis(X, rx, w);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int zi = (k & 4) ? az.i1 : az.i0, yi = (k & 2) ? ay.i1 : ay.i0, xi = (k & 1) ? ax.i1 : ax.i0;
+        float wt = ((k & 4) ? az.w1 : 1.f - az.w1) * ((k & 2) ? ay.w1 : 1.f - ay.w1) * ((k & 1) ? ax.w1 : 1.f - ax.w1);
+        acc += wt * (float)src[((long long)zi * h + yi) * w + xi];
+      }
+      dst[i] = (az.inside && ay.inside && ax.inside) ? cast_out<T>(acc) : (T)0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RAM -> heat map
+// as k_ram_upsample_mask_scatter (ram.cu) but the lobe mask is read from the scan-sized label volume
+__global__ void __launch_bounds__(256)
+k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __restrict__ labels, int label,
+                             float* __restrict__ heat, int d, int h, int w, int cd, int ch, int cw, int SH, int SW, int oz,
+                             int oy, int ox, int act, float gain, float sz, float sy, float sx) {
+  const long long total = (long long)cd * ch * cw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % cw), Y = (int)((i / cw) % ch), Z = (int)(i / ((long long)cw * ch));
+    long long off = ((long long)(Z + oz) * SH + (Y + oy)) * SW + (X + ox);
+    if (labels[off] != label) continue;
+    Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int zi = (k & 4) ? lz.i1 : lz.i0, yi = (k & 2) ? ly.i1 : ly.i0, xi = (k & 1) ? lx.i1 : lx.i0;
+      float wt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
+      float v = __ldg(ram + ((long long)zi * h + yi) * w + xi);
+      acc += wt * (act == 1 ? sigmoidf_(v) : v);
+    }
+    if (act == 2) acc = fmaxf(acc, 0.f);
+    heat[off] = acc * gain;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Otsu inputs / masks
+// histogram of uint8(window(v, lo, hi) * 255) over voxels with labels > 0  (utils.binary_cam utils.py:226-242);
+// integer-exact: the uint8 conversion is the same truncation numpy's astype performs
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_masked_hist_u8(const T* __restrict__ v, const uint8_t* __restrict__ labels, long long n, float lo, float hi,
+                 unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  // numpy evaluates the windowing in the array's float type: float32 for the heat map, float64 for the int16 scan
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (labels[i] == 0) continue;
+    int bin;
+    if (sizeof(T) == 4) {
+      float x = (float)v[i];
+      x = fminf(fmaxf(x, lo), hi);
+      bin = (int)(((x - lo) / (hi - lo)) * 255.0f);
+    } else {
+      double x = (double)v[i];
+      x = x < lo ? (double)lo : (x > hi ? (double)hi : x);
+      bin = (int)(((x - (double)lo) / ((double)hi - (double)lo)) * 255.0);
+    }
+    atomicAdd(&sh[bin & 255], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// lesion = heat > th;  post = lesion && (window(scan) > th2) && !vessel      (job_runner.py:1009-1015)
+__global__ void __launch_bounds__(256)
+k_threshold_masks(const float* __restrict__ heat, const short* __restrict__ scan, const uint8_t* __restrict__ vessel,
+                  long long n, double th, double th2, float win_lo, float win_hi, uint8_t* __restrict__ lesion,
+                  uint8_t* __restrict__ post) {
+  const double span = (double)win_hi - (double)win_lo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    bool les = heat[i] > (float)th;          // numpy compares the float32 heat map against th cast to float32
+    lesion[i] = les ? 1 : 0;
+    if (post) {
+      double x = (double)scan[i];
+      x = x < win_lo ? (double)win_lo : (x > win_hi ? (double)win_hi : x);
+      bool keep = les && ((x - (double)win_lo) / span > th2) && !(vessel && vessel[i] > 0);
+      post[i] = keep ? 1 : 0;
+    }
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" {
+
+int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, int* out, void* stream) {
+  DRAM_REQUIRE(labels && out && D > 0 && H > 0 && W > 0 && nlabels >= 1 && nlabels <= 7, "label_bboxes: bad arguments (1..7 labels)");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_bbox_init<<<1, 64, 0, st>>>(out, (nlabels + 1) * 6);
+  DRAM_LAUNCH_CHECK();
+  k_label_bboxes<<<grid_for((long long)D * H * W, 256 * 8, 8), 256, 0, st>>>(labels, D, H, W, nlabels, out);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_lobe_chunk_preprocess(const short* scan, const uint8_t* labels, int SD, int SH, int SW, int label, int cz, int cy,
+                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, float* img,
+                               float* msk, int d, int h, int w, void* stream) {
+  DRAM_REQUIRE(scan && labels && img && msk && d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "lobe_chunk_preprocess: bad arguments");
+  DRAM_REQUIRE(cz >= 0 && cy >= 0 && cx >= 0 && cz + cd <= SD && cy + ch <= SH && cx + cw <= SW, "lobe_chunk_preprocess: crop outside the scan");
+  DRAM_REQUIRE(win_hi > win_lo, "lobe_chunk_preprocess: empty window");
+  k_lobe_chunk_preprocess<<<grid_for((long long)d * h * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      scan, labels, SH, SW, label, cz, cy, cx, cd, ch, cw, win_lo, win_hi, pad_value, img, msk, d, h, w);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, float rz, float ry,
+                      float rx, int mode, void* stream) {
+  DRAM_REQUIRE(src && dst && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1), "itk_resample: bad arguments");
+  DRAM_REQUIRE(rz > 0.f && ry > 0.f && rx > 0.f, "itk_resample: index ratios must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for((long long)D * H * W, 256, 16);
+  if (dtype == 0) k_itk_resample<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
+  else if (dtype == 1) k_itk_resample<short><<<grid, 256, 0, st>>>((const short*)src, (short*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
+  else if (dtype == 2) k_itk_resample<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
+  else DRAM_REQUIRE(false, "itk_resample: dtype %d unknown (0 f32, 1 i16, 2 u8)", dtype);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_ram_upsample_label_scatter(const float* ram, const uint8_t* labels, int label, float* heat, int d, int h, int w,
+                                    int cd, int ch, int cw, int SD, int SH, int SW, int oz, int oy, int ox, int act,
+                                    float gain, void* stream) {
+  DRAM_REQUIRE(ram && labels && heat && d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "ram_upsample_label_scatter: bad arguments");
+  DRAM_REQUIRE(act >= 0 && act <= 2, "ram_upsample_label_scatter: act %d unknown", act);
+  DRAM_REQUIRE(oz >= 0 && oy >= 0 && ox >= 0 && oz + cd <= SD && oy + ch <= SH && ox + cw <= SW, "ram_upsample_label_scatter: crop outside the scan");
+  k_ram_upsample_label_scatter<<<grid_for((long long)cd * ch * cw, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      ram, labels, label, heat, d, h, w, cd, ch, cw, SH, SW, oz, oy, ox, act, gain, ac_scale(d, cd), ac_scale(h, ch), ac_scale(w, cw));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_masked_hist_u8(const void* values, int dtype, const uint8_t* labels, long long n, float lo, float hi,
+                        unsigned int* hist, void* stream) {
+  DRAM_REQUIRE(values && labels && hist && n > 0 && hi > lo, "masked_hist_u8: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), st));
+  int grid = grid_for(n, 256 * 8, 8);
+  if (dtype == 0) k_masked_hist_u8<float><<<grid, 256, 0, st>>>((const float*)values, labels, n, lo, hi, hist);
+  else if (dtype == 1) k_masked_hist_u8<short><<<grid, 256, 0, st>>>((const short*)values, labels, n, lo, hi, hist);
+  else DRAM_REQUIRE(false, "masked_hist_u8: dtype %d unknown (0 f32, 1 i16)", dtype);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_threshold_masks(const float* heat, const short* scan, const uint8_t* vessel, long long n, double th, double th2,
+                         float win_lo, float win_hi, uint8_t* lesion, uint8_t* post, void* stream) {
+  DRAM_REQUIRE(heat && lesion && n > 0, "threshold_masks: bad arguments");
+  DRAM_REQUIRE(!post || (scan && win_hi > win_lo), "threshold_masks: post mask needs the scan and a window");
+  k_threshold_masks<<<grid_for(n, 256 * 4, 8), 256, 0, (cudaStream_t)stream>>>(heat, scan, vessel, n, th, th2, win_lo, win_hi, lesion, post);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

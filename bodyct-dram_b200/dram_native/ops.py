@@ -362,3 +362,74 @@ def pcm_bwd(f, cam, tw, pw, qk, att, dout, connectivity, self_loop, flags):
     dp = dparams.float()
     n = F * Cf
     return dcam, df, dp[:n].view(F, Cf), dp[n:n + F], dp[n + F:2 * n + F].view(F, Cf), dp[2 * n + F:]
+
+
+# ------------------------------------------------------------------------------------------------ scan pre/post-processing
+_DTYPE_CODE = {torch.float32: 0, torch.int16: 1, torch.uint8: 2}
+
+
+def label_bboxes(labels, nlabels=5):
+    """labels: uint8 [D,H,W] CUDA -> int32 [(nlabels+1), 6] (min z,y,x, max z,y,x inclusive); row 0 unused."""
+    _req(labels, "labels", torch.uint8)
+    D, H, W = labels.shape
+    out = torch.empty((nlabels + 1, 6), device=labels.device, dtype=torch.int32)
+    _lib.check(_L().dram_label_bboxes(labels.data_ptr(), D, H, W, nlabels, out.data_ptr(), _stream()), "label_bboxes")
+    return out
+
+
+def lobe_chunk_preprocess(scan, labels, label, crop, window, pad_value, img_out, msk_out):
+    """scan int16 / labels uint8 [SD,SH,SW]; crop = ((z0,z1),(y0,y1),(x0,x1)); writes img_out/msk_out [d,h,w] fp32."""
+    _req(scan, "scan", torch.int16)
+    _req(labels, "labels", torch.uint8)
+    SD, SH, SW = scan.shape
+    (z0, z1), (y0, y1), (x0, x1) = crop
+    d, h, w = img_out.shape
+    _lib.check(_L().dram_lobe_chunk_preprocess(scan.data_ptr(), labels.data_ptr(), SD, SH, SW, int(label), z0, y0, x0,
+                                               z1 - z0, y1 - y0, x1 - x0, float(window[0]), float(window[1]),
+                                               float(pad_value), img_out.data_ptr(), msk_out.data_ptr(), d, h, w, _stream()),
+               "lobe_chunk_preprocess")
+
+
+def itk_resample(src, new_size, mode="linear", ratios=None):
+    """Volume resample with ITK identity-transform semantics; ratios default to in/out ('fixed_size')."""
+    if src.dtype not in _DTYPE_CODE or not src.is_cuda or not src.is_contiguous():
+        raise _lib.DramLibraryError("itk_resample: need a contiguous CUDA tensor of dtype float32 / int16 / uint8")
+    d, h, w = src.shape
+    D, H, W = (int(s) for s in new_size)
+    if ratios is None:
+        ratios = (d / D, h / H, w / W)
+    dst = torch.empty((D, H, W), device=src.device, dtype=src.dtype)
+    _lib.check(_L().dram_itk_resample(src.data_ptr(), dst.data_ptr(), _DTYPE_CODE[src.dtype], d, h, w, D, H, W,
+                                      float(ratios[0]), float(ratios[1]), float(ratios[2]), 0 if mode == "linear" else 1,
+                                      _stream()), "itk_resample")
+    return dst
+
+
+def ram_upsample_label_scatter(ram, labels, label, heat, crop, act, gain=1.0):
+    """ram [d,h,w] fp32 -> heat[crop] (scan-sized fp32, in place) where labels == label."""
+    d, h, w = ram.shape
+    SD, SH, SW = heat.shape
+    (z0, z1), (y0, y1), (x0, x1) = crop
+    _lib.PROFILE.note(bytes=4.0 * d * h * w + 5.0 * (z1 - z0) * (y1 - y0) * (x1 - x0))
+    _lib.check(_L().dram_ram_upsample_label_scatter(ram.data_ptr(), labels.data_ptr(), int(label), heat.data_ptr(), d, h, w,
+                                                    z1 - z0, y1 - y0, x1 - x0, SD, SH, SW, z0, y0, x0, int(act), float(gain),
+                                                    _stream()), "ram_upsample_label_scatter")
+
+
+def masked_hist_u8(values, labels, lo, hi):
+    """-> int64 [256] histogram of uint8(window(values,(lo,hi))*255) over labels > 0 (device tensor)."""
+    if values.dtype not in (torch.float32, torch.int16):
+        raise _lib.DramLibraryError("masked_hist_u8: values must be float32 or int16")
+    hist = torch.empty(256, device=values.device, dtype=torch.int32)
+    _lib.check(_L().dram_masked_hist_u8(values.data_ptr(), _DTYPE_CODE[values.dtype], labels.data_ptr(), values.numel(),
+                                        float(lo), float(hi), hist.data_ptr(), _stream()), "masked_hist_u8")
+    return hist
+
+
+def threshold_masks(heat, th, scan=None, vessel=None, th2=0.0, window=(-1150.0, 350.0), want_post=True):
+    lesion = torch.empty(heat.shape, device=heat.device, dtype=torch.uint8)
+    post = torch.empty_like(lesion) if (want_post and scan is not None) else None
+    _lib.check(_L().dram_threshold_masks(heat.data_ptr(), _p(scan), _p(vessel), heat.numel(), float(th), float(th2),
+                                         float(window[0]), float(window[1]), lesion.data_ptr(), _p(post), _stream()),
+               "threshold_masks")
+    return lesion, post

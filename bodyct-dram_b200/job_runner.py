@@ -131,3 +131,157 @@ class LesionSegChunkTrain(JobRunner):
                                  f"Loss {loss_record.val:.6f} ({loss_record.avg:.6f}), "
                                  f"losses: {[f'{l.item():.5f}' for l in loss_tuple]}")
         return {'tr_loss': loss_record.avg, 'tr_batch_time': batch_time.avg}
+
+
+class LesionSegTest(JobRunner):
+    """Full-CT inference runner (job_runner.py:814-1067) with the working constructor process_pipeline.py assumes
+    (SURVEY D3): `LesionSegTest(input_image_path, input_lobe_path, output_path, settings, checkpoint)`.
+
+    `run_scan` keeps one scan on the GPU from upload to mask download: lobe bounding boxes -> per-lobe crop / blank /
+    window / ITK-style resample to the chunk grid (one kernel per lobe) -> the five chunks as ONE batch through the model
+    (eval-mode BatchNorm is batch independent, so batching does not change results) -> RAM upsample + activation + paste
+    under the lobe mask -> 8-bit histograms -> Otsu (256 bins, host) -> lesion masks.
+    head='sigmoid' is LesionSegChunkTrain.evaluate_scan's path (job_runner.py:764-770); head='literal' reproduces
+    LesionSegTest.run verbatim, which zeroes every heat map when out_ch == 1 (job_runner.py:988-1000)."""
+
+    def __init__(self, input_image_path=None, input_lobe_path=None, output_path=None, settings_module=None,
+                 checkpoint=None, task_name='test', head='sigmoid', build_model=True):
+        super().__init__(None, settings_module)
+        self.scan_path, self.lobe_path, self.output_path, self.task_name, self.head = \
+            input_image_path, input_lobe_path, output_path, task_name, head
+        self.crop_border = 5                                                 # mm, dataset.py crop_border
+        if build_model:
+            self.init()
+            if checkpoint is not None:
+                path = checkpoint if os.path.isabs(checkpoint) else os.path.join(self.exp_path, checkpoint)
+                self.reload_model_from_cache(path)
+        self.model_eval = None
+
+    # ---- stages -------------------------------------------------------------------------------------------------
+    def lobe_crops(self, lobe_t, spacing):
+        """utils.find_crops for the 5 lobes; one 120-byte device->host read per scan."""
+        from dram_native import ops
+        import math
+        boxes = ops.label_bboxes(lobe_t, 5).cpu().numpy()
+        crops = {}
+        for label in range(1, 6):
+            mn, mx = boxes[label, :3], boxes[label, 3:]
+            if mx[0] < 0:
+                continue
+            crops[label] = tuple((max(0, int(mn[a]) - int(math.ceil(self.crop_border / spacing[a]))),
+                                  min(int(lobe_t.shape[a]), int(mx[a]) + 1 + int(math.ceil(self.crop_border / spacing[a]))))
+                                 for a in range(3))
+        return crops
+
+    def preprocess(self, scan_t, lobe_t, crops):
+        from dram_native import ops
+        size = tuple(self.settings.RESAMPLE_SIZE)
+        n = len(crops)
+        imgs = torch.empty((n, 1) + size, device=scan_t.device, dtype=torch.float32)
+        msks = torch.empty((n, 1) + size, device=scan_t.device, dtype=torch.float32)
+        window = (self.settings.WINDOWING_MIN, self.settings.WINDOWING_MAX)
+        for i, (label, crop) in enumerate(crops.items()):
+            ops.lobe_chunk_preprocess(scan_t, lobe_t, label, crop, window, self.settings.PAD_VALUE, imgs[i, 0], msks[i, 0])
+        return imgs, msks
+
+    def paste(self, dense, msks, lobe_t, crops, heat):
+        from dram_native import ops
+        import models
+        if self.head == 'literal':
+            pool = models.pooling_dense_features(dense, msks)
+            cls_pred = torch.max(pool, dim=-1)[-1].tolist()                # always 0 for out_ch == 1
+        for i, (label, crop) in enumerate(crops.items()):
+            if self.head == 'literal':
+                if cls_pred[i] < 1e-7:
+                    continue                                                 # dense_out.zero_() -> heat map stays 0
+                mx = torch.zeros(1, device=dense.device)
+                (z0, z1), (y0, y1), (x0, x1) = crop
+                ops.ram_upsample_mask_scatter(dense[i, cls_pred[i]], (lobe_t[z0:z1, y0:y1, x0:x1] == label).to(torch.uint8).contiguous(),
+                                              None, (0, 0, 0), 2, 1.0, mx)
+                ops.ram_upsample_label_scatter(dense[i, cls_pred[i]], lobe_t, label, heat, crop, 2, 1.0 / mx.item())
+            else:
+                ops.ram_upsample_label_scatter(dense[i, 0], lobe_t, label, heat, crop, 1, 1.0)
+
+    def postprocess(self, heat, scan_t, lobe_t, vessel_t=None):
+        """binary_cam / Otsu thresholds and lesion masks (job_runner.py:1006-1015)."""
+        from dram_native import ops
+        from utils import otsu_threshold_from_histogram
+
+        def otsu(values, lo, hi, scaler):
+            hist = ops.masked_hist_u8(values, lobe_t, lo, hi).cpu().numpy().astype(np.int64)     # 1 KB device->host
+            if hist.sum() == 0:
+                raise ValueError("empty array encountered! cam_probs.size == 0.")
+            if np.count_nonzero(hist) < 2:
+                return float(np.nonzero(hist)[0][0]) / 255.0
+            return min(otsu_threshold_from_histogram(hist) * scaler, 255.0) / 255.0
+
+        th = otsu(heat, 0.0, 1.0, 1.0)
+        th2 = otsu(scan_t, -1150.0, 350.0, 0.75)
+        lesion, post = ops.threshold_masks(heat, th, scan_t, vessel_t, th2, (-1150.0, 350.0))
+        return lesion, post, th, th2
+
+    # ---- one scan -----------------------------------------------------------------------------------------------
+    def run_scan(self, scan, lobe, spacing, vessel=None, return_device=False):
+        """scan: int16 [D,H,W] (numpy or tensor, already at TEST_RESAMPLE_SPACING), lobe: uint8 labels 0..5."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev, dt, non_blocking=True)
+        scan_t, lobe_t = as_t(scan, torch.int16), as_t(lobe, torch.uint8)
+        vessel_t = as_t(vessel, torch.uint8) if vessel is not None else None
+        self.model.eval()
+        with torch.no_grad():
+            crops = self.lobe_crops(lobe_t, spacing)
+            heat = torch.zeros(scan_t.shape, device=dev, dtype=torch.float32)
+            if crops:
+                imgs, msks = self.preprocess(scan_t, lobe_t, crops)
+                _, dense = self.model(imgs, msks)
+                self.paste(dense, msks, lobe_t, crops, heat)
+            lesion, post, th, th2 = self.postprocess(heat, scan_t, lobe_t, vessel_t)
+            inside = (lobe_t > 0)
+            ratio = (heat * inside).sum() / inside.sum().clamp_min(1)       # job_runner.py:772
+        out = {"heatmap": heat, "lesion": lesion, "lesion_post": post, "threshold": th, "threshold_post": th2,
+               "ratio": ratio, "crops": crops}
+        if not return_device:
+            out.update(heatmap=heat.cpu().numpy(), lesion=lesion.cpu().numpy(), lesion_post=post.cpu().numpy(),
+                       ratio=float(ratio.item()))
+        return out
+
+    def resample_to_working_grid(self, arr_t, spacing, mode):
+        """Resample('fixed_spacing', TEST_RESAMPLE_SPACING) of a whole scan (job_runner.py:827-835)."""
+        from dram_native import ops
+        new_sp = float(self.settings.TEST_RESAMPLE_SPACING)
+        new_size = [int(np.ceil(s * sp / new_sp)) for s, sp in zip(arr_t.shape, spacing)]
+        return ops.itk_resample(arr_t, new_size, mode, ratios=[new_sp / sp for sp in spacing])
+
+    def run(self):
+        """Process every `<uid>.npz` (keys: image int16, lobe uint8, spacing[, vessel]) under input_image_path."""
+        os.makedirs(os.path.join(self.output_path, self.task_name), exist_ok=True)
+        records = []
+        for path in sorted(glob.glob(os.path.join(self.scan_path, "*.npz"))):
+            uid = os.path.splitext(os.path.basename(path))[0]
+            target = os.path.join(self.output_path, self.task_name, uid + ".npz")
+            if os.path.exists(target):
+                self.logger.warning("We have already archived results for scan %s", uid)
+                continue
+            data = np.load(path)
+            lobe = np.load(os.path.join(self.lobe_path, uid + ".npz"))["lobe"] if self.lobe_path and "lobe" not in data else data["lobe"]
+            start = time.time()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            spacing = [float(s) for s in data["spacing"]]
+            scan_t = self.resample_to_working_grid(torch.from_numpy(data["image"].astype(np.int16)).to(dev), spacing, "linear")
+            lobe_t = self.resample_to_working_grid(torch.from_numpy(lobe.astype(np.uint8)).to(dev), spacing, "nearest")
+            new_sp = [float(self.settings.TEST_RESAMPLE_SPACING)] * 3
+            out = self.run_scan(scan_t, lobe_t, new_sp, return_device=True)
+            back = lambda t, mode: ops_itk_back(t, data["image"].shape, new_sp, spacing, mode)
+            np.savez_compressed(target, lesion=back(out["lesion"], "nearest").cpu().numpy(),
+                                lesion_post=back(out["lesion_post"], "nearest").cpu().numpy(),
+                                heatmap=back(out["heatmap"], "linear").cpu().numpy(), threshold=out["threshold"])
+            records.append({"uid": uid, "seconds": time.time() - start, "ratio": float(out["ratio"].item())})
+            self.logger.info("Finished %s, in %.3f seconds.", uid, records[-1]["seconds"])
+        return records
+
+
+def ops_itk_back(t, original_size, spacing, original_spacing, mode):
+    """resample a working-grid volume back to the scan's original grid (job_runner.py:1017-1030)."""
+    from dram_native import ops
+    return ops.itk_resample(t.contiguous(), tuple(int(s) for s in original_size), mode,
+                            ratios=[o / s for o, s in zip(original_spacing, spacing)])

@@ -78,11 +78,14 @@ def find_crops(mask, spacing, border):
     return tuple(out)
 
 
-def otsu_threshold_from_histogram(hist, lo, hi):
-    """Otsu threshold of data summarised by a 256-bin histogram over [lo, hi] (bin centres, first maximum wins)."""
-    hist = np.asarray(hist, dtype=np.float64)
-    edges = np.linspace(lo, hi, 257)
-    centers = (edges[:-1] + edges[1:]) / 2.0
+def otsu_threshold_from_histogram(hist_by_value):
+    """Otsu threshold of uint8 data given its 256-entry value histogram (what skimage computes for integer images:
+    one bin per integer between min and max, first maximum of the between-class variance, returns the bin centre)."""
+    hist_by_value = np.asarray(hist_by_value, dtype=np.float64)
+    nz = np.nonzero(hist_by_value)[0]
+    lo, hi = int(nz[0]), int(nz[-1])
+    hist = hist_by_value[lo:hi + 1]
+    centers = np.arange(lo, hi + 1, dtype=np.float64)
     w1 = np.cumsum(hist)
     w2 = np.cumsum(hist[::-1])[::-1]
     m1 = np.cumsum(hist * centers) / np.maximum(w1, 1e-300)
@@ -96,13 +99,10 @@ def binary_cam(cam_probs, scaler=1.0, from_span=(0, 1)):
     if cam.size == 0:
         raise ValueError("empty array encountered! cam_probs.size == 0.")
     w = windowing(cam, from_span=from_span).astype(np.uint8)
-    u = np.unique(w)
-    if len(u) < 2:
-        return np.ones_like(w).astype(bool), u[0] / 255.0
     hist = np.bincount(w.ravel(), minlength=256)
-    lo, hi = float(u[0]), float(u[-1])
-    h256, _ = np.histogram(w, bins=256, range=(lo, hi))
-    th = min(otsu_threshold_from_histogram(h256, lo, hi) * scaler, 255.0)
+    if np.count_nonzero(hist) < 2:
+        return np.ones_like(w).astype(bool), float(np.nonzero(hist)[0][0]) / 255.0
+    th = min(otsu_threshold_from_histogram(hist) * scaler, 255.0)
     return w >= th, th / 255.0
 
 

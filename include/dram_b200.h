@@ -168,6 +168,36 @@ int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const f
                  double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------ scan pre/post-processing
+ * What LesionSegTest.run / evaluate_scan do on the host around the model (job_runner.py:730-772, 951-1015), on the GPU.
+ * scan: int16 HU [SD][SH][SW]; labels: uint8 lobe labels (0 = background, 1..5 = lobes); heat: fp32 [SD][SH][SW]. */
+/* utils.find_crops (utils.py:244-254) for all labels at once: out[l*6 + {0,1,2}] = min z,y,x, out[l*6 + {3,4,5}] = max
+ * z,y,x (inclusive) for l in 1..nlabels (<= 7); empty labels keep min = INT_MAX, max = -1.  out: int[(nlabels+1)*6]. */
+int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, int* out, void* stream);
+/* job_runner.py:961-984: crop [cz,cz+cd)x[cy,cy+ch)x[cx,cx+cw), voxels outside `label` -> pad_value (-2048), Windowing
+ * (data_transforms.py:37-54) to [0,1], Resample('fixed_size') (data_transforms.py:170-175, ITK identity-transform
+ * resample: index o -> o*in/out, linear for the image, nearest for the mask) to the chunk grid (d,h,w). */
+int dram_lobe_chunk_preprocess(const short* scan, const uint8_t* labels, int SD, int SH, int SW, int label, int cz, int cy,
+                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, float* img,
+                               float* msk, int d, int h, int w, void* stream);
+/* utils.resample (utils.py:414-434) of a whole volume [d][h][w] -> [D][H][W]; output index o reads the continuous input
+ * index o*r (r = new_spacing/old_spacing per axis; = in/out for a fixed-size resample); outside the ITK buffer -> 0.
+ * dtype 0 = f32, 1 = i16 (truncating cast), 2 = u8; mode 0 = linear, 1 = nearest (round half up). */
+int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, float rz, float ry,
+                      float rx, int mode, void* stream);
+/* dram_ram_upsample_mask_scatter with the mask read from the scan-sized label volume (labels == label) */
+int dram_ram_upsample_label_scatter(const float* ram, const uint8_t* labels, int label, float* heat, int d, int h, int w,
+                                    int cd, int ch, int cw, int SD, int SH, int SW, int oz, int oy, int ox, int act,
+                                    float gain, void* stream);
+/* utils.binary_cam (utils.py:226-242): 256-bin histogram of uint8(windowing(v, (lo,hi)) -> [0,255]) over labels > 0,
+ * integer-exact (dtype 0 = f32 values, 1 = i16 values); hist: unsigned[256], overwritten.  Otsu runs on the host. */
+int dram_masked_hist_u8(const void* values, int dtype, const uint8_t* labels, long long n, float lo, float hi,
+                        unsigned int* hist, void* stream);
+/* job_runner.py:1009-1015: lesion = heat > th; post = lesion && windowing(scan,(win_lo,win_hi)->(0,1)) > th2 && !vessel
+ * (post / scan / vessel may be NULL) */
+int dram_threshold_masks(const float* heat, const short* scan, const uint8_t* vessel, long long n, double th, double th2,
+                         float win_lo, float win_hi, uint8_t* lesion, uint8_t* post, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,37 +310,61 @@ def find_crops(mask, spacing, border):
     return tuple(sl)
 
 
-def itk_resample(arr, new_size, interpolator="linear"):
-    """SimpleITK ResampleImageFilter as used by utils.resample utils.py:414-434 + Resample('fixed_size')
-    data_transforms.py:170-175: identity transform, same origin, new_spacing = spacing*size/new_size, fill 0.
-    Output index i maps to continuous input index i*(in/out) (pixel-centre origin, NO half-pixel shift).
-    Linear: neighbours beyond the last sample are clamped (ITK evaluates inside [-0.5, size-0.5)).
-    Nearest: round-half-up.  (SimpleITK 1.1.0 is not vendored: parity unpinned.)"""
-    if tuple(arr.shape) == tuple(new_size):
+def itk_resample(arr, new_size, interpolator="linear", ratios=None):
+    """SimpleITK ResampleImageFilter as used by utils.resample utils.py:414-434 (+ resample_sitk_image :299-384) and
+    Resample('fixed_size') data_transforms.py:170-175: identity transform, same origin, fill 0.
+    Output index i maps to the continuous input index i*r with r = new_spacing/old_spacing (= in/out for 'fixed_size';
+    pixel-centre origin, NO half-pixel shift).  Indices >= n-0.5 are outside the ITK buffer -> 0.
+    Linear: float32 8-tap, neighbours beyond the last sample clamped.  Nearest: round-half-up.
+    (SimpleITK 1.1.0 is not vendored: parity unpinned.)"""
+    if ratios is None and tuple(arr.shape) == tuple(new_size):
         return arr                                                              # utils.py:415-417
-    coords = []
-    for n_in, n_out in zip(arr.shape, new_size):
-        coords.append(np.arange(n_out, dtype=np.float64) * (float(n_in) / float(n_out)))
+    ratios = [np.float32(n_in) / np.float32(n_out) for n_in, n_out in zip(arr.shape, new_size)] if ratios is None else ratios
+    coords = [np.arange(n_out, dtype=np.float32) * np.float32(r) for n_out, r in zip(new_size, ratios)]
+    inside = [c < np.float32(n) - np.float32(0.5) for c, n in zip(coords, arr.shape)]
+    inside3 = inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
     if interpolator == "nearest":
-        idx = [np.clip(np.floor(c + 0.5).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
-        return arr[np.ix_(*idx)]
-    out = arr.astype(np.float64)
-    for ax, (c, n) in enumerate(zip(coords, arr.shape)):
-        i0 = np.clip(np.floor(c).astype(np.int64), 0, n - 1)
-        i1 = np.clip(i0 + 1, 0, n - 1)
-        w = (c - np.floor(c)).reshape([-1 if a == ax else 1 for a in range(3)])
-        out = np.take(out, i0, axis=ax) * (1.0 - w) + np.take(out, i1, axis=ax) * w
-    return out.astype(arr.dtype if np.issubdtype(arr.dtype, np.floating) else np.float32)
+        idx = [np.clip(np.floor(c + np.float32(0.5)).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
+        out = arr[np.ix_(*idx)].copy()
+        out[~inside3] = 0
+        return out
+    i0 = [np.clip(np.floor(c).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
+    i1 = [np.clip(np.floor(c).astype(np.int64) + 1, 0, n - 1) for c, n in zip(coords, arr.shape)]
+    w1 = [(c - np.floor(c)).astype(np.float32) for c in coords]
+    src = arr.astype(np.float32)
+    out = np.zeros(tuple(new_size), dtype=np.float32)
+    for k in range(8):                                                          # same tap order / fp32 math as the kernel
+        iz = i1[0] if k & 4 else i0[0]
+        iy = i1[1] if k & 2 else i0[1]
+        ix = i1[2] if k & 1 else i0[2]
+        wz = w1[0] if k & 4 else np.float32(1) - w1[0]
+        wy = w1[1] if k & 2 else np.float32(1) - w1[1]
+        wx = w1[2] if k & 1 else np.float32(1) - w1[2]
+        wt = (wz[:, None, None] * wy[None, :, None]) * wx[None, None, :]
+        out += wt * src[np.ix_(iz, iy, ix)]
+    out[~inside3] = 0
+    if np.issubdtype(arr.dtype, np.integer):
+        info = np.iinfo(arr.dtype)
+        return np.trunc(np.clip(out, info.min, info.max)).astype(arr.dtype)     # ITK static_cast: truncation
+    return out
+
+
+def resample_to_spacing(arr, spacing, new_spacing, interpolator="linear"):
+    """Resample('fixed_spacing') data_transforms.py:76-83 + resample_sitk_image utils.py:369-371:
+    new_size = ceil(size * spacing / new_spacing), index ratio = new_spacing / spacing."""
+    spacing, new_spacing = np.asarray(spacing, np.float64), np.asarray(new_spacing, np.float64)
+    new_size = np.ceil(np.asarray(arr.shape) * (spacing / new_spacing)).astype(int)
+    return itk_resample(arr, tuple(new_size), interpolator, ratios=[np.float32(a / b) for a, b in zip(new_spacing, spacing)])
 
 
 def threshold_otsu_u8(values_u8):
-    """skimage.filters.threshold_otsu on uint8 data (utils.py:239), restated: 256-bin histogram over
-    [min,max], bin centres, maximise w1*w2*(mu1-mu2)^2, return the bin centre (scikit-image <=0.17, unpinned)."""
-    v = np.asarray(values_u8).ravel()
-    lo, hi = float(v.min()), float(v.max())
-    hist, edges = np.histogram(v, bins=256, range=(lo, hi))
-    centers = (edges[:-1] + edges[1:]) / 2.0
-    hist = hist.astype(np.float64)
+    """skimage.filters.threshold_otsu on uint8 data (utils.py:239), restated: for integer images skimage histograms with
+    bincount (one bin per integer value between min and max, bin centres = the integer values), maximises
+    w1*w2*(mu1-mu2)^2 between neighbouring bins and returns the bin centre (scikit-image <= 0.17, unpinned)."""
+    v = np.asarray(values_u8).ravel().astype(np.int64)
+    lo, hi = int(v.min()), int(v.max())
+    hist = np.bincount(v - lo, minlength=hi - lo + 1).astype(np.float64)
+    centers = np.arange(lo, hi + 1, dtype=np.float64)
     w1 = np.cumsum(hist)
     w2 = np.cumsum(hist[::-1])[::-1]
     m1 = np.cumsum(hist * centers) / np.maximum(w1, 1e-300)

@@ -108,6 +108,7 @@ def test_inference_plumbing_restatement():
     v = np.concatenate([rng.randint(0, 60, 5000), rng.randint(180, 255, 3000)]).astype(np.uint8)
     th = O.threshold_otsu_u8(v)
     assert 58 <= th <= 180      # flat maximum over the empty gap: first bin wins, like skimage
+    assert th == int(th)        # integer images: bincount histogram, integer bin centres
     assert 0.2 < O.binary_cam(v / 255.0) < 0.75
 
 

@@ -1,0 +1,136 @@
+"""GPU parity tests of the scan-level pre/post-processing kernels and of the whole-scan inference runner
+(job_runner.LesionSegTest.run_scan) against the CPU oracle's restatement of job_runner.py:730-772 / 951-1015.
+Index / mask / histogram work must be bit-exact; interpolated values within fp32 tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ops():
+    from dram_native import ops as o
+    return o
+
+
+def test_label_bboxes_match_find_crops():
+    from oracle_import import O
+    scan, lobe, lesion, spacing = O.synthetic_scan((40, 56, 48), (1.0, 0.7, 0.7), seed=1)
+    boxes = ops().label_bboxes(torch.from_numpy(lobe).cuda(), 5).cpu().numpy()
+    for label in range(1, 6):
+        sl = O.find_crops(lobe == label, spacing, 0)
+        assert [int(boxes[label, a]) for a in range(3)] == [s.start for s in sl]
+        assert [int(boxes[label, 3 + a]) + 1 for a in range(3)] == [s.stop for s in sl]
+    lobe[lobe == 3] = 0                                                      # empty label
+    boxes = ops().label_bboxes(torch.from_numpy(lobe).cuda(), 5).cpu().numpy()
+    assert boxes[3, 3] < 0
+
+
+@pytest.mark.parametrize("chunk", [(16, 16, 16), (24, 20, 28)])
+def test_lobe_chunk_preprocess(chunk):
+    from oracle_import import O
+    scan, lobe, lesion, spacing = O.synthetic_scan((40, 56, 48), (1.0, 0.7, 0.7), seed=2)
+    scan_t, lobe_t = torch.from_numpy(scan).cuda(), torch.from_numpy(lobe).cuda()
+    for label in (1, 4):
+        sl, lobe_chunk, img_ref, msk_ref = O.preprocess_lobe_chunk(scan, lobe, label, spacing, (-1000, -700), chunk)
+        img = torch.empty(chunk, device="cuda")
+        msk = torch.empty(chunk, device="cuda")
+        crop = tuple((s.start, s.stop) for s in sl)
+        ops().lobe_chunk_preprocess(scan_t, lobe_t, label, crop, (-1000, -700), -2048, img, msk)
+        assert torch.equal(msk.cpu(), torch.from_numpy(msk_ref)), "nearest-resampled lobe mask must be bit-exact"
+        assert (img.cpu() - torch.from_numpy(img_ref)).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int16, np.uint8])
+@pytest.mark.parametrize("mode", ["linear", "nearest"])
+@pytest.mark.parametrize("src,dst", [((20, 24, 18), (10, 16, 18)), ((9, 10, 11), (20, 31, 15))])
+def test_itk_resample(dtype, mode, src, dst):
+    from oracle_import import O
+    rng = np.random.RandomState(3)
+    a = (rng.rand(*src) * 200 - 50).astype(dtype) if dtype != np.uint8 else rng.randint(0, 6, size=src).astype(np.uint8)
+    ref = O.itk_resample(a, dst, mode)
+    got = ops().itk_resample(torch.from_numpy(a).cuda(), dst, mode).cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    if mode == "nearest":
+        assert np.array_equal(got, ref)
+    elif dtype == np.float32:
+        assert np.abs(got - ref).max() <= 1e-4
+    else:                                                       # truncating cast: at most 1 LSB on rounding ties
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_itk_resample_fixed_spacing_round_trip_sizes():
+    from oracle_import import O
+    rng = np.random.RandomState(4)
+    a = rng.randint(-1000, 400, size=(20, 30, 30)).astype(np.int16)
+    ref = O.resample_to_spacing(a, (1.5, 0.7, 0.7), (1.0, 1.0, 1.0), "linear")
+    new_size = ref.shape
+    got = ops().itk_resample(torch.from_numpy(a).cuda(), new_size, "linear", ratios=[1.0 / 1.5, 1.0 / 0.7, 1.0 / 0.7]).cpu().numpy()
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert new_size == (30, 21, 21) and diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_masked_histogram_and_thresholds_are_integer_exact():
+    rng = np.random.RandomState(5)
+    heat = rng.rand(24, 20, 28).astype(np.float32)
+    scan = rng.randint(-1500, 600, size=heat.shape).astype(np.int16)
+    lobe = (rng.rand(*heat.shape) > 0.5).astype(np.uint8) * rng.randint(1, 6, size=heat.shape).astype(np.uint8)
+    vessel = (rng.rand(*heat.shape) > 0.9).astype(np.uint8)
+    o = ops()
+    from oracle_import import O
+    h = o.masked_hist_u8(torch.from_numpy(heat).cuda(), torch.from_numpy(lobe).cuda(), 0.0, 1.0).cpu().numpy()
+    ref = np.bincount(O.windowing(heat[lobe > 0], from_span=(0, 1)).astype(np.uint8), minlength=256)
+    assert np.array_equal(h, ref)
+    w_scan = O.windowing(scan, to_span=(0, 1))
+    h2 = o.masked_hist_u8(torch.from_numpy(scan).cuda(), torch.from_numpy(lobe).cuda(), -1150.0, 350.0).cpu().numpy()
+    ref2 = np.bincount(O.windowing(w_scan[lobe > 0], from_span=(0, 1)).astype(np.uint8), minlength=256)
+    assert np.array_equal(h2, ref2)
+    th, th2 = 0.4392156862745098, 0.3
+    lesion, post = o.threshold_masks(torch.from_numpy(heat).cuda(), th, torch.from_numpy(scan).cuda(),
+                                     torch.from_numpy(vessel).cuda(), th2)
+    ref_les = heat > np.float32(th)
+    ref_post = ref_les & (w_scan > th2) & ~(vessel > 0)
+    assert np.array_equal(lesion.cpu().numpy().astype(bool), ref_les)
+    assert np.array_equal(post.cpu().numpy().astype(bool), ref_post)
+
+
+@pytest.mark.parametrize("head", ["sigmoid", "literal"])
+def test_run_scan_matches_oracle(head):
+    """whole-scan inference on a small synthetic CT with the reference-initialised tiny attention model"""
+    from oracle_import import O
+    import job_runner
+    import models
+    from utils import Settings
+    g = torch.load(os.path.join(GOLDEN, "dc3dat_div16_16.pt"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = Settings(os.path.join(root, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    s.MODEL = dict(g["cfg"])
+    s.RESAMPLE_SIZE = (16, 16, 16)
+    runner = job_runner.LesionSegTest(None, None, None, s, None, head=head)
+    runner.model.load_state_dict(g["state_dict"])
+    scan, lobe, lesion, spacing = O.synthetic_scan((40, 56, 48), (1.0, 1.0, 1.0), seed=6)
+    out = runner.run_scan(scan, lobe, [1.0, 1.0, 1.0])
+
+    sd = {k: v.clone() for k, v in g["state_dict"].items()}
+    model_fn = lambda img, lb: O.dc3dat_forward(sd, img, g["cfg"], False)
+    ref = O.infer_scan(model_fn, scan, lobe, np.asarray([1.0, 1.0, 1.0]), window=(s.WINDOWING_MIN, s.WINDOWING_MAX),
+                       chunk_size=(16, 16, 16), head=head)
+    assert np.array_equal(out["heatmap"] != 0, ref["heatmap"] != 0), "lobe masking / paste indices must be bit-exact"
+    assert (out["heatmap"][lobe == 0] == 0).all()
+    if head == "literal":
+        assert (out["heatmap"] == 0).all() and (ref["heatmap"] == 0).all()
+        return
+    assert_close(torch.from_numpy(out["heatmap"]), torch.from_numpy(ref["heatmap"]), 2e-4, "heat map")
+    assert abs(out["threshold"] - ref["threshold"]) < 1e-12, (out["threshold"], ref["threshold"])
+    a, b = out["lesion"].astype(bool), ref["lesion"].astype(bool)
+    dice = (2.0 * (a & b).sum() + 1e-5) / (a.sum() + b.sum() + 1e-5)
+    assert dice >= 0.999, dice
+    a, b = out["lesion_post"].astype(bool), ref["lesion_post"].astype(bool)
+    assert (2.0 * (a & b).sum() + 1e-5) / (a.sum() + b.sum() + 1e-5) >= 0.999
+    assert abs(out["ratio"] - ref["ratio"]) <= 1e-4 * abs(ref["ratio"])
