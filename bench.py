@@ -238,6 +238,23 @@ def run_b200(args):
                                             **({"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} if v["flops"] else {})}
                  for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]}
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        del runner
+        torch.cuda.empty_cache()
+        extra = {"hbm_kernels": hbm_kernel_rooflines(peaks)}
+        att = build_att_runner()
+        m = att.model.eval()
+        b5 = make_batch(5, seed=1, pinned=False)
+        i5, l5 = b5["#image"].unsqueeze(1).cuda(), b5["#lobe_reference"].unsqueeze(1).cuda()
+
+        def infer5():
+            with torch.no_grad():
+                _, r = m(i5, l5)
+                return m.pooling_dense_features(r, l5)
+        ms5 = time_cuda(infer5, 5, 3)
+        extra["infer"] = {"metric": "infer_lobe_chunks_per_s", "value": 5 / (ms5 / 1e3), "ms_per_batch_of_5": ms5,
+                          "workload": "DC3DATGeneric eval forward + pooling, 5 lobe chunks of one scan (see --workload infer)"}
     cpu = None
     if world == 1 and not args.no_cpu:
         v, s_per, threads = cpu_train_chunks_per_s(1, 0, batch=1)
@@ -267,9 +284,293 @@ def run_b200(args):
                      "whole_step_tflops_per_gpu": B * TRAIN_GFLOP_PER_CHUNK / 1e3 / (ms_total / args.steps / 1e3)},
         "kernels": breakdown,
         "cpu_baseline": cpu,
+        "extra": extra,
         "loss": final_loss,
     }
     print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------ inference workloads
+def build_att_runner(head="sigmoid"):
+    import torch
+    import job_runner
+    from utils import Settings
+    settings = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    torch.manual_seed(0)
+    return job_runner.LesionSegTest(None, None, None, settings, None, head=head)
+
+
+def time_cuda(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def hbm_kernel_rooflines(peaks):
+    """Stand-alone HBM rooflines of the RAM-head and PCM kernels: algorithmic bytes / CUDA-event time."""
+    import torch
+    from dram_native import ops
+    import models
+    out = {}
+    B, C, V = 8, 64, 80 * 80 * 80
+    feat = ops.new_volume(B, C, 80, 80, 80, "cuda")
+    feat.normal_()
+    w, b = torch.randn(1, C, device="cuda"), torch.randn(1, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=10):
+        ts = []
+        for _ in range(reps + 3):
+            flush.zero_()                                   # evict L2 (126 MB) between iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts[3:])
+
+    ms = timed(lambda: ops.ram_reduce(feat, w, b))
+    nbytes = 4.0 * B * V * (C + 1)
+    out["ram_reduce_fwd"] = {"bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6, "unit": "GB/s",
+                             "peak": peaks["hbm_gbs"], "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"]}
+    ram = torch.randn(B, V, device="cuda")
+    mask = (torch.rand(B, V, device="cuda") > 0.4).float()
+    ms = timed(lambda: ops.masked_pool(ram, mask, True, True))
+    nbytes = 8.0 * B * V
+    out["masked_pool_fwd"] = {"bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6, "unit": "GB/s",
+                              "peak": peaks["hbm_gbs"], "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"]}
+    SD, SH, SW = 400, 358, 358
+    labels = torch.ones((SD, SH, SW), dtype=torch.uint8, device="cuda")
+    heat = torch.zeros((SD, SH, SW), device="cuda")
+    crop = ((20, 260), (30, 230), (40, 220))
+    vc = 240 * 200 * 180
+    r1 = torch.randn(80, 80, 80, device="cuda")
+    ms = timed(lambda: ops.ram_upsample_label_scatter(r1, labels, 1, heat, crop, 1, 1.0))
+    nbytes = 4.0 * V + 5.0 * vc
+    out["ram_upsample_label_scatter"] = {"bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6,
+                                         "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+                                         "crop_voxels": vc}
+    Bp, G = 5, 64
+    f = ops.new_volume(Bp, 17, G, G, G, "cuda")
+    f.normal_()
+    cam = torch.randn(Bp, 1, G, G, G, device="cuda")
+    pcm = models.PCM((G, G, G), 17, 1, 8, 0, 8, 1, 3, "scaled_dot_product_relu", False, p_enc_dim=0).cuda()
+    with torch.no_grad():
+        ms = timed(lambda: pcm(cam, f))
+    nbytes = 76.0 * Bp * G ** 3
+    out["pcm_fwd"] = {"bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6, "unit": "GB/s",
+                      "peak": peaks["hbm_gbs"], "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+                      "note": "algorithmic 76 B/voxel (f 17x4 + cam 4 in, 4 out); this round's kernels also write/read the "
+                              "theta|phi projections (64 B) and the softmax weights (72 B) kept for the backward"}
+    return out
+
+
+def cpu_infer_chunks_per_s(att=True, batch=1, threads=None):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dram_oracle as O
+    import models
+    from utils import Settings
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    s = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py" if att else "st_dram_ref.py"))
+    cfg = dict(s.MODEL)
+    cls = getattr(models, cfg.pop("method").split(".")[-1])
+    torch.manual_seed(0)
+    m = cls(**cfg)
+    m.init(models.HeNorm(mode="fan_in"))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    images, lobes, _, _ = O.synthetic_batch(batch, CHUNK, seed=0)
+    fwd = O.dc3dat_forward if att else O.dc3d_forward
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        d, r = fwd(sd, images, dict(s.MODEL), False)
+        O.masked_pool(r, lobes)
+    dt = time.perf_counter() - t0
+    return batch / dt, dt, threads
+
+
+def run_infer(args):
+    """BASELINE configs[0]/[3]-[4] building block: DC3DATGeneric eval forward + per-lobe pooling on the 5 lobe chunks of
+    a scan (batch 5), chunks/s."""
+    import torch
+    import torch.distributed as td
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dram_native import lib
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    runner = build_att_runner()
+    model = runner.model.eval()
+    B = 5
+    batch = make_batch(B, seed=rank, pinned=True)
+    img_h, lobe_h = batch["#image"].unsqueeze(1), batch["#lobe_reference"].unsqueeze(1)
+    img_h, lobe_h = img_h.contiguous().pin_memory(), lobe_h.contiguous().pin_memory()
+    img_d, lobe_d = img_h.cuda(), lobe_h.cuda()
+
+    def fwd_dev():
+        with torch.no_grad():
+            _, r = model(img_d, lobe_d)
+            return model.pooling_dense_features(r, lobe_d)
+
+    def fwd_host():
+        with torch.no_grad():
+            i, l = img_h.cuda(non_blocking=True), lobe_h.cuda(non_blocking=True)
+            _, r = model(i, l)
+            return model.pooling_dense_features(r, l).cpu()
+
+    for _ in range(args.warmup):
+        fwd_dev()
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.PROFILE.reset()
+    lib.PROFILE.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fwd_dev()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.PROFILE.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    launches, prof = lib.PROFILE.launches, lib.PROFILE.summary()
+    fwd_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd_host()
+    torch.cuda.synchronize()
+    e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        td.all_reduce(e2e, op=td.ReduceOp.MAX)
+    if rank == 0:
+        peaks = load_peaks()
+        k = prof.get("dram_conv3d_umma_fwd", {"ms": 0.0, "flops": 0.0})
+        achieved = k["flops"] / (k["ms"] / 1e3) / 1e12 if k["ms"] else 0.0
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, dt, threads = cpu_infer_chunks_per_s(True, 1)
+            cpu = {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port",
+                   "sample": f"1 eval forward of DC3DATGeneric + pooling, batch 1, 80^3 chunk ({dt:.1f} s), torch CPU fp32 oracle"}
+        print(json.dumps({
+            "metric": "infer_lobe_chunks_per_s", "value": world * B * args.steps / (ms.item() / 1e3), "unit": "chunks/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item() / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32 elsewhere)", "data": "synthetic",
+            "config": {"workload": "DC3DATGeneric eval forward (U-Net + RAM head + PCM refinement) + per-lobe pooling on the "
+                                   "5 lobe chunks of one scan, 80^3, batch 5 per GPU", "per_gpu_batch": B, "chunk": list(CHUNK),
+                       "l2": "activations (~5 GB per batch) stream through L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / e2e.item(), "unit": "chunks/s",
+                    "h2d_bytes_per_step": 2 * img_h.numel() * 4, "d2h_bytes_per_step": B * 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd", "achieved": achieved, "peak": peaks["tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                         "peak_source": peaks["source"]},
+            "cpu_baseline": cpu}))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def run_scan(args):
+    """BASELINE configs[3]/[4]: process_pipeline full-CT inference on a synthetic 512x512x400 scan (spacing 0.7 mm in-plane,
+    1.0 mm slices): resample to 1 mm, 5 lobe chunks, DC3DATGeneric, RAM -> heat map -> Otsu -> lesion masks, back-resample.
+    N > 1: scans are sharded across GPUs, no collective."""
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dram_oracle as O
+    import job_runner
+    from dram_native import lib
+    runner = build_att_runner()
+    shape = (400, 512, 512) if not args.small else (100, 128, 128)
+    spacing = [1.0, 0.7, 0.7]
+    scan, lobe, _, _ = O.synthetic_scan(shape, spacing, seed=rank)
+    scan_h, lobe_h = torch.from_numpy(scan).pin_memory(), torch.from_numpy(lobe).pin_memory()
+    new_sp = [1.0, 1.0, 1.0]
+
+    def one_scan(scan_in, lobe_in, download):
+        s_t = runner.resample_to_working_grid(scan_in.cuda(non_blocking=True), spacing, "linear")
+        l_t = runner.resample_to_working_grid(lobe_in.cuda(non_blocking=True), spacing, "nearest")
+        out = runner.run_scan(s_t, l_t, new_sp, return_device=True)
+        les = job_runner.ops_itk_back(out["lesion"], shape, new_sp, spacing, "nearest")
+        post = job_runner.ops_itk_back(out["lesion_post"], shape, new_sp, spacing, "nearest")
+        if download:
+            return les.cpu(), post.cpu(), float(out["ratio"].item())
+        return les, post, out["ratio"]
+
+    scan_d, lobe_d = scan_h.cuda(), lobe_h.cuda()
+    for _ in range(args.warmup):
+        one_scan(scan_d, lobe_d, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.PROFILE.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_scan(scan_d, lobe_d, False)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.PROFILE.launches
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    one_scan(scan_h, lobe_h, True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_scan(scan_h, lobe_h, True)
+    torch.cuda.synchronize()
+    e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        td.all_reduce(e2e, op=td.ReduceOp.MAX)
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, dt, threads = cpu_infer_chunks_per_s(True, 1)
+            cpu = {"value": 5.0 * dt, "unit": "s/scan", "cores": threads, "kind": "port",
+                   "sample": f"model part only: one of the scan's 5 lobe chunks through the CPU oracle ({dt:.1f} s) x 5; the "
+                             "reference additionally spends CPU time in SimpleITK resampling and numpy masking"}
+        s_per_scan = ms.item() / 1e3 / args.steps
+        print(json.dumps({
+            "metric": "seconds_per_ct_scan", "value": s_per_scan / world, "unit": "s/scan (wall time per scan of the whole job)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item() / args.steps,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32 elsewhere)", "data": "synthetic",
+            "config": {"workload": "process_pipeline full-CT inference, synthetic scan %dx%dx%d @ (1.0,0.7,0.7) mm + 5-lobe mask, "
+                                   "one scan per step per GPU" % shape, "scans_per_s": world / s_per_scan},
+            "clocks": clocks,
+            "e2e": {"value": e2e.item() / args.steps / world, "unit": "s/scan",
+                    "h2d_bytes_per_step": int(scan_h.numel() * 2 + lobe_h.numel()), "d2h_bytes_per_step": int(2 * lobe_h.numel() + 4)},
+            "gpu_launches": launches, "cpu_baseline": cpu,
+            "roofline": None}))
     if world > 1:
         td.destroy_process_group()
 
@@ -282,9 +583,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch of lobe chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "scan"],
+                    help="train = BASELINE configs[1] (default, the driver's line); infer = chunk inference; scan = full-CT pipeline")
+    ap.add_argument("--small", action="store_true", help="scan workload: 128x128x100 scan (quick check)")
+    ap.add_argument("--no-extra", action="store_true", help="train workload: skip the extra inference / HBM-roofline figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_infer(args)
+    elif args.workload == "scan":
+        run_scan(args)
     else:
         run_b200(args)
 
