@@ -212,6 +212,10 @@ def run_b200(args):
     ms_total = ms.item()
     launches = lib.PROFILE.launches
     prof = lib.PROFILE.summary()
+    if os.environ.get("DRAM_BENCH_LAYERS") and rank == 0:
+        for k, v in sorted(lib.PROFILE.summary(by_tag=True).items(), key=lambda kv: -kv[1]["ms"])[:45]:
+            tf = v["flops"] / (v["ms"] / 1e3) / 1e12 if v["flops"] else 0.0
+            print(f"# {k:46s} calls/step {v['calls'] / args.steps:4.1f} ms/step {v['ms'] / args.steps:8.3f} TFLOP/s {tf:7.1f}", file=sys.stderr)
     final_loss = loss.item()
 
     # ---- end-to-end leg: pinned host batch -> runner.train_step -> loss.item()
@@ -236,13 +240,13 @@ def run_b200(args):
 
     peaks = load_peaks()
     value = world * B * args.steps / (ms_total / 1e3)
-    kern = {k: v for k, v in prof.items()}
+    kern = {k: v for k, v in prof.items()} or {"none": {"ms": 0.0, "flops": 0.0, "calls": 0, "bytes": 0.0}}
     conv_names = ("dram_conv3d_umma_fwd", "dram_conv3d_umma_wgrad")
     dom = max(kern, key=lambda k: kern[k]["ms"])
     roof_k = dom if dom in conv_names else max(conv_names, key=lambda k: kern.get(k, {"ms": 0})["ms"])
     rk = kern.get(roof_k, {"ms": 0.0, "flops": 0.0, "calls": 0})
     achieved = rk["flops"] / (rk["ms"] / 1e3) / 1e12 if rk["ms"] > 0 else 0.0
-    total_kernel_ms = sum(v["ms"] for v in kern.values())
+    total_kernel_ms = sum(v["ms"] for v in kern.values()) or 1.0
     breakdown = {k.replace("dram_", ""): {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
                                             "share": v["ms"] / total_kernel_ms,
                                             **({"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} if v["flops"] else {})}

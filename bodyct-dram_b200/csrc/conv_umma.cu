@@ -21,6 +21,7 @@
 //   LBO bytes apart), N = Cout tile.  Voxel chunks are split across CTAs (split-K); partial tiles go to a workspace and
 //   a second kernel reduces them in a fixed order into the nn.Parameter layout [Cout][Cin][taps] (deterministic).
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -129,7 +130,11 @@ struct FwdParams {
   const float* shift;
   int N, D, H, W, Cout, BN, kblocks_c, taps, pad;
   int TW, TH, TD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles;
-  int passes, stages, stage_bytes, tmem_cols;
+  int passes, stages, stage_bytes, tmem_cols, acc_cols;
+  // kw-reuse mode (w3 = 1): one A box of (TW+2) x TH voxels per (kd,kh,channel block) serves the three kw taps.  The box is
+  // loaded through a tensor map whose dimension order is (C,H,W,D,N), so shared-memory rows are ordered [w][h]: with
+  // TH = 8 every w column is one 8-row / 1024-byte swizzle group and a kw shift is a 1024-byte-aligned descriptor offset.
+  int w3, a_plane_bytes, taps_per_stage, b_tap_bytes;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -146,7 +151,7 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool three = p.passes == 3;
   const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t offAlo = kATileBytes, offBhi = three ? 2 * kATileBytes : kATileBytes,
+  const uint32_t offAlo = (uint32_t)p.a_plane_bytes, offBhi = (three ? 2u : 1u) * (uint32_t)p.a_plane_bytes,
                  offBlo = offBhi + b_tile_bytes;
 
   if (threadIdx.x == 0) {
@@ -161,14 +166,16 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_tiles = p.n_mtiles * p.n_ntiles;
-  const int kblocks = p.taps * p.kblocks_c;
+  const int tps = p.taps_per_stage;
+  const int kblocks = (p.taps / tps) * p.kblocks_c;
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
       if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
       // bytes TMA will actually deliver: the A box has TW*TH*TD rows (<= 128), zero-filled halo included
-      const uint32_t stage_tx = (three ? 2u : 1u) * ((uint32_t)(p.TW * p.TH * p.TD) * 128u + b_tile_bytes);
+      const uint32_t a_box_bytes = (uint32_t)((p.w3 ? (p.TW + 2) : p.TW) * p.TH * p.TD) * 128u;
+      const uint32_t stage_tx = (three ? 2u : 1u) * (a_box_bytes + (uint32_t)tps * b_tile_bytes);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
@@ -177,18 +184,26 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int h0 = (mt % p.tiles_h) * p.TH; mt /= p.tiles_h;
         const int d0 = (mt % p.tiles_d) * p.TD;
         const int n = mt / p.tiles_d;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kd = p.taps == 1 ? 0 : tap / 9, kh = p.taps == 1 ? 0 : (tap / 3) % 3, kw = p.taps == 1 ? 0 : tap % 3;
+        for (int g = 0; g < p.taps / tps; ++g) {
+          // g = tap (generic) or (kd,kh) pair (kw-reuse)
+          const int tap0 = g * tps;
+          const int kd = p.taps == 1 ? 0 : tap0 / 9, kh = p.taps == 1 ? 0 : (tap0 / 3) % 3, kw = p.taps == 1 ? 0 : tap0 % 3;
           for (int cb = 0; cb < p.kblocks_c; ++cb, ++it) {
             const uint32_t s = it % S, ph = (it / S) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
             const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes), fb = full0 + 8 * s;
             mbar_expect_tx(fb, stage_tx);
-            tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
-            tma_load_2d(sb + offBhi, &tmB_hi, fb, cb * 64, tap * p.Cout + nt * p.BN);
-            if (three) {
-              tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
-              tma_load_2d(sb + offBlo, &tmB_lo, fb, cb * 64, tap * p.Cout + nt * p.BN);
+            if (p.w3) {                                 // map dims (C,H,W,D,N); kw = 0 here, box starts at w0 - 1
+              tma_load_5d(sb, &tmA_hi, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+              if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+            } else {
+              tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+              if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+            }
+            for (int t = 0; t < tps; ++t) {
+              const uint32_t bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
+              tma_load_2d(sb + offBhi + bo, &tmB_hi, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
+              if (three) tma_load_2d(sb + offBlo + bo, &tmB_lo, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
             }
           }
         }
@@ -196,27 +211,36 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.BN, 0, 0);
+      // split-bf16: the B_lo tile sits directly behind B_hi in shared memory, so A_hi x [B_hi | B_lo] is ONE MMA with
+      // N = 2*BN (accumulator columns [0,BN) = hi*hi, [BN,2BN) = hi*lo) followed by A_lo x B_hi into [0,BN).
+      // SS-mode operand reads cost 64 + 8192/N bytes per cycle against ~128 B/cycle of shared-memory bandwidth:
+      // doubling N is what lifts the Cout = 64 layers off that bound.  The epilogue adds the two halves.
+      const uint32_t idesc = umma_idesc(p.BN, 0, 0), idesc2 = umma_idesc(2 * p.BN, 0, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_cols;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint64_t a_hi = umma_desc(sb, 16, 1024), b_hi = umma_desc(sb + offBhi, 16, 1024);
-          const uint64_t a_lo = umma_desc(sb + offAlo, 16, 1024), b_lo = umma_desc(sb + offBlo, 16, 1024);
+          for (int t = 0; t < tps; ++t) {              // kw-reuse: tap t reads the halo box shifted by t columns = t*1024 B
+            const uint32_t ao = (uint32_t)t * 1024u, bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
+            const uint64_t a_hi = umma_desc(sb + ao, 16, 1024), b_hi = umma_desc(sb + offBhi + bo, 16, 1024);
+            const uint64_t a_lo = umma_desc(sb + offAlo + ao, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {               // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-            const uint64_t adv = (uint64_t)(k * 2);
-            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-            if (three) {
-              umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {             // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+              const uint64_t adv = (uint64_t)(k * 2);
+              const uint32_t accum = (kb | t | k) ? 1u : 0u;
+              if (three) {
+                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
+                umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+              }
             }
           }
           umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
@@ -227,7 +251,8 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else {
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int tw = row % p.TW, th = (row / p.TW) % p.TH, td = row / (p.TW * p.TH);
+    const int tw = p.w3 ? (row >> 3) : row % p.TW, th = p.w3 ? (row & 7) : (row / p.TW) % p.TH,
+              td = p.w3 ? 0 : row / (p.TW * p.TH);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
@@ -241,15 +266,16 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       float* out = p.y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * p.Cout + nt * p.BN;
       mbar_wait(tfull0 + 8 * acc, aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_cols;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
+        uint32_t r[16], r2[16];
         tmem_ld16(taddr + c0, r);
+        if (three) tmem_ld16(taddr + p.BN + c0, r2);
         tmem_ld_wait();
         if (valid) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) v[j] = three ? __uint_as_float(r[j]) + __uint_as_float(r2[j]) : __uint_as_float(r[j]);
           if (p.scale) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -280,7 +306,7 @@ struct WgParams {
   float* ws;                                    // [slabs][n_mtiles][n_ntiles][128][BN]
   int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles, n_ntiles, BN;
   int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, chunks_per_slab;
-  int passes, stages, stage_bytes, tmem_cols;
+  int passes, stages, stage_bytes, tmem_cols, concat;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -354,7 +380,7 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.BN, 1, 1);
+      const uint32_t idesc = umma_idesc(p.BN, 1, 1), idesc2 = umma_idesc(2 * p.BN, 1, 1);
       uint32_t it = 0, tcount = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         const int slab = item / (p.n_ntiles * p.n_mtiles);
@@ -374,10 +400,16 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
 #pragma unroll
           for (int k = 0; k < kWgKV / 16; ++k) {        // 16 voxel rows (2048 B) per MMA
             const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (ch > c_begin || k) ? 1u : 0u);
-            if (three) {
-              umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            const uint32_t first = (ch > c_begin || k) ? 1u : 0u;
+            if (p.concat) {                             // X_hi x [dY_hi | dY_lo] (N = 2*BN), then X_lo x dY_hi
+              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, first);
               umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              if (three) {
+                umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
             }
           }
           umma_commit(empty0 + 8 * s);
@@ -398,14 +430,17 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)acc_stride;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
+        uint32_t r[16], r2[16];
         tmem_ld16(taddr + c0, r);
+        if (p.concat) tmem_ld16(taddr + p.BN + c0, r2);
         tmem_ld_wait();
         if (valid) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = p.concat ? __uint_as_float(r[j]) + __uint_as_float(r2[j]) : __uint_as_float(r[j]);
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
       tc_fence_before();
@@ -502,12 +537,18 @@ static EncodeTiledFn get_encode() {
 }
 
 // 5-D map over a channels-last bf16 volume [N][D][H][W][C]; box = (64 channels, bw, bh, bd, bn), 128-byte swizzle
-static int make_volume_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bw, int bh, int bd, int bn) {
+static int make_volume_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bw, int bh, int bd, int bn,
+                           bool h_fastest = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DRAM_E_CUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
+  if (h_fastest) {       // dimension order (C,H,W,D,N): box rows land in shared memory ordered [w][h]
+    dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
+    strides[0] = (cuuint64_t)W * C * 2; strides[1] = (cuuint64_t)C * 2;
+    box[1] = (cuuint32_t)bh; box[2] = (cuuint32_t)bw;
+  }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -607,22 +648,31 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   p.y = y; p.scale = scale; p.shift = shift;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
   p.kblocks_c = Cin_pad / 64; p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
-  pick_fwd_tile(D, H, W, p.TW, p.TH, p.TD);
+  // kw-reuse for the layers whose L2->smem fill rate is the bound (N tile <= 64: 125 B/cycle/SM needed, ~75-80 sustained)
+  static const bool allow_w3 = getenv("DRAM_CONV_NO_W3") == nullptr;
+  p.w3 = (allow_w3 && ksize == 3 && p.BN <= 64 && W % 16 == 0 && H % 8 == 0) ? 1 : 0;
+  if (p.w3) { p.TW = 16; p.TH = 8; p.TD = 1; }
+  else pick_fwd_tile(D, H, W, p.TW, p.TH, p.TD);
   p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD);
   p.n_mtiles = N * p.tiles_d * p.tiles_h * p.tiles_w;
   p.n_ntiles = Cout / p.BN;
   p.passes = x_lo ? 3 : 1;
-  p.stage_bytes = (x_lo ? 2 : 1) * (kATileBytes + p.BN * 128);
+  p.taps_per_stage = p.w3 ? 3 : 1;
+  p.a_plane_bytes = p.w3 ? (p.TW + 2) * p.TH * 128 : kATileBytes;
+  p.b_tap_bytes = (x_lo ? 2 : 1) * p.BN * 128;
+  p.stage_bytes = (x_lo ? 2 : 1) * p.a_plane_bytes + p.taps_per_stage * p.b_tap_bytes;
   p.stages = (kSmemBudget - 1024) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
   DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_fwd: pipeline does not fit in shared memory");
-  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.acc_cols = (x_lo ? 2 : 1) * p.BN;
+  p.tmem_cols = pow2_cols(2 * p.acc_cols);
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc;
-  if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, 1))) return rc;
+  const int abw = p.w3 ? p.TW + 2 : p.TW;
+  if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
   if ((rc = make_weight_map(&tmB_hi, w_hi, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
   if (x_lo) {
-    if ((rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, 1))) return rc;
+    if ((rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
     if ((rc = make_weight_map(&tmB_lo, w_lo, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
   } else {
     tmA_lo = tmA_hi; tmB_lo = tmB_hi;
@@ -646,18 +696,29 @@ static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int 
   pick_wgrad_chunk(N, D, H, W, p.TW, p.TH, p.TD, p.TN);
   p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD); p.tiles_n = cdiv(N, p.TN);
   p.n_chunks = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  // split-K: pick the number of voxel slabs so that the work items fill whole waves of the 148 persistent CTAs
+  // (308 items = 2.08 waves costs a third wave); prefer fewer slabs on ties (less workspace, shorter reduction).
   const int tiles = p.n_mtiles * p.n_ntiles;
-  int slabs = cdiv(2 * kNumSMs, tiles);                    // ~2 waves of work items
-  const int max_slabs = cdiv(p.n_chunks, 8);               // >= 8 chunks per item so the pipeline fills
-  if (slabs > max_slabs) slabs = max_slabs;
-  if (slabs < 1) slabs = 1;
-  p.chunks_per_slab = cdiv(p.n_chunks, slabs);
+  const int max_slabs = cdiv(p.n_chunks, 8) < 48 ? cdiv(p.n_chunks, 8) : 48;    // >= 8 chunks per item
+  int best = 1;
+  double best_score = -1.0;
+  for (int sl = 1; sl <= (max_slabs > 1 ? max_slabs : 1); ++sl) {
+    const int cps = cdiv(p.n_chunks, sl), ns = cdiv(p.n_chunks, cps);
+    const long long items = (long long)ns * tiles;
+    const long long waves = (items + kNumSMs - 1) / kNumSMs;
+    const double lastslab = (double)(p.n_chunks - (ns - 1) * cps) / cps;          // a short last slab idles its CTAs
+    const double eff = ((double)items - tiles * (1.0 - lastslab)) / (double)(waves * kNumSMs);
+    const double score = eff - 0.003 * sl;
+    if (score > best_score) { best_score = score; best = sl; }
+  }
+  p.chunks_per_slab = cdiv(p.n_chunks, best);
   p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
   p.passes = passes;
   p.stage_bytes = (passes == 3 ? 2 : 1) * (2 * kWgBlkBytes + (p.BN / 64) * kWgBlkBytes);
   p.stages = (kSmemBudget - 1024) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.concat = (passes == 3 && p.BN <= 128) ? 1 : 0;
+  p.tmem_cols = pow2_cols(2 * (p.concat ? 2 * p.BN : p.BN));
   return DRAM_OK;
 }
 

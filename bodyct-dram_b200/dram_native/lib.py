@@ -64,11 +64,12 @@ class Profile:
         """Attach algorithmic flops / bytes to the NEXT call (consumed by it)."""
         self.pending_note = kw
 
-    def summary(self):
-        """-> {name: {"calls", "ms", "flops", "bytes"}} after a device synchronize."""
+    def summary(self, by_tag=False):
+        """-> {name: {"calls", "ms", "flops", "bytes"}} after a device synchronize (by_tag: key = name + layer tag)."""
         out = {}
         for name, note, s, e in self.records:
-            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            key = name + ":" + str(note.get("tag")) if (by_tag and note and note.get("tag")) else name
+            d = out.setdefault(key, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["calls"] += 1
             d["ms"] += s.elapsed_time(e)
             if note:

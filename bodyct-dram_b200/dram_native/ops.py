@@ -154,7 +154,7 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None):
     """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32."""
     N, Cin, D, H, W = xs.shape
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
-    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3)          # algorithmic (unpadded, 1 pass)
+    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")   # algorithmic (unpadded, 1 pass)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
                                          y.data_ptr(), N, D, H, W, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
     return y
@@ -168,7 +168,7 @@ def conv_umma_wgrad(dys, xs, Cin, Cout, ksize):
         raise _lib.DramLibraryError("conv3d_umma_wgrad: unsupported shape")
     ws = torch.empty(nbytes // 4, device=xs.hi.device, dtype=torch.float32)
     dw = torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
-    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3)
+    _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")
     _lib.check(_L().dram_conv3d_umma_wgrad(dys.hi.data_ptr(), _p(dys.lo), xs.hi.data_ptr(), _p(xs.lo), dw.data_ptr(),
                                            ws.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize, _stream()),
                "conv3d_umma_wgrad")

@@ -104,6 +104,9 @@ UMMA_CASES = [
     (2, 128, 256, (10, 10, 10), 3),    # ragged tile (5,5,5), 2 N tiles (bg shape class)
     (1, 64, 32, (20, 20, 20), 3),      # BN=32 (dgrad of ds0.c1 shape class)
     (1, 128, 16, (6, 7, 9), 1),        # 1x1x1, odd spatial sizes
+    (1, 64, 64, (4, 24, 48), 3),       # kw-reuse mode, 3x3 tiles of (16w x 8h), halo on every side
+    (2, 192, 64, (3, 16, 32), 3),      # kw-reuse mode, 3 channel blocks, batch 2
+    (1, 64, 32, (5, 8, 16), 3),        # kw-reuse mode with BN=32 (dgrad of ds0.c1 at 80^3)
 ]
 
 
