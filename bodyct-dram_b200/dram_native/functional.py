@@ -23,6 +23,10 @@ class _WeightCache:
 
     def __init__(self):
         self.misses = 0
+        self.generation = 0        # bumped after CUDA-graph replays: they update weights without touching `_version`
+
+    def invalidate(self):
+        self.generation += 1
 
     def get(self, w, kind, builder):
         packs = getattr(w, "_dram_packs", None)
@@ -34,11 +38,11 @@ class _WeightCache:
                 pass
         key = (kind, ops.precision())
         hit = packs.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+        if hit is not None and hit[0] == (w._version, self.generation) and hit[1] == w.data_ptr():
             return hit[2]
         self.misses += 1
         val = builder()
-        packs[key] = (w._version, w.data_ptr(), val)
+        packs[key] = ((w._version, self.generation), w.data_ptr(), val)
         return val
 
 

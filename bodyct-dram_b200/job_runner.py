@@ -49,6 +49,7 @@ class JobRunner:
         opt_cls = get_callable_by_name(opt_cfg.pop('method'))
         if opt_cls is torch.optim.Adam:
             opt_cfg.setdefault("fused", True)
+            opt_cfg.setdefault("capturable", True)          # step counter on the device: the step can live in a CUDA graph
         self.optimizer = opt_cls(self.model.parameters(), **opt_cfg)
         self.loss_func = get_callable_by_name(loss_cfg.pop('method'))(**loss_cfg)
         self.scheduler = get_callable_by_name(sched_cfg.pop('method'))(self.optimizer, **sched_cfg)
@@ -93,30 +94,75 @@ class JobRunner:
 class LesionSegChunkTrain(JobRunner):
     """Training runner: `train_step(batch)` is the body of the reference's hot loop (job_runner.py:657-674)."""
 
+    GRAPH_WARMUP_STEPS = 2        # eager steps before capture (lazy one-time setup, allocator warm-up, Adam state)
+
     def __init__(self, settings_module=None, setting_module_file_path=None):
         super().__init__(setting_module_file_path, settings_module)
         self.init()
+        self._graph = self._graph_key = self._static_in = self._static_labels = self._static_out = None
+        self._eager_steps = 0
+        self.kernels_per_step = None
 
-    def train_step(self, batch_data):
-        """batch_data: {"#image", "#lobe_reference", "#pseudo_lesion_reference": [B,D,H,W] host or device tensors,
-        "meta": {"cle": [...]}} -> (loss tensor, loss tuple).  Includes the H2D copy, backward, gradient all-reduce
-        (data parallel) and the optimizer step; does NOT sync with the host."""
-        self.model.train()
-        dev = torch.device("cuda", torch.cuda.current_device())
-        images = batch_data["#image"].to(dev, torch.float32, non_blocking=True).unsqueeze(1)
-        lobes = batch_data["#lobe_reference"].to(dev, torch.float32, non_blocking=True).unsqueeze(1)
-        lesions = batch_data["#pseudo_lesion_reference"].to(dev, torch.float32, non_blocking=True).unsqueeze(1)
-        metas = batch_data["meta"]
+    def _step_body(self, images, lobes, lesions, ctsses, metas, labels):
+        """forward + loss + backward (+ gradient all-reduce) + optimizer step; enqueues only, never syncs."""
         self.optimizer.zero_grad(set_to_none=True)
-        loss_tuple = self.loss_func(self.model, images, lobes, lesions, metas["cle"], obj=self, metas=metas)
+        loss_tuple = self.loss_func(self.model, images, lobes, lesions, ctsses, obj=self, metas=metas, label_tensors=labels)
         factors = self.settings.LOSS_FACTORS[:len(loss_tuple)]
         loss = torch.stack([l * w for l, w in zip(loss_tuple, factors)]).sum()
         loss.backward()
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
-        self.current_iteration += 1
         return loss, loss_tuple
+
+    def train_step(self, batch_data):
+        """batch_data: {"#image", "#lobe_reference", "#pseudo_lesion_reference": [B,D,H,W] host or device tensors,
+        "meta": {"cle": [...]}} -> (loss tensor, loss tuple).  Includes the H2D copy, backward, gradient all-reduce
+        (data parallel) and the optimizer step; does NOT sync with the host.
+
+        Single-GPU steps with a stable batch shape are captured once into a CUDA graph (after `GRAPH_WARMUP_STEPS` eager
+        steps) and replayed, so the ~500 kernel launches of a step cost one launch and host jitter cannot starve the
+        GPU; set DRAM_CUDA_GRAPH=0 to stay eager.  The returned tensors are then the graph's static outputs."""
+        self.model.train()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        metas = batch_data["meta"]
+        ctsses = metas["cle"]
+        labels = self.loss_func.label_tensors(ctsses, self.ctss_frequency_map, dev) \
+            if hasattr(self.loss_func, "label_tensors") else None
+        srcs = [batch_data[k] for k in ("#image", "#lobe_reference", "#pseudo_lesion_reference")]
+        key = tuple(tuple(t.shape) for t in srcs)
+        use_graph = (os.environ.get("DRAM_CUDA_GRAPH", "1") == "1" and self.reducer is None and labels is not None)
+        self.current_iteration += 1
+        if not use_graph or self._graph_key not in (None, key):
+            self._graph = None
+            images, lobes, lesions = (t.to(dev, torch.float32, non_blocking=True).unsqueeze(1) for t in srcs)
+            return self._step_body(images, lobes, lesions, ctsses, metas, labels)
+        if self._graph is None:
+            self._graph_key = key
+            self._eager_steps += 1
+            images, lobes, lesions = (t.to(dev, torch.float32, non_blocking=True).unsqueeze(1) for t in srcs)
+            if self._eager_steps <= self.GRAPH_WARMUP_STEPS:
+                return self._step_body(images, lobes, lesions, ctsses, metas, labels)
+            self._static_in = [torch.empty_like(t) for t in (images, lobes, lesions)]
+            self._static_labels = {k: torch.empty_like(v) for k, v in labels.items()}
+            from dram_native import lib as _dlib
+            torch.cuda.synchronize()
+            was_profiling, _dlib.PROFILE.enabled = _dlib.PROFILE.enabled, False      # no event records inside a capture
+            launches0 = _dlib.PROFILE.launches
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._static_out = self._step_body(*self._static_in, ctsses, metas, self._static_labels)
+            self.kernels_per_step = _dlib.PROFILE.launches - launches0             # libdram_b200 kernels in one step
+            _dlib.PROFILE.enabled = was_profiling
+            self._graph = graph
+        for dst, src in zip(self._static_in, srcs):
+            dst.copy_(src.unsqueeze(1), non_blocking=True)             # H2D (pinned) or D2D into the graph's inputs
+        for k, v in labels.items():
+            self._static_labels[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        from dram_native import functional as _DF
+        _DF.WEIGHTS.invalidate()           # the replay changed the weights behind PyTorch's version counters
+        return self._static_out
 
     def train(self, loader):
         batch_time, loss_record = AverageMeter(), AverageMeter()

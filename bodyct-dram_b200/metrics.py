@@ -78,10 +78,19 @@ class IntRegLoss:
     def get_one_label(self, ctss):
         return self.ctss_ratio_map[int(float(ctss))]
 
-    def get_labels(self, ctsses, lesion_ps):
+    def label_tensors(self, ctsses, freq_map, device):
+        """Everything the loss derives from the per-chunk CT severity scores, as small device tensors.  Built OUTSIDE a
+        captured CUDA graph (they come from Python lists) and handed to __call__ through `label_tensors=`."""
+        band = torch.tensor([self.ctss_ratio_map[int(float(c))] for c in ctsses], dtype=torch.float64)
+        w = torch.tensor([freq_map[int(float(c))] for c in ctsses], dtype=torch.float32).clamp(0.2, 0.8)
+        keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in ctsses], dtype=torch.float32)
+        return {"band": band.to(device), "w": w.to(device), "keep": keep.to(device)}
+
+    def get_labels(self, ctsses, lesion_ps, band=None):
         """metrics.py:121-137 on the device, in float64 like the Python-float arithmetic it replaces, no `.item()`."""
         p = lesion_ps.reshape(-1).double()
-        band = torch.tensor([self.ctss_ratio_map[int(float(c))] for c in ctsses], dtype=torch.float64, device=p.device)
+        if band is None:
+            band = torch.tensor([self.ctss_ratio_map[int(float(c))] for c in ctsses], dtype=torch.float64, device=p.device)
         clb, cub = band[:, 0], band[:, 1]
         lb, ub = (p - self.band_width).clamp_min(0.0), (p + self.band_width).clamp_max(1.0)
         lo, hi = torch.maximum(clb, lb), torch.minimum(cub, ub)
@@ -92,17 +101,15 @@ class IntRegLoss:
         return torch.stack([lo, hi], dim=1).float()
 
     def _reg_loss(self, values, lobes, lesion_candidates, ctsses, use_sigmoid, **kwargs):
-        B = values.shape[0]
+        labels = kwargs.get("label_tensors") or self.label_tensors(ctsses, kwargs.get('obj').ctss_frequency_map, values.device)
         with torch.no_grad():
             rub, _ = DF.MaskedMean.apply(lesion_candidates, lobes, False, False)     # sum(lesion*lobe)/sum(lobe)
         pred_ratio, _ = DF.MaskedMean.apply(values, lobes, use_sigmoid, True)       # mean of probs over lobe > 0
-        tg = self.get_labels(ctsses, rub)
+        tg = self.get_labels(ctsses, rub, labels["band"])
         K = (0.5 * (tg[:, 1] - tg[:, 0])) ** 2
         loss_unhinge = (pred_ratio - (tg[:, 1] + tg[:, 0]) / 2.0) ** 2 - K
         loss_unweight = torch.clamp_min(loss_unhinge, 0.0)
-        freq = kwargs.get('obj').ctss_frequency_map
-        w = torch.tensor([freq[int(float(c))] for c in ctsses], dtype=torch.float32, device=values.device).clamp(0.2, 0.8)
-        return (loss_unweight / w).sum()
+        return (loss_unweight / labels["w"]).sum()
 
     def compute_reg_loss_with_probs(self, probs, lobes, lesion_candidates, ctsses, **kwargs):
         """metrics.py:158-177 (same signature: takes sigmoid(RAM))."""
@@ -128,24 +135,27 @@ class IntRegRefineLoss(IntRegLoss):
         self.config_param = config_param
         self.bootstrap_loss = BootBinCrossEntropy(smoothing)
 
-    def pseudo_labels(self, dense_outs, lobes, lesions, ctsses):
+    def pseudo_labels(self, dense_outs, lobes, lesions, ctsses, keep=None):
         """metrics.py:333-354 + threshold_postprocessing :325-329, without leaving the device."""
         if self.refine_method != 'th':
             raise NotImplementedError(f"Do not support refine method :{self.refine_method}!")
         with torch.no_grad():
             pred = (torch.sigmoid(dense_outs) > 0.5) & (lobes != 0)
-            keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in ctsses], dtype=dense_outs.dtype,
-                                device=dense_outs.device).view(-1, 1, 1, 1, 1)
-            return (pred & (lesions > 0)).to(dense_outs.dtype) * keep
+            if keep is None:
+                keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in ctsses], dtype=dense_outs.dtype,
+                                    device=dense_outs.device)
+            return (pred & (lesions > 0)).to(dense_outs.dtype) * keep.view(-1, 1, 1, 1, 1)
 
-    def compute_seg_loss(self, dense_outs, refined_dense_outs, images, lobes, lesions, scores, metas, obj, tag='fixed'):
-        t = self.pseudo_labels(dense_outs, lobes, lesions, scores)
+    def compute_seg_loss(self, dense_outs, refined_dense_outs, images, lobes, lesions, scores, metas, obj, tag='fixed',
+                         keep=None):
+        t = self.pseudo_labels(dense_outs, lobes, lesions, scores, keep)
         return self.bootstrap_loss(torch.sigmoid(refined_dense_outs), t, lobes > 0)
 
     def __call__(self, model, images, lobes, lesions, ctsses, **kwargs):
         self.before_call(model, **kwargs)
         dense_outs, refined_dense_outs = model(images, lobes)
         reg_loss = self.compute_reg_loss_with_logits(dense_outs, lobes, lesions, ctsses, **kwargs)
+        labels = kwargs.get("label_tensors")
         seg_loss = self.compute_seg_loss(dense_outs, refined_dense_outs, images, lobes, lesions, ctsses,
-                                         kwargs.get("metas"), kwargs.get("obj"))
+                                         kwargs.get("metas"), kwargs.get("obj"), keep=labels["keep"] if labels else None)
         return reg_loss, seg_loss
