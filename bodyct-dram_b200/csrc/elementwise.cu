@@ -35,11 +35,12 @@ __global__ void k_cl2nc(const float* __restrict__ src, float* __restrict__ dst, 
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
-// y [rows][C].  Block = 256 threads arranged as (row lanes) x (channel groups of VEC).  Each block owns a contiguous
-// slab of rows (<= kRowsPerBlock so fp32 partials stay short), reduces across row lanes in shared memory and adds
-// its per-channel partial to the double accumulators.
+// y [rows][C].  Block = 256 threads arranged as (row lanes) x (channel groups of VEC).  The grid is a multiple of the 148
+// SMs and every block owns one contiguous, equally sized range of rows; each thread keeps UNROLL independent loads in
+// flight (the kernel is a pure HBM stream), accumulates in fp32 over <= a few hundred rows, the block reduces across
+// row lanes in shared memory and adds its per-channel partial to the double accumulators.
 constexpr int kStatThreads = 256;
-constexpr int kRowsPerBlock = 2048;
+constexpr int kStatUnroll = 4;
 
 template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kStatThreads)
@@ -48,54 +49,61 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
             double* __restrict__ sums, long long rows, int C) {
   extern __shared__ float sm[];  // [2][kStatThreads][VEC]
   const int groups = (C + VEC - 1) / VEC;             // channel groups per row
-  const int lanes = kStatThreads / groups > 0 ? kStatThreads / groups : 1;  // row lanes per pass
+  const int gl = groups < kStatThreads ? groups : kStatThreads;
+  const int lanes = kStatThreads / gl;                // row lanes per pass
+  const long long per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r_begin = (long long)blockIdx.x * per_block;
+  const long long r_end = r_begin + per_block < rows ? r_begin + per_block : rows;
   // when groups > kStatThreads each thread loops over several channel groups
   for (int g0 = 0; g0 < groups; g0 += kStatThreads) {
-    const int g = g0 + (threadIdx.x % (groups < kStatThreads ? groups : kStatThreads));
-    const int lane = groups < kStatThreads ? threadIdx.x / groups : 0;
+    const int g = g0 + (threadIdx.x % gl);
+    const int lane = threadIdx.x / gl;
     float a0[VEC], a1[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
     const bool active = (g < groups) && (lane < lanes);
     float sc[VEC], sh[VEC], mu[VEC], rs[VEC];
-    if (BWD && active) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        int c = g * VEC + v;
-        bool ok = c < C;
-        sc[v] = ok ? scale[c] : 0.f; sh[v] = ok ? shift[c] : 0.f; mu[v] = ok ? mean[c] : 0.f; rs[v] = ok ? rstd[c] : 0.f;
-      }
+    for (int v = 0; v < VEC; ++v) {
+      int c = g * VEC + v;
+      bool ok = BWD && active && c < C;
+      sc[v] = ok ? scale[c] : 0.f; sh[v] = ok ? shift[c] : 0.f; mu[v] = ok ? mean[c] : 0.f; rs[v] = ok ? rstd[c] : 0.f;
     }
-    for (long long slab = (long long)blockIdx.x * kRowsPerBlock; slab < rows; slab += (long long)gridDim.x * kRowsPerBlock) {
-      long long end = slab + kRowsPerBlock < rows ? slab + kRowsPerBlock : rows;
-      if (active) {
-        for (long long r = slab + lane; r < end; r += lanes) {
-          const float* p = y + r * C + (long long)g * VEC;
-          float yv[VEC], dv[VEC];
+    if (active) {
+      for (long long r0 = r_begin + lane; r0 < r_end; r0 += (long long)lanes * kStatUnroll) {
+        float yv[kStatUnroll][VEC], dv[kStatUnroll][VEC];
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {                 // issue all loads first
+          const long long r = r0 + (long long)u * lanes;
+          const bool rok = r < r_end;
           if (VEC == 4) {
-            float4 t = *reinterpret_cast<const float4*>(p);
-            yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3 % VEC] = t.w;
+            float4 t = rok ? __ldg(reinterpret_cast<const float4*>(y + r * C) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yv[u][0] = t.x; yv[u][1] = t.y; yv[u][2] = t.z; yv[u][3 % VEC] = t.w;
             if (BWD) {
-              float4 u = *reinterpret_cast<const float4*>(da + r * C + (long long)g * VEC);
-              dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3 % VEC] = u.w;
+              float4 q = rok ? __ldg(reinterpret_cast<const float4*>(da + r * C) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+              dv[u][0] = q.x; dv[u][1] = q.y; dv[u][2] = q.z; dv[u][3 % VEC] = q.w;
             }
           } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-              bool ok = g * VEC + v < C;
-              yv[v] = ok ? p[v] : 0.f;
-              if (BWD) dv[v] = ok ? da[r * C + (long long)g * VEC + v] : 0.f;
+              const bool ok = rok && (g * VEC + v < C);
+              yv[u][v] = ok ? y[r * C + (long long)g * VEC + v] : 0.f;
+              if (BWD) dv[u][v] = ok ? da[r * C + (long long)g * VEC + v] : 0.f;
             }
           }
+        }
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             if (!BWD) {
-              a0[v] += yv[v];
-              a1[v] += yv[v] * yv[v];
+              a0[v] += yv[u][v];
+              a1[v] += yv[u][v] * yv[u][v];
             } else {
-              float dz = (yv[v] * sc[v] + sh[v] > 0.f) ? dv[v] : 0.f;
+              // out-of-range rows carry dv = 0, so they contribute nothing
+              float dz = (yv[u][v] * sc[v] + sh[v] > 0.f) ? dv[u][v] : 0.f;
               a0[v] += dz;
-              a1[v] += dz * (yv[v] - mu[v]) * rs[v];
+              a1[v] += dz * (yv[u][v] - mu[v]) * rs[v];
             }
           }
         }
@@ -111,7 +119,6 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
     }
     __syncthreads();
     if (active && lane == 0) {
-      const int gl = groups < kStatThreads ? groups : kStatThreads;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         int c = g * VEC + v;
@@ -342,17 +349,26 @@ __global__ void k_trilinear_fwd(const float* __restrict__ src, float* __restrict
   }
 }
 
-// candidate destination range along one axis whose taps may touch source index i
+// candidate destination range along one axis whose taps may touch source index i: o*scale in (i-1, i+1), one index of
+// slack on both sides for the float rounding of o*scale
 __device__ __forceinline__ void adj_range(int i, float scale, int out_size, int& lo, int& hi) {
   if (scale <= 0.f) { lo = 0; hi = out_size - 1; return; }
   float inv = 1.0f / scale;
-  lo = (int)floorf((float)(i - 1) * inv) - 1;
-  hi = (int)ceilf((float)(i + 1) * inv) + 1;
+  lo = (int)ceilf((float)(i - 1) * inv) - 1;
+  hi = (int)floorf((float)(i + 1) * inv) + 1;
   if (lo < 0) lo = 0;
   if (hi > out_size - 1) hi = out_size - 1;
 }
+// weight with which destination index O contributes to source index i (0 if it does not)
+__device__ __forceinline__ float adj_weight(int O, int i, float scale, int in_size) {
+  Lerp l = lerp_setup(O, scale, in_size);
+  return (l.i0 == i ? l.w0 : 0.f) + (l.i1 == i ? l.w1 : 0.f);
+}
 
-// exact adjoint of k_trilinear_fwd in gather form: dsrc[n][z][y][x][c] = sum over dst voxels of weight * ddst
+// exact adjoint of k_trilinear_fwd in gather form: dsrc[n][z][y][x][c] = sum over dst voxels of weight * ddst.
+// The per-axis candidate weights are evaluated once (<= kAdj candidates per axis when the resize factor is <= ~3,
+// which covers every resize on the training path); wider ranges take the generic loop.
+constexpr int kAdj = 8;
 template <int VEC>
 __global__ void k_trilinear_bwd(const float* __restrict__ ddst, float* __restrict__ dsrc, int N, int d, int h, int w,
                                 int D, int H, int W, int C, int dstC, int dstOff, float sz, float sy, float sx) {
@@ -370,25 +386,53 @@ __global__ void k_trilinear_bwd(const float* __restrict__ ddst, float* __restric
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    for (int Z = zl; Z <= zh; ++Z) {
-      Lerp lz = lerp_setup(Z, sz, d);
-      float wz = (lz.i0 == z ? lz.w0 : 0.f) + (lz.i1 == z ? lz.w1 : 0.f);
-      if (wz == 0.f) continue;
-      for (int Y = yl; Y <= yh; ++Y) {
-        Lerp ly = lerp_setup(Y, sy, h);
-        float wy = (ly.i0 == y ? ly.w0 : 0.f) + (ly.i1 == y ? ly.w1 : 0.f);
-        if (wy == 0.f) continue;
-        for (int X = xl; X <= xh; ++X) {
-          Lerp lx = lerp_setup(X, sx, w);
-          float wx = (lx.i0 == x ? lx.w0 : 0.f) + (lx.i1 == x ? lx.w1 : 0.f);
-          if (wx == 0.f) continue;
-          float wt = wz * wy * wx;
-          const float* p = ddst + ((((long long)n * D + Z) * H + Y) * W + X) * dstC + dstOff + (long long)g * VEC;
-          if (VEC == 4) {
-            float4 t = *reinterpret_cast<const float4*>(p);
-            acc[0] += wt * t.x; acc[1] += wt * t.y; acc[2] += wt * t.z; acc[3 % VEC] += wt * t.w;
-          } else {
-            acc[0] += wt * p[0];
+    if (zh - zl < kAdj && yh - yl < kAdj && xh - xl < kAdj) {
+      float wy[kAdj], wx[kAdj];
+#pragma unroll
+      for (int t = 0; t < kAdj; ++t) {
+        wy[t] = (yl + t <= yh) ? adj_weight(yl + t, y, sy, h) : 0.f;
+        wx[t] = (xl + t <= xh) ? adj_weight(xl + t, x, sx, w) : 0.f;
+      }
+      for (int Z = zl; Z <= zh; ++Z) {
+        const float wz = adj_weight(Z, z, sz, d);
+        if (wz == 0.f) continue;
+#pragma unroll
+        for (int ty = 0; ty < kAdj; ++ty) {
+          if (wy[ty] == 0.f) continue;
+          const float wzy = wz * wy[ty];
+          const float* row = ddst + (((long long)n * D + Z) * H + (yl + ty)) * (long long)W * dstC + dstOff + (long long)g * VEC;
+#pragma unroll
+          for (int tx = 0; tx < kAdj; ++tx) {
+            if (wx[tx] == 0.f) continue;
+            const float wt = wzy * wx[tx];
+            const float* p = row + (long long)(xl + tx) * dstC;
+            if (VEC == 4) {
+              float4 t = __ldg(reinterpret_cast<const float4*>(p));
+              acc[0] += wt * t.x; acc[1] += wt * t.y; acc[2] += wt * t.z; acc[3 % VEC] += wt * t.w;
+            } else {
+              acc[0] += wt * p[0];
+            }
+          }
+        }
+      }
+    } else {
+      for (int Z = zl; Z <= zh; ++Z) {
+        const float wz = adj_weight(Z, z, sz, d);
+        if (wz == 0.f) continue;
+        for (int Y = yl; Y <= yh; ++Y) {
+          const float wy = adj_weight(Y, y, sy, h);
+          if (wy == 0.f) continue;
+          for (int X = xl; X <= xh; ++X) {
+            const float wx = adj_weight(X, x, sx, w);
+            if (wx == 0.f) continue;
+            float wt = wz * wy * wx;
+            const float* p = ddst + ((((long long)n * D + Z) * H + Y) * W + X) * dstC + dstOff + (long long)g * VEC;
+            if (VEC == 4) {
+              float4 t = *reinterpret_cast<const float4*>(p);
+              acc[0] += wt * t.x; acc[1] += wt * t.y; acc[2] += wt * t.z; acc[3 % VEC] += wt * t.w;
+            } else {
+              acc[0] += wt * p[0];
+            }
           }
         }
       }
@@ -484,9 +528,13 @@ int dram_ndhwc_to_ncdhw(const float* src, float* dst, int N, int C, long long S,
 }
 
 static int stat_grid(long long rows) {
-  long long slabs = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
-  long long cap = (long long)kNumSMs * 8;
-  return (int)(slabs < cap ? (slabs < 1 ? 1 : slabs) : cap);
+  // whole waves of the 148 SMs, >= 256 rows per block, <= ~2048 rows per block (short fp32 partial sums)
+  long long want = (rows + 2047) / 2048;
+  long long waves = (want + kNumSMs - 1) / kNumSMs;
+  if (waves > 8) waves = 8;
+  long long g = waves * kNumSMs;
+  if (g * 256 > rows) g = (rows + 255) / 256;
+  return (int)(g < 1 ? 1 : g);
 }
 
 int dram_bn_stats(const float* y, double* sums, long long rows, int C, void* stream) {

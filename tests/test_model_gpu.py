@@ -231,3 +231,41 @@ def test_no_cpu_fallback():
     m = cls(**cfg)                                   # parameters on the CPU
     with pytest.raises(lib.DramLibraryError):
         m(g["images"], g["lobes"])
+
+
+def test_cuda_graph_training_steps_match_eager(monkeypatch):
+    """job_runner.LesionSegChunkTrain.train_step: CUDA-graph replay vs plain eager execution, 4 optimizer steps"""
+    import job_runner
+    from utils import Settings
+    from oracle_import import O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = torch.load(os.path.join(GOLDEN, "dc3d_div8_16.pt"))
+    finals = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DRAM_CUDA_GRAPH", mode)
+        s = Settings(os.path.join(root, "bodyct-dram_b200", "exp_settings", "st_dram_ref.py"))
+        s.MODEL = dict(g["cfg"])
+        s.OPTIMIZER = dict(s.OPTIMIZER, lr=1e-3)
+        runner = job_runner.LesionSegChunkTrain(settings_module=s)
+        runner.model.load_state_dict(g["state_dict"])
+        losses = []
+        for step in range(4):
+            images, lobes, lesions, ctsses = O.synthetic_batch(2, (16, 16, 16), seed=40 + step)
+            batch = {"#image": images[:, 0], "#lobe_reference": lobes[:, 0], "#pseudo_lesion_reference": lesions[:, 0],
+                     "meta": {"cle": ctsses}}
+            loss, _ = runner.train_step(batch)
+            losses.append(loss.item())
+        assert (runner._graph is not None) == (mode == "1")
+        finals[mode] = (losses, {k: v.detach().clone() for k, v in runner.model.state_dict().items()})
+        runner.model.eval()                          # an eager forward after replays must see the updated weights
+        with torch.no_grad():
+            d, _ = runner.model(images.cuda(), lobes.cuda())
+        finals[mode] += (d.clone(),)
+    for a, b in zip(finals["0"][0], finals["1"][0]):
+        assert abs(a - b) <= 1e-4 * abs(a), (finals["0"][0], finals["1"][0])
+    for k, v in finals["0"][1].items():
+        if v.is_floating_point():
+            assert_close(finals["1"][1][k], v, 2e-3, k)
+        else:
+            assert torch.equal(finals["1"][1][k], v), k
+    assert rel_err(finals["1"][2], finals["0"][2]) <= 1e-3
