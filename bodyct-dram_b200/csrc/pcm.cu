@@ -118,6 +118,98 @@ k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restr
   }
 }
 
+// Inference variant (no attention weights kept): F = 8, online softmax in registers, neighbour keys as two float4 loads.
+// Warp-level sharing: consecutive lanes hold consecutive x of one grid row, so for the three offsets (dz,dy,-1|0|+1) the
+// key vector and the cam value of the (dz,dy) row are loaded ONCE per lane (at the lane's own x) and the x-1 / x+1
+// neighbours come from the adjacent lanes through __shfl_sync; only the lanes at a warp or row edge load them directly.
+__global__ void __launch_bounds__(256)
+k_pcm_attend_infer(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float* __restrict__ out) {
+  const long long V = (long long)g.D * g.H * g.W;
+  const long long total = (long long)g.B * V;
+  const int lane = threadIdx.x & 31;
+  const int O = g.O;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long iters = (total + stride - 1) / stride;          // warp-uniform trip count: shuffles need converged warps
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = first + it * stride;
+    const bool live = i < total;
+    const long long ii = live ? i : total - 1;
+    const long long v = ii % V, b = ii / V;
+    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
+    const float4* qp = reinterpret_cast<const float4*>(qk + ii * 16);
+    const float4 q0 = __ldg(qp), q1 = __ldg(qp + 1);
+    // lanes lane-1 / lane+1 hold x-1 / x+1 of the same row?
+    const int xl = __shfl_up_sync(0xffffffffu, x, 1), xr = __shfl_down_sync(0xffffffffu, x, 1);
+    const long long il = __shfl_up_sync(0xffffffffu, ii, 1), ir = __shfl_down_sync(0xffffffffu, ii, 1);
+    const bool left_ok = lane > 0 && xl == x - 1 && il == ii - 1;
+    const bool right_ok = lane < 31 && xr == x + 1 && ir == ii + 1;
+    int deg = 0;
+    for (int o = 0; o < O; ++o) {
+      int zz = z + g.off[o][0], yy = y + g.off[o][1], xx = x + g.off[o][2];
+      deg += (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? 1 : 0;
+    }
+    const float invT = 1.f / temperature(g, deg);
+    float m = -INFINITY, l = 0.f, acc = 0.f;
+    int cur_dz = 127, cur_dy = 127;
+    float4 kc0 = make_float4(0.f, 0.f, 0.f, 0.f), kc1 = kc0;
+    float cc = 0.f;
+    for (int o = 0; o < O; ++o) {
+      const int dz = g.off[o][0], dy = g.off[o][1], dx = g.off[o][2];
+      const int zz = z + dz, yy = y + dy, xx = x + dx;
+      const bool row_ok = zz >= 0 && zz < g.D && yy >= 0 && yy < g.H;
+      if (dz != cur_dz || dy != cur_dy) {                       // new (dz,dy) row: load key / cam at the lane's own x
+        cur_dz = dz; cur_dy = dy;
+        if (row_ok) {
+          const long long nb = b * V + ((long long)zz * g.H + yy) * g.W + x;
+          const float4* kp = reinterpret_cast<const float4*>(qk + nb * 16 + 8);
+          kc0 = __ldg(kp); kc1 = __ldg(kp + 1);
+          cc = __ldg(cam + nb);
+        }
+      }
+      // neighbour at x+dx of that row: own registers, an adjacent lane, or (edges) a direct load
+      float4 k0 = kc0, k1 = kc1;
+      float cv = cc;
+      if (dx != 0) {                                             // uniform across the warp (same offset table)
+        float4 s0, s1;
+        float sc;
+        if (dx < 0) {
+          s0.x = __shfl_up_sync(0xffffffffu, kc0.x, 1); s0.y = __shfl_up_sync(0xffffffffu, kc0.y, 1);
+          s0.z = __shfl_up_sync(0xffffffffu, kc0.z, 1); s0.w = __shfl_up_sync(0xffffffffu, kc0.w, 1);
+          s1.x = __shfl_up_sync(0xffffffffu, kc1.x, 1); s1.y = __shfl_up_sync(0xffffffffu, kc1.y, 1);
+          s1.z = __shfl_up_sync(0xffffffffu, kc1.z, 1); s1.w = __shfl_up_sync(0xffffffffu, kc1.w, 1);
+          sc = __shfl_up_sync(0xffffffffu, cc, 1);
+        } else {
+          s0.x = __shfl_down_sync(0xffffffffu, kc0.x, 1); s0.y = __shfl_down_sync(0xffffffffu, kc0.y, 1);
+          s0.z = __shfl_down_sync(0xffffffffu, kc0.z, 1); s0.w = __shfl_down_sync(0xffffffffu, kc0.w, 1);
+          s1.x = __shfl_down_sync(0xffffffffu, kc1.x, 1); s1.y = __shfl_down_sync(0xffffffffu, kc1.y, 1);
+          s1.z = __shfl_down_sync(0xffffffffu, kc1.z, 1); s1.w = __shfl_down_sync(0xffffffffu, kc1.w, 1);
+          sc = __shfl_down_sync(0xffffffffu, cc, 1);
+        }
+        const bool via_lane = dx < 0 ? left_ok : right_ok;
+        if (via_lane) { k0 = s0; k1 = s1; cv = sc; }
+        else if (row_ok && xx >= 0 && xx < g.W) {
+          const long long nb = b * V + ((long long)zz * g.H + yy) * g.W + xx;
+          const float4* kp = reinterpret_cast<const float4*>(qk + nb * 16 + 8);
+          k0 = __ldg(kp); k1 = __ldg(kp + 1);
+          cv = __ldg(cam + nb);
+        }
+      }
+      if (row_ok && xx >= 0 && xx < g.W) {
+        float d = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+        if (g.flags & 1) d = fmaxf(d, 0.f);
+        const float sv = d * invT;
+        const float mn = fmaxf(m, sv);
+        const float corr = __expf(m - mn), e = __expf(sv - mn);     // m = -inf on the first neighbour -> corr = 0
+        l = l * corr + e;
+        acc = acc * corr + e * cv;
+        m = mn;
+      }
+    }
+    if (live) out[i] = deg > 0 ? acc / l : 0.f;
+  }
+}
+
 // backward pass 1 (per node x): dd[x][o] = d loss / d <q_x,k_{x+o}>,  dq[x] = sum_o dd_o k_{x+o}
 __global__ void __launch_bounds__(256)
 k_pcm_bwd_node(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float* __restrict__ att,
@@ -273,7 +365,7 @@ int dram_pcm_num_offsets(int connectivity, int self_loop) {
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* att, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream) {
-  DRAM_REQUIRE(f && cam && theta_w && theta_b && phi_w && phi_b && qk && att && out, "pcm_fwd: null pointer");
+  DRAM_REQUIRE(f && cam && theta_w && theta_b && phi_w && phi_b && qk && out, "pcm_fwd: null pointer");
   PcmGeom g;
   int rc = pcm_geom(g, B, D, H, W, Cf, F, connectivity, self_loop, flags);
   if (rc) return rc;
@@ -281,7 +373,12 @@ int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const f
   long long rows = (long long)B * D * H * W;
   k_pcm_project<<<grid_for(rows, 256, 8), 256, 0, st>>>(f, theta_w, theta_b, phi_w, phi_b, qk, rows, Cf, F);
   DRAM_LAUNCH_CHECK();
-  k_pcm_attend<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, att, out);
+  if (att == nullptr && F == 8) {       // inference: no attention weights kept, warp-shuffle neighbour sharing
+    k_pcm_attend_infer<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, out);
+  } else {
+    DRAM_REQUIRE(att != nullptr, "pcm_fwd: the attention-weight buffer may only be NULL for F == 8 (inference kernel)");
+    k_pcm_attend<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, att, out);
+  }
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

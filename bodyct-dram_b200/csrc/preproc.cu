@@ -124,22 +124,38 @@ __global__ void __launch_bounds__(256)
 k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __restrict__ labels, int label,
                              float* __restrict__ heat, int d, int h, int w, int cd, int ch, int cw, int SH, int SW, int oz,
                              int oy, int ox, int act, float gain, float sz, float sy, float sx) {
-  const long long total = (long long)cd * ch * cw;
+  // one thread = 4 consecutive x voxels of the crop: the z/y interpolation set-up and the 4 source rows are shared
+  const int cw4 = (cw + 3) >> 2;
+  const long long total = (long long)cd * ch * cw4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % cw), Y = (int)((i / cw) % ch), Z = (int)(i / ((long long)cw * ch));
-    long long off = ((long long)(Z + oz) * SH + (Y + oy)) * SW + (X + ox);
-    if (labels[off] != label) continue;
-    Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
-    float acc = 0.f;
+    const int X0 = (int)(i % cw4) << 2, Y = (int)((i / cw4) % ch), Z = (int)(i / ((long long)cw4 * ch));
+    const long long off = ((long long)(Z + oz) * SH + (Y + oy)) * SW + (X0 + ox);
+    bool in[4];
+    bool any = false;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int zi = (k & 4) ? lz.i1 : lz.i0, yi = (k & 2) ? ly.i1 : ly.i0, xi = (k & 1) ? lx.i1 : lx.i0;
-      float wt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
-      float v = __ldg(ram + ((long long)zi * h + yi) * w + xi);
-      acc += wt * (act == 1 ? sigmoidf_(v) : v);
+    for (int j = 0; j < 4; ++j) { in[j] = (X0 + j < cw) && (labels[off + j] == label); any |= in[j]; }
+    if (!any) continue;
+    const Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h);
+    const float* r00 = ram + ((long long)lz.i0 * h + ly.i0) * w;
+    const float* r01 = ram + ((long long)lz.i0 * h + ly.i1) * w;
+    const float* r10 = ram + ((long long)lz.i1 * h + ly.i0) * w;
+    const float* r11 = ram + ((long long)lz.i1 * h + ly.i1) * w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!in[j]) continue;
+      const Lerp lx = lerp_setup(X0 + j, sx, w);
+      float a00 = __ldg(r00 + lx.i0), b00 = __ldg(r00 + lx.i1), a01 = __ldg(r01 + lx.i0), b01 = __ldg(r01 + lx.i1);
+      float a10 = __ldg(r10 + lx.i0), b10 = __ldg(r10 + lx.i1), a11 = __ldg(r11 + lx.i0), b11 = __ldg(r11 + lx.i1);
+      if (act == 1) {
+        a00 = sigmoidf_(a00); b00 = sigmoidf_(b00); a01 = sigmoidf_(a01); b01 = sigmoidf_(b01);
+        a10 = sigmoidf_(a10); b10 = sigmoidf_(b10); a11 = sigmoidf_(a11); b11 = sigmoidf_(b11);
+      }
+      // same nesting as ATen's upsample_trilinear3d: d(h(w))
+      float v = lz.w0 * (ly.w0 * (lx.w0 * a00 + lx.w1 * b00) + ly.w1 * (lx.w0 * a01 + lx.w1 * b01)) +
+                lz.w1 * (ly.w0 * (lx.w0 * a10 + lx.w1 * b10) + ly.w1 * (lx.w0 * a11 + lx.w1 * b11));
+      if (act == 2) v = fmaxf(v, 0.f);
+      heat[off + j] = v * gain;
     }
-    if (act == 2) acc = fmaxf(acc, 0.f);
-    heat[off] = acc * gain;
   }
 }
 
@@ -238,7 +254,7 @@ int dram_ram_upsample_label_scatter(const float* ram, const uint8_t* labels, int
   DRAM_REQUIRE(ram && labels && heat && d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "ram_upsample_label_scatter: bad arguments");
   DRAM_REQUIRE(act >= 0 && act <= 2, "ram_upsample_label_scatter: act %d unknown", act);
   DRAM_REQUIRE(oz >= 0 && oy >= 0 && ox >= 0 && oz + cd <= SD && oy + ch <= SH && ox + cw <= SW, "ram_upsample_label_scatter: crop outside the scan");
-  k_ram_upsample_label_scatter<<<grid_for((long long)cd * ch * cw, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  k_ram_upsample_label_scatter<<<grid_for((long long)cd * ch * ((cw + 3) / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(
       ram, labels, label, heat, d, h, w, cd, ch, cw, SH, SW, oz, oy, ox, act, gain, ac_scale(d, cd), ac_scale(h, ch), ac_scale(w, cw));
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;

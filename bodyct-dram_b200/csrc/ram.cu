@@ -21,20 +21,28 @@ k_ram_reduce_fwd(const float* __restrict__ feat, const float* __restrict__ scale
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool fused = scale != nullptr;
   if (fused) { sc = reinterpret_cast<const float4*>(scale)[sub]; sh = reinterpret_cast<const float4*>(shift)[sub]; }
-  for (long long r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
-    long long r = r0 + rsub;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) t = __ldg(reinterpret_cast<const float4*>(feat + r * C) + sub);
-    if (fused) {
-      t.x = fmaxf(t.x * sc.x + sh.x, 0.f); t.y = fmaxf(t.y * sc.y + sh.y, 0.f);
-      t.z = fmaxf(t.z * sc.z + sh.z, 0.f); t.w = fmaxf(t.w * sc.w + sh.w, 0.f);
-    }
-    for (int o = 0; o < O; ++o) {
-      float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)o * C) + sub);
-      float p = t.x * wv.x + t.y * wv.y + t.z * wv.z + t.w * wv.w;
+  constexpr int U = 4;                             // independent row batches in flight per warp (pure HBM stream)
+  for (long long r0 = warp * RPW * U; r0 < rows; r0 += nwarps * RPW * U) {
+    float4 t[U];
 #pragma unroll
-      for (int s = G / 2; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
-      if (sub == 0 && r < rows) ram[r * O + o] = p + b[o];
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + (long long)u * RPW + rsub;
+      t[u] = r < rows ? __ldg(reinterpret_cast<const float4*>(feat + r * C) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + (long long)u * RPW + rsub;
+      if (fused) {
+        t[u].x = fmaxf(t[u].x * sc.x + sh.x, 0.f); t[u].y = fmaxf(t[u].y * sc.y + sh.y, 0.f);
+        t[u].z = fmaxf(t[u].z * sc.z + sh.z, 0.f); t[u].w = fmaxf(t[u].w * sc.w + sh.w, 0.f);
+      }
+      for (int o = 0; o < O; ++o) {
+        float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)o * C) + sub);
+        float p = t[u].x * wv.x + t[u].y * wv.y + t[u].z * wv.z + t[u].w * wv.w;
+#pragma unroll
+        for (int sft = G / 2; sft > 0; sft >>= 1) p += __shfl_xor_sync(0xffffffffu, p, sft);
+        if (sub == 0 && r < rows) ram[r * O + o] = p + b[o];
+      }
     }
   }
 }
@@ -109,7 +117,8 @@ __global__ void k_ram_dfeat_multi(const float* __restrict__ dram, const float* _
   }
 }
 
-// masked pooling: per sample b: sum f(x)*m and sum m
+// masked pooling: per sample b: sum f(x)*m and sum m (float4 loads when the volume size allows)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_masked_pool_fwd(const float* __restrict__ x, const float* __restrict__ mask, double* __restrict__ out, long long V,
                   int use_sigmoid, int mode_gt0) {
@@ -117,13 +126,24 @@ k_masked_pool_fwd(const float* __restrict__ x, const float* __restrict__ mask, d
   const float* xb = x + (long long)b * V;
   const float* mb = mask + (long long)b * V;
   float s = 0.f, cnt = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
-    float m = mb[i];
-    if (mode_gt0) m = m > 0.f ? 1.f : 0.f;
-    float v = xb[i];
-    if (use_sigmoid) v = sigmoidf_(v);
-    s = fmaf(v, m, s);
-    cnt += m;
+  const long long n = V / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float xv[VEC], mv[VEC];
+    if (VEC == 4) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(xb) + i), m4 = __ldg(reinterpret_cast<const float4*>(mb) + i);
+      xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3 % VEC] = a.w;
+      mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3 % VEC] = m4.w;
+    } else {
+      xv[0] = xb[i]; mv[0] = mb[i];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float m = mv[v];
+      if (mode_gt0) m = m > 0.f ? 1.f : 0.f;
+      float val = use_sigmoid ? sigmoidf_(xv[v]) : xv[v];
+      s = fmaf(val, m, s);
+      cnt += m;
+    }
   }
   s = warp_sum(s);
   cnt = warp_sum(cnt);
@@ -152,6 +172,13 @@ __global__ void k_masked_pool_bwd(const float* __restrict__ x, const float* __re
     float d = gb * m;
     if (use_sigmoid) { float s = sigmoidf_(xb[i]); d *= s * (1.f - s); }
     db[i] = d;
+  }
+}
+
+__global__ void k_ram_activation(const float* __restrict__ in, float* __restrict__ out, long long n, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = in[i];
+    out[i] = act == 1 ? sigmoidf_(v) : (act == 2 ? fmaxf(v, 0.f) : v);
   }
 }
 
@@ -246,8 +273,13 @@ int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, 
   DRAM_REQUIRE(x && mask && out && B > 0 && V > 0, "masked_pool_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   DRAM_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * B, st));
-  int gx = grid_for(V, 256 * 8, 4);
-  k_masked_pool_fwd<<<dim3(gx, B), 256, 0, st>>>(x, mask, out, V, use_sigmoid, mode_gt0);
+  const bool vec = (V % 4 == 0) && (((uintptr_t)x | (uintptr_t)mask) % 16 == 0);
+  long long per_sample = (long long)kNumSMs * 4 / B;
+  if (per_sample < 1) per_sample = 1;
+  long long need = (V / (vec ? 4 : 1) + 255) / 256;
+  int gx = (int)(need < per_sample ? (need < 1 ? 1 : need) : per_sample);
+  if (vec) k_masked_pool_fwd<4><<<dim3(gx, B), 256, 0, st>>>(x, mask, out, V, use_sigmoid, mode_gt0);
+  else k_masked_pool_fwd<1><<<dim3(gx, B), 256, 0, st>>>(x, mask, out, V, use_sigmoid, mode_gt0);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
@@ -257,6 +289,13 @@ int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, floa
   DRAM_REQUIRE(x && mask && g && dx && B > 0 && V > 0, "masked_pool_bwd: bad arguments");
   int gx = grid_for(V, 256 * 4, 4);
   k_masked_pool_bwd<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, mask, g, dx, V, use_sigmoid, mode_gt0);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_ram_activation(const float* in, float* out, long long n, int act, void* stream) {
+  DRAM_REQUIRE(in && out && n > 0 && act >= 0 && act <= 2, "ram_activation: bad arguments");
+  k_ram_activation<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(in, out, n, act);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

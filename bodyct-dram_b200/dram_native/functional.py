@@ -232,8 +232,10 @@ class PcmAttend(torch.autograd.Function):
         f = ops.to_cl(f, "attention features")
         cam = cam.contiguous()
         tw, tb, pw, pb = tw.contiguous(), tb.contiguous(), pw.contiguous(), pb.contiguous()
-        out, qk, att = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags)
-        ctx.save_for_backward(f, cam, tw, pw, qk, att)
+        need_grad = any(ctx.needs_input_grad[:6])
+        out, qk, att = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_att=need_grad)
+        if need_grad:
+            ctx.save_for_backward(f, cam, tw, pw, qk, att)
         ctx.cfg = (connectivity, self_loop, flags)
         return out
 

@@ -311,6 +311,14 @@ def masked_pool_bwd(x, mask, g, use_sigmoid=False, mode_gt0=False):
     return dx
 
 
+def ram_activation(x, act):
+    """act(x) elementwise: 1 = sigmoid, 2 = relu"""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_L().dram_ram_activation(x.data_ptr(), out.data_ptr(), x.numel(), int(act), _stream()), "ram_activation")
+    return out
+
+
 def ram_upsample_mask_scatter(ram, crop_mask, heat, offset, act, gain=1.0, maxval=None):
     """ram [d,h,w] fp32; crop_mask [cd,ch,cw] uint8; heat [SD,SH,SW] fp32 (in place) or None."""
     d, h, w = ram.shape
@@ -332,17 +340,19 @@ def pcm_num_offsets(connectivity, self_loop):
     return _L().dram_pcm_num_offsets(int(connectivity), int(bool(self_loop)))
 
 
-def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags):
-    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk, att)"""
+def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_att=True):
+    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk, att | None)"""
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
     O = pcm_num_offsets(connectivity, self_loop)
     V = D * H * W
+    keep_att = keep_att or F != 8
     qk = torch.empty((B * V, 2 * F), device=f.device, dtype=torch.float32)
-    att = torch.empty((B * V, O), device=f.device, dtype=torch.float32)
+    att = torch.empty((B * V, O), device=f.device, dtype=torch.float32) if keep_att else None
     out = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
+    _lib.PROFILE.note(bytes=4.0 * B * V * (Cf + 2))
     _lib.check(_L().dram_pcm_fwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), tb.data_ptr(), pw.data_ptr(), pb.data_ptr(),
-                                 qk.data_ptr(), att.data_ptr(), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
+                                 qk.data_ptr(), _p(att), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
                                  int(bool(self_loop)), int(flags), _stream()), "pcm_fwd")
     return out, qk, att
 

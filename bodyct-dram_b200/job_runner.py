@@ -236,6 +236,7 @@ class LesionSegTest(JobRunner):
         if self.head == 'literal':
             pool = models.pooling_dense_features(dense, msks)
             cls_pred = torch.max(pool, dim=-1)[-1].tolist()                # always 0 for out_ch == 1
+        probs = ops.ram_activation(dense, 1) if self.head != 'literal' else None      # F.sigmoid(dense_outs), job_runner.py:765
         for i, (label, crop) in enumerate(crops.items()):
             if self.head == 'literal':
                 if cls_pred[i] < 1e-7:
@@ -246,7 +247,7 @@ class LesionSegTest(JobRunner):
                                               None, (0, 0, 0), 2, 1.0, mx)
                 ops.ram_upsample_label_scatter(dense[i, cls_pred[i]], lobe_t, label, heat, crop, 2, 1.0 / mx.item())
             else:
-                ops.ram_upsample_label_scatter(dense[i, 0], lobe_t, label, heat, crop, 1, 1.0)
+                ops.ram_upsample_label_scatter(probs[i, 0], lobe_t, label, heat, crop, 0, 1.0)
 
     def postprocess(self, heat, scan_t, lobe_t, vessel_t=None):
         """binary_cam / Otsu thresholds and lesion masks (job_runner.py:1006-1015)."""

@@ -140,6 +140,8 @@ int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, 
 /* dx[b][v] = g[b] * f'(x) * m[b][v]   (g already divided by the mask count by the caller) */
 int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, float* dx, int B, long long V,
                          int use_sigmoid, int mode_gt0, void* stream);
+/* out = act(in) elementwise (0 identity, 1 sigmoid, 2 relu): job_runner.py:765 `probs = F.sigmoid(dense_outs)` */
+int dram_ram_activation(const float* in, float* out, long long n, int act, void* stream);
 /* Inference epilogue (job_runner.py:765-770 / 993-1004): trilinear-upsample one chunk's RAM [d][h][w] to the lobe crop
  * [cd][ch][cw] (align_corners=True), apply `act` (0 = identity, 1 = sigmoid, 2 = relu), multiply by `gain`
  * (1/max for the max-normalised head) and write it into the scan-sized heat map at offset (oz,oy,ox) ONLY where
@@ -157,7 +159,8 @@ int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, f
  * flags bit0: relu on logits; bits1-2: temperature (0 none, 1 sqrt(degree) — models.py:274-277, 2 = 0.01);
  * connectivity 1|2|3, self_loop 0|1. */
 int dram_pcm_num_offsets(int connectivity, int self_loop); /* O: 18 for (2, no self loop) */
-/* qk  [B][V][2F] (out): theta|phi projections;  att [B][V][O] (out): softmax weights, kept for the backward */
+/* qk  [B][V][2F] (out): theta|phi projections;  att [B][V][O] (out): softmax weights, kept for the backward;
+ * att == NULL (F == 8): inference kernel — online softmax in registers, x-neighbours shared through warp shuffles */
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* att, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream);

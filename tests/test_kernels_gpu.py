@@ -367,7 +367,9 @@ def test_ram_upsample_mask_scatter(act):
 
 # ------------------------------------------------------------------------------------------------ PCM stencil attention
 @pytest.mark.parametrize("merge,self_loop,conn,grid", [("scaled_dot_product_relu", False, 2, (6, 7, 8)), ("sm", True, 1, (5, 5, 5)),
-                                                       ("scaled_dot_product", False, 3, (4, 6, 5)), ("smrelu", False, 2, (2, 1, 3))])
+                                                       ("scaled_dot_product", False, 3, (4, 6, 5)), ("smrelu", False, 2, (2, 1, 3)),
+                                                       ("scaled_dot_product_relu", False, 2, (3, 4, 64)),
+                                                       ("scaled_dot_product_relu", False, 2, (2, 3, 37))])
 def test_pcm_attention(merge, self_loop, conn, grid):
     from oracle_import import O
     import models
@@ -384,6 +386,8 @@ def test_pcm_attention(merge, self_loop, conn, grid):
     camg, fg = cam.detach().cuda().requires_grad_(True), cuda_cl(f.detach()).requires_grad_(True)
     got = pcm(camg, fg)
     assert_close(got, ref, 5e-5, "pcm fwd")
+    with torch.no_grad():                                   # inference kernel: online softmax + warp-shuffle sharing
+        assert_close(pcm(camg.detach(), fg.detach()), ref, 5e-5, "pcm fwd (inference kernel)")
     got.backward(g.cuda())
     assert_close(camg.grad, cam.grad, 1e-4, "pcm dcam")
     assert_close(fg.grad, f.grad, 1e-4, "pcm df")
