@@ -5,6 +5,7 @@ Granularity follows the reference's building blocks (parts.py): one Function per
 are logical NCDHW / channels-last memory fp32.
 """
 import torch
+import torch.optim.optimizer as _torch_optimizer
 
 from . import dist as ddist
 from . import ops
@@ -18,12 +19,14 @@ def _cl_grad(g, like):
 
 class _WeightCache:
     """Packed weights live ON the parameter object (attribute `_dram_packs`) and are rebuilt whenever the parameter
-    changes (`_version` bumps on optimizer.step / load_state_dict).  Nothing is keyed on addresses: the caching
-    allocator reuses them across models."""
+    may have changed: `_version` bumps on load_state_dict / copy_ / foreach optimizers, and `generation` bumps after
+    EVERY optimizer step (global post-step hook below: fused Adam updates parameters without touching `_version`),
+    after CUDA-graph replays and before a capture (so the pack kernels are part of the captured step).  Nothing is
+    keyed on addresses alone: the caching allocator reuses them across models."""
 
     def __init__(self):
         self.misses = 0
-        self.generation = 0        # bumped after CUDA-graph replays: they update weights without touching `_version`
+        self.generation = 0
 
     def invalidate(self):
         self.generation += 1
@@ -47,6 +50,7 @@ class _WeightCache:
 
 
 WEIGHTS = _WeightCache()
+_torch_optimizer.register_optimizer_step_post_hook(lambda *_a, **_k: WEIGHTS.invalidate())
 
 
 def conv_forward(x, w, bias=None):
@@ -228,11 +232,11 @@ class PcmAttend(torch.autograd.Function):
     """sum_o softmax_o(act(<theta f_x, phi f_{x+o}>)/T) * cam_{x+o} — the DGL update_all of models.py:322-411."""
 
     @staticmethod
-    def forward(ctx, cam, f, tw, tb, pw, pb, connectivity, self_loop, flags):
+    def forward(ctx, cam, f, tw, tb, pw, pb, connectivity, self_loop, flags, keep_for_backward=True):
         f = ops.to_cl(f, "attention features")
         cam = cam.contiguous()
         tw, tb, pw, pb = tw.contiguous(), tb.contiguous(), pw.contiguous(), pb.contiguous()
-        need_grad = any(ctx.needs_input_grad[:6])
+        need_grad = keep_for_backward and any(ctx.needs_input_grad[:6])   # grad mode is off inside forward: the caller tells us
         out, qk, att = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_att=need_grad)
         if need_grad:
             ctx.save_for_backward(f, cam, tw, pw, qk, att)
@@ -243,4 +247,4 @@ class PcmAttend(torch.autograd.Function):
     def backward(ctx, g):
         f, cam, tw, pw, qk, att = ctx.saved_tensors
         dcam, df, dtw, dtb, dpw, dpb = ops.pcm_bwd(f, cam, tw, pw, qk, att, g.contiguous(), *ctx.cfg)
-        return dcam, df, dtw, dtb, dpw, dpb, None, None, None
+        return dcam, df, dtw, dtb, dpw, dpb, None, None, None, None

@@ -102,6 +102,7 @@ class LesionSegChunkTrain(JobRunner):
         self._graph = self._graph_key = self._static_in = self._static_labels = self._static_out = None
         self._eager_steps = 0
         self.kernels_per_step = None
+        self._warm_stream = None
 
     def _step_body(self, images, lobes, lesions, ctsses, metas, labels):
         """forward + loss + backward (+ gradient all-reduce) + optimizer step; enqueues only, never syncs."""
@@ -142,13 +143,23 @@ class LesionSegChunkTrain(JobRunner):
             self._eager_steps += 1
             images, lobes, lesions = (t.to(dev, torch.float32, non_blocking=True).unsqueeze(1) for t in srcs)
             if self._eager_steps <= self.GRAPH_WARMUP_STEPS:
-                return self._step_body(images, lobes, lesions, ctsses, metas, labels)
+                # warm up on a side stream (torch CUDA-graph recipe): autograd's AccumulateGrad nodes must not be bound to
+                # the legacy default stream, or the later capture would have to synchronise with it
+                if self._warm_stream is None:
+                    self._warm_stream = torch.cuda.Stream()
+                self._warm_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._warm_stream):
+                    out = self._step_body(images, lobes, lesions, ctsses, metas, labels)
+                torch.cuda.current_stream().wait_stream(self._warm_stream)
+                return out
             self._static_in = [torch.empty_like(t) for t in (images, lobes, lesions)]
             self._static_labels = {k: torch.empty_like(v) for k, v in labels.items()}
             from dram_native import lib as _dlib
             torch.cuda.synchronize()
             was_profiling, _dlib.PROFILE.enabled = _dlib.PROFILE.enabled, False      # no event records inside a capture
             launches0 = _dlib.PROFILE.launches
+            from dram_native import functional as _DF
+            _DF.WEIGHTS.invalidate()              # the weight re-pack kernels must be part of the captured step
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._static_out = self._step_body(*self._static_in, ctsses, metas, self._static_labels)

@@ -194,7 +194,7 @@ class PCM(nn.Module):
             coef = const = None
         for _ in range(self.non_local_iter):
             s = DF.PcmAttend.apply(cam, f, self.theta.weight, self.theta.bias, self.phi.weight, self.phi.bias,
-                                   self.connectivity, bool(self.self_loop), flags)
+                                   self.connectivity, bool(self.self_loop), flags, torch.is_grad_enabled())
             refined = s * coef + const if coef is not None else s
             cam = refined + cam if self.residual else refined
         return cam
