@@ -42,12 +42,17 @@ __global__ void k_cl2nc(const float* __restrict__ src, float* __restrict__ dst, 
 constexpr int kStatThreads = 256;
 constexpr int kStatUnroll = 4;
 
-template <int VEC, bool BWD>
+// MODE 0: forward statistics (sum y, sum y^2).  MODE 1: backward sums (sum dz, sum dz*xhat) with dz = da * relu'; `da` rows
+// are `da_pitch` floats apart (a channel slice of a wider gradient tensor is read in place).  MODE 2: the same with the
+// rank-1 gradient of the fused RAM head, da[r][c] = g[r] * wtop[c] (`da` = g, one float per row), plus the RAM head's own
+// sums: sums[2C + c] = sum g * relu(y*scale+shift)  (d top_layer.weight) and sums[3C] = sum g (d top_layer.bias).
+template <int VEC, int MODE>
 __global__ void __launch_bounds__(kStatThreads)
-k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const float* __restrict__ scale,
-            const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-            double* __restrict__ sums, long long rows, int C) {
-  extern __shared__ float sm[];  // [2][kStatThreads][VEC]
+k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, long long da_pitch, const float* __restrict__ wtop,
+            const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+            const float* __restrict__ rstd, double* __restrict__ sums, long long rows, int C) {
+  constexpr bool BWD = MODE != 0;
+  extern __shared__ float sm[];  // [2 or 4][kStatThreads][VEC]
   const int groups = (C + VEC - 1) / VEC;             // channel groups per row
   const int gl = groups < kStatThreads ? groups : kStatThreads;
   const int lanes = kStatThreads / gl;                // row lanes per pass
@@ -58,16 +63,17 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
   for (int g0 = 0; g0 < groups; g0 += kStatThreads) {
     const int g = g0 + (threadIdx.x % gl);
     const int lane = threadIdx.x / gl;
-    float a0[VEC], a1[VEC];
+    float a0[VEC], a1[VEC], a2[VEC], a3 = 0.f;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
+    for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = a2[v] = 0.f;
     const bool active = (g < groups) && (lane < lanes);
-    float sc[VEC], sh[VEC], mu[VEC], rs[VEC];
+    float sc[VEC], sh[VEC], mu[VEC], rs[VEC], wt[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       int c = g * VEC + v;
       bool ok = BWD && active && c < C;
       sc[v] = ok ? scale[c] : 0.f; sh[v] = ok ? shift[c] : 0.f; mu[v] = ok ? mean[c] : 0.f; rs[v] = ok ? rstd[c] : 0.f;
+      wt[v] = (MODE == 2 && ok) ? wtop[c] : 0.f;
     }
     if (active) {
       for (long long r0 = r_begin + lane; r0 < r_end; r0 += (long long)lanes * kStatUnroll) {
@@ -79,8 +85,8 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
           if (VEC == 4) {
             float4 t = rok ? __ldg(reinterpret_cast<const float4*>(y + r * C) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
             yv[u][0] = t.x; yv[u][1] = t.y; yv[u][2] = t.z; yv[u][3 % VEC] = t.w;
-            if (BWD) {
-              float4 q = rok ? __ldg(reinterpret_cast<const float4*>(da + r * C) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 1) {
+              float4 q = rok ? __ldg(reinterpret_cast<const float4*>(da + r * da_pitch) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
               dv[u][0] = q.x; dv[u][1] = q.y; dv[u][2] = q.z; dv[u][3 % VEC] = q.w;
             }
           } else {
@@ -88,8 +94,13 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
             for (int v = 0; v < VEC; ++v) {
               const bool ok = rok && (g * VEC + v < C);
               yv[u][v] = ok ? y[r * C + (long long)g * VEC + v] : 0.f;
-              if (BWD) dv[u][v] = ok ? da[r * C + (long long)g * VEC + v] : 0.f;
+              if (MODE == 1) dv[u][v] = ok ? da[r * da_pitch + (long long)g * VEC + v] : 0.f;
             }
+          }
+          if (MODE == 2) {
+            const float gr = rok ? __ldg(da + r) : 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dv[u][v] = gr;          // g[r]; multiplied by wtop[c] below
           }
         }
 #pragma unroll
@@ -101,11 +112,17 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
               a1[v] += yv[u][v] * yv[u][v];
             } else {
               // out-of-range rows carry dv = 0, so they contribute nothing
-              float dz = (yv[u][v] * sc[v] + sh[v] > 0.f) ? dv[u][v] : 0.f;
+              const float act = yv[u][v] * sc[v] + sh[v];
+              float dz = (act > 0.f) ? dv[u][v] : 0.f;
+              if (MODE == 2) {
+                a2[v] += dz * act;                                   // g * relu(act)
+                dz *= wt[v];
+              }
               a0[v] += dz;
               a1[v] += dz * (yv[u][v] - mu[v]) * rs[v];
             }
           }
+          if (MODE == 2 && g == 0) a3 += dv[u][0];
         }
       }
     }
@@ -134,6 +151,29 @@ k_bn_reduce(const float* __restrict__ y, const float* __restrict__ da, const flo
       }
     }
     __syncthreads();
+    if (MODE == 2) {                                                 // second round for the RAM head's sums
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s0[threadIdx.x * VEC + v] = a2[v];
+      s1[threadIdx.x] = a3;
+      __syncthreads();
+      if (active && lane == 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          int c = g * VEC + v;
+          if (c < C) {
+            double t0 = 0.0;
+            for (int l = 0; l < lanes; ++l) t0 += (double)s0[(l * gl + (threadIdx.x % gl)) * VEC + v];
+            atomicAdd(&sums[2 * C + c], t0);
+          }
+        }
+        if (g == 0) {
+          double t1 = 0.0;
+          for (int l = 0; l < lanes; ++l) t1 += (double)s1[l * gl];
+          atomicAdd(&sums[3 * C], t1);
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -243,19 +283,20 @@ __global__ void k_bn_relu_bwd_apply(const float* __restrict__ da, const float* _
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums, double count,
-                                    float* __restrict__ dy, long long rows, int C) {
+                                    float* __restrict__ dy, long long rows, int C, long long da_pitch) {
   const int groups = C / VEC;
   const long long total = rows * groups;
   const float inv = sums ? (float)(1.0 / count) : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int g = (int)(i % groups);
+    const long long r = i / groups;
     float yv[VEC], dv[VEC], o[VEC];
     if (VEC == 4) {
-      float4 t = reinterpret_cast<const float4*>(y)[i], u = reinterpret_cast<const float4*>(da)[i];
+      float4 t = reinterpret_cast<const float4*>(y)[i], u = reinterpret_cast<const float4*>(da + r * da_pitch)[g];
       yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3 % VEC] = t.w;
       dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3 % VEC] = u.w;
     } else {
-      yv[0] = y[i]; dv[0] = da[i];
+      yv[0] = y[i]; dv[0] = da[r * da_pitch + g];
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -542,11 +583,11 @@ int dram_bn_stats(const float* y, double* sums, long long rows, int C, void* str
   cudaStream_t st = (cudaStream_t)stream;
   DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
   if (C % 4 == 0)
-    k_bn_reduce<4, false><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
+    k_bn_reduce<4, 0><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
+        y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
   else
-    k_bn_reduce<1, false><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
+    k_bn_reduce<1, 0><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
+        y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, sums, rows, C);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
@@ -589,29 +630,47 @@ int dram_bn_relu_apply(const float* y, const float* scale, const float* shift, f
   return DRAM_OK;
 }
 
-int dram_bn_relu_bwd_reduce(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
-                            const float* rstd, double* sums, long long rows, int C, void* stream) {
+int dram_bn_relu_bwd_reduce(const float* da, long long da_pitch, const float* wtop, const float* y, const float* scale,
+                            const float* shift, const float* mean, const float* rstd, double* sums, long long rows, int C,
+                            void* stream) {
   DRAM_REQUIRE(da && y && scale && shift && mean && rstd && sums && rows > 0 && C > 0, "bn_relu_bwd_reduce: bad arguments");
+  if (da_pitch == 0) da_pitch = C;
+  DRAM_REQUIRE(wtop || da_pitch >= C, "bn_relu_bwd_reduce: da_pitch %lld < C %d", da_pitch, C);
   cudaStream_t st = (cudaStream_t)stream;
-  DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-  if (C % 4 == 0)
-    k_bn_reduce<4, true><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
-        y, da, scale, shift, mean, rstd, sums, rows, C);
-  else
-    k_bn_reduce<1, true><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
-        y, da, scale, shift, mean, rstd, sums, rows, C);
+  const bool vec = C % 4 == 0 && da_pitch % 4 == 0;
+  if (wtop) {
+    DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (3 * C + 1), st));
+    if (vec)
+      k_bn_reduce<4, 2><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
+          y, da, 0, wtop, scale, shift, mean, rstd, sums, rows, C);
+    else
+      k_bn_reduce<1, 2><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
+          y, da, 0, wtop, scale, shift, mean, rstd, sums, rows, C);
+  } else {
+    DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    if (vec)
+      k_bn_reduce<4, 1><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * 4 * sizeof(float), st>>>(
+          y, da, da_pitch, nullptr, scale, shift, mean, rstd, sums, rows, C);
+    else
+      k_bn_reduce<1, 1><<<stat_grid(rows), kStatThreads, 2 * kStatThreads * sizeof(float), st>>>(
+          y, da, da_pitch, nullptr, scale, shift, mean, rstd, sums, rows, C);
+  }
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
 
-int dram_bn_relu_bwd_apply(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
-                           const float* rstd, const float* gamma, const double* sums, double count, float* dy,
-                           long long rows, int C, void* stream) {
+int dram_bn_relu_bwd_apply(const float* da, long long da_pitch, const float* y, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, const float* gamma, const double* sums, double count,
+                           float* dy, long long rows, int C, void* stream) {
   DRAM_REQUIRE(da && y && scale && shift && dy && rows > 0 && C > 0, "bn_relu_bwd_apply: bad arguments");
   DRAM_REQUIRE(!sums || (mean && rstd && count > 0), "bn_relu_bwd_apply: training mode needs mean/rstd/count");
+  if (da_pitch == 0) da_pitch = C;
+  DRAM_REQUIRE(da_pitch >= C, "bn_relu_bwd_apply: da_pitch %lld < C %d", da_pitch, C);
   cudaStream_t st = (cudaStream_t)stream;
-  VEC_DISPATCH(C, (k_bn_relu_bwd_apply<4><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C)),
-               (k_bn_relu_bwd_apply<1><<<grid_for(rows * C, 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C)));
+  if (C % 4 == 0 && da_pitch % 4 == 0)
+    k_bn_relu_bwd_apply<4><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C, da_pitch);
+  else
+    k_bn_relu_bwd_apply<1><<<grid_for(rows * C, 256), 256, 0, st>>>(da, y, scale, shift, mean, rstd, gamma, sums, count, dy, rows, C, da_pitch);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
@@ -682,12 +741,13 @@ int dram_upsample2x_concat_fwd(const float* x, const float* skip, float* cat, in
 
 int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N, int d, int h, int w, int C1, int Ds,
                                int Hs, int Ws, int C2, void* stream) {
-  DRAM_REQUIRE(dcat && dx && dskip && N > 0 && d > 0 && h > 0 && w > 0 && C1 > 0 && C2 > 0, "upsample2x_concat_bwd: bad arguments");
+  DRAM_REQUIRE(dcat && dx && N > 0 && d > 0 && h > 0 && w > 0 && C1 > 0 && C2 > 0, "upsample2x_concat_bwd: bad arguments");
   const int D = 2 * d, H = 2 * h, W = 2 * w;
   DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_bwd: bad skip size");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_trilinear_bwd(dcat, dx, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);
   if (rc) return rc;
+  if (!dskip) return DRAM_OK;            // the caller reads dcat[..., C1:] in place (no crop: Ds == D etc.)
   int oz = ceil_half(Ds - D), oy = ceil_half(Hs - H), ox = ceil_half(Ws - W);
   long long vox = (long long)N * Ds * Hs * Ws;
   if (C1 % 4 == 0 && C2 % 4 == 0)

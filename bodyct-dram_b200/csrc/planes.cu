@@ -1,0 +1,515 @@
+// Elementwise kernels whose activation operands live as bf16 split planes (hi = bf16(x), lo = bf16(x - hi)), the operand
+// format of the tcgen05 convolutions.  Between two tensor-core convolutions an activation is written ONCE, as planes, by
+// the BatchNorm+ReLU(+pool) kernel / the upsample+concat kernel / the BatchNorm backward kernel and read by the next
+// convolution's TMA loads: the fp32 copy and the separate split pass do not exist (4 B/element either way).
+// hi + lo is exact in fp32 and carries 16-17 significant bits of the fp32 value it was split from.
+// All kernels are HBM-bound streams: 8 channels (2 x float4 in, one 16-byte store per plane) per thread.
+#include "common.cuh"
+
+namespace dram {
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  split2(v[0], v[1], hi.x, lo.x);
+  split2(v[2], v[3], hi.y, lo.y);
+  split2(v[4], v[5], hi.z, lo.z);
+  split2(v[6], v[7], hi.w, lo.w);
+}
+// bf16 -> fp32 is a 16-bit shift
+__device__ __forceinline__ void merge2(uint32_t hi, uint32_t lo, float& a, float& b) {
+  a = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+  b = __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u);
+}
+__device__ __forceinline__ void merge8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+  merge2(hi.x, lo.x, v[0], v[1]);
+  merge2(hi.y, lo.y, v[2], v[3]);
+  merge2(hi.z, lo.z, v[4], v[5]);
+  merge2(hi.w, lo.w, v[6], v[7]);
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------ BN + ReLU (+ pool) -> planes
+// y [rows][C] fp32 -> a planes [rows][Cpad]; channels [C, Cpad) are written as zeros
+__global__ void __launch_bounds__(256)
+k_bn_relu_apply_planes(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                       uint4* __restrict__ hi, uint4* __restrict__ lo, long long rows, int C, int Cpad) {
+  const int groups = Cpad / 8;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long r = i / groups;
+    uint4 H = make_uint4(0, 0, 0, 0), L = make_uint4(0, 0, 0, 0);
+    if (g * 8 < C) {
+      float v[8], sc[8], sh[8];
+      load8(y + r * C + g * 8, v);
+      load8(scale + g * 8, sc);
+      load8(shift + g * 8, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+      split8(v, H, L);
+    }
+    hi[i] = H;
+    if (lo) lo[i] = L;
+  }
+}
+
+// one thread per (2x2x2 pool cell, 8-channel group): writes the 8 activations of the cell and their max, all as planes
+__global__ void __launch_bounds__(256)
+k_bn_relu_pool_planes(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                      uint4* __restrict__ hi, uint4* __restrict__ lo, uint4* __restrict__ phi, uint4* __restrict__ plo,
+                      int N, int D, int H, int W, int C, int Cpad) {
+  const int groups = Cpad / 8;
+  const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;   // cells incl. ragged tail
+  const int pd = D / 2, ph = H / 2, pw = W / 2;                       // pooled size (floor)
+  const long long total = (long long)N * cd * ch * cw * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int x = (int)(r % cw); r /= cw;
+    const int yy = (int)(r % ch); r /= ch;
+    const int z = (int)(r % cd);
+    const int n = (int)(r / cd);
+    const bool real = g * 8 < C;
+    float sc[8], sh[8], mx[8];
+    if (real) { load8(scale + g * 8, sc); load8(shift + g * 8, sh); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int zz = 2 * z + (k >> 2), yv = 2 * yy + ((k >> 1) & 1), xv = 2 * x + (k & 1);
+      if (zz < D && yv < H && xv < W) {
+        const long long row = (((long long)n * D + zz) * H + yv) * W + xv;
+        uint4 Hh = make_uint4(0, 0, 0, 0), Ll = make_uint4(0, 0, 0, 0);
+        if (real) {
+          float v[8];
+          load8(y + row * C + g * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f); mx[j] = fmaxf(mx[j], v[j]); }
+          split8(v, Hh, Ll);
+        }
+        hi[row * groups + g] = Hh;
+        if (lo) lo[row * groups + g] = Ll;
+      }
+    }
+    if (z < pd && yy < ph && x < pw) {
+      const long long prow = (((long long)n * pd + z) * ph + yy) * pw + x;
+      uint4 Hh = make_uint4(0, 0, 0, 0), Ll = make_uint4(0, 0, 0, 0);
+      if (real) split8(mx, Hh, Ll);
+      phi[prow * groups + g] = Hh;
+      if (plo) plo[prow * groups + g] = Ll;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN + ReLU backward -> dy planes
+// RANK1: da[r][c] = g[r] * wtop[c] (fused RAM head), otherwise da rows are da_pitch floats apart.
+template <bool RANK1>
+__global__ void __launch_bounds__(256)
+k_bn_relu_bwd_apply_planes(const float* __restrict__ da, long long da_pitch, const float* __restrict__ wtop,
+                           const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const double* __restrict__ sums, double count, uint4* __restrict__ hi, uint4* __restrict__ lo,
+                           long long rows, int C, int Cpad) {
+  const int groups = Cpad / 8;
+  const long long total = rows * groups;
+  const float inv = sums ? (float)(1.0 / count) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long r = i / groups;
+    uint4 H = make_uint4(0, 0, 0, 0), L = make_uint4(0, 0, 0, 0);
+    if (g * 8 < C) {
+      float yv[8], dv[8], sc[8], sh[8], o[8];
+      load8(y + r * C + g * 8, yv);
+      load8(scale + g * 8, sc);
+      load8(shift + g * 8, sh);
+      if (RANK1) {
+        const float gr = __ldg(da + r);
+        load8(wtop + g * 8, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dv[j] *= gr;
+      } else {
+        load8(da + r * da_pitch + g * 8, dv);
+      }
+      if (sums) {
+        float mu[8], rs[8];
+        load8(mean + g * 8, mu);
+        load8(rstd + g * 8, rs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = g * 8 + j;
+          const float dz = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? dv[j] : 0.f;
+          const float xh = (yv[j] - mu[j]) * rs[j];
+          const float gm = gamma ? __ldg(gamma + c) : 1.f;
+          o[j] = gm * rs[j] * (dz - (float)sums[c] * inv - xh * (float)sums[C + c] * inv);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? dv[j] * sc[j] : 0.f;
+      }
+      split8(o, H, L);
+    }
+    hi[i] = H;
+    if (lo) lo[i] = L;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooled unit backward
+// [conv -> BN -> ReLU -> (a, maxpool(a))]: the gradient of a is  ga (skip path, rows ga_pitch apart, nullable) plus gp
+// routed to the FIRST maximum of each 2x2x2 window (ATen: val > max || isnan), recomputed here from y — neither `a` nor
+// a dense `da` exist.  4 channels per thread, one thread per window (ragged tail cells have no pooled output).
+struct PoolCell {
+  int n, z, y, x;
+};
+__device__ __forceinline__ PoolCell decode_cell(long long cell, int cd, int ch, int cw) {
+  PoolCell c;
+  c.x = (int)(cell % cw); cell /= cw;
+  c.y = (int)(cell % ch); cell /= ch;
+  c.z = (int)(cell % cd);
+  c.n = (int)(cell / cd);
+  return c;
+}
+
+// dz[k][v] of one window for a 4-channel group; returns the validity mask of the 8 voxels
+__device__ __forceinline__ unsigned pool_window_dz(const float* __restrict__ y, const float* __restrict__ ga, long long ga_pitch,
+                                                   const float* __restrict__ gp, const PoolCell& pc, int g, int D, int H,
+                                                   int W, int C, const float (&sc)[4], const float (&sh)[4],
+                                                   float (&yv)[8][4], float (&dz)[8][4]) {
+  const int pd = D / 2, ph = H / 2, pw = W / 2;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  unsigned valid = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int zz = 2 * pc.z + (k >> 2), yy = 2 * pc.y + ((k >> 1) & 1), xx = 2 * pc.x + (k & 1);
+    if (zz < D && yy < H && xx < W) {
+      valid |= 1u << k;
+      const long long row = (((long long)pc.n * D + zz) * H + yy) * W + xx;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(y + row * C) + g);
+      yv[k][0] = t.x; yv[k][1] = t.y; yv[k][2] = t.z; yv[k][3] = t.w;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ga) q = __ldg(reinterpret_cast<const float4*>(ga + row * ga_pitch) + g);
+      dz[k][0] = q.x; dz[k][1] = q.y; dz[k][2] = q.z; dz[k][3] = q.w;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float a = fmaxf(fmaf(yv[k][v], sc[v], sh[v]), 0.f);
+        if (a > mx[v] || a != a) { mx[v] = a; arg[v] = k; }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { yv[k][v] = 0.f; dz[k][v] = 0.f; }
+    }
+  }
+  if (gp && pc.z < pd && pc.y < ph && pc.x < pw) {
+    const long long prow = (((long long)pc.n * pd + pc.z) * ph + pc.y) * pw + pc.x;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(gp + prow * C) + g);
+    const float gpv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (arg[v] == k) dz[k][v] += gpv[v];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (!(fmaf(yv[k][v], sc[v], sh[v]) > 0.f)) dz[k][v] = 0.f;
+  return valid;
+}
+
+constexpr int kPoolThreads = 256;
+__global__ void __launch_bounds__(kPoolThreads)
+k_bn_pool_bwd_reduce(const float* __restrict__ ga, long long ga_pitch, const float* __restrict__ gp,
+                     const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums, int N, int D,
+                     int H, int W, int C) {
+  __shared__ float s0[kPoolThreads * 4], s1[kPoolThreads * 4];
+  const int groups = C / 4;
+  const int gl = groups < kPoolThreads ? groups : kPoolThreads;
+  const int lanes = kPoolThreads / gl;
+  const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;
+  const long long cells = (long long)N * cd * ch * cw;
+  const long long per_block = (cells + gridDim.x - 1) / gridDim.x;
+  const long long c_begin = (long long)blockIdx.x * per_block;
+  const long long c_end = c_begin + per_block < cells ? c_begin + per_block : cells;
+  for (int g0 = 0; g0 < groups; g0 += kPoolThreads) {
+    const int g = g0 + (threadIdx.x % gl);
+    const int lane = threadIdx.x / gl;
+    const bool active = g < groups && lane < lanes;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      float sc[4], sh[4], mu[4], rs[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { sc[v] = scale[g * 4 + v]; sh[v] = shift[g * 4 + v]; mu[v] = mean[g * 4 + v]; rs[v] = rstd[g * 4 + v]; }
+      for (long long cell = c_begin + lane; cell < c_end; cell += lanes) {
+        float yv[8][4], dz[8][4];
+        const PoolCell pc = decode_cell(cell, cd, ch, cw);
+        pool_window_dz(y, ga, ga_pitch, gp, pc, g, D, H, W, C, sc, sh, yv, dz);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            a0[v] += dz[k][v];
+            a1[v] += dz[k][v] * (yv[k][v] - mu[v]) * rs[v];
+          }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { s0[threadIdx.x * 4 + v] = a0[v]; s1[threadIdx.x * 4 + v] = a1[v]; }
+    __syncthreads();
+    if (active && lane == 0) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int l = 0; l < lanes; ++l) {
+          t0 += (double)s0[(l * gl + (threadIdx.x % gl)) * 4 + v];
+          t1 += (double)s1[(l * gl + (threadIdx.x % gl)) * 4 + v];
+        }
+        atomicAdd(&sums[g * 4 + v], t0);
+        atomicAdd(&sums[C + g * 4 + v], t1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_pool_bwd_apply_planes(const float* __restrict__ ga, long long ga_pitch, const float* __restrict__ gp,
+                           const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const double* __restrict__ sums, double count, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                           int N, int D, int H, int W, int C, int Cpad) {
+  const int groups = Cpad / 4;
+  const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;
+  const long long total = (long long)N * cd * ch * cw * groups;
+  const float inv = sums ? (float)(1.0 / count) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const PoolCell pc = decode_cell(i / groups, cd, ch, cw);
+    const bool real = g * 4 < C;
+    float yv[8][4], dz[8][4], sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    float k1[4], k2[4], k3[4], mu[4];          // dy = k1*dz - k2 - (y - mu)*k3
+    if (real) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int c = g * 4 + v;
+        sc[v] = scale[c]; sh[v] = shift[c];
+        if (sums) {
+          const float rs = rstd[c], gm = gamma ? gamma[c] : 1.f;
+          mu[v] = mean[c];
+          k1[v] = gm * rs;
+          k2[v] = gm * rs * (float)sums[c] * inv;
+          k3[v] = gm * rs * rs * (float)sums[C + c] * inv;
+        } else {
+          mu[v] = 0.f; k1[v] = sc[v]; k2[v] = 0.f; k3[v] = 0.f;
+        }
+      }
+      pool_window_dz(y, ga, ga_pitch, gp, pc, g, D, H, W, C, sc, sh, yv, dz);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int zz = 2 * pc.z + (k >> 2), yy = 2 * pc.y + ((k >> 1) & 1), xx = 2 * pc.x + (k & 1);
+      if (zz < D && yy < H && xx < W) {
+        const long long row = (((long long)pc.n * D + zz) * H + yy) * W + xx;
+        uint2 Hh = make_uint2(0, 0), Ll = make_uint2(0, 0);
+        if (real) {
+          float o[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) o[v] = k1[v] * dz[k][v] - k2[v] - (yv[k][v] - mu[v]) * k3[v];
+          split2(o[0], o[1], Hh.x, Ll.x);
+          split2(o[2], o[3], Hh.y, Ll.y);
+        }
+        hi[row * groups + g] = Hh;
+        if (lo) lo[row * groups + g] = Ll;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsample x2 + concat on planes
+// cat[..., 0:C1] = trilinear x2 (align_corners=True) of x, cat[..., C1:C1+C2] = skip (centre crop, ceil offsets); all
+// three tensors are planes (pitches P1, P2, Pc in channels).  One thread per (output voxel, 8-channel group).
+__global__ void __launch_bounds__(256)
+k_upsample2x_concat_planes(const uint4* __restrict__ xh, const uint4* __restrict__ xl, const uint4* __restrict__ sh_,
+                           const uint4* __restrict__ sl, uint4* __restrict__ ch_, uint4* __restrict__ cl, int N, int d,
+                           int h, int w, int C1, int P1, int Ds, int Hs, int Ws, int C2, int P2, int Pc, int oz, int oy,
+                           int ox, float sz, float sy, float sx) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const int groups = Pc / 8, g1 = C1 / 8, g2 = (C1 + C2) / 8, pg1 = P1 / 8, pg2 = P2 / 8;
+  const long long total = (long long)N * D * H * W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H); r /= H;
+    const int Z = (int)(r % D);
+    const int n = (int)(r / D);
+    uint4 Hh = make_uint4(0, 0, 0, 0), Ll = make_uint4(0, 0, 0, 0);
+    if (g < g1) {
+      const Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int zi = (k & 4) ? lz.i1 : lz.i0, yi = (k & 2) ? ly.i1 : ly.i0, xi = (k & 1) ? lx.i1 : lx.i0;
+        const float wt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
+        const long long row = (((long long)n * d + zi) * h + yi) * w + xi;
+        const uint4 a = __ldg(xh + row * pg1 + g);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (xl) b = __ldg(xl + row * pg1 + g);
+        float v[8];
+        merge8(a, b, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wt * v[j];
+      }
+      split8(acc, Hh, Ll);
+    } else if (g < g2) {
+      const long long row = (((long long)n * Ds + Z + oz) * Hs + Y + oy) * Ws + X + ox;
+      Hh = __ldg(sh_ + row * pg2 + (g - g1));
+      if (sl) Ll = __ldg(sl + row * pg2 + (g - g1));
+    }
+    ch_[i] = Hh;
+    if (cl) cl[i] = Ll;
+  }
+}
+
+// planes [rows][P] -> fp32 [rows][C]  (materialises an activation for a consumer that is not a tensor-core convolution)
+__global__ void __launch_bounds__(256)
+k_merge_planes(const uint4* __restrict__ hi, const uint4* __restrict__ lo, float* __restrict__ out, long long rows, int C,
+               int P) {
+  const int groups = C / 8, pg = P / 8;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long r = i / groups;
+    const uint4 a = __ldg(hi + r * pg + g);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (lo) b = __ldg(lo + r * pg + g);
+    float v[8];
+    merge8(a, b, v);
+    float4* q = reinterpret_cast<float4*>(out + r * C + g * 8);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" {
+
+int dram_bn_relu_apply_planes(const float* y, const float* scale, const float* shift, void* a_hi, void* a_lo, void* p_hi,
+                              void* p_lo, int N, int D, int H, int W, int C, int Cpad, void* stream) {
+  DRAM_REQUIRE(y && scale && shift && a_hi && N > 0 && D > 0 && H > 0 && W > 0, "bn_relu_apply_planes: bad arguments");
+  DRAM_REQUIRE(C > 0 && C % 8 == 0 && Cpad >= C && Cpad % 8 == 0, "bn_relu_apply_planes: C=%d must be a multiple of 8 (Cpad=%d)", C, Cpad);
+  DRAM_REQUIRE(!p_lo || p_hi, "bn_relu_apply_planes: p_lo without p_hi");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)N * D * H * W;
+  if (!p_hi) {
+    k_bn_relu_apply_planes<<<grid_for(rows * (Cpad / 8), 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo, rows, C, Cpad);
+  } else {
+    DRAM_REQUIRE(D >= 2 && H >= 2 && W >= 2, "bn_relu_apply_planes: pooling needs every spatial size >= 2");
+    const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+    k_bn_relu_pool_planes<<<grid_for(cells * (Cpad / 8), 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo,
+                                                                            (uint4*)p_hi, (uint4*)p_lo, N, D, H, W, C, Cpad);
+  }
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_relu_bwd_apply_planes(const float* da, long long da_pitch, const float* wtop, const float* y, const float* scale,
+                                  const float* shift, const float* mean, const float* rstd, const float* gamma,
+                                  const double* sums, double count, void* dy_hi, void* dy_lo, long long rows, int C, int Cpad,
+                                  void* stream) {
+  DRAM_REQUIRE(da && y && scale && shift && dy_hi && rows > 0, "bn_relu_bwd_apply_planes: bad arguments");
+  DRAM_REQUIRE(C > 0 && C % 8 == 0 && Cpad >= C && Cpad % 8 == 0, "bn_relu_bwd_apply_planes: C=%d must be a multiple of 8 (Cpad=%d)", C, Cpad);
+  DRAM_REQUIRE(!sums || (mean && rstd && count > 0), "bn_relu_bwd_apply_planes: training mode needs mean/rstd/count");
+  if (da_pitch == 0) da_pitch = C;
+  DRAM_REQUIRE(wtop || (da_pitch >= C && da_pitch % 4 == 0), "bn_relu_bwd_apply_planes: da_pitch %lld invalid for C %d", da_pitch, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(rows * (Cpad / 8), 256);
+  if (wtop)
+    k_bn_relu_bwd_apply_planes<true><<<grid, 256, 0, st>>>(da, 0, wtop, y, scale, shift, mean, rstd, gamma, sums, count,
+                                                           (uint4*)dy_hi, (uint4*)dy_lo, rows, C, Cpad);
+  else
+    k_bn_relu_bwd_apply_planes<false><<<grid, 256, 0, st>>>(da, da_pitch, nullptr, y, scale, shift, mean, rstd, gamma, sums,
+                                                            count, (uint4*)dy_hi, (uint4*)dy_lo, rows, C, Cpad);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_pool_bwd_reduce(const float* ga, long long ga_pitch, const float* gp, const float* y, const float* scale,
+                            const float* shift, const float* mean, const float* rstd, double* sums, int N, int D, int H,
+                            int W, int C, void* stream) {
+  DRAM_REQUIRE((ga || gp) && y && scale && shift && mean && rstd && sums && N > 0 && D >= 2 && H >= 2 && W >= 2,
+               "bn_pool_bwd_reduce: bad arguments");
+  DRAM_REQUIRE(C > 0 && C % 4 == 0, "bn_pool_bwd_reduce: C=%d must be a multiple of 4", C);
+  if (ga_pitch == 0) ga_pitch = C;
+  DRAM_REQUIRE(ga_pitch >= C && ga_pitch % 4 == 0, "bn_pool_bwd_reduce: ga_pitch %lld invalid for C %d", ga_pitch, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+  long long want = (cells + 255) / 256;                     // ~256 windows (2048 voxels) per block, whole waves
+  long long waves = (want + kNumSMs - 1) / kNumSMs;
+  if (waves > 8) waves = 8;
+  long long grid = waves * kNumSMs;
+  if (grid > cells) grid = cells;
+  k_bn_pool_bwd_reduce<<<(int)grid, kPoolThreads, 0, st>>>(ga, ga_pitch, gp, y, scale, shift, mean, rstd, sums, N, D, H, W, C);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_bn_pool_bwd_apply_planes(const float* ga, long long ga_pitch, const float* gp, const float* y, const float* scale,
+                                  const float* shift, const float* mean, const float* rstd, const float* gamma,
+                                  const double* sums, double count, void* dy_hi, void* dy_lo, int N, int D, int H, int W,
+                                  int C, int Cpad, void* stream) {
+  DRAM_REQUIRE((ga || gp) && y && scale && shift && dy_hi && N > 0 && D >= 2 && H >= 2 && W >= 2, "bn_pool_bwd_apply_planes: bad arguments");
+  DRAM_REQUIRE(C > 0 && C % 4 == 0 && Cpad >= C && Cpad % 8 == 0, "bn_pool_bwd_apply_planes: C=%d / Cpad=%d unsupported", C, Cpad);
+  DRAM_REQUIRE(!sums || (mean && rstd && count > 0), "bn_pool_bwd_apply_planes: training mode needs mean/rstd/count");
+  if (ga_pitch == 0) ga_pitch = C;
+  DRAM_REQUIRE(ga_pitch >= C && ga_pitch % 4 == 0, "bn_pool_bwd_apply_planes: ga_pitch %lld invalid for C %d", ga_pitch, C);
+  const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+  k_bn_pool_bwd_apply_planes<<<grid_for(cells * (Cpad / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      ga, ga_pitch, gp, y, scale, shift, mean, rstd, gamma, sums, count, (uint2*)dy_hi, (uint2*)dy_lo, N, D, H, W, C, Cpad);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static inline int ceil_half_(int a) { return (a + 1) / 2; }
+
+int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void* skip_hi, const void* skip_lo, void* cat_hi,
+                                  void* cat_lo, int N, int d, int h, int w, int C1, int P1, int Ds, int Hs, int Ws, int C2,
+                                  int P2, int Pc, void* stream) {
+  DRAM_REQUIRE(x_hi && skip_hi && cat_hi && N > 0 && d > 0 && h > 0 && w > 0, "upsample2x_concat_planes: bad arguments");
+  DRAM_REQUIRE((x_lo == nullptr) == (skip_lo == nullptr) && (x_lo == nullptr) == (cat_lo == nullptr),
+               "upsample2x_concat_planes: lo planes must be all set or all NULL");
+  DRAM_REQUIRE(C1 > 0 && C2 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && P1 >= C1 && P2 >= C2 && Pc >= C1 + C2 && P1 % 8 == 0 &&
+               P2 % 8 == 0 && Pc % 8 == 0, "upsample2x_concat_planes: channel counts must be multiples of 8 (C1=%d C2=%d)", C1, C2);
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_planes: skip (%d,%d,%d) smaller than upsampled (%d,%d,%d)", Ds, Hs, Ws, D, H, W);
+  const long long total = (long long)N * D * H * W * (Pc / 8);
+  k_upsample2x_concat_planes<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x_hi, (const uint4*)x_lo, (const uint4*)skip_hi, (const uint4*)skip_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d,
+      h, w, C1, P1, Ds, Hs, Ws, C2, P2, Pc, ceil_half_(Ds - D), ceil_half_(Hs - H), ceil_half_(Ws - W), ac_scale(d, D),
+      ac_scale(h, H), ac_scale(w, W));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_merge_planes(const void* hi, const void* lo, float* out, long long rows, int C, int Cpad, void* stream) {
+  DRAM_REQUIRE(hi && out && rows > 0 && C > 0 && C % 8 == 0 && Cpad >= C && Cpad % 8 == 0, "merge_planes: bad arguments (C=%d Cpad=%d)", C, Cpad);
+  k_merge_planes<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)hi, (const uint4*)lo, out, rows, C, Cpad);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+}  // extern "C"

@@ -83,13 +83,73 @@ def conv_wgrad(saved_in, dy, w, dys=None):
     return ops.conv_simt_wgrad(saved_in, dy, k)
 
 
+class Act:
+    """An activation volume that exists ONLY as bf16 split planes (the tensor-core convolutions' operand format).
+
+    `planes` holds the data; `t` is the autograd handle: an fp32 tensor of the logical shape [N, C, D, H, W] with no
+    storage behind it (one element, expanded), so the graph, shapes and gradient flow are ordinary PyTorch while the
+    fp32 activation is never written.  Gradients w.r.t. `t` are real dense fp32 tensors."""
+    __slots__ = ("t", "planes")
+
+    def __init__(self, t, planes):
+        self.t, self.planes = t, planes
+
+    @property
+    def shape(self):
+        return self.planes.shape
+
+    def detach(self):
+        return Act(self.t.detach(), self.planes)
+
+
+def _handle(shape, device):
+    return torch.empty(1, device=device, dtype=torch.float32).expand(tuple(shape))
+
+
+def planes_enabled():
+    return ops.conv_path() == "umma"
+
+
+def _grad_rows(g, name="grad"):
+    """-> (tensor to take the pointer from, row pitch in floats) for a gradient that is channels-last dense OR a channel
+    slice of a wider channels-last tensor (read in place); anything else is converted with our layout kernel."""
+    if g.dim() == 5 and g.stride(1) == 1 and g.is_cuda and g.dtype == torch.float32:
+        N, C, D, H, W = g.shape
+        P = g.stride(4)
+        if P >= C and P % 4 == 0 and g.stride(3) == W * P and g.stride(2) == H * W * P and g.stride(0) == D * H * W * P \
+                and g.data_ptr() % 16 == 0:
+            return g, P
+    return ops.to_cl(g, name), g.shape[1]
+
+
 class ConvBnRelu(torch.autograd.Function):
-    """[Conv3d(bias optional) -> BatchNorm3d -> ReLU (-> MaxPool3d(2,2,0))]  — parts.py:103-110,184-196."""
+    """[Conv3d(bias optional) -> BatchNorm3d -> ReLU (-> MaxPool3d(2,2,0))]  — parts.py:103-110,184-196.
+
+    Input: fp32 volume `x`, or split planes (x_hi, x_lo) with `x` their storage-less handle.  Output: fp32 volumes, or
+    (out_planes) planes + handles.  Returns (a, a_hi, a_lo, pooled, p_hi, p_lo); unused slots are None."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates, pool):
-        x = ops.to_cl(x, "conv input")
-        y, saved_in = conv_forward(x, w, bias)
+    def forward(ctx, x, x_hi, x_lo, w, bias, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates,
+                pool, out_planes):
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        umma = ops.umma_ok_fwd(Cin, Cout, k) and bias is None
+        # the backward writes dy straight to planes when both consumers (dgrad, wgrad) are tensor-core kernels
+        planes_dy = umma and Cout % 8 == 0 and (ops.umma_ok_fwd(Cout, Cin, k) or not ctx.needs_input_grad[0])
+        xs = x_real = None
+        if x_hi is not None:
+            xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1])
+            if not umma:
+                x_real = ops.merge_planes(xs)
+        else:
+            x_real = ops.to_cl(x, "conv input")
+        if umma:
+            if xs is None:
+                xs = ops.split_bf16(x_real)
+            w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_fwd", lambda: ops.pack_weight_bf16(w.detach(), 0))
+            y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
+        else:
+            pack = WEIGHTS.get(w, "f32_fwd", lambda: ops.pack_weight_f32(w.detach(), 0))
+            y = ops.conv_simt(x_real, pack, bias, Cout, k)
         N, C, D, H, W = y.shape
         count = N * D * H * W
         if training:
@@ -100,67 +160,215 @@ class ConvBnRelu(torch.autograd.Function):
         else:
             scale, shift = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
             mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)      # only for dgamma/dbeta in eval mode
-        a, pooled = ops.bn_relu_apply(y, scale, shift, pool)
-        ctx.training, ctx.pool, ctx.count, ctx.has_bias = training, pool, count, bias is not None
-        ctx.saved_in = saved_in if isinstance(saved_in, ops.SplitPlanes) else None
-        tensors = [w, gamma, y, scale, shift, a if pool else None, mean, rstd,
-                   None if isinstance(saved_in, ops.SplitPlanes) else saved_in]
-        ctx.save_for_backward(*tensors)
-        if pool:
-            return a, pooled
-        return a
+        planes_out = bool(out_planes) and planes_enabled() and C % 8 == 0 and (planes_dy or not pool)
+        a_hi = a_lo = p_hi = p_lo = pooled = None
+        if planes_out:
+            ap, pp = ops.bn_relu_apply_planes(y, scale, shift, pool)
+            a, a_hi, a_lo = _handle(y.shape, y.device), ap.hi, ap.lo
+            if pool:
+                pooled, p_hi, p_lo = _handle(pp.shape, y.device), pp.hi, pp.lo
+        else:
+            a, pooled = ops.bn_relu_apply(y, scale, shift, pool)
+        ctx.training, ctx.pool, ctx.count, ctx.has_bias, ctx.umma = training, pool, count, bias is not None, umma
+        ctx.planes_dy = planes_dy
+        ctx.saved_planes = xs if umma else None
+        ctx.save_for_backward(w, gamma, y, scale, shift, a if (pool and not planes_dy) else None, mean, rstd,
+                              None if umma else x_real)
+        ctx.mark_non_differentiable(*[t for t in (a_hi, a_lo, p_hi, p_lo) if t is not None])
+        return a, a_hi, a_lo, pooled, p_hi, p_lo
 
     @staticmethod
-    def backward(ctx, *grads):
+    def backward(ctx, ga, _g1, _g2, gp, _g3, _g4):
         w, gamma, y, scale, shift, a, mean, rstd, x_plain = ctx.saved_tensors
-        saved_in = ctx.saved_in if ctx.saved_in is not None else x_plain
-        ga = grads[0]
-        if ctx.pool:
-            gp = grads[1]
-            if ga is None:
-                da = torch.zeros_like(y)
-            else:
-                da = ops.to_cl(ga, "grad").clone() if gp is not None else ops.to_cl(ga, "grad")
-            if gp is not None:
-                ops.maxpool2_bwd(a, ops.to_cl(gp, "grad"), da)
-        else:
-            da = ops.to_cl(ga, "grad")
         N, C, D, H, W = y.shape
-        if ctx.training:
-            sums = ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd)
-            dbeta = sums[:C].float()
-            dgamma = sums[C:].float()
-            gsums = ddist.allreduce_sums(sums)
-            dy = ops.bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, gsums, ctx.count)
-        else:
-            dy = ops.bn_relu_bwd_apply(da, y, scale, shift, None, None, gamma, None, 1.0)
-            dgamma = dbeta = None
-            if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
-                sums = ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd)
-                dbeta, dgamma = sums[:C].float(), sums[C:].float()
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
-        dys = None
-        if isinstance(saved_in, ops.SplitPlanes) or (ctx.needs_input_grad[0] and ops.umma_ok_fwd(Cout, Cin, k)):
+        want_gb = ctx.needs_input_grad[5] or ctx.needs_input_grad[6]
+        dgamma = dbeta = dys = dy = None
+        if ctx.planes_dy:
+            # dy goes straight to split planes, the operand of dgrad and wgrad
+            if ctx.pool:
+                ga_t, pitch = _grad_rows(ga) if ga is not None else (None, 0)
+                gp_t = ops.to_cl(gp, "grad") if gp is not None else None
+                if ga_t is None and gp_t is None:
+                    ga_t, pitch = torch.zeros_like(y), C
+                red = lambda: ops.bn_pool_bwd_reduce(ga_t, pitch, gp_t, y, scale, shift, mean, rstd)
+                app = lambda gs, cnt: ops.bn_pool_bwd_apply_planes(ga_t, pitch, gp_t, y, scale, shift, mean if gs is not None else None,
+                                                                   rstd if gs is not None else None, gamma, gs, cnt)
+            else:
+                ga_t, pitch = _grad_rows(ga)
+                red = lambda: ops.bn_relu_bwd_reduce(ga_t, y, scale, shift, mean, rstd, pitch=pitch)
+                app = lambda gs, cnt: ops.bn_relu_bwd_apply_planes(ga_t, pitch, None, y, scale, shift, mean if gs is not None else None,
+                                                                   rstd if gs is not None else None, gamma, gs, cnt)
+            if ctx.training:
+                sums = red()
+                dbeta, dgamma = sums[:C].float(), sums[C:].float()
+                dys = app(ddist.allreduce_sums(sums), ctx.count)
+            else:
+                dys = app(None, 1.0)
+                if want_gb:
+                    sums = red()
+                    dbeta, dgamma = sums[:C].float(), sums[C:].float()
+        else:
+            if ctx.pool:
+                if ga is None:
+                    da = torch.zeros_like(y)
+                else:
+                    da = ops.to_cl(ga, "grad").clone() if gp is not None else ops.to_cl(ga, "grad")
+                if gp is not None:
+                    ops.maxpool2_bwd(a, ops.to_cl(gp, "grad"), da)
+                pitch = C
+            else:
+                da, pitch = _grad_rows(ga)
+            if ctx.training:
+                sums = ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd, pitch=pitch)
+                dbeta, dgamma = sums[:C].float(), sums[C:].float()
+                gsums = ddist.allreduce_sums(sums)
+                dy = ops.bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, gsums, ctx.count, pitch=pitch)
+            else:
+                dy = ops.bn_relu_bwd_apply(da, y, scale, shift, None, None, gamma, None, 1.0, pitch=pitch)
+                if want_gb:
+                    sums = ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd, pitch=pitch)
+                    dbeta, dgamma = sums[:C].float(), sums[C:].float()
+        saved_in = ctx.saved_planes if ctx.umma else x_plain
+        if dys is None and (ctx.umma or (ctx.needs_input_grad[0] and ops.umma_ok_fwd(Cout, Cin, k))):
             dys = ops.split_bf16(dy)
         dx = conv_dgrad(dy, w, dys) if ctx.needs_input_grad[0] else None
-        dw = conv_wgrad(saved_in, dy, w, dys) if ctx.needs_input_grad[1] else None
+        dw = conv_wgrad(saved_in, dy, w, dys) if ctx.needs_input_grad[3] else None
         dbias = dy.sum(dim=(0, 2, 3, 4)) if ctx.has_bias else None
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, None, None, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
-class UpsampleConcat(torch.autograd.Function):
-    """nn.Upsample(x2, trilinear, align_corners=True) + crop_concat_5d([up, skip]) — parts.py:149-153."""
+def _wrap(t, hi, lo):
+    if hi is None:
+        return t
+    return Act(t, ops.SplitPlanes(hi, lo, tuple(t.shape), hi.shape[-1]))
+
+
+def _unwrap(x):
+    return (x.t, x.planes.hi, x.planes.lo) if isinstance(x, Act) else (x, None, None)
+
+
+def conv_bn_relu(x, w, bias, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates=1, pool=False,
+                 out_planes=False):
+    """One [conv -> BN -> ReLU (-> pool)] unit on a tensor or an `Act`; returns tensors, or `Act`s when out_planes is set
+    and the shape allows it.  With pool: (a, pooled)."""
+    a, a_hi, a_lo, p, p_hi, p_lo = ConvBnRelu.apply(*_unwrap(x), w, bias, gamma, beta, running_mean, running_var, training,
+                                                    momentum, eps, n_updates, pool, out_planes)
+    if pool:
+        return _wrap(a, a_hi, a_lo), _wrap(p, p_hi, p_lo)
+    return _wrap(a, a_hi, a_lo)
+
+
+class Materialize(torch.autograd.Function):
+    """planes -> fp32 channels-last volume (for consumers outside the tensor-core path); gradient passes through."""
 
     @staticmethod
-    def forward(ctx, x, skip):
-        x, skip = ops.to_cl(x, "upsample input"), ops.to_cl(skip, "skip")
-        ctx.shapes = (tuple(x.shape), tuple(skip.shape))
-        return ops.upsample2x_concat(x, skip)
+    def forward(ctx, t, hi, lo):
+        return ops.merge_planes(ops.SplitPlanes(hi, lo, tuple(t.shape), hi.shape[-1]))
 
     @staticmethod
     def backward(ctx, g):
-        dx, dskip = ops.upsample2x_concat_bwd(ops.to_cl(g, "grad"), *ctx.shapes)
-        return dx, dskip
+        return g, None, None
+
+
+def as_tensor(x):
+    return Materialize.apply(x.t, x.planes.hi, x.planes.lo) if isinstance(x, Act) else x
+
+
+class ConvBnReluRam(torch.autograd.Function):
+    """Last decoder unit fused with the RAM head: [Conv3d -> BatchNorm3d -> ReLU] -> top_layer (1x1x1, C -> 1)
+    (parts.py:103-110 + models.py:109-110,145).  The unit's activation is never stored: the RAM reduce applies BN+ReLU
+    to the raw conv output on the fly, and the backward forms da = g (x) w_top inside the BatchNorm backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, x_hi, x_lo, w, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates, w_top,
+                b_top):
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]) if x_hi is not None else \
+            ops.split_bf16(ops.to_cl(x, "conv input"))
+        w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_fwd", lambda: ops.pack_weight_bf16(w.detach(), 0))
+        y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
+        N, C, D, H, W = y.shape
+        count = N * D * H * W
+        if training:
+            sums = ops.bn_stats(y)
+            count = ddist.allreduce_stats(sums, count)
+            mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                                       n_updates)
+        else:
+            scale, shift = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
+            mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)
+        w2 = w_top.reshape(1, C).contiguous()
+        ram = ops.ram_reduce(y, w2, b_top.contiguous(), scale, shift)
+        ctx.training, ctx.count, ctx.saved_planes, ctx.wshape = training, count, xs, tuple(w_top.shape)
+        ctx.save_for_backward(w, gamma, y, scale, shift, mean, rstd, w2)
+        return ram
+
+    @staticmethod
+    def backward(ctx, g):
+        w, gamma, y, scale, shift, mean, rstd, w2 = ctx.saved_tensors
+        N, C, D, H, W = y.shape
+        g = g.contiguous()                                   # [N,1,D,H,W]: one float per voxel row
+        sums = ops.bn_relu_bwd_reduce(g, y, scale, shift, mean, rstd, wtop=w2)
+        dbeta, dgamma = sums[:C].float(), sums[C:2 * C].float()
+        dw_top, db_top = sums[2 * C:3 * C].float().view(ctx.wshape), sums[3 * C:3 * C + 1].float()
+        if ctx.training:
+            dys = ops.bn_relu_bwd_apply_planes(g, 0, w2, y, scale, shift, mean, rstd, gamma,
+                                               ddist.allreduce_sums(sums[:2 * C].contiguous()), ctx.count)
+        else:
+            dys = ops.bn_relu_bwd_apply_planes(g, 0, w2, y, scale, shift, None, None, gamma, None, 1.0)
+        dx = conv_dgrad(None, w, dys) if ctx.needs_input_grad[0] else None
+        dw = conv_wgrad(ctx.saved_planes, None, w, dys) if ctx.needs_input_grad[3] else None
+        return dx, None, None, dw, dgamma, dbeta, None, None, None, None, None, None, dw_top, db_top
+
+
+def ram_fusable(w, w_top, bias):
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+    return (planes_enabled() and bias is None and ops.umma_ok_fwd(Cin, Cout, k) and ops.umma_ok_fwd(Cout, Cin, k)
+            and Cout % 8 == 0 and w_top.shape[0] == 1 and tuple(w_top.shape[2:]) == (1, 1, 1))
+
+
+def conv_bn_relu_ram(x, w, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates, w_top, b_top):
+    return ConvBnReluRam.apply(*_unwrap(x), w, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates,
+                               w_top, b_top)
+
+
+class UpsampleConcat(torch.autograd.Function):
+    """nn.Upsample(x2, trilinear, align_corners=True) + crop_concat_5d([up, skip]) — parts.py:149-153.
+    Planes in -> planes out when both inputs are planes; fp32 otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, x_hi, x_lo, skip, s_hi, s_lo):
+        ctx.shapes = (tuple(x.shape), tuple(skip.shape))
+        ctx.planes = x_hi is not None and s_hi is not None
+        if ctx.planes:
+            cat = ops.upsample2x_concat_planes(ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]),
+                                               ops.SplitPlanes(s_hi, s_lo, tuple(skip.shape), s_hi.shape[-1]))
+            ctx.mark_non_differentiable(*[t for t in (cat.hi, cat.lo) if t is not None])
+            return _handle(cat.shape, x_hi.device), cat.hi, cat.lo
+        if x_hi is not None:
+            x = ops.merge_planes(ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]))
+        if s_hi is not None:
+            skip = ops.merge_planes(ops.SplitPlanes(s_hi, s_lo, tuple(skip.shape), s_hi.shape[-1]))
+        return ops.upsample2x_concat(ops.to_cl(x, "upsample input"), ops.to_cl(skip, "skip")), None, None
+
+    @staticmethod
+    def backward(ctx, g, _g1, _g2):
+        (N, C1, d, h, w), (_, C2, Ds, Hs, Ws) = ctx.shapes
+        g = ops.to_cl(g, "grad")
+        if (Ds, Hs, Ws) == (2 * d, 2 * h, 2 * w) and C1 % 4 == 0 and C2 % 4 == 0:
+            # no crop: the skip gradient is the channel slice [C1:] of g, handed on as a view and read in place by the
+            # BatchNorm backward kernels of the encoder unit (row pitch C1 + C2)
+            dx, _ = ops.upsample2x_concat_bwd(g, *ctx.shapes, want_dskip=False)
+            dskip = g[:, C1:]
+        else:
+            dx, dskip = ops.upsample2x_concat_bwd(g, *ctx.shapes)
+        return dx, None, None, dskip, None, None
+
+
+def upsample_concat(x, skip):
+    t, hi, lo = UpsampleConcat.apply(*_unwrap(x), *_unwrap(skip))
+    return _wrap(t, hi, lo)
 
 
 class TrilinearResize(torch.autograd.Function):

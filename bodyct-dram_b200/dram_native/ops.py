@@ -209,22 +209,86 @@ def bn_relu_apply(y, scale, shift, pool=False):
     return a, pooled
 
 
-def bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd):
+def alloc_planes(shape, three=None):
+    """Uninitialised split planes for a volume of logical shape [N,C,D,H,W] (every kernel that fills them also zeroes
+    the pad channels)."""
+    N, C, D, H, W = shape
+    three = (precision() == "bf16x3") if three is None else three
+    Cpad = _pad64(C)
+    rows = N * D * H * W
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hi = torch.empty((rows, Cpad), device=dev, dtype=torch.bfloat16)
+    lo = torch.empty((rows, Cpad), device=dev, dtype=torch.bfloat16) if three else None
+    return SplitPlanes(hi, lo, (N, C, D, H, W), Cpad)
+
+
+def bn_relu_apply_planes(y, scale, shift, pool=False):
+    """a = relu(y*scale+shift) (and its 2x2x2 max-pool) written directly as split planes -> (a, pooled | None)"""
     N, C, D, H, W = y.shape
-    sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
-    _lib.check(_L().dram_bn_relu_bwd_reduce(da.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                            mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), N * D * H * W, C,
-                                            _stream()), "bn_relu_bwd_reduce")
+    a = alloc_planes((N, C, D, H, W))
+    p = alloc_planes((N, C, D // 2, H // 2, W // 2)) if pool else None
+    _lib.check(_L().dram_bn_relu_apply_planes(y.data_ptr(), scale.data_ptr(), shift.data_ptr(), a.hi.data_ptr(), _p(a.lo),
+                                              _p(p.hi) if pool else 0, _p(p.lo) if pool else 0, N, D, H, W, C, a.Cpad,
+                                              _stream()), "bn_relu_apply_planes")
+    return a, p
+
+
+def merge_planes(xs):
+    """split planes -> fp32 channels-last volume"""
+    N, C, D, H, W = xs.shape
+    out = new_volume(N, C, D, H, W, xs.hi.device)
+    _lib.check(_L().dram_merge_planes(xs.hi.data_ptr(), _p(xs.lo), out.data_ptr(), N * D * H * W, C, xs.Cpad, _stream()),
+               "merge_planes")
+    return out
+
+
+def bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd, pitch=0, wtop=None):
+    """-> double sums [2C] (sum dz, sum dz*xhat); with wtop (fused RAM head, da = g [rows]): [3C+1], see the header"""
+    N, C, D, H, W = y.shape
+    sums = torch.empty(2 * C if wtop is None else 3 * C + 1, device=y.device, dtype=torch.float64)
+    _lib.check(_L().dram_bn_relu_bwd_reduce(da.data_ptr(), int(pitch), _p(wtop), y.data_ptr(), scale.data_ptr(),
+                                            shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(),
+                                            N * D * H * W, C, _stream()), "bn_relu_bwd_reduce")
     return sums
 
 
-def bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, sums, count):
+def bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, sums, count, pitch=0):
     N, C, D, H, W = y.shape
     dy = new_volume(N, C, D, H, W, y.device)
-    _lib.check(_L().dram_bn_relu_bwd_apply(da.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(mean),
-                                           _p(rstd), _p(gamma), _p(sums), float(count), dy.data_ptr(), N * D * H * W, C,
-                                           _stream()), "bn_relu_bwd_apply")
+    _lib.check(_L().dram_bn_relu_bwd_apply(da.data_ptr(), int(pitch), y.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                           _p(mean), _p(rstd), _p(gamma), _p(sums), float(count), dy.data_ptr(),
+                                           N * D * H * W, C, _stream()), "bn_relu_bwd_apply")
     return dy
+
+
+def bn_relu_bwd_apply_planes(da, pitch, wtop, y, scale, shift, mean, rstd, gamma, sums, count):
+    """dy of the BatchNorm+ReLU backward as split planes (operand of dgrad / wgrad)"""
+    N, C, D, H, W = y.shape
+    dys = alloc_planes((N, C, D, H, W))
+    _lib.check(_L().dram_bn_relu_bwd_apply_planes(da.data_ptr(), int(pitch), _p(wtop), y.data_ptr(), scale.data_ptr(),
+                                                  shift.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count),
+                                                  dys.hi.data_ptr(), _p(dys.lo), N * D * H * W, C, dys.Cpad, _stream()),
+               "bn_relu_bwd_apply_planes")
+    return dys
+
+
+def bn_pool_bwd_reduce(ga, pitch, gp, y, scale, shift, mean, rstd):
+    N, C, D, H, W = y.shape
+    sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+    _lib.check(_L().dram_bn_pool_bwd_reduce(_p(ga), int(pitch), _p(gp), y.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                            mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), N, D, H, W, C, _stream()),
+               "bn_pool_bwd_reduce")
+    return sums
+
+
+def bn_pool_bwd_apply_planes(ga, pitch, gp, y, scale, shift, mean, rstd, gamma, sums, count):
+    N, C, D, H, W = y.shape
+    dys = alloc_planes((N, C, D, H, W))
+    _lib.check(_L().dram_bn_pool_bwd_apply_planes(_p(ga), int(pitch), _p(gp), y.data_ptr(), scale.data_ptr(),
+                                                  shift.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count),
+                                                  dys.hi.data_ptr(), _p(dys.lo), N, D, H, W, C, dys.Cpad, _stream()),
+               "bn_pool_bwd_apply_planes")
+    return dys
 
 
 def maxpool2_bwd(a, dpooled, da):
@@ -244,12 +308,23 @@ def upsample2x_concat(x, skip):
     return cat
 
 
-def upsample2x_concat_bwd(dcat, x_shape, skip_shape):
+def upsample2x_concat_planes(xs, skips):
+    """planes of x [N,C1,d,h,w] and skip [N,C2,Ds,Hs,Ws] -> planes of cat [N,C1+C2,2d,2h,2w]"""
+    N, C1, d, h, w = xs.shape
+    _, C2, Ds, Hs, Ws = skips.shape
+    cat = alloc_planes((N, C1 + C2, 2 * d, 2 * h, 2 * w), three=xs.lo is not None)
+    _lib.check(_L().dram_upsample2x_concat_planes(xs.hi.data_ptr(), _p(xs.lo), skips.hi.data_ptr(), _p(skips.lo),
+                                                  cat.hi.data_ptr(), _p(cat.lo), N, d, h, w, C1, xs.Cpad, Ds, Hs, Ws, C2,
+                                                  skips.Cpad, cat.Cpad, _stream()), "upsample2x_concat_planes")
+    return cat
+
+
+def upsample2x_concat_bwd(dcat, x_shape, skip_shape, want_dskip=True):
     N, C1, d, h, w = x_shape
     _, C2, Ds, Hs, Ws = skip_shape
     dx = new_volume(N, C1, d, h, w, dcat.device)
-    dskip = new_volume(N, C2, Ds, Hs, Ws, dcat.device)
-    _lib.check(_L().dram_upsample2x_concat_bwd(dcat.data_ptr(), dx.data_ptr(), dskip.data_ptr(), N, d, h, w, C1, Ds, Hs,
+    dskip = new_volume(N, C2, Ds, Hs, Ws, dcat.device) if want_dskip else None
+    _lib.check(_L().dram_upsample2x_concat_bwd(dcat.data_ptr(), dx.data_ptr(), _p(dskip), N, d, h, w, C1, Ds, Hs,
                                                Ws, C2, _stream()), "upsample2x_concat_bwd")
     return dx, dskip
 

@@ -86,32 +86,43 @@ class _UNet(nn.Module):
             self.us_modules = None
         self.top_layer = nn.Conv3d(end_ch_list[n + stacking], out_ch, kernel_size=1, padding=0)
 
-    def _encode_decode(self, x, decoder_ckpt_offset, tap=None):
-        """Returns the decoder output; `tap(idx, features)` is called with pre-pool encoder / bottleneck / decoder
-        features under the reference's layer numbering (models.py:563-585)."""
+    def _encode_decode(self, x, decoder_ckpt_offset, tap=None, size=None):
+        """Encoder / bottleneck / decoder + RAM head -> dense_outs (models.py:123-146 / 563-588).  `tap(idx, features)` is
+        called with pre-pool encoder / bottleneck / decoder features under the reference's layer numbering
+        (models.py:563-585).  Activations stay in split planes (`DF.Act`) from the first unit to the RAM head; the last
+        decoder unit is fused with `top_layer` unless its features are tapped."""
         n = self.n_layers
+        planes = DF.planes_enabled()
         skips = []
         h = x
         for idx, ds in enumerate(self.ds_modules):
-            y, h = ds(h, stat_updates=_stat_updates(self, self.checkpoint_layers[idx]))
+            y, h = ds(h, stat_updates=_stat_updates(self, self.checkpoint_layers[idx]), planes=planes)
             skips.append(y)
             if tap is not None:
                 tap(idx, y)
-        h = self.bg(h, stat_updates=_stat_updates(self, self.checkpoint_layers[n]))
+        h = self.bg(h, stat_updates=_stat_updates(self, self.checkpoint_layers[n]), planes=planes)
         if tap is not None:
             tap(n, h)
+        dense = None
         if self.us_modules is not None:
+            n_dec = min(len(self.us_modules), self.stacking)
             for idx, (us, skip) in enumerate(zip(self.us_modules, reversed(skips))):
                 if self.stacking == idx:
                     break
-                h = us(h, skip, stat_updates=_stat_updates(self, self.checkpoint_layers[decoder_ckpt_offset + idx]))
-                if tap is not None:
+                su = _stat_updates(self, self.checkpoint_layers[decoder_ckpt_offset + idx])
+                tapped = tap is not None and (n + idx + 1) in getattr(self, "at_layers", ())
+                if planes and idx == n_dec - 1 and not tapped:
+                    h = us(h, skip, stat_updates=su, planes=True, skip_last=True)
+                    dense = us.run_last_with_ram(h, self.top_layer, su)
+                    if dense is None:
+                        h = us._run(h, su, planes=True, only_last=True)
+                else:
+                    h = us(h, skip, stat_updates=su, planes=planes)
+                if tap is not None and dense is None:
                     tap(n + idx + 1, h)
-        return h
-
-    def _ram(self, feats, size):
-        dense = DF.RamReduce.apply(feats, self.top_layer.weight, self.top_layer.bias)        # models.py:145
-        return DF.TrilinearResize.apply(dense, tuple(size))                                  # models.py:146 / 588
+        if dense is None:
+            dense = DF.RamReduce.apply(DF.as_tensor(h), self.top_layer.weight, self.top_layer.bias)        # models.py:145
+        return DF.TrilinearResize.apply(dense, tuple(size))                                                   # models.py:146 / 588
 
     def init(self, initializer):
         initializer.initialize(self)
@@ -140,8 +151,7 @@ class DC3D(_UNet):
 
     def forward(self, x, lungs=None):
         x = ops.to_cl(x, "DC3D input")
-        feats = self._encode_decode(x, decoder_ckpt_offset=self.n_layers)       # models.py:140 indexing
-        dense_outs = self._ram(feats, x.shape[-3:])
+        dense_outs = self._encode_decode(x, decoder_ckpt_offset=self.n_layers, size=x.shape[-3:])   # models.py:140 indexing
         return dense_outs, dense_outs
 
 
@@ -233,8 +243,8 @@ class DC3DATGeneric(_UNet):
 
     def _reshape_head(self, nc, feats):
         conv, bn = self.reshape[nc][0], self.reshape[nc][1]
-        out = DF.ConvBnRelu.apply(feats.detach(), conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                  bn.running_var, bn.training, bn.momentum, bn.eps, 1, False)       # models.py:564
+        out = DF.conv_bn_relu(feats.detach(), conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                              bn.running_var, bn.training, bn.momentum, bn.eps, 1, False)           # models.py:564
         if bn.training:
             bn.num_batches_tracked += 1
         return out
@@ -254,8 +264,8 @@ class DC3DATGeneric(_UNet):
             if idx in self.at_layers:
                 att.append(self._reshape_head(len(att) - (1 if -1 in self.at_layers else 0), feats))
 
-        feats = self._encode_decode(x, decoder_ckpt_offset=self.n_layers + 1, tap=tap)          # models.py:578 indexing
-        dense_outs = self._ram(feats, x.shape[-3:])
+        dense_outs = self._encode_decode(x, decoder_ckpt_offset=self.n_layers + 1, tap=tap,     # models.py:578 indexing
+                                         size=x.shape[-3:])
         size = tuple(self.at_spatial_size)
         att = torch.cat([DF.TrilinearResize.apply(f, size) for f in att], dim=1)               # models.py:591-594
         refined = self.apply_attention(x, lungs, dense_outs, att)

@@ -68,27 +68,50 @@ def _make_units(in_chs, out_chs, ksizes, pads, strides, conv_bias, norm_method, 
 
 
 class _FusedUnits(nn.Module):
-    """Shared execution of a stack of [conv, norm, relu] units through the fused kernels."""
+    """Shared execution of a stack of [conv, norm, relu] units through the fused kernels.
 
-    def _run(self, x, stat_updates=1, pool_last=False):
+    Between units (and, with `planes=True`, towards the caller) activations travel as `DF.Act`: bf16 split planes, the
+    tensor-core convolutions' operand format, with a storage-less autograd handle.  The public `forward`s return plain
+    fp32 tensors; the models in this package pass `planes=True` and keep everything in planes."""
+
+    def _unit_args(self, i):
+        conv, bn = self.conv_blocks[i][0], self.conv_blocks[i][1]
+        if not isinstance(bn, nn.BatchNorm3d):
+            raise NotImplementedError("conv units without batch-norm are not on the B200 path")
+        return conv, bn, (bn.training or bn.running_mean is None)
+
+    def _count(self, bn, stat_updates):
+        if bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += stat_updates
+
+    def _run(self, x, stat_updates=1, pool_last=False, planes=False, skip_last=False, only_last=False):
+        """skip_last: stop before the last unit (the caller fuses it with the RAM head); only_last: run just that unit."""
         n = len(self.conv_blocks)
         pooled = None
-        for i, unit in enumerate(self.conv_blocks):
-            conv, bn = unit[0], unit[1]
-            if not isinstance(bn, nn.BatchNorm3d):
-                raise NotImplementedError("conv units without batch-norm are not on the B200 path")
-            training = bn.training
-            use_batch_stats = training or bn.running_mean is None
+        for i in range(n - 1 if only_last else 0, n - 1 if skip_last else n):
+            conv, bn, use_batch_stats = self._unit_args(i)
             pool = pool_last and i == n - 1
-            out = DF.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      use_batch_stats, bn.momentum, bn.eps, stat_updates, pool)
-            if training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += stat_updates
+            out = DF.conv_bn_relu(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                  use_batch_stats, bn.momentum, bn.eps, stat_updates, pool,
+                                  out_planes=planes or i < n - 1)
+            self._count(bn, stat_updates)
             if pool:
                 x, pooled = out
             else:
                 x = out
+        if not planes:
+            x, pooled = DF.as_tensor(x), (DF.as_tensor(pooled) if pooled is not None else None)
         return (x, pooled) if pool_last else x
+
+    def run_last_with_ram(self, x, top_layer, stat_updates=1):
+        """Last unit + `top_layer` (the RAM reduce, models.py:145) as one fused op, or None if the shapes do not allow it."""
+        conv, bn, use_batch_stats = self._unit_args(len(self.conv_blocks) - 1)
+        if not DF.ram_fusable(conv.weight, top_layer.weight, conv.bias):
+            return None
+        ram = DF.conv_bn_relu_ram(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch_stats,
+                                  bn.momentum, bn.eps, stat_updates, top_layer.weight, top_layer.bias)
+        self._count(bn, stat_updates)
+        return ram
 
 
 class ConvBlock5d(_FusedUnits):
@@ -104,8 +127,8 @@ class ConvBlock5d(_FusedUnits):
         self.conv_blocks = _make_units(in_chs, base_chs, _as_list(conv_ksize, n), _as_list(conv_pad, n),
                                        _as_list(conv_strides, n), conv_bias, norm_method, dropout)
 
-    def forward(self, x, args=None, stat_updates=1):
-        return self._run(x, stat_updates)
+    def forward(self, x, args=None, stat_updates=1, planes=False):
+        return self._run(x, stat_updates, planes=planes)
 
 
 class UpsampleConvBlock5d(_FusedUnits):
@@ -125,9 +148,9 @@ class UpsampleConvBlock5d(_FusedUnits):
         self.merge_func = kwargs.get('merge_func', crop_concat_5d)
         self.upsample = nn.Upsample(size=None, scale_factor=self.scale_factor, mode='trilinear', align_corners=True)
 
-    def forward(self, inputs, cats, args=None, stat_updates=1):
-        x = DF.UpsampleConcat.apply(inputs, cats)
-        return self._run(x, stat_updates)
+    def forward(self, inputs, cats, args=None, stat_updates=1, planes=False, skip_last=False):
+        x = DF.upsample_concat(inputs, cats)
+        return self._run(x, stat_updates, planes=planes, skip_last=skip_last)
 
 
 class ConvPoolBlock5d(_FusedUnits):
@@ -144,6 +167,6 @@ class ConvPoolBlock5d(_FusedUnits):
                                        _as_list(conv_strdes, n), conv_bias, norm_method, dropout)
         self.maxpool = nn.MaxPool3d(kernel_size=pool_ksize, stride=pool_strides, padding=pool_pad)
 
-    def forward(self, x, args=None, stat_updates=1):
-        y, pooled = self._run(x, stat_updates, pool_last=True)
+    def forward(self, x, args=None, stat_updates=1, planes=False):
+        y, pooled = self._run(x, stat_updates, pool_last=True, planes=planes)
         return y, pooled

@@ -95,16 +95,52 @@ int dram_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
 /* a = max(0, y*scale + shift); if pooled != NULL also MaxPool3d(2,2,0) of a (parts.py:191,195), floor semantics */
 int dram_bn_relu_apply(const float* y, const float* scale, const float* shift, float* a, float* pooled /*nullable*/,
                        int N, int D, int H, int W, int C, void* stream);
-/* backward, pass 1: dz = da * (y*scale+shift > 0); sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat */
-int dram_bn_relu_bwd_reduce(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
-                            const float* rstd, double* sums, long long rows, int C, void* stream);
+/* backward, pass 1: dz = da * (y*scale+shift > 0); sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat.
+ * `da` rows are `da_pitch` floats apart (0 = C): the skip half of a decoder gradient is read in place.
+ * wtop != NULL: fused RAM head (models.py:145) — `da` is g [rows] and da[r][c] = g[r]*wtop[c]; sums is then
+ * double[3*C+1] with sums[2C+c] = sum g*relu(y*scale+shift)[c] (= d top_layer.weight), sums[3C] = sum g (= d bias). */
+int dram_bn_relu_bwd_reduce(const float* da, long long da_pitch, const float* wtop /*nullable*/, const float* y,
+                            const float* scale, const float* shift, const float* mean, const float* rstd, double* sums,
+                            long long rows, int C, void* stream);
 /* backward, pass 2 (training): dy = gamma*rstd*(dz - sum_dz/count - xhat*sum_dz_xhat/count);
  * eval (sums == NULL): dy = dz*scale */
-int dram_bn_relu_bwd_apply(const float* da, const float* y, const float* scale, const float* shift, const float* mean,
-                           const float* rstd, const float* gamma, const double* sums /*nullable*/, double count,
-                           float* dy, long long rows, int C, void* stream);
+int dram_bn_relu_bwd_apply(const float* da, long long da_pitch, const float* y, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, const float* gamma, const double* sums /*nullable*/,
+                           double count, float* dy, long long rows, int C, void* stream);
 /* MaxPool3d(2,2,0) backward: da[first argmax of each window] += dpooled (da is read-modify-write; windows are disjoint) */
 int dram_maxpool2_bwd(const float* a, const float* dpooled, float* da, int N, int D, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ the same units on bf16 split planes
+ * Between two tensor-core convolutions an activation exists ONLY as split planes [rows][Cpad] (hi, lo; lo == NULL in the
+ * single-pass bf16 mode; channels [C,Cpad) zero): the kernels below write the next convolution's TMA operand directly, so
+ * no fp32 activation and no separate split pass exist.  C must be a multiple of 8. */
+/* parts.py:107-108 (+191,195): a = max(0, y*scale+shift) -> planes; p_hi != NULL: also MaxPool3d(2,2,0)(a) -> planes */
+int dram_bn_relu_apply_planes(const float* y, const float* scale, const float* shift, void* a_hi, void* a_lo /*nullable*/,
+                              void* p_hi /*nullable*/, void* p_lo /*nullable*/, int N, int D, int H, int W, int C, int Cpad,
+                              void* stream);
+/* dram_bn_relu_bwd_apply writing dy as planes (the operand of dgrad and wgrad); wtop != NULL: da[r][c] = g[r]*wtop[c] */
+int dram_bn_relu_bwd_apply_planes(const float* da, long long da_pitch, const float* wtop /*nullable*/, const float* y,
+                                  const float* scale, const float* shift, const float* mean, const float* rstd,
+                                  const float* gamma, const double* sums /*nullable*/, double count, void* dy_hi,
+                                  void* dy_lo /*nullable*/, long long rows, int C, int Cpad, void* stream);
+/* Backward of a pooled unit (parts.py:193-196: returns (a, maxpool(a))): da = ga (nullable, rows ga_pitch apart) + gp
+ * routed to the first maximum of each 2x2x2 window, recomputed from y (ATen max_pool3d backward semantics); fused with
+ * the BatchNorm+ReLU backward so that neither `a` nor a dense `da` is ever stored.  C must be a multiple of 4. */
+int dram_bn_pool_bwd_reduce(const float* ga /*nullable*/, long long ga_pitch, const float* gp /*nullable*/, const float* y,
+                            const float* scale, const float* shift, const float* mean, const float* rstd, double* sums,
+                            int N, int D, int H, int W, int C, void* stream);
+int dram_bn_pool_bwd_apply_planes(const float* ga /*nullable*/, long long ga_pitch, const float* gp /*nullable*/,
+                                  const float* y, const float* scale, const float* shift, const float* mean,
+                                  const float* rstd, const float* gamma, const double* sums /*nullable*/, double count,
+                                  void* dy_hi, void* dy_lo /*nullable*/, int N, int D, int H, int W, int C, int Cpad,
+                                  void* stream);
+/* parts.py:149-153 on planes: cat = [trilinear x2 (align_corners=True) of x | centre-cropped skip]; P1/P2/Pc = channel
+ * pitches of the x / skip / cat planes */
+int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void* skip_hi, const void* skip_lo, void* cat_hi,
+                                  void* cat_lo, int N, int d, int h, int w, int C1, int P1, int Ds, int Hs, int Ws, int C2,
+                                  int P2, int Pc, void* stream);
+/* planes -> fp32 [rows][C]: materialises an activation for a consumer outside the tensor-core path */
+int dram_merge_planes(const void* hi, const void* lo /*nullable*/, float* out, long long rows, int C, int Cpad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ decoder glue
  * nn.Upsample(scale_factor=2, trilinear, align_corners=True) + crop_concat_5d: parts.py:149-153,37-46.
@@ -112,8 +148,9 @@ int dram_maxpool2_bwd(const float* a, const float* dpooled, float* da, int N, in
  * skip: [N][Ds][Hs][Ws][C2], cat: [N][2d][2h][2w][C1+C2]. */
 int dram_upsample2x_concat_fwd(const float* x, const float* skip, float* cat, int N, int d, int h, int w, int C1,
                                int Ds, int Hs, int Ws, int C2, void* stream);
-/* dx (gather form of the transposed interpolation, no atomics) and dskip (zero outside the crop) */
-int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N, int d, int h, int w, int C1,
+/* dx (gather form of the transposed interpolation, no atomics) and dskip (zero outside the crop; NULL = not wanted,
+ * the caller reads dcat[..., C1:] in place) */
+int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip /*nullable*/, int N, int d, int h, int w, int C1,
                                int Ds, int Hs, int Ws, int C2, void* stream);
 /* F.interpolate(size=..., trilinear, align_corners=True): models.py:146,514-518,588,591-592; job_runner.py:766,993.
  * src [N][d][h][w][C] -> dst [N][D][H][W][C]; the backward is the exact adjoint, gather form. */

