@@ -46,6 +46,34 @@ static inline int grid_for(long long work_items, int block, int max_waves = 32) 
   return (int)g;
 }
 
+// Grid-stride walk over (row, group) pairs of a [rows][groups] problem without a 64-bit division per element: the
+// per-thread start is divided once, every further step is an add and a compare.
+struct RowGroupIter {
+  long long r, dr;
+  int g, dg, groups;
+  __device__ __forceinline__ RowGroupIter(int groups_) : groups(groups_) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long T = (long long)gridDim.x * blockDim.x;
+    r = tid / groups; g = (int)(tid - r * groups);
+    dr = T / groups; dg = (int)(T - dr * groups);
+  }
+  __device__ __forceinline__ void next() {
+    r += dr; g += dg;
+    if (g >= groups) { g -= groups; ++r; }
+  }
+};
+
+// Grid whose total thread count is a multiple of `groups`, so that a thread of a [rows][groups] grid-stride loop keeps
+// ONE group (its per-channel constants are loaded once, outside the loop) and only walks rows.
+static inline int grid_fixed_group(long long rows, int groups, int block, int max_waves = 32) {
+  int a = groups, b = block;
+  while (b) { int t = a % b; a = b; b = t; }
+  const int m = groups / a;                       // grid must be a multiple of groups / gcd(groups, block)
+  long long g = grid_for(rows * groups, block, max_waves);
+  g = (g + m - 1) / m * m;
+  return (int)g;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

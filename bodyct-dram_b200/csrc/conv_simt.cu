@@ -207,6 +207,104 @@ k_conv_simt_wgrad(const float* __restrict__ x, const float* __restrict__ dy, flo
   }
 }
 
+// ------------------------------------------------------------------------------------------------ first layer (Cin = 1)
+// ds0.c0 (1 -> 32 channels, k = 3): K = 27, 13 FLOP/B — bandwidth-bound on the write of y (forward) / the read of dy
+// (wgrad), so no GEMM tiling: every thread owns a few output channels of one voxel and keeps the 27 taps in registers.
+// The launch guarantees (gridDim.x * blockDim.x) % groups == 0: a thread keeps its channel group.
+constexpr int kC1MaxCout = 64, kC1MaxCoutWgrad = 32;
+
+__device__ __forceinline__ void c1_taps(const float* __restrict__ x, unsigned m, int D, int H, int W, float (&xv)[27]) {
+  unsigned r = m;
+  const int xx = (int)(r % (unsigned)W); r /= (unsigned)W;
+  const int yy = (int)(r % (unsigned)H); r /= (unsigned)H;
+  const int zz = (int)(r % (unsigned)D);
+  const long long base = (long long)m;
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int dz = t / 9 - 1, dy = (t / 3) % 3 - 1, dx = t % 3 - 1;
+    const bool ok = (unsigned)(zz + dz) < (unsigned)D && (unsigned)(yy + dy) < (unsigned)H && (unsigned)(xx + dx) < (unsigned)W;
+    xv[t] = ok ? __ldg(x + base + ((long long)dz * H + dy) * W + dx) : 0.f;
+  }
+}
+
+// thread = (voxel, 8 output channels); y [M][Cout]
+__global__ void __launch_bounds__(256)
+k_conv_c1_fwd(const float* __restrict__ x, const float* __restrict__ pack, const float* __restrict__ bias,
+              float* __restrict__ y, long long M, int D, int H, int W, int Cout) {
+  __shared__ __align__(16) float ws[27 * kC1MaxCout];
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = pack[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dm = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);
+  float b8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b8[j] = bias ? bias[g * 8 + j] : 0.f;
+  for (long long m = tid / groups; m < M; m += dm) {
+    float xv[27], acc[8];
+    c1_taps(x, (unsigned)m, D, H, W, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b8[j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8 + 4]);
+      acc[0] = fmaf(xv[t], w0.x, acc[0]); acc[1] = fmaf(xv[t], w0.y, acc[1]);
+      acc[2] = fmaf(xv[t], w0.z, acc[2]); acc[3] = fmaf(xv[t], w0.w, acc[3]);
+      acc[4] = fmaf(xv[t], w1.x, acc[4]); acc[5] = fmaf(xv[t], w1.y, acc[5]);
+      acc[6] = fmaf(xv[t], w1.z, acc[6]); acc[7] = fmaf(xv[t], w1.w, acc[7]);
+    }
+    float4* q = reinterpret_cast<float4*>(y + m * Cout + g * 8);
+    q[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    q[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// thread = (voxel lane, 4 output channels) accumulating dpack[27][4] over its voxels; lanes of a warp that share the
+// channel group are folded with shuffles, warps through shared memory, blocks with one atomicAdd per output.
+// groups = Cout / 4 must be a power of two <= 32.
+__global__ void __launch_bounds__(256)
+k_conv_c1_wgrad(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dpack, long long M, int D,
+                int H, int W, int Cout) {
+  __shared__ float red[8][27 * kC1MaxCoutWgrad];
+  const int groups = Cout / 4;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dm = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);             // == lane % groups (256 and 32 are multiples of groups)
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  for (long long m = tid / groups; m < M; m += dm) {
+    float xv[27];
+    c1_taps(x, (unsigned)m, D, H, W, xv);
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(dy + m * Cout) + g);
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      acc[t][0] = fmaf(xv[t], d4.x, acc[t][0]); acc[t][1] = fmaf(xv[t], d4.y, acc[t][1]);
+      acc[t][2] = fmaf(xv[t], d4.z, acc[t][2]); acc[t][3] = fmaf(xv[t], d4.w, acc[t][3]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[t][j];
+      for (int o = 16; o >= groups; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < groups) red[warp][t * Cout + lane * 4 + j] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) v += red[wp][i];
+    atomicAdd(&dpack[i], v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // w [Cout][Cin][T]  ->  mode 0: pack[t][ci][co]   mode 1: pack[t][co][ci] with flipped taps
 __global__ void k_pack_weight_f32(const float* __restrict__ w, float* __restrict__ pack, int Cout, int Cin, int T, int mode) {
@@ -259,6 +357,11 @@ int dram_conv3d_simt_fwd(const float* x, const float* pack, const float* bias, f
   DRAM_REQUIRE(x && pack && y && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_simt_fwd: bad arguments");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_simt_fwd: kernel size %d unsupported (1 or 3)", ksize);
   long long M = (long long)N * D * H * W;
+  if (Cin == 1 && ksize == 3 && Cout % 8 == 0 && Cout <= kC1MaxCout && M < (1ll << 31)) {
+    k_conv_c1_fwd<<<grid_fixed_group(M, Cout / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, M, D, H, W, Cout);
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN));
   if (ksize == 3) k_conv_simt_fwd<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, N, D, H, W, Cin, Cout);
   else k_conv_simt_fwd<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, N, D, H, W, Cin, Cout);
@@ -271,6 +374,12 @@ int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack, int N,
   DRAM_REQUIRE(x && dy && dpack && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_simt_wgrad: bad arguments");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_simt_wgrad: kernel size %d unsupported (1 or 3)", ksize);
   long long M = (long long)N * D * H * W;
+  const int c1g = Cout / 4;
+  if (Cin == 1 && ksize == 3 && Cout % 4 == 0 && Cout <= kC1MaxCoutWgrad && c1g <= 32 && (c1g & (c1g - 1)) == 0 && M < (1ll << 31)) {
+    k_conv_c1_wgrad<<<grid_fixed_group(M, c1g, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, M, D, H, W, Cout);
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   int Ktot = ksize * ksize * ksize * Cin;
   long long slabs = (M + kWgradSlab - 1) / kWgradSlab;
   long long tiles = (long long)((Ktot + WK - 1) / WK) * ((Cout + WN - 1) / WN);

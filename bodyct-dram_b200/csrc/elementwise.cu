@@ -484,6 +484,96 @@ __global__ void k_trilinear_bwd(const float* __restrict__ ddst, float* __restric
   }
 }
 
+// Adjoint of the exact x2 upsample (D = 2d ...), gather form, register-blocked: one thread produces a 2x2x2 block of
+// source voxels for 4 channels.  With align_corners=True and an exact factor 2, source index i receives from destination
+// indices 2i-1 .. 2i+2 only, so the block needs the 6x6x6 destination neighbourhood (27 float4 loads per output instead of
+// 64) and the three axes are reduced one after the other in registers.  Weights come from the forward's own lerp_setup,
+// so this is the exact transpose of k_trilinear_fwd (a destination index that touches a source index only through float
+// rounding of o*scale, weight ~1e-7, is ignored).
+__global__ void __launch_bounds__(128)
+k_up2x_adjoint(const float* __restrict__ ddst, float* __restrict__ dsrc, int N, int d, int h, int w, int C, int dstC,
+               int dstOff, float sz, float sy, float sx) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const int groups = C / 4;
+  const int bd = (d + 1) / 2, bh = (h + 1) / 2, bw = (w + 1) / 2;
+  const long long blocks = (long long)N * bd * bh * bw;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long db = ((long long)gridDim.x * blockDim.x) / groups;     // launch: total threads % groups == 0
+  const int g = (int)(tid % groups);
+  for (long long b = tid / groups; b < blocks; b += db) {
+    unsigned r = (unsigned)b;
+    const int x0 = 2 * (int)(r % (unsigned)bw); r /= (unsigned)bw;
+    const int y0 = 2 * (int)(r % (unsigned)bh); r /= (unsigned)bh;
+    const int z0 = 2 * (int)(r % (unsigned)bd);
+    const int n = (int)(r / (unsigned)bd);
+    float wz[6][2], wy[6][2], wx[6][2];
+#pragma unroll
+    for (int t = 0; t < 6; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int Z = 2 * z0 - 1 + t, Y = 2 * y0 - 1 + t, X = 2 * x0 - 1 + t;
+        wz[t][j] = (Z >= 0 && Z < D && z0 + j < d) ? adj_weight(Z, z0 + j, sz, d) : 0.f;
+        wy[t][j] = (Y >= 0 && Y < H && y0 + j < h) ? adj_weight(Y, y0 + j, sy, h) : 0.f;
+        wx[t][j] = (X >= 0 && X < W && x0 + j < w) ? adj_weight(X, x0 + j, sx, w) : 0.f;
+      }
+    // Destination indices are clamped into the volume and every load is unconditional (an out-of-range candidate has
+    // weight 0): no data-dependent branch stands between the loads, so the 6 loads of a row and the rows of a plane
+    // overlap instead of each paying a full memory latency.
+    int Xc[6], Yc[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      Xc[t] = min(max(2 * x0 - 1 + t, 0), W - 1);
+      Yc[t] = min(max(2 * y0 - 1 + t, 0), H - 1);
+    }
+    float4 out[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i >> 2][(i >> 1) & 1][i & 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int tz = 0; tz < 6; ++tz) {
+      const int Z = min(max(2 * z0 - 1 + tz, 0), D - 1);
+      const long long zbase = ((long long)n * D + Z) * H;
+      float4 u[2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i >> 1][i & 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ty = 0; ty < 6; ++ty) {
+        const float* row = ddst + (zbase + Yc[ty]) * (long long)W * dstC + dstOff + g * 4;
+        float4 v[6];
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) v[tx] = __ldg(reinterpret_cast<const float4*>(row + (long long)Xc[tx] * dstC));
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) {
+          t0.x = fmaf(wx[tx][0], v[tx].x, t0.x); t0.y = fmaf(wx[tx][0], v[tx].y, t0.y); t0.z = fmaf(wx[tx][0], v[tx].z, t0.z); t0.w = fmaf(wx[tx][0], v[tx].w, t0.w);
+          t1.x = fmaf(wx[tx][1], v[tx].x, t1.x); t1.y = fmaf(wx[tx][1], v[tx].y, t1.y); t1.z = fmaf(wx[tx][1], v[tx].z, t1.z); t1.w = fmaf(wx[tx][1], v[tx].w, t1.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float a = wy[ty][j];
+          u[j][0].x = fmaf(a, t0.x, u[j][0].x); u[j][0].y = fmaf(a, t0.y, u[j][0].y); u[j][0].z = fmaf(a, t0.z, u[j][0].z); u[j][0].w = fmaf(a, t0.w, u[j][0].w);
+          u[j][1].x = fmaf(a, t1.x, u[j][1].x); u[j][1].y = fmaf(a, t1.y, u[j][1].y); u[j][1].z = fmaf(a, t1.z, u[j][1].z); u[j][1].w = fmaf(a, t1.w, u[j][1].w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float a = wz[tz][j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4& o = out[j][i >> 1][i & 1];
+          const float4 uu = u[i >> 1][i & 1];
+          o.x = fmaf(a, uu.x, o.x); o.y = fmaf(a, uu.y, o.y); o.z = fmaf(a, uu.z, o.z); o.w = fmaf(a, uu.w, o.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int z = z0 + (i >> 2), y = y0 + ((i >> 1) & 1), x = x0 + (i & 1);
+      if (z < d && y < h && x < w)
+        *reinterpret_cast<float4*>(dsrc + ((((long long)n * d + z) * h + y) * w + x) * C + g * 4) = out[i >> 2][(i >> 1) & 1][i & 1];
+    }
+  }
+}
+
 // copy the (centre-cropped) skip tensor into / out of channels [C1, C1+C2) of the concat buffer
 template <int VEC, bool BWD>
 __global__ void k_concat_skip(const float* __restrict__ in, float* __restrict__ out, int N, int D, int H, int W,
@@ -745,8 +835,15 @@ int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N
   const int D = 2 * d, H = 2 * h, W = 2 * w;
   DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_bwd: bad skip size");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_trilinear_bwd(dcat, dx, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);
-  if (rc) return rc;
+  if (C1 % 4 == 0 && C2 % 4 == 0 && (long long)N * d * h * w < (1ll << 31)) {
+    const long long blocks = (long long)N * ((d + 1) / 2) * ((h + 1) / 2) * ((w + 1) / 2);
+    k_up2x_adjoint<<<grid_fixed_group(blocks, C1 / 4, 128, 64), 128, 0, st>>>(dcat, dx, N, d, h, w, C1, C1 + C2, 0, ac_scale(d, D),
+                                                                           ac_scale(h, H), ac_scale(w, W));
+    DRAM_LAUNCH_CHECK();
+  } else {
+    int rc = launch_trilinear_bwd(dcat, dx, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);
+    if (rc) return rc;
+  }
   if (!dskip) return DRAM_OK;            // the caller reads dcat[..., C1:] in place (no crop: Ds == D etc.)
   int oz = ceil_half(Ds - D), oy = ceil_half(Hs - H), ox = ceil_half(Ws - W);
   long long vox = (long long)N * Ds * Hs * Ws;

@@ -4,6 +4,7 @@
 // convolution's TMA loads: the fp32 copy and the separate split pass do not exist (4 B/element either way).
 // hi + lo is exact in fp32 and carries 16-17 significant bits of the fp32 value it was split from.
 // All kernels are HBM-bound streams: 8 channels (2 x float4 in, one 16-byte store per plane) per thread.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dram {
@@ -38,27 +39,29 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------ BN + ReLU (+ pool) -> planes
-// y [rows][C] fp32 -> a planes [rows][Cpad]; channels [C, Cpad) are written as zeros
+// y [rows][C] fp32 -> a planes [rows][Cpad]; channels [C, Cpad) are written as zeros.
+// The launch guarantees (gridDim.x * blockDim.x) % groups == 0: a thread keeps its channel group.
 __global__ void __launch_bounds__(256)
 k_bn_relu_apply_planes(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                        uint4* __restrict__ hi, uint4* __restrict__ lo, long long rows, int C, int Cpad) {
   const int groups = Cpad / 8;
-  const long long total = rows * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long r = i / groups;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dr = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);
+  const bool real = g * 8 < C;
+  float sc[8], sh[8];
+  if (real) { load8(scale + g * 8, sc); load8(shift + g * 8, sh); }
+  for (long long r = tid / groups; r < rows; r += dr) {
     uint4 H = make_uint4(0, 0, 0, 0), L = make_uint4(0, 0, 0, 0);
-    if (g * 8 < C) {
-      float v[8], sc[8], sh[8];
+    if (real) {
+      float v[8];
       load8(y + r * C + g * 8, v);
-      load8(scale + g * 8, sc);
-      load8(shift + g * 8, sh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
       split8(v, H, L);
     }
-    hi[i] = H;
-    if (lo) lo[i] = L;
+    hi[r * groups + g] = H;
+    if (lo) lo[r * groups + g] = L;
   }
 }
 
@@ -70,17 +73,20 @@ k_bn_relu_pool_planes(const float* __restrict__ y, const float* __restrict__ sca
   const int groups = Cpad / 8;
   const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;   // cells incl. ragged tail
   const int pd = D / 2, ph = H / 2, pw = W / 2;                       // pooled size (floor)
-  const long long total = (long long)N * cd * ch * cw * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int x = (int)(r % cw); r /= cw;
-    const int yy = (int)(r % ch); r /= ch;
-    const int z = (int)(r % cd);
-    const int n = (int)(r / cd);
-    const bool real = g * 8 < C;
-    float sc[8], sh[8], mx[8];
-    if (real) { load8(scale + g * 8, sc); load8(shift + g * 8, sh); }
+  const long long cells = (long long)N * cd * ch * cw;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dcell = ((long long)gridDim.x * blockDim.x) / groups;   // launch: total threads % groups == 0
+  const int g = (int)(tid % groups);
+  const bool real = g * 8 < C;
+  float sc[8], sh[8];
+  if (real) { load8(scale + g * 8, sc); load8(shift + g * 8, sh); }
+  for (long long cell = tid / groups; cell < cells; cell += dcell) {
+    unsigned r = (unsigned)cell;                                        // cells < 2^31 (checked by the host)
+    const int x = (int)(r % (unsigned)cw); r /= (unsigned)cw;
+    const int yy = (int)(r % (unsigned)ch); r /= (unsigned)ch;
+    const int z = (int)(r % (unsigned)cd);
+    const int n = (int)(r / (unsigned)cd);
+    float mx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
 #pragma unroll
@@ -112,6 +118,8 @@ k_bn_relu_pool_planes(const float* __restrict__ y, const float* __restrict__ sca
 
 // ------------------------------------------------------------------------------------------------ BN + ReLU backward -> dy planes
 // RANK1: da[r][c] = g[r] * wtop[c] (fused RAM head), otherwise da rows are da_pitch floats apart.
+// dy = k1*dz - k2 - (y - mean)*k3 with per-channel constants folded once per thread (the launch guarantees
+// (gridDim.x * blockDim.x) % groups == 0, so a thread keeps its channel group).
 template <bool RANK1>
 __global__ void __launch_bounds__(256)
 k_bn_relu_bwd_apply_planes(const float* __restrict__ da, long long da_pitch, const float* __restrict__ wtop,
@@ -120,45 +128,51 @@ k_bn_relu_bwd_apply_planes(const float* __restrict__ da, long long da_pitch, con
                            const double* __restrict__ sums, double count, uint4* __restrict__ hi, uint4* __restrict__ lo,
                            long long rows, int C, int Cpad) {
   const int groups = Cpad / 8;
-  const long long total = rows * groups;
-  const float inv = sums ? (float)(1.0 / count) : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long r = i / groups;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dr = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);
+  const bool real = g * 8 < C;
+  float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8], wt[8];
+  if (real) {
+    const float inv = sums ? (float)(1.0 / count) : 0.f;
+    load8(scale + g * 8, sc);
+    load8(shift + g * 8, sh);
+    if (RANK1) load8(wtop + g * 8, wt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      if (sums) {
+        const float rs = rstd[c], gm = gamma ? gamma[c] : 1.f;
+        mu[j] = mean[c];
+        k1[j] = gm * rs;
+        k2[j] = gm * rs * ((float)sums[c] * inv);
+        k3[j] = gm * rs * rs * ((float)sums[C + c] * inv);
+      } else {
+        mu[j] = 0.f; k1[j] = sc[j]; k2[j] = 0.f; k3[j] = 0.f;
+      }
+    }
+  }
+  for (long long r = tid / groups; r < rows; r += dr) {
     uint4 H = make_uint4(0, 0, 0, 0), L = make_uint4(0, 0, 0, 0);
-    if (g * 8 < C) {
-      float yv[8], dv[8], sc[8], sh[8], o[8];
+    if (real) {
+      float yv[8], dv[8], o[8];
       load8(y + r * C + g * 8, yv);
-      load8(scale + g * 8, sc);
-      load8(shift + g * 8, sh);
       if (RANK1) {
         const float gr = __ldg(da + r);
-        load8(wtop + g * 8, dv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dv[j] *= gr;
+        for (int j = 0; j < 8; ++j) dv[j] = wt[j] * gr;
       } else {
         load8(da + r * da_pitch + g * 8, dv);
       }
-      if (sums) {
-        float mu[8], rs[8];
-        load8(mean + g * 8, mu);
-        load8(rstd + g * 8, rs);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = g * 8 + j;
-          const float dz = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? dv[j] : 0.f;
-          const float xh = (yv[j] - mu[j]) * rs[j];
-          const float gm = gamma ? __ldg(gamma + c) : 1.f;
-          o[j] = gm * rs[j] * (dz - (float)sums[c] * inv - xh * (float)sums[C + c] * inv);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? dv[j] * sc[j] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const float dz = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? dv[j] : 0.f;
+        o[j] = k1[j] * dz - k2[j] - (yv[j] - mu[j]) * k3[j];
       }
       split8(o, H, L);
     }
-    hi[i] = H;
-    if (lo) lo[i] = L;
+    hi[r * groups + g] = H;
+    if (lo) lo[r * groups + g] = L;
   }
 }
 
@@ -169,12 +183,13 @@ k_bn_relu_bwd_apply_planes(const float* __restrict__ da, long long da_pitch, con
 struct PoolCell {
   int n, z, y, x;
 };
-__device__ __forceinline__ PoolCell decode_cell(long long cell, int cd, int ch, int cw) {
+__device__ __forceinline__ PoolCell decode_cell(long long cell64, int cd, int ch, int cw) {
+  unsigned cell = (unsigned)cell64;                                     // cells < 2^31 (checked by the host)
   PoolCell c;
-  c.x = (int)(cell % cw); cell /= cw;
-  c.y = (int)(cell % ch); cell /= ch;
-  c.z = (int)(cell % cd);
-  c.n = (int)(cell / cd);
+  c.x = (int)(cell % (unsigned)cw); cell /= (unsigned)cw;
+  c.y = (int)(cell % (unsigned)ch); cell /= (unsigned)ch;
+  c.z = (int)(cell % (unsigned)cd);
+  c.n = (int)(cell / (unsigned)cd);
   return c;
 }
 
@@ -290,31 +305,34 @@ k_bn_pool_bwd_apply_planes(const float* __restrict__ ga, long long ga_pitch, con
                            int N, int D, int H, int W, int C, int Cpad) {
   const int groups = Cpad / 4;
   const int cd = (D + 1) / 2, ch = (H + 1) / 2, cw = (W + 1) / 2;
-  const long long total = (long long)N * cd * ch * cw * groups;
+  const long long cells = (long long)N * cd * ch * cw;
   const float inv = sums ? (float)(1.0 / count) : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const PoolCell pc = decode_cell(i / groups, cd, ch, cw);
-    const bool real = g * 4 < C;
-    float yv[8][4], dz[8][4], sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-    float k1[4], k2[4], k3[4], mu[4];          // dy = k1*dz - k2 - (y - mu)*k3
-    if (real) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dcell = ((long long)gridDim.x * blockDim.x) / groups;   // launch: total threads % groups == 0
+  const int g = (int)(tid % groups);
+  const bool real = g * 4 < C;
+  float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  float k1[4], k2[4], k3[4], mu[4];          // dy = k1*dz - k2 - (y - mu)*k3
+  if (real) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const int c = g * 4 + v;
-        sc[v] = scale[c]; sh[v] = shift[c];
-        if (sums) {
-          const float rs = rstd[c], gm = gamma ? gamma[c] : 1.f;
-          mu[v] = mean[c];
-          k1[v] = gm * rs;
-          k2[v] = gm * rs * (float)sums[c] * inv;
-          k3[v] = gm * rs * rs * (float)sums[C + c] * inv;
-        } else {
-          mu[v] = 0.f; k1[v] = sc[v]; k2[v] = 0.f; k3[v] = 0.f;
-        }
+    for (int v = 0; v < 4; ++v) {
+      const int c = g * 4 + v;
+      sc[v] = scale[c]; sh[v] = shift[c];
+      if (sums) {
+        const float rs = rstd[c], gm = gamma ? gamma[c] : 1.f;
+        mu[v] = mean[c];
+        k1[v] = gm * rs;
+        k2[v] = gm * rs * ((float)sums[c] * inv);
+        k3[v] = gm * rs * rs * ((float)sums[C + c] * inv);
+      } else {
+        mu[v] = 0.f; k1[v] = sc[v]; k2[v] = 0.f; k3[v] = 0.f;
       }
-      pool_window_dz(y, ga, ga_pitch, gp, pc, g, D, H, W, C, sc, sh, yv, dz);
     }
+  }
+  for (long long cell = tid / groups; cell < cells; cell += dcell) {
+    const PoolCell pc = decode_cell(cell, cd, ch, cw);
+    float yv[8][4], dz[8][4];
+    if (real) pool_window_dz(y, ga, ga_pitch, gp, pc, g, D, H, W, C, sc, sh, yv, dz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int zz = 2 * pc.z + (k >> 2), yy = 2 * pc.y + ((k >> 1) & 1), xx = 2 * pc.x + (k & 1);
@@ -345,14 +363,15 @@ k_upsample2x_concat_planes(const uint4* __restrict__ xh, const uint4* __restrict
                            int ox, float sz, float sy, float sx) {
   const int D = 2 * d, H = 2 * h, W = 2 * w;
   const int groups = Pc / 8, g1 = C1 / 8, g2 = (C1 + C2) / 8, pg1 = P1 / 8, pg2 = P2 / 8;
-  const long long total = (long long)N * D * H * W * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int X = (int)(r % W); r /= W;
-    const int Y = (int)(r % H); r /= H;
-    const int Z = (int)(r % D);
-    const int n = (int)(r / D);
+  const long long rows = (long long)N * D * H * W;
+  for (RowGroupIter it(groups); it.r < rows; it.next()) {
+    const int g = it.g;
+    const long long i = it.r * groups + g;
+    unsigned r = (unsigned)it.r;                                        // rows < 2^31 (checked by the host)
+    const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int Y = (int)(r % (unsigned)H); r /= (unsigned)H;
+    const int Z = (int)(r % (unsigned)D);
+    const int n = (int)(r / (unsigned)D);
     uint4 Hh = make_uint4(0, 0, 0, 0), Ll = make_uint4(0, 0, 0, 0);
     if (g < g1) {
       const Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h), lx = lerp_setup(X, sx, w);
@@ -381,15 +400,142 @@ k_upsample2x_concat_planes(const uint4* __restrict__ xh, const uint4* __restrict
   }
 }
 
+// Register-blocked variant: one thread produces the 2x2x2 block of output voxels (2k, 2k+1 per axis) of one 8-channel
+// group.  With align_corners=True and an exact factor 2 those outputs read source indices k-1, k, k+1 only, so the block
+// needs 27 source loads (3.4 per output instead of 8) and the axes are interpolated one after the other in registers.
+// Weights come from the same lerp_setup as every other trilinear kernel of the library.
+__global__ void __launch_bounds__(128)
+k_up2x_planes_blocked(const uint4* __restrict__ xh, const uint4* __restrict__ xl, uint4* __restrict__ ch_,
+                      uint4* __restrict__ cl, int N, int d, int h, int w, int C1, int P1, int Pc, float sz, float sy, float sx) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const int groups = C1 / 8, pg1 = P1 / 8, pgc = Pc / 8;
+  const long long blocks = (long long)N * d * h * w;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long db = ((long long)gridDim.x * blockDim.x) / groups;     // launch: total threads % groups == 0
+  const int g = (int)(tid % groups);
+  for (long long b = tid / groups; b < blocks; b += db) {
+    unsigned r = (unsigned)b;
+    const int kx = (int)(r % (unsigned)w); r /= (unsigned)w;
+    const int ky = (int)(r % (unsigned)h); r /= (unsigned)h;
+    const int kz = (int)(r % (unsigned)d);
+    const int n = (int)(r / (unsigned)d);
+    float wz[2][3], wy[2][3], wx[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const Lerp lz = lerp_setup(2 * kz + j, sz, d), ly = lerp_setup(2 * ky + j, sy, h), lx = lerp_setup(2 * kx + j, sx, w);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        wz[j][t] = (lz.i0 == kz - 1 + t ? lz.w0 : 0.f) + (lz.i1 == kz - 1 + t ? lz.w1 : 0.f);
+        wy[j][t] = (ly.i0 == ky - 1 + t ? ly.w0 : 0.f) + (ly.i1 == ky - 1 + t ? ly.w1 : 0.f);
+        wx[j][t] = (lx.i0 == kx - 1 + t ? lx.w0 : 0.f) + (lx.i1 == kx - 1 + t ? lx.w1 : 0.f);
+      }
+    }
+    // Source indices are clamped into the volume and every load is unconditional (an out-of-range candidate has weight
+    // 0), so the 9 x 2 loads of a z-plane are all in flight before the first one is consumed.
+    int xi[3], yi[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      xi[t] = min(max(kx - 1 + t, 0), w - 1);
+      yi[t] = min(max(ky - 1 + t, 0), h - 1);
+    }
+    float out[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[i][c] = 0.f;
+#pragma unroll
+    for (int tz = 0; tz < 3; ++tz) {
+      const int zi = min(max(kz - 1 + tz, 0), d - 1);
+      const long long zbase = ((long long)n * d + zi) * h;
+      uint4 A[3][3], B[3][3];
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+          const long long row = (zbase + yi[ty]) * w + xi[tx];
+          A[ty][tx] = __ldg(xh + row * pg1 + g);
+          B[ty][tx] = xl ? __ldg(xl + row * pg1 + g) : make_uint4(0, 0, 0, 0);
+        }
+      float u[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) u[i][c] = 0.f;
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        float t0[8], t1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t0[c] = t1[c] = 0.f;
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+          float v[8];
+          merge8(A[ty][tx], B[ty][tx], v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { t0[c] = fmaf(wx[0][tx], v[c], t0[c]); t1[c] = fmaf(wx[1][tx], v[c], t1[c]); }
+        }
+#pragma unroll
+        for (int jy = 0; jy < 2; ++jy)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            u[jy * 2 + 0][c] = fmaf(wy[jy][ty], t0[c], u[jy * 2 + 0][c]);
+            u[jy * 2 + 1][c] = fmaf(wy[jy][ty], t1[c], u[jy * 2 + 1][c]);
+          }
+      }
+#pragma unroll
+      for (int jz = 0; jz < 2; ++jz)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) out[jz * 4 + i][c] = fmaf(wz[jz][tz], u[i][c], out[jz * 4 + i][c]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int Z = 2 * kz + (i >> 2), Y = 2 * ky + ((i >> 1) & 1), X = 2 * kx + (i & 1);
+      const long long row = (((long long)n * D + Z) * H + Y) * W + X;
+      uint4 Hh, Ll;
+      split8(out[i], Hh, Ll);
+      ch_[row * pgc + g] = Hh;
+      if (cl) cl[row * pgc + g] = Ll;
+    }
+  }
+}
+
+// cat[..., C1:C1+C2] = skip (centre crop), cat[..., C1+C2:Pc] = 0: 16-byte chunks, one thread per (voxel, chunk)
+__global__ void __launch_bounds__(256)
+k_skip_copy_planes(const uint4* __restrict__ sh_, const uint4* __restrict__ sl, uint4* __restrict__ ch_, uint4* __restrict__ cl,
+                   int N, int D, int H, int W, int C1, int Ds, int Hs, int Ws, int C2, int P2, int Pc, int oz, int oy, int ox) {
+  const int g1 = C1 / 8, g2 = (C1 + C2) / 8, pg2 = P2 / 8, pgc = Pc / 8;
+  const int groups = pgc - g1;
+  const long long rows = (long long)N * D * H * W;
+  for (RowGroupIter it(groups); it.r < rows; it.next()) {
+    const int g = g1 + it.g;
+    uint4 Hh = make_uint4(0, 0, 0, 0), Ll = make_uint4(0, 0, 0, 0);
+    if (g < g2) {
+      long long srow = it.r;
+      if (oz | oy | ox | (Ds - D) | (Hs - H) | (Ws - W)) {
+        unsigned r = (unsigned)it.r;
+        const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+        const int Y = (int)(r % (unsigned)H); r /= (unsigned)H;
+        const int Z = (int)(r % (unsigned)D);
+        const int n = (int)(r / (unsigned)D);
+        srow = (((long long)n * Ds + Z + oz) * Hs + Y + oy) * Ws + X + ox;
+      }
+      Hh = __ldg(sh_ + srow * pg2 + (g - g1));
+      if (sl) Ll = __ldg(sl + srow * pg2 + (g - g1));
+    }
+    ch_[it.r * pgc + g] = Hh;
+    if (cl) cl[it.r * pgc + g] = Ll;
+  }
+}
+
 // planes [rows][P] -> fp32 [rows][C]  (materialises an activation for a consumer that is not a tensor-core convolution)
 __global__ void __launch_bounds__(256)
 k_merge_planes(const uint4* __restrict__ hi, const uint4* __restrict__ lo, float* __restrict__ out, long long rows, int C,
                int P) {
   const int groups = C / 8, pg = P / 8;
-  const long long total = rows * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long r = i / groups;
+  for (RowGroupIter it(groups); it.r < rows; it.next()) {
+    const int g = it.g;
+    const long long r = it.r;
     const uint4 a = __ldg(hi + r * pg + g);
     uint4 b = make_uint4(0, 0, 0, 0);
     if (lo) b = __ldg(lo + r * pg + g);
@@ -415,11 +561,12 @@ int dram_bn_relu_apply_planes(const float* y, const float* scale, const float* s
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)N * D * H * W;
   if (!p_hi) {
-    k_bn_relu_apply_planes<<<grid_for(rows * (Cpad / 8), 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo, rows, C, Cpad);
+    k_bn_relu_apply_planes<<<grid_fixed_group(rows, Cpad / 8, 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo, rows, C, Cpad);
   } else {
     DRAM_REQUIRE(D >= 2 && H >= 2 && W >= 2, "bn_relu_apply_planes: pooling needs every spatial size >= 2");
+    DRAM_REQUIRE(rows < (1ll << 31), "bn_relu_apply_planes: volume too large");
     const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
-    k_bn_relu_pool_planes<<<grid_for(cells * (Cpad / 8), 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo,
+    k_bn_relu_pool_planes<<<grid_fixed_group(cells, Cpad / 8, 256), 256, 0, st>>>(y, scale, shift, (uint4*)a_hi, (uint4*)a_lo,
                                                                             (uint4*)p_hi, (uint4*)p_lo, N, D, H, W, C, Cpad);
   }
   DRAM_LAUNCH_CHECK();
@@ -436,7 +583,7 @@ int dram_bn_relu_bwd_apply_planes(const float* da, long long da_pitch, const flo
   if (da_pitch == 0) da_pitch = C;
   DRAM_REQUIRE(wtop || (da_pitch >= C && da_pitch % 4 == 0), "bn_relu_bwd_apply_planes: da_pitch %lld invalid for C %d", da_pitch, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(rows * (Cpad / 8), 256);
+  const int grid = grid_fixed_group(rows, Cpad / 8, 256);
   if (wtop)
     k_bn_relu_bwd_apply_planes<true><<<grid, 256, 0, st>>>(da, 0, wtop, y, scale, shift, mean, rstd, gamma, sums, count,
                                                            (uint4*)dy_hi, (uint4*)dy_lo, rows, C, Cpad);
@@ -478,7 +625,7 @@ int dram_bn_pool_bwd_apply_planes(const float* ga, long long ga_pitch, const flo
   if (ga_pitch == 0) ga_pitch = C;
   DRAM_REQUIRE(ga_pitch >= C && ga_pitch % 4 == 0, "bn_pool_bwd_apply_planes: ga_pitch %lld invalid for C %d", ga_pitch, C);
   const long long cells = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
-  k_bn_pool_bwd_apply_planes<<<grid_for(cells * (Cpad / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+  k_bn_pool_bwd_apply_planes<<<grid_fixed_group(cells, Cpad / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       ga, ga_pitch, gp, y, scale, shift, mean, rstd, gamma, sums, count, (uint2*)dy_hi, (uint2*)dy_lo, N, D, H, W, C, Cpad);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
@@ -497,6 +644,20 @@ int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void
   const int D = 2 * d, H = 2 * h, W = 2 * w;
   DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_planes: skip (%d,%d,%d) smaller than upsampled (%d,%d,%d)", Ds, Hs, Ws, D, H, W);
   const long long total = (long long)N * D * H * W * (Pc / 8);
+  DRAM_REQUIRE((long long)N * D * H * W < (1ll << 31), "upsample2x_concat_planes: volume too large");
+  static const bool blocked = getenv("DRAM_UP2X_SIMPLE") == nullptr;
+  if (blocked) {
+    cudaStream_t st = (cudaStream_t)stream;
+    k_up2x_planes_blocked<<<grid_fixed_group((long long)N * d * h * w, C1 / 8, 128, 64), 128, 0, st>>>(
+        (const uint4*)x_hi, (const uint4*)x_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d, h, w, C1, P1, Pc, ac_scale(d, D),
+        ac_scale(h, H), ac_scale(w, W));
+    DRAM_LAUNCH_CHECK();
+    k_skip_copy_planes<<<grid_for((long long)N * D * H * W * ((Pc - C1) / 8), 256), 256, 0, st>>>(
+        (const uint4*)skip_hi, (const uint4*)skip_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, D, H, W, C1, Ds, Hs, Ws, C2, P2, Pc,
+        ceil_half_(Ds - D), ceil_half_(Hs - H), ceil_half_(Ws - W));
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   k_upsample2x_concat_planes<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)x_hi, (const uint4*)x_lo, (const uint4*)skip_hi, (const uint4*)skip_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d,
       h, w, C1, P1, Ds, Hs, Ws, C2, P2, Pc, ceil_half_(Ds - D), ceil_half_(Hs - H), ceil_half_(Ws - W), ac_scale(d, D),
