@@ -453,6 +453,179 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, kw-reuse (Cout <= 64)
+// For the 64-channel layers of the 80^3 / 40^3 levels the generic kernel above is bound by the L2 -> shared-memory fill:
+// an N = 64 tile needs 48 KB of operands per 384 tensor-pipe cycles (125 B/cycle/SM).  Here one work item owns up to SIX
+// 64-row blocks of dW — the three kw taps of two "sources" (kd, kh, 64-channel block) — over a slab of voxel chunks:
+//   * a chunk is 8(w) x 8(h) voxels of one (n, d) plane, its rows ordered [w][h] (tensor map with H before W), so that a
+//     kw shift is exactly one 8-row / 1024-byte swizzle group: ONE halo box of 10 x 8 voxels per source serves its three
+//     taps as three descriptor start addresses 1024 B apart;
+//   * the dY tile of the chunk is loaded once and reused by all six blocks;
+//   * the six blocks form three M = 128 tiles (blocks b, b+1 are LBO bytes apart: 1024 inside a source, 8192 across the
+//     two), each accumulating X_hi^T x [dY_hi | dY_lo] (N = 128) + X_lo^T x dY_hi (N = 64) in its own 128 TMEM columns.
+// 56 KB of operands per 1152 tensor-pipe cycles = 50 B/cycle/SM.  Partial tiles go to the workspace
+// [item][tile][128][64] and k_wgrad_w3_reduce sums the slabs in a fixed order (deterministic).
+constexpr int kW3XBox = 10 * 8 * 128;           // one halo box: 10 w-columns x 8 h-rows x 128 B
+constexpr int kW3YBox = 8 * 8 * 128;            // one dY tile
+constexpr int kW3Stage = 4 * kW3XBox + 2 * kW3YBox;
+
+struct Wg3Params {
+  float* ws;
+  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                     const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                     const Wg3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * kW3Stage);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), tfull = smem_u32(bars + 2 * S),
+                 tempty = smem_u32(bars + 2 * S + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t offXlo = 2 * kW3XBox, offYhi = 4 * kW3XBox, offYlo = 4 * kW3XBox + kW3YBox;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = p.n_slabs * p.n_pairs;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pair = item % p.n_pairs, slab = item / p.n_pairs;
+        const int nsrc = (2 * pair + 1 < p.n_src) ? 2 : 1;
+        const uint32_t tx = 2u * (uint32_t)nsrc * kW3XBox + 2u * kW3YBox;
+        int kd[2], kh[2], cb[2];
+        for (int j = 0; j < 2; ++j) {
+          const int s = min(2 * pair + j, p.n_src - 1);
+          cb[j] = s % p.CB; kh[j] = (s / p.CB) % 3; kd[j] = s / (3 * p.CB);
+        }
+        const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+          int t = ch;
+          const int w0 = (t % p.tiles_w) * 8; t /= p.tiles_w;
+          const int h0 = (t % p.tiles_h) * 8; t /= p.tiles_h;
+          const int d0 = t % p.D;
+          const int n0 = t / p.D;
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t sb = smem_u32(smem + (size_t)s * kW3Stage), fb = full0 + 8 * s;
+          mbar_expect_tx(fb, tx);
+          for (int j = 0; j < nsrc; ++j) {           // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
+            tma_load_5d(sb + j * kW3XBox, &tmX_hi, fb, cb[j] * 64, h0 + kh[j] - 1, w0 - 1, d0 + kd[j] - 1, n0);
+            tma_load_5d(sb + offXlo + j * kW3XBox, &tmX_lo, fb, cb[j] * 64, h0 + kh[j] - 1, w0 - 1, d0 + kd[j] - 1, n0);
+          }
+          tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
+          tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(64, 1, 1), idesc2 = umma_idesc(128, 1, 1);
+      // block b = src*3 + kw sits at src*kW3XBox + kw*1024; tile t = blocks (2t, 2t+1)
+      const uint32_t tile_off[3] = {0u, 2048u, (uint32_t)kW3XBox + 1024u};
+      const uint32_t tile_lbo[3] = {1024u, (uint32_t)kW3XBox - 2048u, 1024u};
+      uint32_t it = 0, icount = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+        const int pair = item % p.n_pairs, slab = item / p.n_pairs;
+        const int ntiles = (2 * pair + 1 < p.n_src) ? 3 : 2;
+        const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        mbar_wait(tempty, (icount & 1) ^ 1);
+        tc_fence_after();
+        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (size_t)s * kW3Stage);
+          const uint64_t b_hi = umma_desc(sb + offYhi, kW3YBox, 1024);      // [dY_hi | dY_lo]: lo is LBO = 8192 B behind hi
+          for (int t = 0; t < ntiles; ++t) {
+            const uint64_t a_hi = umma_desc(sb + tile_off[t], tile_lbo[t], 1024);
+            const uint64_t a_lo = umma_desc(sb + offXlo + tile_off[t], tile_lbo[t], 1024);
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {               // 16 voxel rows (two w columns, 2048 B) per MMA
+              const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, (ch > c_begin || k) ? 1u : 0u);
+              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t icount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+      const int pair = item % p.n_pairs;
+      const int ntiles = (2 * pair + 1 < p.n_src) ? 3 : 2;
+      mbar_wait(tfull, icount & 1);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) {
+        float* out = p.ws + (((long long)item * 3 + t) * 128 + row) * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 128u;
+        const bool valid = (t < 2) || (ntiles == 3);         // the last tile of a single-source item has no second block
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16], r2[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld16(taddr + 64 + c0, r2);
+          tmem_ld_wait();
+          if (valid || row < 64) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(out + c0 + j) =
+                  make_float4(__uint_as_float(r[j]) + __uint_as_float(r2[j]), __uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]),
+                              __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// dw[co][ci][tap] = sum_slab ws[slab*n_pairs + pair][tile][row][co]
+__global__ void k_wgrad_w3_reduce(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int CB, int n_pairs,
+                                  int n_slabs) {
+  const long long total = 27ll * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int ci = (int)(r % Cin), tap = (int)(r / Cin);
+    const int kw = tap % 3, g = tap / 3;                 // g = kd*3 + kh
+    const int s = g * CB + ci / 64;
+    const int pair = s >> 1, b = (s & 1) * 3 + kw;
+    const int tile = b >> 1, row = (b & 1) * 64 + (ci & 63);
+    const float* src = ws + (((long long)pair * 3 + tile) * 128 + row) * 64 + co;
+    const long long slab_stride = (long long)n_pairs * 3 * 128 * 64;
+    float acc = 0.f;
+    for (int sl = 0; sl < n_slabs; ++sl) acc += src[sl * slab_stride];
+    dw[((long long)co * Cin + ci) * 27 + tap] = acc;
+  }
+}
+
 // dw[co][ci][tap] = sum_slab ws[slab][mt][nt][row][n]   (fixed summation order => deterministic)
 __global__ void k_wgrad_reduce(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int taps, int CB,
                                int n_mtiles, int n_ntiles, int BN, int n_slabs) {
@@ -722,13 +895,57 @@ static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int 
   return DRAM_OK;
 }
 
+// kw-reuse plan: slabs chosen so that the static round-robin schedule (item i -> CTA i % 148; a single-source item costs
+// 2 tiles, a full one 3) has the shortest makespan; more slabs cost workspace and reduction time.
+static bool wgrad_w3_ok(int H, int W, int Cout_pad, int ksize, int passes) {
+  static const bool allow = getenv("DRAM_WGRAD_NO_W3") == nullptr;
+  return allow && ksize == 3 && Cout_pad == 64 && passes == 3 && H % 8 == 0 && W % 8 == 0;
+}
+static void wgrad_w3_plan(Wg3Params& p, int N, int D, int H, int W, int Cin_pad) {
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.CB = Cin_pad / 64; p.n_src = 9 * p.CB; p.n_pairs = (p.n_src + 1) / 2;
+  p.tiles_w = W / 8; p.tiles_h = H / 8;
+  p.n_chunks = p.tiles_w * p.tiles_h * D * N;
+  const bool odd = p.n_src & 1;
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_slabs = p.n_chunks / 16 < 128 ? (p.n_chunks / 16 > 1 ? p.n_chunks / 16 : 1) : 128;
+  for (int sl = 1; sl <= max_slabs; ++sl) {
+    const int cps = cdiv(p.n_chunks, sl), ns = cdiv(p.n_chunks, cps);
+    const long long items = (long long)ns * p.n_pairs;
+    double worst = 0.0;
+    const int ctas = items < kNumSMs ? (int)items : kNumSMs;
+    for (int c = 0; c < ctas; ++c) {
+      double load = 0.0;
+      for (long long it = c; it < items; it += ctas) {
+        const int pair = (int)(it % p.n_pairs), slab = (int)(it / p.n_pairs);
+        const int chunks = slab == ns - 1 ? p.n_chunks - (ns - 1) * cps : cps;
+        load += (double)chunks * ((odd && pair == p.n_pairs - 1) ? 2.0 : 3.0) + 40.0;   // + epilogue / pipeline fill
+      }
+      if (load > worst) worst = load;
+    }
+    const double cost = worst * (1.0 + 0.002 * sl);
+    if (cost < best_cost) { best_cost = cost; best = sl; }
+  }
+  p.chunks_per_slab = cdiv(p.n_chunks, best);
+  p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
+  p.stages = (kSmemBudget - 1024) / kW3Stage;
+}
+
 size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize) {
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin_pad <= 0 || Cin_pad % 64 || Cout_pad <= 0 || Cout_pad % 64 ||
       (ksize != 1 && ksize != 3))
     return 0;
+  size_t w3 = 0;
+  if (wgrad_w3_ok(H, W, Cout_pad, ksize, 3)) {
+    Wg3Params q;
+    wgrad_w3_plan(q, N, D, H, W, Cin_pad);
+    w3 = (size_t)q.n_slabs * q.n_pairs * 3 * 128 * 64 * sizeof(float);
+  }
   WgParams p;
   wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, 3);
-  return (size_t)p.n_slabs * p.n_mtiles * p.n_ntiles * 128 * p.BN * sizeof(float);
+  const size_t generic = (size_t)p.n_slabs * p.n_mtiles * p.n_ntiles * 128 * p.BN * sizeof(float);
+  return generic > w3 ? generic : w3;
 }
 
 int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* dw,
@@ -739,6 +956,27 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_wgrad: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin > 0 && Cin_pad >= Cin && Cin_pad % 64 == 0 && Cout > 0 && Cout_pad >= Cout && Cout_pad % 64 == 0,
                "conv3d_umma_wgrad: channel pads must be multiples of 64 (Cin %d/%d, Cout %d/%d)", Cin, Cin_pad, Cout, Cout_pad);
+  if (wgrad_w3_ok(H, W, Cout_pad, ksize, dy_lo ? 3 : 1)) {
+    Wg3Params q;
+    wgrad_w3_plan(q, N, D, H, W, Cin_pad);
+    q.ws = (float*)workspace;
+    CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo;
+    int rc3;
+    if ((rc3 = make_volume_map(&mX_hi, x_hi, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
+    if ((rc3 = make_volume_map(&mX_lo, x_lo, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
+    if ((rc3 = make_volume_map(&mY_hi, dy_hi, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3;
+    if ((rc3 = make_volume_map(&mY_lo, dy_lo, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3;
+    const size_t smem3 = (size_t)q.stages * kW3Stage + 1024 + 256;
+    static std::once_flag once3;
+    std::call_once(once3, [] { cudaFuncSetAttribute(k_conv_umma_wgrad_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const int items3 = q.n_slabs * q.n_pairs;
+    cudaStream_t st3 = (cudaStream_t)stream;
+    k_conv_umma_wgrad_w3<<<items3 < kNumSMs ? items3 : kNumSMs, kFwdThreads, smem3, st3>>>(mX_hi, mX_lo, mY_hi, mY_lo, q);
+    DRAM_LAUNCH_CHECK();
+    k_wgrad_w3_reduce<<<grid_for(27ll * Cin * Cout, 256), 256, 0, st3>>>(q.ws, dw, Cout, Cin, q.CB, q.n_pairs, q.n_slabs);
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   WgParams p;
   wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, dy_lo ? 3 : 1);
   DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_wgrad: pipeline does not fit in shared memory");

@@ -150,7 +150,11 @@ def test_conv_umma_dgrad(N, Cin, Cout, S, k):
     assert_close(dx, x.grad, TOL_X3, "conv_umma dgrad")
 
 
-@pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES + [(8, 256, 512, (10, 10, 10), 3), (3, 64, 64, (12, 20, 16), 3)])
+@pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES + [
+    (8, 256, 512, (10, 10, 10), 3), (3, 64, 64, (12, 20, 16), 3),
+    (2, 128, 48, (6, 16, 24), 3),      # kw-reuse wgrad: Cout padded 48 -> 64, even number of (kd,kh,channel-block) sources
+    (4, 64, 64, (8, 40, 40), 3),       # kw-reuse wgrad: several voxel slabs, odd number of sources (single-source last item)
+])
 @pytest.mark.parametrize("three", [True, False])
 def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
     o = ops()

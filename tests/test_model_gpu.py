@@ -286,9 +286,12 @@ def test_cuda_graph_training_steps_match_eager(monkeypatch):
             assert abs(a - b) <= 2e-3 * abs(b), (mode, finals[mode][0], ref_losses)
     for a, b in zip(finals["0"][0], finals["1"][0]):
         assert abs(a - b) <= 1e-4 * abs(a), (finals["0"][0], finals["1"][0])
+    # Adam turns every gradient into a step of ~lr whatever its size, so last-bit differences between the two runs (the
+    # order of the double/float atomics in the BatchNorm and first-layer reductions) can move a parameter whose gradient
+    # is ~0 by up to lr per step: bound the drift by a fraction of that budget, not by rounding error
     for k, v in finals["0"][1].items():
         if v.is_floating_point():
-            assert_close(finals["1"][1][k], v, 2e-3, k)
+            assert_close(finals["1"][1][k], v, 1e-2, k)
         else:
             assert torch.equal(finals["1"][1][k], v), k
     assert rel_err(finals["1"][2], finals["0"][2]) <= 1e-3
