@@ -121,9 +121,10 @@ class LesionSegChunkTrain(JobRunner):
         "meta": {"cle": [...]}} -> (loss tensor, loss tuple).  Includes the H2D copy, backward, gradient all-reduce
         (data parallel) and the optimizer step; does NOT sync with the host.
 
-        Single-GPU steps with a stable batch shape are captured once into a CUDA graph (after `GRAPH_WARMUP_STEPS` eager
-        steps) and replayed, so the ~500 kernel launches of a step cost one launch and host jitter cannot starve the
-        GPU; set DRAM_CUDA_GRAPH=0 to stay eager.  The returned tensors are then the graph's static outputs."""
+        Steps with a stable batch shape are captured once into a CUDA graph (after `GRAPH_WARMUP_STEPS` eager steps) —
+        under data parallelism together with their NCCL all-reduces — and replayed, so the ~800 kernel launches of a
+        step cost one launch and host jitter cannot starve the GPU; set DRAM_CUDA_GRAPH=0 to stay eager.  The returned
+        tensors are then the graph's static outputs."""
         self.model.train()
         dev = torch.device("cuda", torch.cuda.current_device())
         metas = batch_data["meta"]
@@ -132,7 +133,7 @@ class LesionSegChunkTrain(JobRunner):
             if hasattr(self.loss_func, "label_tensors") else None
         srcs = [batch_data[k] for k in ("#image", "#lobe_reference", "#pseudo_lesion_reference")]
         key = tuple(tuple(t.shape) for t in srcs)
-        use_graph = (os.environ.get("DRAM_CUDA_GRAPH", "1") == "1" and self.reducer is None and labels is not None)
+        use_graph = os.environ.get("DRAM_CUDA_GRAPH", "1") == "1" and labels is not None
         self.current_iteration += 1
         if not use_graph or self._graph_key not in (None, key):
             self._graph = None
@@ -161,7 +162,10 @@ class LesionSegChunkTrain(JobRunner):
             from dram_native import functional as _DF
             _DF.WEIGHTS.invalidate()              # the weight re-pack kernels must be part of the captured step
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # data parallel: the NCCL all-reduces (BatchNorm sums, gradient buckets, loss normalisers) are captured with
+            # the step; NCCL's watchdog thread polls events meanwhile, hence the thread-local capture mode
+            mode = "thread_local" if self.reducer is not None else "global"
+            with torch.cuda.graph(graph, capture_error_mode=mode):
                 self._static_out = self._step_body(*self._static_in, ctsses, metas, self._static_labels)
             self.kernels_per_step = _dlib.PROFILE.launches - launches0             # libdram_b200 kernels in one step
             _dlib.PROFILE.enabled = was_profiling
