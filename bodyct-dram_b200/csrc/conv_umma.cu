@@ -298,6 +298,253 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ forward / dgrad, weight-sharing tile pairs
+// ncu on k_conv_umma_fwd (profiles/r01_conv_fwd_us2c0_ncu_full.md): tensor pipe 44 % active, HBM 5 %, and
+// l1tex__m_xbar2l1tex_read_bytes = 9.2 TB/s = 34.5 B/cycle/SM, i.e. the kernel sits on the chip-wide L2 -> SM limit
+// (~6300 B/cycle).  Per 128-voxel tile and (kd,kh,channel block) it pulls 37 KB of activations but 49 KB of weights.
+// This kernel halves the weight traffic and keeps the kw reuse of the activations:
+//   * a work item is a PAIR of M tiles (two accumulators in TMEM) that share every weight tile;
+//   * activations and weights travel through separate rings: an "A stage" holds the halo boxes of both tiles for one
+//     (kd,kh,channel block) and serves the three kw taps through descriptor offsets; a "B stage" holds the weights of one tap;
+//   * the tile is 8(h) x TDD(d) x TW(w) voxels with TDD*TW = 16, loaded through a tensor map with dimension order
+//     (C,H,D,W,N): shared-memory rows are ordered [w][d][h], every (w,d) column is one 8-row / 1024-byte swizzle group
+//     and a kw shift is TDD*1024 bytes, so (TW,TDD) = (16,1) covers W % 16 == 0 and (8,2) covers the 40^3 level.
+// L2 bytes per tile and 3 taps: 37 + 3*B/2 KB against 3*(32 + B) KB (generic) or 37 + 3*B KB (kw reuse only).
+// Accumulators: 2 sets x 2 tiles x <= 128 columns.  BN <= 64 keeps the [B_hi | B_lo] N-concatenation; BN = 96 / 128
+// issues hi*hi, hi*lo, lo*hi as three N = BN MMAs into the same columns.
+struct Fwd2Params {
+  float* y;
+  const float* scale;
+  const float* shift;
+  int N, D, H, W, Cout, BN, kblocks_c;
+  int TW, TDD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles, n_items;
+  int SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes, acc_cols, tmem_cols;
+  long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
+};
+
+// One lane of a fully converged warp.  The loops around the TMA / MMA issue stay warp-uniform and only the issue itself
+// is predicated on this: with `if (lane == 0)` around the whole loop nest the compiler keeps descriptors in vector
+// registers and wraps every UTCHMMA / UTMALDG in a waterfall loop (R2UR + ELECT + BRA.ANY, ~70 issue cycles per MMA),
+// which made the single issuing thread the bottleneck of every N <= 128 MMA sequence.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// MODE 0: one pass (bf16); 1: split-bf16 with the [B_hi | B_lo] N-concatenation (BN <= 64); 2: split-bf16, three N = BN MMAs
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const Fwd2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool three = MODE != 0, concat = MODE == 1;
+  const int SB = p.SB;
+  uint8_t* smemB = smem + 2 * (size_t)p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)SB * p.b_stage_bytes);
+  const uint32_t fullA0 = smem_u32(bars), emptyA0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6),
+                 fullB0 = smem_u32(bars + 8), emptyB0 = smem_u32(bars + 8 + SB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * SB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smemA_u = smem_u32(smem), smemB_u = smem_u32(smemB);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1);
+      mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4);
+    }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
+      if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    }
+    constexpr uint32_t planes = three ? 2u : 1u;
+    const uint32_t b_tx = planes * (uint32_t)p.BN * 128u;
+    uint32_t itA = 0, sB = 0, phB = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int nt = item % p.n_ntiles, pair = item / p.n_ntiles;
+      const int ntile = (2 * pair + 1 < p.n_mtiles) ? 2 : 1;
+      int mt0 = 2 * pair, mt1 = min(2 * pair + 1, p.n_mtiles - 1);
+      const int w00 = (mt0 % p.tiles_w) * p.TW - 1; mt0 /= p.tiles_w;
+      const int h00 = (mt0 % p.tiles_h) * 8 - 1; mt0 /= p.tiles_h;
+      const int d00 = (mt0 % p.tiles_d) * p.TDD - 1;
+      const int n0 = mt0 / p.tiles_d;
+      const int w01 = (mt1 % p.tiles_w) * p.TW - 1; mt1 /= p.tiles_w;
+      const int h01 = (mt1 % p.tiles_h) * 8 - 1; mt1 /= p.tiles_h;
+      const int d01 = (mt1 % p.tiles_d) * p.TDD - 1;
+      const int n1 = mt1 / p.tiles_d;
+      const uint32_t a_tx = (uint32_t)ntile * planes * (uint32_t)p.a_plane_bytes;
+      for (int g = 0; g < 9; ++g) {
+        const int kd = g / 3, kh = g - 3 * kd;
+        for (int cb = 0; cb < p.kblocks_c; ++cb, ++itA) {
+          const uint32_t sA = itA & 1;
+          mbar_wait(emptyA0 + 8 * sA, ((itA >> 1) & 1) ^ 1);
+          if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
+            const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes, fa = fullA0 + 8 * sA;
+            mbar_expect_tx(fa, a_tx);
+            tma_load_5d(ab, &tmA_hi, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
+            if (three) tma_load_5d(ab + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
+            if (ntile == 2) {
+              tma_load_5d(ab + p.a_tile_bytes, &tmA_hi, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
+              if (three) tma_load_5d(ab + p.a_tile_bytes + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(emptyB0 + 8 * sB, phB ^ 1);
+            if (elect_one()) {
+              const uint32_t bb = smemB_u + sB * (uint32_t)p.b_stage_bytes, fb = fullB0 + 8 * sB;
+              mbar_expect_tx(fb, b_tx);
+              const int brow = (g * 3 + kw) * p.Cout + nt * p.BN;
+              tma_load_2d(bb, &tmB_hi, fb, cb * 64, brow);
+              if (three) tma_load_2d(bb + p.BN * 128, &tmB_lo, fb, cb * 64, brow);
+            }
+            __syncwarp();
+            if (++sB == (uint32_t)SB) { sB = 0; phB ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    const uint32_t idesc = umma_idesc(p.BN, 0, 0), idesc2 = umma_idesc(2 * p.BN, 0, 0);
+    const uint32_t kw_shift = (uint32_t)p.TDD * 1024u;
+    const int n_g = 9 * p.kblocks_c;
+    uint32_t itA = 0, sB = 0, phB = 0, icount = 0;
+    long long t_te = 0, t_fa = 0, t_fb = 0, t0 = 0, t_start = clock64();
+    const bool prof = p.prof != nullptr;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+      const int pair = item / p.n_ntiles;
+      const int ntile = (2 * pair + 1 < p.n_mtiles) ? 2 : 1;
+      const uint32_t set = icount & 1;
+      if (prof) t0 = clock64();
+      mbar_wait(tempty0 + 8 * set, ((icount >> 1) & 1) ^ 1);
+      if (prof) t_te += clock64() - t0;
+      tc_fence_after();
+      const uint32_t d_set = tmem_base + set * 2u * (uint32_t)p.acc_cols;
+      for (int g = 0; g < n_g; ++g, ++itA) {
+        const uint32_t sA = itA & 1;
+        if (prof) t0 = clock64();
+        mbar_wait(fullA0 + 8 * sA, (itA >> 1) & 1);
+        if (prof) t_fa += clock64() - t0;
+        tc_fence_after();
+        const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if (prof) t0 = clock64();
+          mbar_wait(fullB0 + 8 * sB, phB);
+          if (prof) t_fb += clock64() - t0;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bb = smemB_u + sB * (uint32_t)p.b_stage_bytes;
+            const uint64_t b_hi = umma_desc(bb, 16, 1024), b_lo = umma_desc(bb + (uint32_t)p.BN * 128u, 16, 1024);
+            for (int j = 0; j < ntile; ++j) {
+              const uint32_t aj = ab + (uint32_t)j * (uint32_t)p.a_tile_bytes + (uint32_t)kw * kw_shift;
+              const uint64_t a_hi = umma_desc(aj, 16, 1024), a_lo = umma_desc(aj + (uint32_t)p.a_plane_bytes, 16, 1024);
+              const uint32_t d_tmem = d_set + (uint32_t)j * (uint32_t)p.acc_cols;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {          // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                const uint64_t adv = (uint64_t)(k * 2);
+                const uint32_t accum = (g | kw | k) ? 1u : 0u;
+                if (concat) {
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
+                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                } else {
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+                  if (three) {
+                    umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                  }
+                }
+              }
+            }
+            umma_commit(emptyB0 + 8 * sB);             // frees the weight stage when these MMAs retire
+            if (kw == 2) umma_commit(emptyA0 + 8 * sA);
+            if (kw == 2 && g == n_g - 1) umma_commit(tfull0 + 8 * set);   // accumulators complete -> epilogue
+          }
+          __syncwarp();
+          if (++sB == (uint32_t)SB) { sB = 0; phB ^= 1; }
+        }
+      }
+    }
+    if (prof && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 8;
+      o[0] = clock64() - t_start; o[1] = t_te; o[2] = t_fa; o[3] = t_fb;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> fp32 channels-last
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row / (8 * p.TDD), tdd = (row >> 3) % p.TDD, th = row & 7;
+    uint32_t icount = 0;
+    long long e_wait = 0, e_work = 0, e0 = 0;
+    const bool prof = p.prof != nullptr;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+      const int nt = item % p.n_ntiles, pair = item / p.n_ntiles;
+      const int ntile = (2 * pair + 1 < p.n_mtiles) ? 2 : 1;
+      const uint32_t set = icount & 1;
+      if (prof) e0 = clock64();
+      mbar_wait(tfull0 + 8 * set, (icount >> 1) & 1);
+      if (prof) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
+      tc_fence_after();
+      for (int j = 0; j < ntile; ++j) {
+        int mt = 2 * pair + j;
+        const int w = (mt % p.tiles_w) * p.TW + tw; mt /= p.tiles_w;
+        const int h = (mt % p.tiles_h) * 8 + th; mt /= p.tiles_h;
+        const int d = (mt % p.tiles_d) * p.TDD + tdd;
+        const int n = mt / p.tiles_d;
+        float* out = p.y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * p.Cout + nt * p.BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * 2u + (uint32_t)j) * (uint32_t)p.acc_cols;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          uint32_t r[16], r2[16];
+          tmem_ld16(taddr + c0, r);
+          if (concat) tmem_ld16(taddr + p.BN + c0, r2);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            v[jj] = concat ? __uint_as_float(r[jj]) + __uint_as_float(r2[jj]) : __uint_as_float(r[jj]);
+          if (p.scale) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = nt * p.BN + c0 + jj;
+              v[jj] = fmaxf(fmaf(v[jj], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 4)
+            *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+      if (prof) e_work += clock64() - e0;
+    }
+    if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 4] = e_wait; p.prof[blockIdx.x * 8 + 5] = e_work; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 constexpr int kWgKV = 64;                       // voxels per K chunk (one TMA box)
 constexpr int kWgBlkBytes = kWgKV * 128;        // one 64-voxel x 64-channel MN-major block
@@ -744,6 +991,22 @@ static int make_weight_map(CUtensorMap* m, const void* base, long long rows, int
   return DRAM_OK;
 }
 
+// 5-D map with dimension order (C,H,D,W,N) over the same channels-last volume: box = (64 channels, 8 h, bd, bw, 1);
+// shared-memory rows are ordered [w][d][h] (k_conv_umma_fwd2)
+static int make_volume_map_hdw(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bw, int bd) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DRAM_E_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)W, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {64, 8, (cuuint32_t)bd, (cuuint32_t)bw, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(volume hdw %dx%dx%dx%dx%d box %dx%d) failed: %d", N, D, H, W, C, bd, bw, (int)r); return DRAM_E_CUDA; }
+  return DRAM_OK;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // output tile (TW,TH,TD), TW*TH*TD <= 128, maximising the fraction of useful MMA rows
@@ -815,6 +1078,66 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin_pad > 0 && Cin_pad % 64 == 0, "conv3d_umma_fwd: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  // weight-sharing tile pairs (k_conv_umma_fwd2) wherever the volume tiles into 8(h) x TDD(d) x TW(w) boxes
+  static const bool allow_v2 = getenv("DRAM_CONV_NO_V2") == nullptr;
+  if (allow_v2 && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) && Cout % 32 == 0) {
+    Fwd2Params q;
+    q.BN = Cout <= 64 ? Cout : (Cout % 128 == 0 ? 128 : (Cout % 96 == 0 ? 96 : (Cout % 64 == 0 ? 64 : 32)));
+    const int mode = !x_lo ? 0 : (q.BN <= 64 ? 1 : 2);
+    q.acc_cols = mode == 1 ? 2 * q.BN : q.BN;
+    q.tmem_cols = pow2_cols(4 * q.acc_cols);
+    q.y = y; q.scale = scale; q.shift = shift;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64;
+    if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
+    q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
+    q.n_mtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
+    q.n_ntiles = Cout / q.BN;
+    q.n_items = cdiv(q.n_mtiles, 2) * q.n_ntiles;
+    q.a_plane_bytes = (q.TW + 2) * q.TDD * 1024;
+    q.a_tile_bytes = (x_lo ? 2 : 1) * q.a_plane_bytes;
+    q.a_stage_bytes = 2 * q.a_tile_bytes;
+    q.b_stage_bytes = (x_lo ? 2 : 1) * q.BN * 128;
+    const int smem_max = 227 * 1024;
+    q.SB = (smem_max - 1024 - 512 - 2 * q.a_stage_bytes) / q.b_stage_bytes;
+    if (q.SB > 8) q.SB = 8;
+    DRAM_REQUIRE(q.SB >= 2 && q.tmem_cols <= 512, "conv3d_umma_fwd: tile-pair pipeline does not fit (SB=%d, tmem=%d)", q.SB, q.tmem_cols);
+    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+    int rc2;
+    if ((rc2 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
+    if ((rc2 = make_weight_map(&mB_hi, w_hi, 27ll * Cout, Cin_pad, q.BN))) return rc2;
+    if (x_lo) {
+      if ((rc2 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
+      if ((rc2 = make_weight_map(&mB_lo, w_lo, 27ll * Cout, Cin_pad, q.BN))) return rc2;
+    } else {
+      mA_lo = mA_hi; mB_lo = mB_hi;
+    }
+    const size_t smem2 = 2 * (size_t)q.a_stage_bytes + (size_t)q.SB * q.b_stage_bytes + 1024 + 512;
+    static std::once_flag once2;
+    std::call_once(once2, [] {
+      cudaFuncSetAttribute(k_conv_umma_fwd2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    static long long* prof_buf = nullptr;
+    static const bool want_prof = getenv("DRAM_CONV_PROF") != nullptr;
+    if (want_prof && !prof_buf) cudaMalloc(&prof_buf, kNumSMs * 8 * sizeof(long long));
+    q.prof = want_prof ? prof_buf : nullptr;
+    const int grid2 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
+    if (mode == 0) k_conv_umma_fwd2<0><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    else if (mode == 1) k_conv_umma_fwd2<1><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    else k_conv_umma_fwd2<2><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    DRAM_LAUNCH_CHECK();
+    if (want_prof) {                         // diagnostics: per-CTA averages of the MMA thread's and one epilogue warp's cycle split
+      long long h[kNumSMs * 8];
+      cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      double a[6] = {0, 0, 0, 0, 0, 0};
+      const int nb = q.n_items < kNumSMs ? q.n_items : kNumSMs;
+      for (int b = 0; b < nb; ++b) for (int j = 0; j < 6; ++j) a[j] += (double)h[b * 8 + j] / nb;
+      fprintf(stderr, "[fwd2 prof] items/CTA %.1f BN %d cb %d | mma thread: total %.0f, wait tmem-empty %.0f, wait A %.0f, wait B %.0f | epilogue: wait %.0f, work %.0f (cycles)\n",
+              (double)q.n_items / nb, q.BN, q.kblocks_c, a[0], a[1], a[2], a[3], a[4], a[5]);
+    }
+    return DRAM_OK;
+  }
   FwdParams p;
   p.BN = pick_bn(Cout);
   DRAM_REQUIRE(p.BN > 0, "conv3d_umma_fwd: Cout=%d must be a multiple of 16", Cout);

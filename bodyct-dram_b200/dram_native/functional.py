@@ -132,6 +132,7 @@ class ConvBnRelu(torch.autograd.Function):
     def forward(ctx, x, x_hi, x_lo, w, bias, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates,
                 pool, out_planes):
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        ctx.set_materialize_grads(False)       # the plane outputs carry no gradient: do not let autograd zero-fill GBs for them
         umma = ops.umma_ok_fwd(Cin, Cout, k) and bias is None
         # the backward writes dy straight to planes when both consumers (dgrad, wgrad) are tensor-core kernels
         planes_dy = umma and Cout % 8 == 0 and (ops.umma_ok_fwd(Cout, Cin, k) or not ctx.needs_input_grad[0])
@@ -180,6 +181,8 @@ class ConvBnRelu(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ga, _g1, _g2, gp, _g3, _g4):
         w, gamma, y, scale, shift, a, mean, rstd, x_plain = ctx.saved_tensors
+        if ga is None and gp is None:
+            return (None,) * 15
         N, C, D, H, W = y.shape
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
         want_gb = ctx.needs_input_grad[5] or ctx.needs_input_grad[6]
@@ -340,6 +343,7 @@ class UpsampleConcat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x_hi, x_lo, skip, s_hi, s_lo):
         ctx.shapes = (tuple(x.shape), tuple(skip.shape))
+        ctx.set_materialize_grads(False)
         ctx.planes = x_hi is not None and s_hi is not None
         if ctx.planes:
             cat = ops.upsample2x_concat_planes(ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]),
@@ -355,6 +359,8 @@ class UpsampleConcat(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g1, _g2):
         (N, C1, d, h, w), (_, C2, Ds, Hs, Ws) = ctx.shapes
+        if g is None:
+            return (None,) * 6
         g = ops.to_cl(g, "grad")
         if (Ds, Hs, Ws) == (2 * d, 2 * h, 2 * w) and C1 % 4 == 0 and C2 % 4 == 0:
             # no crop: the skip gradient is the channel slice [C1:] of g, handed on as a view and read in place by the

@@ -106,7 +106,11 @@ UMMA_CASES = [
     (1, 128, 16, (6, 7, 9), 1),        # 1x1x1, odd spatial sizes
     (1, 64, 64, (4, 24, 48), 3),       # kw-reuse mode, 3x3 tiles of (16w x 8h), halo on every side
     (2, 192, 64, (3, 16, 32), 3),      # kw-reuse mode, 3 channel blocks, batch 2
-    (1, 64, 32, (5, 8, 16), 3),        # kw-reuse mode with BN=32 (dgrad of ds0.c1 at 80^3)
+    (1, 64, 32, (5, 8, 16), 3),        # kw-reuse mode with BN=32 (dgrad of ds0.c1 at 80^3); odd tile count (single-tile last item)
+    (1, 64, 128, (6, 8, 24), 3),       # tile pairs, (TW,TDD) = (8,2), BN=128 (three N=128 MMAs per K step)
+    (1, 128, 384, (2, 8, 16), 3),      # tile pairs, 3 N tiles of 128 (dgrad of us1.c0 shape class)
+    (2, 64, 64, (16, 40, 40), 3),      # tile pairs at the 40^3 tiling, 200 items on 148 persistent CTAs
+    (1, 384, 128, (4, 16, 8), 3),      # tile pairs, 6 channel blocks
 ]
 
 
