@@ -102,6 +102,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully converged warp.  The loops around the TMA / MMA issue stay warp-uniform and only the issue itself
+// is predicated on this: with `if (lane == 0)` around the whole loop nest the compiler keeps descriptors in vector
+// registers and wraps every UTCHMMA / UTMALDG in a waterfall loop (R2UR + ELECT + BRA.ANY, ~70 issue cycles per MMA),
+// which made the single issuing thread the bottleneck of every N <= 128 MMA sequence.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle, sm_100 version field = 1.
 //   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart, LBO unused (1).
 //   MN-major: K rows of 128 B (= 64 MN elements), 8-row groups SBO = 1024 B apart, 64-element MN blocks LBO bytes apart.
@@ -170,13 +184,16 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int kblocks = (p.taps / tps) * p.kblocks_c;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (see elect_one)
+    if (elect_one()) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
       if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    }
+    {
       // bytes TMA will actually deliver: the A box has TW*TH*TD rows (<= 128), zero-filled halo included
       const uint32_t a_box_bytes = (uint32_t)((p.w3 ? (p.TW + 2) : p.TW) * p.TH * p.TD) * 128u;
       const uint32_t stage_tx = (three ? 2u : 1u) * (a_box_bytes + (uint32_t)tps * b_tile_bytes);
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
         int mt = tile / p.n_ntiles;
@@ -188,64 +205,70 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           // g = tap (generic) or (kd,kh) pair (kw-reuse)
           const int tap0 = g * tps;
           const int kd = p.taps == 1 ? 0 : tap0 / 9, kh = p.taps == 1 ? 0 : (tap0 / 3) % 3, kw = p.taps == 1 ? 0 : tap0 % 3;
-          for (int cb = 0; cb < p.kblocks_c; ++cb, ++it) {
-            const uint32_t s = it % S, ph = (it / S) & 1;
+          for (int cb = 0; cb < p.kblocks_c; ++cb) {
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes), fb = full0 + 8 * s;
-            mbar_expect_tx(fb, stage_tx);
-            if (p.w3) {                                 // map dims (C,H,W,D,N); kw = 0 here, box starts at w0 - 1
-              tma_load_5d(sb, &tmA_hi, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
-              if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
-            } else {
-              tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
-              if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+            if (elect_one()) {
+              const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes, fb = full0 + 8 * s;
+              mbar_expect_tx(fb, stage_tx);
+              if (p.w3) {                                 // map dims (C,H,W,D,N); kw = 0 here, box starts at w0 - 1
+                tma_load_5d(sb, &tmA_hi, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+                if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+              } else {
+                tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+                if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+              }
+              for (int t = 0; t < tps; ++t) {
+                const uint32_t bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
+                tma_load_2d(sb + offBhi + bo, &tmB_hi, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
+                if (three) tma_load_2d(sb + offBlo + bo, &tmB_lo, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
+              }
             }
-            for (int t = 0; t < tps; ++t) {
-              const uint32_t bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
-              tma_load_2d(sb + offBhi + bo, &tmB_hi, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
-              if (three) tma_load_2d(sb + offBlo + bo, &tmB_lo, fb, cb * 64, (tap0 + t) * p.Cout + nt * p.BN);
-            }
+            __syncwarp();
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // split-bf16: the B_lo tile sits directly behind B_hi in shared memory, so A_hi x [B_hi | B_lo] is ONE MMA with
       // N = 2*BN (accumulator columns [0,BN) = hi*hi, [BN,2BN) = hi*lo) followed by A_lo x B_hi into [0,BN).
       // SS-mode operand reads cost 64 + 8192/N bytes per cycle against ~128 B/cycle of shared-memory bandwidth:
       // doubling N is what lifts the Cout = 64 layers off that bound.  The epilogue adds the two halves.
       const uint32_t idesc = umma_idesc(p.BN, 0, 0), idesc2 = umma_idesc(2 * p.BN, 0, 0);
-      uint32_t it = 0, tcount = 0;
+      uint32_t s = 0, ph = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_cols;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes);
-          for (int t = 0; t < tps; ++t) {              // kw-reuse: tap t reads the halo box shifted by t columns = t*1024 B
-            const uint32_t ao = (uint32_t)t * 1024u, bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
-            const uint64_t a_hi = umma_desc(sb + ao, 16, 1024), b_hi = umma_desc(sb + offBhi + bo, 16, 1024);
-            const uint64_t a_lo = umma_desc(sb + offAlo + ao, 16, 1024);
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes;
+            for (int t = 0; t < tps; ++t) {            // kw-reuse: tap t reads the halo box shifted by t columns = t*1024 B
+              const uint32_t ao = (uint32_t)t * 1024u, bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
+              const uint64_t a_hi = umma_desc(sb + ao, 16, 1024), b_hi = umma_desc(sb + offBhi + bo, 16, 1024);
+              const uint64_t a_lo = umma_desc(sb + offAlo + ao, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {             // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-              const uint64_t adv = (uint64_t)(k * 2);
-              const uint32_t accum = (kb | t | k) ? 1u : 0u;
-              if (three) {
-                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
-                umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              } else {
-                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+              for (int k = 0; k < 4; ++k) {           // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                const uint64_t adv = (uint64_t)(k * 2);
+                const uint32_t accum = (kb | t | k) ? 1u : 0u;
+                if (three) {
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
+                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                } else {
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+                }
               }
             }
+            umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
           }
-          umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);                 // accumulator complete -> epilogue
       }
     }
   } else {
@@ -321,20 +344,6 @@ struct Fwd2Params {
   int SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes, acc_cols, tmem_cols;
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
 };
-
-// One lane of a fully converged warp.  The loops around the TMA / MMA issue stay warp-uniform and only the issue itself
-// is predicated on this: with `if (lane == 0)` around the whole loop nest the compiler keeps descriptors in vector
-// registers and wraps every UTCHMMA / UTMALDG in a waterfall loop (R2UR + ELECT + BRA.ANY, ~70 issue cycles per MMA),
-// which made the single issuing thread the bottleneck of every N <= 128 MMA sequence.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 
 // MODE 0: one pass (bf16); 1: split-bf16 with the [B_hi | B_lo] N-concatenation (BN <= 64); 2: split-bf16, three N = BN MMAs
 template <int MODE>
@@ -587,10 +596,13 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
   const int n_items = p.n_slabs * p.n_mtiles * p.n_ntiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (see elect_one)
+    if (elect_one()) {
       tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmY_hi);
       if (three) { tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_lo); }
-      uint32_t it = 0;
+    }
+    {
+      uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int nt = item % p.n_ntiles;
         const int mt = (item / p.n_ntiles) % p.n_mtiles;
@@ -598,37 +610,41 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
         const int mb0 = 2 * mt, mb1 = 2 * mt + 1;
         const bool has1 = mb1 < p.MB;
         const uint32_t tx = (three ? 2u : 1u) * ((has1 ? 2u : 1u) * kWgBlkBytes + b_bytes);
-        int tapv[2] = {mb0 / p.CB, has1 ? mb1 / p.CB : 0}, cbv[2] = {mb0 % p.CB, has1 ? mb1 % p.CB : 0};
+        const int tap0 = mb0 / p.CB, cb0 = mb0 % p.CB, tap1 = has1 ? mb1 / p.CB : 0, cb1 = has1 ? mb1 % p.CB : 0;
+        const int kd0 = p.taps == 1 ? 0 : tap0 / 9 - p.pad, kh0 = p.taps == 1 ? 0 : (tap0 / 3) % 3 - p.pad, kw0 = p.taps == 1 ? 0 : tap0 % 3 - p.pad;
+        const int kd1 = p.taps == 1 ? 0 : tap1 / 9 - p.pad, kh1 = p.taps == 1 ? 0 : (tap1 / 3) % 3 - p.pad, kw1 = p.taps == 1 ? 0 : tap1 % 3 - p.pad;
         const int c_begin = slab * p.chunks_per_slab;
         const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
-        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+        for (int ch = c_begin; ch < c_end; ++ch) {
           int t = ch;
           const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
           const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
           const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
           const int n0 = t * p.TN;
-          const uint32_t s = it % S, ph = (it / S) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes), fb = full0 + 8 * s;
-          mbar_expect_tx(fb, tx);
-          for (int j = 0; j < (has1 ? 2 : 1); ++j) {
-            const int tap = tapv[j];
-            const int kd = p.taps == 1 ? 0 : tap / 9, kh = p.taps == 1 ? 0 : (tap / 3) % 3, kw = p.taps == 1 ? 0 : tap % 3;
-            tma_load_5d(sb + j * kWgBlkBytes, &tmX_hi, fb, cbv[j] * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n0);
-            if (three)
-              tma_load_5d(sb + offAlo + j * kWgBlkBytes, &tmX_lo, fb, cbv[j] * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n0);
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes, fb = full0 + 8 * s;
+            mbar_expect_tx(fb, tx);
+            tma_load_5d(sb, &tmX_hi, fb, cb0 * 64, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+            if (three) tma_load_5d(sb + offAlo, &tmX_lo, fb, cb0 * 64, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+            if (has1) {
+              tma_load_5d(sb + kWgBlkBytes, &tmX_hi, fb, cb1 * 64, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+              if (three) tma_load_5d(sb + offAlo + kWgBlkBytes, &tmX_lo, fb, cb1 * 64, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+            }
+            for (int j = 0; j < nb; ++j) {
+              tma_load_5d(sb + offBhi + j * kWgBlkBytes, &tmY_hi, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
+              if (three) tma_load_5d(sb + offBlo + j * kWgBlkBytes, &tmY_lo, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
+            }
           }
-          for (int j = 0; j < nb; ++j) {
-            tma_load_5d(sb + offBhi + j * kWgBlkBytes, &tmY_hi, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
-            if (three) tma_load_5d(sb + offBlo + j * kWgBlkBytes, &tmY_lo, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
-          }
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc(p.BN, 1, 1), idesc2 = umma_idesc(2 * p.BN, 1, 1);
-      uint32_t it = 0, tcount = 0;
+      uint32_t s = 0, ph = 0, tcount = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         const int slab = item / (p.n_ntiles * p.n_mtiles);
         const int c_begin = slab * p.chunks_per_slab;
@@ -637,31 +653,34 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)acc_stride;
-        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
+        for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint64_t a_hi = umma_desc(sb, kWgBlkBytes, 1024), b_hi = umma_desc(sb + offBhi, kWgBlkBytes, 1024);
-          const uint64_t a_lo = umma_desc(sb + offAlo, kWgBlkBytes, 1024), b_lo = umma_desc(sb + offBlo, kWgBlkBytes, 1024);
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes;
+            const uint64_t a_hi = umma_desc(sb, kWgBlkBytes, 1024), b_hi = umma_desc(sb + offBhi, kWgBlkBytes, 1024);
+            const uint64_t a_lo = umma_desc(sb + offAlo, kWgBlkBytes, 1024), b_lo = umma_desc(sb + offBlo, kWgBlkBytes, 1024);
 #pragma unroll
-          for (int k = 0; k < kWgKV / 16; ++k) {        // 16 voxel rows (2048 B) per MMA
-            const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-            const uint32_t first = (ch > c_begin || k) ? 1u : 0u;
-            if (p.concat) {                             // X_hi x [dY_hi | dY_lo] (N = 2*BN), then X_lo x dY_hi
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, first);
-              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            } else {
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
-              if (three) {
-                umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            for (int k = 0; k < kWgKV / 16; ++k) {      // 16 voxel rows (2048 B) per MMA
+              const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+              const uint32_t first = (ch > c_begin || k) ? 1u : 0u;
+              if (p.concat) {                           // X_hi x [dY_hi | dY_lo] (N = 2*BN), then X_lo x dY_hi
+                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, first);
                 umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+                if (three) {
+                  umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
               }
             }
+            umma_commit(empty0 + 8 * s);
+            if (ch == c_end - 1) umma_commit(tfull0 + 8 * acc);
           }
-          umma_commit(empty0 + 8 * s);
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);
       }
     }
   } else {
@@ -749,71 +768,83 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
   const int n_items = p.n_slabs * p.n_pairs;
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo);
-      uint32_t it = 0;
+    // whole warp converged, one elected lane issues (see elect_one)
+    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo); }
+    {
+      uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pair = item % p.n_pairs, slab = item / p.n_pairs;
         const int nsrc = (2 * pair + 1 < p.n_src) ? 2 : 1;
         const uint32_t tx = 2u * (uint32_t)nsrc * kW3XBox + 2u * kW3YBox;
-        int kd[2], kh[2], cb[2];
-        for (int j = 0; j < 2; ++j) {
-          const int s = min(2 * pair + j, p.n_src - 1);
-          cb[j] = s % p.CB; kh[j] = (s / p.CB) % 3; kd[j] = s / (3 * p.CB);
-        }
+        const int s0 = 2 * pair, s1 = min(2 * pair + 1, p.n_src - 1);
+        const int cb0 = s0 % p.CB, kh0 = (s0 / p.CB) % 3 - 1, kd0 = s0 / (3 * p.CB) - 1;
+        const int cb1 = s1 % p.CB, kh1 = (s1 / p.CB) % 3 - 1, kd1 = s1 / (3 * p.CB) - 1;
         const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
-        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
+        for (int ch = c_begin; ch < c_end; ++ch) {
           int t = ch;
           const int w0 = (t % p.tiles_w) * 8; t /= p.tiles_w;
           const int h0 = (t % p.tiles_h) * 8; t /= p.tiles_h;
           const int d0 = t % p.D;
           const int n0 = t / p.D;
-          const uint32_t s = it % S, ph = (it / S) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const uint32_t sb = smem_u32(smem + (size_t)s * kW3Stage), fb = full0 + 8 * s;
-          mbar_expect_tx(fb, tx);
-          for (int j = 0; j < nsrc; ++j) {           // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
-            tma_load_5d(sb + j * kW3XBox, &tmX_hi, fb, cb[j] * 64, h0 + kh[j] - 1, w0 - 1, d0 + kd[j] - 1, n0);
-            tma_load_5d(sb + offXlo + j * kW3XBox, &tmX_lo, fb, cb[j] * 64, h0 + kh[j] - 1, w0 - 1, d0 + kd[j] - 1, n0);
+          if (elect_one()) {                         // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)kW3Stage, fb = full0 + 8 * s;
+            mbar_expect_tx(fb, tx);
+            tma_load_5d(sb, &tmX_hi, fb, cb0 * 64, h0 + kh0, w0 - 1, d0 + kd0, n0);
+            tma_load_5d(sb + offXlo, &tmX_lo, fb, cb0 * 64, h0 + kh0, w0 - 1, d0 + kd0, n0);
+            if (nsrc == 2) {
+              tma_load_5d(sb + kW3XBox, &tmX_hi, fb, cb1 * 64, h0 + kh1, w0 - 1, d0 + kd1, n0);
+              tma_load_5d(sb + offXlo + kW3XBox, &tmX_lo, fb, cb1 * 64, h0 + kh1, w0 - 1, d0 + kd1, n0);
+            }
+            tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
+            tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
           }
-          tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
-          tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc(64, 1, 1), idesc2 = umma_idesc(128, 1, 1);
-      // block b = src*3 + kw sits at src*kW3XBox + kw*1024; tile t = blocks (2t, 2t+1)
-      const uint32_t tile_off[3] = {0u, 2048u, (uint32_t)kW3XBox + 1024u};
-      const uint32_t tile_lbo[3] = {1024u, (uint32_t)kW3XBox - 2048u, 1024u};
-      uint32_t it = 0, icount = 0;
+      // block b = src*3 + kw sits at src*kW3XBox + kw*1024; tile t = blocks (2t, 2t+1):
+      //   tile 0 at 0 (LBO 1024), tile 1 at 2048 (LBO kW3XBox - 2048), tile 2 at kW3XBox + 1024 (LBO 1024)
+      uint32_t s = 0, ph = 0, icount = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
         const int pair = item % p.n_pairs, slab = item / p.n_pairs;
         const int ntiles = (2 * pair + 1 < p.n_src) ? 3 : 2;
         const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
         mbar_wait(tempty, (icount & 1) ^ 1);
         tc_fence_after();
-        for (int ch = c_begin; ch < c_end; ++ch, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
+        for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem + (size_t)s * kW3Stage);
-          const uint64_t b_hi = umma_desc(sb + offYhi, kW3YBox, 1024);      // [dY_hi | dY_lo]: lo is LBO = 8192 B behind hi
-          for (int t = 0; t < ntiles; ++t) {
-            const uint64_t a_hi = umma_desc(sb + tile_off[t], tile_lbo[t], 1024);
-            const uint64_t a_lo = umma_desc(sb + offXlo + tile_off[t], tile_lbo[t], 1024);
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u;
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)kW3Stage;
+            const uint64_t b_hi = umma_desc(sb + offYhi, kW3YBox, 1024);    // [dY_hi | dY_lo]: lo is LBO = 8192 B behind hi
+            const uint32_t first = ch > c_begin ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {               // 16 voxel rows (two w columns, 2048 B) per MMA
-              const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, (ch > c_begin || k) ? 1u : 0u);
-              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            for (int t = 0; t < 3; ++t) {
+              if (t < ntiles) {
+                const uint32_t toff = t == 0 ? 0u : (t == 1 ? 2048u : (uint32_t)kW3XBox + 1024u);
+                const uint32_t tlbo = t == 1 ? (uint32_t)kW3XBox - 2048u : 1024u;
+                const uint64_t a_hi = umma_desc(sb + toff, tlbo, 1024);
+                const uint64_t a_lo = umma_desc(sb + offXlo + toff, tlbo, 1024);
+                const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {           // 16 voxel rows (two w columns, 2048 B) per MMA
+                  const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, k ? 1u : first);
+                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+              }
             }
+            umma_commit(empty0 + 8 * s);
+            if (ch == c_end - 1) umma_commit(tfull);
           }
-          umma_commit(empty0 + 8 * s);
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull);
       }
     }
   } else {
