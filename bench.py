@@ -90,6 +90,22 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic_per_launch(kernel_prefixes):
+    """Mean DRAM bytes (read + write) per launch of the given kernels, from the committed ncu launch list of this same
+    command (profiles/*_launches.json, written by profiles/summarize_launches.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    n = b = 0
+    for k, v in d["kernels"].items():
+        if any(k.startswith(pfx) for pfx in kernel_prefixes):
+            n += v["launches"]
+            b += v["dram_bytes_per_launch"] * v["launches"]
+    return (b / n if n else None), os.path.basename(files[-1])
+
+
 def make_batch(B, seed, pinned):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "bodyct-dram_b200"))
@@ -263,6 +279,8 @@ def run_b200(args):
                                             **({"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} if v["flops"] else {})}
                  for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]}
 
+    traffic, traffic_src = ncu_traffic_per_launch(
+        ("dram::k_conv_umma_fwd",) if roof_k == "dram_conv3d_umma_fwd" else ("dram::k_conv_umma_wgrad",))
     extra = None
     if world == 1 and not args.no_extra:
         del runner
@@ -300,10 +318,13 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd (forward + dgrad launches)",
-                                                    "dram_conv3d_umma_wgrad": "k_conv_umma_wgrad"}.get(roof_k, roof_k),
+        "roofline": {"bound": "tensor", "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd2 / k_conv_umma_fwd (forward + dgrad launches)",
+                                                    "dram_conv3d_umma_wgrad": "k_conv_umma_wgrad(_w3)"}.get(roof_k, roof_k),
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over this kernel's "
+                                     f"launches in profiles/{traffic_src})" if traffic else None,
+                     "algorithmic_flops_per_launch": rk["flops"] / max(rk["calls"], 1),
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      "note": "achieved = algorithmic FLOPs (unpadded channels, one pass; the split-bf16 kernel issues 3 MMAs "
                              "per algorithmic MAC) / CUDA-event time of this kernel's launches, events taken on the launching "

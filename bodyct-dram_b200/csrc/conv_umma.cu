@@ -616,10 +616,10 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
         const int c_begin = slab * p.chunks_per_slab;
         const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
         for (int ch = c_begin; ch < c_end; ++ch) {
-          int t = ch;
+          int t = ch;                                // depth fastest (see k_conv_umma_wgrad_w3)
+          const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
           const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
           const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
-          const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
           const int n0 = t * p.TN;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           if (elect_one()) {
@@ -737,7 +737,7 @@ constexpr int kW3Stage = 4 * kW3XBox + 2 * kW3YBox;
 
 struct Wg3Params {
   float* ws;
-  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages;
+  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages, dfast;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -781,11 +781,20 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         const int cb1 = s1 % p.CB, kh1 = (s1 / p.CB) % 3 - 1, kd1 = s1 / (3 * p.CB) - 1;
         const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
         for (int ch = c_begin; ch < c_end; ++ch) {
-          int t = ch;
-          const int w0 = (t % p.tiles_w) * 8; t /= p.tiles_w;
-          const int h0 = (t % p.tiles_h) * 8; t /= p.tiles_h;
-          const int d0 = t % p.D;
-          const int n0 = t / p.D;
+          // chunk order: depth fastest.  The kd = 0,1,2 sources of a chunk read planes d-1, d, d+1; walking d first puts
+          // their re-use one or two chunks apart (L2 hits) instead of a whole plane of chunks apart (3x the DRAM reads).
+          int t = ch, w0, h0, d0, n0;
+          if (p.dfast) {
+            d0 = t % p.D; t /= p.D;
+            w0 = (t % p.tiles_w) * 8; t /= p.tiles_w;
+            h0 = (t % p.tiles_h) * 8;
+            n0 = t / p.tiles_h;
+          } else {
+            w0 = (t % p.tiles_w) * 8; t /= p.tiles_w;
+            h0 = (t % p.tiles_h) * 8; t /= p.tiles_h;
+            d0 = t % p.D;
+            n0 = t / p.D;
+          }
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           if (elect_one()) {                         // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
             const uint32_t sb = smem_u32(smem) + s * (uint32_t)kW3Stage, fb = full0 + 8 * s;
@@ -1284,6 +1293,7 @@ static void wgrad_w3_plan(Wg3Params& p, int N, int D, int H, int W, int Cin_pad)
   p.chunks_per_slab = cdiv(p.n_chunks, best);
   p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
   p.stages = (kSmemBudget - 1024) / kW3Stage;
+  { const char* e = getenv("DRAM_WGRAD_ORDER"); p.dfast = e ? atoi(e) : 1; }
 }
 
 size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize) {
