@@ -560,14 +560,21 @@ def run_scan(args):
     scan_h, lobe_h = torch.from_numpy(scan).pin_memory(), torch.from_numpy(lobe).pin_memory()
     new_sp = [1.0, 1.0, 1.0]
 
+    pinned_out = {}
+
     def one_scan(scan_in, lobe_in, download):
         s_t = runner.resample_to_working_grid(scan_in.cuda(non_blocking=True), spacing, "linear")
         l_t = runner.resample_to_working_grid(lobe_in.cuda(non_blocking=True), spacing, "nearest")
         out = runner.run_scan(s_t, l_t, new_sp, return_device=True)
         les = job_runner.ops_itk_back(out["lesion"], shape, new_sp, spacing, "nearest")
         post = job_runner.ops_itk_back(out["lesion_post"], shape, new_sp, spacing, "nearest")
-        if download:
-            return les.cpu(), post.cpu(), float(out["ratio"].item())
+        if download:                                    # masks land in pinned host buffers (allocated once)
+            if "les" not in pinned_out:
+                pinned_out["les"] = torch.empty(les.shape, dtype=les.dtype).pin_memory()
+                pinned_out["post"] = torch.empty(post.shape, dtype=post.dtype).pin_memory()
+            pinned_out["les"].copy_(les, non_blocking=True)
+            pinned_out["post"].copy_(post, non_blocking=True)
+            return pinned_out["les"], pinned_out["post"], float(out["ratio"].item())     # .item() syncs the stream
         return les, post, out["ratio"]
 
     scan_d, lobe_d = scan_h.cuda(), lobe_h.cuda()

@@ -554,6 +554,239 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ forward / dgrad, channels on M
+// ncu on k_conv_umma_fwd2 (profiles/r01b_conv_umma_fwd2_ncu_full.md): the busiest unit is the shared-memory operand path
+// of the MMAs.  With voxels on M an MMA of N output channels reads (128 + N) x 32 B for N/2 tensor cycles: 192 B/cycle at
+// N = 64, 128 B/cycle at N = 128, against the 128 B/cycle an SM delivers.  This kernel swaps the roles:
+//   D^T[co][voxel] = sum_k W[co][k] * X[voxel][k]:  A operand = weights (M = 128 rows), B operand = the activation halo
+//   box (N = 256 voxels), so every MMA reads 4 KB + 8 KB for 128 tensor cycles = 96 B/cycle whatever Cout is.
+//   MODE 0 (64-channel tiles): A = [W_hi ; W_lo] stacked on M; two MMAs per K step (x X_hi, x X_lo) give all FOUR split
+//            products (the lo*lo term comes for free); the epilogue adds accumulator rows co and co + 64.
+//   MODE 1 (128-channel tiles): A = W_hi or W_lo; three MMAs per K step (hi*hi, lo*hi, hi*lo) into the same accumulator.
+// Tile = 8(h) x TDD(d) x TW(w) = 256 voxels ((16,2) at 80^3, (8,4) at 40^3), same [w][d][h] row order and kw-shift trick
+// as k_conv_umma_fwd2; accumulator 128 lanes x 256 columns, double buffered (all 512 TMEM columns).
+struct Fwd3Params {
+  float* y;
+  const float* scale;
+  const float* shift;
+  int N, D, H, W, Cout, CT, kblocks_c;
+  int TW, TDD, tiles_w, tiles_h, tiles_d, n_vtiles, n_ctiles, n_items;
+  int SW, x_plane_bytes, x_stage_bytes, w_stage_bytes;
+  long long* prof;   // DRAM_CONV_PROF diagnostics
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                 const Fwd3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kXchgBytes = MODE == 0 ? 8192 : 0;     // 2 pairs x 2 parities x 2 directions x [8 columns][32 lanes] floats
+  const int SW = p.SW;
+  uint8_t* smemW = smem + 2 * (size_t)p.x_stage_bytes;
+  float* xchg = reinterpret_cast<float*>(smemW + (size_t)SW * p.w_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + kXchgBytes);
+  const uint32_t fullX0 = smem_u32(bars), emptyX0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6),
+                 fullW0 = smem_u32(bars + 8), emptyW0 = smem_u32(bars + 8 + SW);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * SW);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smemX_u = smem_u32(smem), smemW_u = smem_u32(smemW);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(fullX0 + 8 * s, 1); mbar_init(emptyX0 + 8 * s, 1);
+      mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4);
+    }
+    for (int s = 0; s < SW; ++s) { mbar_init(fullW0 + 8 * s, 1); mbar_init(emptyW0 + 8 * s, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_g = 9 * p.kblocks_c;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo); }
+    const uint32_t x_tx = 2u * (uint32_t)p.x_plane_bytes, w_tx = (uint32_t)p.w_stage_bytes;
+    uint32_t itX = 0, sW = 0, phW = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int ct = item % p.n_ctiles;
+      int vt = item / p.n_ctiles;
+      const int w0 = (vt % p.tiles_w) * p.TW - 1; vt /= p.tiles_w;
+      const int h0 = (vt % p.tiles_h) * 8 - 1; vt /= p.tiles_h;
+      const int d0 = (vt % p.tiles_d) * p.TDD - 1;
+      const int n = vt / p.tiles_d;
+      for (int g = 0; g < 9; ++g) {
+        const int kd = g / 3, kh = g - 3 * kd;
+        for (int cb = 0; cb < p.kblocks_c; ++cb, ++itX) {
+          const uint32_t sX = itX & 1;
+          mbar_wait(emptyX0 + 8 * sX, ((itX >> 1) & 1) ^ 1);
+          if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
+            const uint32_t xb = smemX_u + sX * (uint32_t)p.x_stage_bytes, fx = fullX0 + 8 * sX;
+            mbar_expect_tx(fx, x_tx);
+            tma_load_5d(xb, &tmX_hi, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
+            tma_load_5d(xb + p.x_plane_bytes, &tmX_lo, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(emptyW0 + 8 * sW, phW ^ 1);
+            if (elect_one()) {
+              const uint32_t wb = smemW_u + sW * (uint32_t)p.w_stage_bytes, fw = fullW0 + 8 * sW;
+              mbar_expect_tx(fw, w_tx);
+              const int wrow = (g * 3 + kw) * p.Cout + ct * p.CT;
+              tma_load_2d(wb, &tmW_hi, fw, cb * 64, wrow);
+              tma_load_2d(wb + (p.w_stage_bytes >> 1), &tmW_lo, fw, cb * 64, wrow);
+            }
+            __syncwarp();
+            if (++sW == (uint32_t)SW) { sW = 0; phW ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc(256, 0, 0);
+    const uint32_t kw_shift = (uint32_t)p.TDD * 1024u;
+    uint32_t itX = 0, sW = 0, phW = 0, icount = 0;
+    long long t_te = 0, t_fx = 0, t_fw = 0, t0 = 0, t_start = clock64();
+    const bool prof = p.prof != nullptr;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+      const uint32_t buf = icount & 1;
+      if (prof) t0 = clock64();
+      mbar_wait(tempty0 + 8 * buf, ((icount >> 1) & 1) ^ 1);
+      if (prof) t_te += clock64() - t0;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * 256u;
+      for (int g = 0; g < n_g; ++g, ++itX) {
+        const uint32_t sX = itX & 1;
+        if (prof) t0 = clock64();
+        mbar_wait(fullX0 + 8 * sX, (itX >> 1) & 1);
+        if (prof) t_fx += clock64() - t0;
+        tc_fence_after();
+        const uint32_t xb = smemX_u + sX * (uint32_t)p.x_stage_bytes;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if (prof) t0 = clock64();
+          mbar_wait(fullW0 + 8 * sW, phW);
+          if (prof) t_fw += clock64() - t0;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t wb = smemW_u + sW * (uint32_t)p.w_stage_bytes;
+            const uint64_t x_hi = umma_desc(xb + (uint32_t)kw * kw_shift, 16, 1024);
+            const uint64_t x_lo = umma_desc(xb + (uint32_t)p.x_plane_bytes + (uint32_t)kw * kw_shift, 16, 1024);
+            const uint64_t w_a = umma_desc(wb, 16, 1024);                                     // MODE 0: [W_hi ; W_lo]; MODE 1: W_hi
+            const uint64_t w_b = umma_desc(wb + ((uint32_t)p.w_stage_bytes >> 1), 16, 1024);  // MODE 1: W_lo
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              const uint32_t accum = (g | kw | k) ? 1u : 0u;
+              if (MODE == 0) {
+                umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
+                umma_bf16(d_tmem, w_a + adv, x_lo + adv, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
+                umma_bf16(d_tmem, w_b + adv, x_hi + adv, idesc, 1u);
+                umma_bf16(d_tmem, w_a + adv, x_lo + adv, idesc, 1u);
+              }
+            }
+            umma_commit(emptyW0 + 8 * sW);
+            if (kw == 2) umma_commit(emptyX0 + 8 * sX);
+            if (kw == 2 && g == n_g - 1) umma_commit(tfull0 + 8 * buf);
+          }
+          __syncwarp();
+          if (++sW == (uint32_t)SW) { sW = 0; phW ^= 1; }
+        }
+      }
+    }
+    if (prof && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 8;
+      o[0] = clock64() - t_start; o[1] = t_te; o[2] = t_fx; o[3] = t_fw;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: accumulator row = channel, column = voxel
+    const int q = warp & 3;
+    const int lg = p.TDD == 4 ? 2 : (p.TDD == 2 ? 1 : 0);     // swizzle groups (8 voxels along h) per w column = TDD = 1 << lg
+    const long long hstride = (long long)p.W * p.Cout;
+    uint32_t icount = 0;
+    long long e_wait = 0, e_work = 0, e0 = 0;
+    const bool prof = p.prof != nullptr;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+      const int ct = item % p.n_ctiles;
+      int vt = item / p.n_ctiles;
+      const int w0 = (vt % p.tiles_w) * p.TW; vt /= p.tiles_w;
+      const int h0 = (vt % p.tiles_h) * 8; vt /= p.tiles_h;
+      const int d0 = (vt % p.tiles_d) * p.TDD;
+      const int n = vt / p.tiles_d;
+      const uint32_t buf = icount & 1;
+      if (prof) e0 = clock64();
+      mbar_wait(tfull0 + 8 * buf, (icount >> 1) & 1);
+      if (prof) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
+      if (MODE == 1) {
+        const int co = ct * p.CT + q * 32 + lane;
+        const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+        for (int c0 = 0; c0 < 256; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int grp = (c0 >> 3) + gi;
+            const int w = w0 + (grp >> lg), d = d0 + (grp & (p.TDD - 1));
+            float* out = p.y + ((((long long)n * p.D + d) * p.H + h0) * p.W + w) * p.Cout + co;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = __uint_as_float(r[gi * 8 + j]);
+              if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
+              out[j * hstride] = v;                    // 32 lanes = 32 consecutive channels of one voxel: 128 B
+            }
+          }
+        }
+      } else {
+        // rows 0..63 hold W_hi * X, rows 64..127 hold W_lo * X for the same channels: warps q and q+2 form a pair, each
+        // owns one of the two 8-voxel groups of every 16 columns and receives the partner's values through shared memory
+        const int pair = q & 1, upper = q >> 1;
+        const int co = ct * p.CT + pair * 32 + lane;
+        const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+        for (int c0 = 0; c0 < 256; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          const int par = (c0 >> 4) & 1;
+          float* snd = xchg + (((pair * 2 + par) * 2 + upper) << 8);        // what this warp sends
+          const float* rcv = xchg + (((pair * 2 + par) * 2 + (upper ^ 1)) << 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) snd[j * 32 + lane] = __uint_as_float(upper ? r[j] : r[j + 8]);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+          const int grp = (c0 >> 3) + upper;                                 // the group this warp owns
+          const int w = w0 + (grp >> lg), d = d0 + (grp & (p.TDD - 1));
+          float* out = p.y + ((((long long)n * p.D + d) * p.H + h0) * p.W + w) * p.Cout + co;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = __uint_as_float(upper ? r[j + 8] : r[j]) + rcv[j * 32 + lane];
+            if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
+            out[j * hstride] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (prof) e_work += clock64() - e0;
+    }
+    if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 4] = e_wait; p.prof[blockIdx.x * 8 + 5] = e_work; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 constexpr int kWgKV = 64;                       // voxels per K chunk (one TMA box)
 constexpr int kWgBlkBytes = kWgKV * 128;        // one 64-voxel x 64-channel MN-major block
@@ -1118,6 +1351,59 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin_pad > 0 && Cin_pad % 64 == 0, "conv3d_umma_fwd: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
+  // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
+  // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
+  const char* v3_env = getenv("DRAM_CONV_V3");
+  const int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && Cin_pad <= 128)) ? 1 : 0);
+  if (use_v3 && x_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
+      ((W % 16 == 0 && D % 2 == 0) || (W % 8 == 0 && D % 4 == 0))) {
+    Fwd3Params q;
+    const int mode = (Cout % 128 == 0) ? 1 : 0;
+    q.y = y; q.scale = scale; q.shift = shift;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = mode ? 128 : 64; q.kblocks_c = Cin_pad / 64;
+    if (W % 16 == 0 && D % 2 == 0) { q.TW = 16; q.TDD = 2; } else { q.TW = 8; q.TDD = 4; }
+    q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
+    q.n_vtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
+    q.n_ctiles = Cout / q.CT;
+    q.n_items = q.n_vtiles * q.n_ctiles;
+    q.x_plane_bytes = (q.TW + 2) * q.TDD * 1024;
+    q.x_stage_bytes = 2 * q.x_plane_bytes;
+    q.w_stage_bytes = 2 * 128 * 128 / (mode ? 1 : 2);          // MODE 0: 64 hi + 64 lo rows; MODE 1: 128 + 128 rows
+    const int xchg = mode ? 0 : 8192;
+    q.SW = (227 * 1024 - 1024 - 512 - xchg - 2 * q.x_stage_bytes) / q.w_stage_bytes;
+    if (q.SW > 6) q.SW = 6;
+    DRAM_REQUIRE(q.SW >= 2, "conv3d_umma_fwd: channels-on-M pipeline does not fit in shared memory");
+    CUtensorMap mX_hi, mX_lo, mW_hi, mW_lo;
+    int rc3;
+    if ((rc3 = make_volume_map_hdw(&mX_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3;
+    if ((rc3 = make_volume_map_hdw(&mX_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3;
+    if ((rc3 = make_weight_map(&mW_hi, w_hi, 27ll * Cout, Cin_pad, q.CT))) return rc3;
+    if ((rc3 = make_weight_map(&mW_lo, w_lo, 27ll * Cout, Cin_pad, q.CT))) return rc3;
+    const size_t smem3 = 2 * (size_t)q.x_stage_bytes + (size_t)q.SW * q.w_stage_bytes + xchg + 1024 + 512;
+    static std::once_flag once3;
+    std::call_once(once3, [] {
+      cudaFuncSetAttribute(k_conv_umma_fwd3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    const int grid3 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
+    static long long* prof_buf3 = nullptr;
+    static const bool want_prof3 = getenv("DRAM_CONV_PROF") != nullptr;
+    if (want_prof3 && !prof_buf3) cudaMalloc(&prof_buf3, kNumSMs * 8 * sizeof(long long));
+    q.prof = want_prof3 ? prof_buf3 : nullptr;
+    if (mode == 0) k_conv_umma_fwd3<0><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    else k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    DRAM_LAUNCH_CHECK();
+    if (want_prof3) {
+      long long h[kNumSMs * 8];
+      cudaMemcpy(h, prof_buf3, sizeof(h), cudaMemcpyDeviceToHost);
+      double a[6] = {0, 0, 0, 0, 0, 0};
+      for (int b = 0; b < grid3; ++b) for (int j = 0; j < 6; ++j) a[j] += (double)h[b * 8 + j] / grid3;
+      fprintf(stderr, "[fwd3 prof] mode %d items/CTA %.1f Cout %d cb %d SW %d | mma warp: total %.0f, wait tmem-empty %.0f, wait X %.0f, wait W %.0f | epilogue: wait %.0f, work %.0f (cycles)\n",
+              mode, (double)q.n_items / grid3, Cout, q.kblocks_c, q.SW, a[0], a[1], a[2], a[3], a[4], a[5]);
+    }
+    return DRAM_OK;
+  }
   // weight-sharing tile pairs (k_conv_umma_fwd2) wherever the volume tiles into 8(h) x TDD(d) x TW(w) boxes
   static const bool allow_v2 = getenv("DRAM_CONV_NO_V2") == nullptr;
   if (allow_v2 && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) && Cout % 32 == 0) {

@@ -44,12 +44,26 @@ def main():
         wf = ops.pack_weight_bf16(w, 0)
         wd = ops.pack_weight_bf16(w, 1)
         gf = 2.0 * B * d ** 3 * ci * co * 27 / 1e9
+        if os.environ.get("MICRO_AB"):            # interleaved A/B of the two forward kernels on the same box state
+            res = {}
+            for rep in range(3):
+                for v in ("0", "1"):
+                    os.environ["DRAM_CONV_V3"] = v
+                    res.setdefault(v, []).append((timed(lambda: ops.conv_umma(xs, wf[0], wf[1], co, 3)),
+                                                  timed(lambda: ops.conv_umma(dys, wd[0], wd[1], ci, 3))))
+            os.environ.pop("DRAM_CONV_V3")
+            best = {v: (min(r[0] for r in res[v]), min(r[1] for r in res[v])) for v in res}
+            print(f"{name:8s} fwd  tile-pair {best['0'][0]:7.3f} ms ({gf / best['0'][0]:4.0f})  channels-on-M {best['1'][0]:7.3f} ms ({gf / best['1'][0]:4.0f}) | "
+                  f"dgrad tile-pair {best['0'][1]:7.3f} ({gf / best['0'][1]:4.0f})  channels-on-M {best['1'][1]:7.3f} ({gf / best['1'][1]:4.0f})")
+            continue
         t_f = timed(lambda: ops.conv_umma(xs, wf[0], wf[1], co, 3))
         t_d = timed(lambda: ops.conv_umma(dys, wd[0], wd[1], ci, 3))
         t_w = timed(lambda: ops.conv_umma_wgrad(dys, xs, ci, co, 3))
         tot["fwd"] += t_f; tot["dgrad"] += t_d; tot["wgrad"] += t_w; totf += gf
         print(f"{name:8s} {f'{ci}->{co}@{d}':>14s} {gf:8.1f} | {t_f:8.3f} {gf / t_f:6.0f} | {t_d:8.3f} {gf / t_d:6.0f} | {t_w:8.3f} {gf / t_w:6.0f}")
         del x, dy, xs, dys
+    if os.environ.get("MICRO_AB"):
+        return
     print(f"{'total':8s} {'':>14s} {totf:8.1f} | {tot['fwd']:8.3f} {totf / tot['fwd']:6.0f} | {tot['dgrad']:8.3f} {totf / tot['dgrad']:6.0f} | {tot['wgrad']:8.3f} {totf / tot['wgrad']:6.0f}")
 
 
