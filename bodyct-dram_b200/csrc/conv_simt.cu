@@ -305,6 +305,129 @@ k_conv_c1_wgrad(const float* __restrict__ x, const float* __restrict__ dy, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ first layer, 4 voxels per thread
+// W % 4 == 0: a thread owns FOUR consecutive-w voxels and one channel group.  The 3x3x6 input window of the quad is 27
+// loads (one aligned float4 + two edge scalars per (dz,dy)) instead of 4 x 27 gathers, and the weights / accumulators are
+// touched once per quad.
+__device__ __forceinline__ void c1_window(const float* __restrict__ x, unsigned quad, int D, int H, int W4, float (&xv)[9][6],
+                                          long long& m0) {
+  unsigned r = quad;
+  const int x0 = (int)(r % (unsigned)W4) * 4; r /= (unsigned)W4;
+  const int yy = (int)(r % (unsigned)H); r /= (unsigned)H;
+  const int zz = (int)(r % (unsigned)D);
+  const int W = W4 * 4;
+  m0 = (long long)quad * 4;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int dz = t / 3 - 1, dy = t % 3 - 1;
+    const bool ok = (unsigned)(zz + dz) < (unsigned)D && (unsigned)(yy + dy) < (unsigned)H;
+    const float* row = x + m0 + ((long long)dz * H + dy) * W;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f, rr = 0.f;
+    if (ok) {
+      c = __ldg(reinterpret_cast<const float4*>(row));
+      if (x0 > 0) l = __ldg(row - 1);
+      if (x0 + 4 < W) rr = __ldg(row + 4);
+    }
+    xv[t][0] = l; xv[t][1] = c.x; xv[t][2] = c.y; xv[t][3] = c.z; xv[t][4] = c.w; xv[t][5] = rr;
+  }
+}
+
+// thread = (quad of voxels, 8 output channels)
+__global__ void __launch_bounds__(256)
+k_conv_c1_fwd_q(const float* __restrict__ x, const float* __restrict__ pack, const float* __restrict__ bias,
+                float* __restrict__ y, long long quads, int D, int H, int W4, int Cout) {
+  __shared__ __align__(16) float ws[27 * kC1MaxCout];
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = pack[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dq = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);
+  float b8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b8[j] = bias ? bias[g * 8 + j] : 0.f;
+  for (long long qd = tid / groups; qd < quads; qd += dq) {
+    float xv[9][6], acc[4][8];
+    long long m0;
+    c1_window(x, (unsigned)qd, D, H, W4, xv, m0);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[v][j] = b8[j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8 + 4]);
+      const int r9 = t / 3, dx = t % 3;                 // tap t = (dz,dy) row r9, column dx: voxel v reads xv[r9][v + dx]
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float xs = xv[r9][v + dx];
+        acc[v][0] = fmaf(xs, w0.x, acc[v][0]); acc[v][1] = fmaf(xs, w0.y, acc[v][1]);
+        acc[v][2] = fmaf(xs, w0.z, acc[v][2]); acc[v][3] = fmaf(xs, w0.w, acc[v][3]);
+        acc[v][4] = fmaf(xs, w1.x, acc[v][4]); acc[v][5] = fmaf(xs, w1.y, acc[v][5]);
+        acc[v][6] = fmaf(xs, w1.z, acc[v][6]); acc[v][7] = fmaf(xs, w1.w, acc[v][7]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float4* o = reinterpret_cast<float4*>(y + (m0 + v) * Cout + g * 8);
+      o[0] = make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
+      o[1] = make_float4(acc[v][4], acc[v][5], acc[v][6], acc[v][7]);
+    }
+  }
+}
+
+// thread = (quad lane, 4 output channels) accumulating dpack[27][4] over its quads; same reduction tree as k_conv_c1_wgrad
+__global__ void __launch_bounds__(256)
+k_conv_c1_wgrad_q(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dpack, long long quads, int D,
+                  int H, int W4, int Cout) {
+  __shared__ float red[8][27 * kC1MaxCoutWgrad];
+  const int groups = Cout / 4;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dq = ((long long)gridDim.x * blockDim.x) / groups;
+  const int g = (int)(tid % groups);
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  for (long long qd = tid / groups; qd < quads; qd += dq) {
+    float xv[9][6];
+    long long m0;
+    c1_window(x, (unsigned)qd, D, H, W4, xv, m0);
+    float4 d4[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) d4[v] = __ldg(reinterpret_cast<const float4*>(dy + (m0 + v) * Cout) + g);
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int r9 = t / 3, dx = t % 3;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float xs = xv[r9][v + dx];
+        acc[t][0] = fmaf(xs, d4[v].x, acc[t][0]); acc[t][1] = fmaf(xs, d4[v].y, acc[t][1]);
+        acc[t][2] = fmaf(xs, d4[v].z, acc[t][2]); acc[t][3] = fmaf(xs, d4[v].w, acc[t][3]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[t][j];
+      for (int o = 16; o >= groups; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < groups) red[warp][t * Cout + lane * 4 + j] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) v += red[wp][i];
+    atomicAdd(&dpack[i], v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // w [Cout][Cin][T]  ->  mode 0: pack[t][ci][co]   mode 1: pack[t][co][ci] with flipped taps
 __global__ void k_pack_weight_f32(const float* __restrict__ w, float* __restrict__ pack, int Cout, int Cin, int T, int mode) {
@@ -358,7 +481,10 @@ int dram_conv3d_simt_fwd(const float* x, const float* pack, const float* bias, f
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_simt_fwd: kernel size %d unsupported (1 or 3)", ksize);
   long long M = (long long)N * D * H * W;
   if (Cin == 1 && ksize == 3 && Cout % 8 == 0 && Cout <= kC1MaxCout && M < (1ll << 31)) {
-    k_conv_c1_fwd<<<grid_fixed_group(M, Cout / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, M, D, H, W, Cout);
+    if (W % 4 == 0 && ((uintptr_t)x & 15) == 0)
+      k_conv_c1_fwd_q<<<grid_fixed_group(M / 4, Cout / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, M / 4, D, H, W / 4, Cout);
+    else
+      k_conv_c1_fwd<<<grid_fixed_group(M, Cout / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, pack, bias, y, M, D, H, W, Cout);
     DRAM_LAUNCH_CHECK();
     return DRAM_OK;
   }
@@ -376,7 +502,10 @@ int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack, int N,
   long long M = (long long)N * D * H * W;
   const int c1g = Cout / 4;
   if (Cin == 1 && ksize == 3 && Cout % 4 == 0 && Cout <= kC1MaxCoutWgrad && c1g <= 32 && (c1g & (c1g - 1)) == 0 && M < (1ll << 31)) {
-    k_conv_c1_wgrad<<<grid_fixed_group(M, c1g, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, M, D, H, W, Cout);
+    if (W % 4 == 0 && ((uintptr_t)x & 15) == 0)
+      k_conv_c1_wgrad_q<<<grid_fixed_group(M / 4, c1g, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, M / 4, D, H, W / 4, Cout);
+    else
+      k_conv_c1_wgrad<<<grid_fixed_group(M, c1g, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, dy, dpack, M, D, H, W, Cout);
     DRAM_LAUNCH_CHECK();
     return DRAM_OK;
   }

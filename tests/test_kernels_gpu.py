@@ -69,7 +69,8 @@ def test_layout_round_trip():
 # ------------------------------------------------------------------------------------------------ CUDA-core convolution
 @pytest.mark.parametrize("N,Cin,Cout,S,k,bias", [(2, 1, 32, (8, 9, 10), 3, False), (1, 5, 7, (6, 5, 7), 3, True),
                                                  (2, 8, 16, (8, 8, 8), 3, False), (2, 12, 8, (5, 6, 7), 1, True),
-                                                 (1, 64, 1, (6, 6, 6), 1, True)])
+                                                 (1, 64, 1, (6, 6, 6), 1, True),
+                                                 (2, 1, 32, (5, 6, 12), 3, True), (1, 1, 32, (4, 4, 4), 3, False)])   # quad-voxel first layer
 def test_conv_simt_forward(N, Cin, Cout, S, k, bias):
     o = ops()
     x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, k, k, k) * 0.2
@@ -80,7 +81,8 @@ def test_conv_simt_forward(N, Cin, Cout, S, k, bias):
     assert_close(y, ref, TOL_F32, "conv_simt fwd")
 
 
-@pytest.mark.parametrize("N,Cin,Cout,S,k", [(2, 1, 32, (8, 9, 10), 3), (2, 6, 10, (6, 5, 7), 3), (2, 12, 8, (5, 6, 7), 1)])
+@pytest.mark.parametrize("N,Cin,Cout,S,k", [(2, 1, 32, (8, 9, 10), 3), (2, 6, 10, (6, 5, 7), 3), (2, 12, 8, (5, 6, 7), 1),
+                                            (2, 1, 32, (6, 5, 12), 3), (1, 1, 32, (4, 4, 4), 3)])   # quad-voxel first layer
 def test_conv_simt_dgrad_wgrad(N, Cin, Cout, S, k):
     o = ops()
     x = torch.randn(N, Cin, *S, requires_grad=True)

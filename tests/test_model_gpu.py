@@ -177,6 +177,46 @@ def test_full_width_training_step_against_oracle(att):
     assert errs[len(errs) // 2] <= 6e-3, errs[len(errs) // 2]
 
 
+@pytest.mark.parametrize("att", [False, True])
+def test_full_size_chunk_against_oracle(att):
+    """BASELINE.json's full size: one 80^3 lobe chunk (attention grid 64^3) at the reference's channel widths, eval forward
+    and one training-mode loss evaluation, against the CPU oracle on the same seeded inputs (a few seconds of CPU time).
+    Exercises every kernel at the exact tile shapes the benchmark runs: (16,2)/(16,1) tiles at 80^3, (8,4)/(8,2) at 40^3,
+    ragged (5,5,5) tiles at 20^3 and 10^3."""
+    from oracle_import import O
+    import metrics
+    g, cfg, m, images, lobes, lesions, ctsses = _full_width_case(att, (80, 80, 80), (64, 64, 64), 1, seed=33)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    fwd = O.dc3dat_forward if att else O.dc3d_forward
+    m = m.cuda().eval()
+    with torch.no_grad():
+        d_ref, r_ref = fwd(sd, images, cfg, False)
+        d, r = m(images.cuda(), lobes.cuda())
+    assert rel_err(d, d_ref) <= 1e-3 and rel_err(r, r_ref) <= 1e-3, (rel_err(d, d_ref), rel_err(r, r_ref))
+    assert_close(m.pooling_dense_features(r, lobes.cuda()), O.masked_pool(r_ref, lobes), 1e-3, "pooled score")
+    assert dice(torch.sigmoid(r.cpu()) > 0.5, torch.sigmoid(r_ref) > 0.5) >= 0.999
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    d_ref, r_ref = fwd(sd, images, cfg, True)                          # train-mode BatchNorm (batch statistics)
+    rl_ref, sl_ref = O.int_reg_refine_loss(d_ref, r_ref, lobes, lesions, ctsses, g["freq_map"])
+    (2.0 * rl_ref + sl_ref).backward()     # checkpointed blocks update their running statistics again while recomputing
+    m.train()
+    loss = metrics.IntRegRefineLoss(**g["loss_cfg"])
+    rl, sl = loss(m, images.cuda(), lobes.cuda(), lesions.cuda(), ctsses, obj=Host(g["freq_map"]), metas={})
+    (2.0 * rl + sl).backward()
+    assert_close(rl, rl_ref, 1e-3, "reg loss")
+    assert_close(sl, sl_ref, 1e-3, "seg loss")
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            assert_close(v, sd[k], 1e-3, k)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # at this size the problem is well conditioned (512 000 voxels per BatchNorm statistic): gradients meet a tight bound
+    ref_grads = {k: (sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])) for k, _ in m.named_parameters()}
+    worst = check_grads(m, ref_grads, 2e-2)
+    print("full-size gradient check: worst parameter", worst)
+
+
 def test_tensor_core_and_cuda_core_paths_agree_on_gradients(monkeypatch):
     """split-bf16 tcgen05 path vs fp32 CUDA-core path, same module / batch, no CPU involved (chunk 32^3)"""
     import metrics
