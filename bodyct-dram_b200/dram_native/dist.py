@@ -99,6 +99,8 @@ class GradReducer:
             self._launch(bi)
 
     def _launch(self, bi):
+        from . import functional as _F
+        _F.SIDE.join()                    # weight gradients are produced on the side stream (functional._SideStream)
         b = self.buckets[bi]
         n = sum(p.numel() for p in b)
         if self.flat[bi] is None or self.flat[bi].numel() != n or self.flat[bi].device != b[0].device:
