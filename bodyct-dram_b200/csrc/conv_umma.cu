@@ -1355,7 +1355,8 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
   // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
   const char* v3_env = getenv("DRAM_CONV_V3");
-  const int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && Cin_pad <= 128)) ? 1 : 0);
+  int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && Cin_pad <= 128)) ? 1 : 0);
+  if (use_v3 == 2) use_v3 = (Cout % 128 == 0) ? 1 : 0;       // experiment: 128-channel tiles only
   if (use_v3 && x_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
       ((W % 16 == 0 && D % 2 == 0) || (W % 8 == 0 && D % 4 == 0))) {
     Fwd3Params q;
