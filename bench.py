@@ -318,7 +318,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd2 / k_conv_umma_fwd (forward + dgrad launches)",
+        "roofline": {"bound": "tensor", "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd3 / k_conv_umma_fwd2 / k_conv_umma_fwd (forward + dgrad launches)",
                                                     "dram_conv3d_umma_wgrad": "k_conv_umma_wgrad(_w3)"}.get(roof_k, roof_k),
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
