@@ -202,17 +202,23 @@ __device__ __forceinline__ unsigned pool_window_dz(const float* __restrict__ y, 
   float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int arg[4] = {0, 0, 0, 0};
   unsigned valid = 0;
+  // All 17 loads of the window are issued before the first one is consumed: coordinates are clamped into the volume and
+  // the loads are unconditional (a ragged-tail voxel is masked afterwards), so no data-dependent branch or argmax chain
+  // stands between them and a thread pays one memory latency per window instead of eight.
+  float4 yt[8], qt[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int zz = 2 * pc.z + (k >> 2), yy = 2 * pc.y + ((k >> 1) & 1), xx = 2 * pc.x + (k & 1);
-    if (zz < D && yy < H && xx < W) {
-      valid |= 1u << k;
-      const long long row = (((long long)pc.n * D + zz) * H + yy) * W + xx;
-      const float4 t = __ldg(reinterpret_cast<const float4*>(y + row * C) + g);
-      yv[k][0] = t.x; yv[k][1] = t.y; yv[k][2] = t.z; yv[k][3] = t.w;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ga) q = __ldg(reinterpret_cast<const float4*>(ga + row * ga_pitch) + g);
-      dz[k][0] = q.x; dz[k][1] = q.y; dz[k][2] = q.z; dz[k][3] = q.w;
+    if (zz < D && yy < H && xx < W) valid |= 1u << k;
+    const long long row = (((long long)pc.n * D + min(zz, D - 1)) * H + min(yy, H - 1)) * W + min(xx, W - 1);
+    yt[k] = __ldg(reinterpret_cast<const float4*>(y + row * C) + g);
+    qt[k] = ga ? __ldg(reinterpret_cast<const float4*>(ga + row * ga_pitch) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (valid & (1u << k)) {
+      yv[k][0] = yt[k].x; yv[k][1] = yt[k].y; yv[k][2] = yt[k].z; yv[k][3] = yt[k].w;
+      dz[k][0] = qt[k].x; dz[k][1] = qt[k].y; dz[k][2] = qt[k].z; dz[k][3] = qt[k].w;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         const float a = fmaxf(fmaf(yv[k][v], sc[v], sh[v]), 0.f);
@@ -242,7 +248,7 @@ __device__ __forceinline__ unsigned pool_window_dz(const float* __restrict__ y, 
 }
 
 constexpr int kPoolThreads = 256;
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kPoolThreads, 2)
 k_bn_pool_bwd_reduce(const float* __restrict__ ga, long long ga_pitch, const float* __restrict__ gp,
                      const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ sums, int N, int D,

@@ -219,6 +219,81 @@ k_ram_upsample_mask_scatter(const float* __restrict__ ram, const uint8_t* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bootstrapped BCE (seg loss)
+// metrics.py:10-51 (BootBinCrossEntropy) + :325-354 (thresholded pseudo labels) as ONE reduction pass and ONE gradient
+// pass over [B][V]: pseudo label t = (sigmoid(dense) > 0.5) & (lobe != 0) & (lesion > 0), zeroed where keep[b] == 0;
+// p = sigmoid(refined); inside = lobe > 0.  The seven sums below are everything the loss needs:
+//   s[0] = #outside, s[1] = #inside, s[2] = sum t*inside,
+//   s[3] = sum nll*outside, s[4] = sum nll*t*inside, s[5] = sum nll*(1-t)*inside, s[6] = sum -log(pt_hat)*inside
+// with nll = -log(clamp(p*t + (1-p)*(1-t), eps, 1-eps)) and pt_hat the same with t_hat = (p > 0.5).
+struct BceVoxel {
+  float inside, t, p, pt, pt_hat, that;
+};
+__device__ __forceinline__ BceVoxel bce_voxel(float dense, float refined, float lobe, float lesion, float keep) {
+  BceVoxel o;
+  o.inside = lobe > 0.f ? 1.f : 0.f;
+  const float pd = 1.f / (1.f + expf(-dense));
+  o.t = (pd > 0.5f && lobe != 0.f && lesion > 0.f) ? keep : 0.f;
+  o.p = 1.f / (1.f + expf(-refined));
+  o.pt = o.p * o.t + (1.f - o.p) * (1.f - o.t);
+  o.that = o.p > 0.5f ? 1.f : 0.f;
+  o.pt_hat = o.p * o.that + (1.f - o.p) * (1.f - o.that);
+  return o;
+}
+
+__global__ void __launch_bounds__(256)
+k_boot_bce_fwd(const float* __restrict__ dense, const float* __restrict__ refined, const float* __restrict__ lobes,
+               const float* __restrict__ lesions, const float* __restrict__ keep, double* __restrict__ sums, long long V,
+               float eps) {
+  const int b = blockIdx.y;
+  const float kp = keep[b];
+  const long long base = (long long)b * V;
+  float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const BceVoxel x = bce_voxel(__ldg(dense + base + v), __ldg(refined + base + v), __ldg(lobes + base + v),
+                                 __ldg(lesions + base + v), kp);
+    const float nll = -logf(fminf(fmaxf(x.pt, eps), 1.f - eps));
+    const float nllh = -logf(fminf(fmaxf(x.pt_hat, eps), 1.f - eps));
+    a[0] += 1.f - x.inside; a[1] += x.inside; a[2] += x.t * x.inside;
+    a[3] += nll * (1.f - x.inside); a[4] += nll * x.t * x.inside; a[5] += nll * (1.f - x.t) * x.inside;
+    a[6] += nllh * x.inside;
+  }
+  __shared__ float red[7][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const float w = warp_sum(a[j]);
+    if (lane == 0) red[j][warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)red[threadIdx.x][w];
+    atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
+// d loss / d refined: coef = (c_out, c_t, c_nt, c_boot), already multiplied by the upstream gradient (device floats):
+//   loss = c_out * s[3] + c_t * s[4] + c_nt * s[5] + c_boot * s[6];  clamp passes gradient on [eps, 1-eps] (ATen).
+__global__ void __launch_bounds__(256)
+k_boot_bce_bwd(const float* __restrict__ dense, const float* __restrict__ refined, const float* __restrict__ lobes,
+               const float* __restrict__ lesions, const float* __restrict__ keep, const float* __restrict__ coef,
+               float* __restrict__ dref, long long V, float eps) {
+  const int b = blockIdx.y;
+  const float kp = keep[b];
+  const float c_out = coef[0], c_t = coef[1], c_nt = coef[2], c_b = coef[3];
+  const long long base = (long long)b * V;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const BceVoxel x = bce_voxel(__ldg(dense + base + v), __ldg(refined + base + v), __ldg(lobes + base + v),
+                                 __ldg(lesions + base + v), kp);
+    const float wv = c_out * (1.f - x.inside) + (c_t * x.t + c_nt * (1.f - x.t)) * x.inside;
+    float g = 0.f;
+    if (x.pt >= eps && x.pt <= 1.f - eps) g += wv * (-(2.f * x.t - 1.f) / x.pt);
+    if (x.pt_hat >= eps && x.pt_hat <= 1.f - eps) g += c_b * x.inside * (-(2.f * x.that - 1.f) / x.pt_hat);
+    dref[base + v] = g * x.p * (1.f - x.p);
+  }
+}
+
 }  // namespace dram
 
 using namespace dram;
@@ -312,6 +387,29 @@ int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, f
   k_ram_upsample_mask_scatter<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       ram, crop_mask, heat, maxval, d, h, w, cd, ch, cw, SD, SH, SW, oz, oy, ox, act, gain, ac_scale(d, cd),
       ac_scale(h, ch), ac_scale(w, cw));
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_boot_bce_fwd(const float* dense, const float* refined, const float* lobes, const float* lesions, const float* keep,
+                      double* sums, int B, long long V, float eps, void* stream) {
+  DRAM_REQUIRE(dense && refined && lobes && lesions && keep && sums && B > 0 && V > 0, "boot_bce_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DRAM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 7, st));
+  long long per_sample = (long long)kNumSMs * 4 / B;
+  if (per_sample < 1) per_sample = 1;
+  const long long need = (V + 255) / 256;
+  const int gx = (int)(need < per_sample ? need : per_sample);
+  k_boot_bce_fwd<<<dim3(gx, B), 256, 0, st>>>(dense, refined, lobes, lesions, keep, sums, V, eps);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_boot_bce_bwd(const float* dense, const float* refined, const float* lobes, const float* lesions, const float* keep,
+                      const float* coef, float* drefined, int B, long long V, float eps, void* stream) {
+  DRAM_REQUIRE(dense && refined && lobes && lesions && keep && coef && drefined && B > 0 && V > 0, "boot_bce_bwd: bad arguments");
+  const int gx = grid_for(V, 256, 4);
+  k_boot_bce_bwd<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(dense, refined, lobes, lesions, keep, coef, drefined, V, eps);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

@@ -503,6 +503,39 @@ class MaskedMean(torch.autograd.Function):
         return dx.view(ctx.xshape), None, None, None
 
 
+class BootBce(torch.autograd.Function):
+    """Segmentation term of IntRegRefineLoss — pseudo labels from the RAM (metrics.py:325-354) + BootBinCrossEntropy on
+    the refined RAM (metrics.py:10-51) — as one reduction kernel and one gradient kernel.  Gradient flows to the refined
+    logits only (the pseudo labels are built under no_grad in the reference)."""
+
+    @staticmethod
+    def forward(ctx, dense, refined, lobes, lesions, keep, smoothing, eps):
+        B = refined.shape[0]
+        flat = lambda t: t.reshape(B, -1).contiguous().float()
+        d2, r2, lo2, le2 = flat(dense), flat(refined), flat(lobes), flat(lesions)
+        keep = keep.contiguous().float()
+        s = ops.boot_bce_sums(d2, r2, lo2, le2, keep, eps)
+        counts = s[:3].clone()
+        if ddist.active():                       # batch-global normalisers (metrics.py:30,37,42,48)
+            ddist.all_reduce_(counts)
+        n_out, n_in, t_in = counts[0], counts[1], counts[2]
+        alpha = (1.0 - t_in / n_in.clamp_min(1.0)).clamp(0.25, 0.75).float().double()    # fp32 like the reference's alpha
+        w_sum = (alpha * t_in + (1.0 - alpha) * (n_in - t_in)).clamp_min(1e-30)
+        has = (n_in > 0).double()
+        coef = torch.stack([1.0 / n_out, has * (1.0 - smoothing) * alpha / w_sum,
+                            has * (1.0 - smoothing) * (1.0 - alpha) / w_sum, has * smoothing / n_in.clamp_min(1.0)])
+        loss = (coef * s[3:7]).sum().float()
+        ctx.save_for_backward(d2, r2, lo2, le2, keep, coef.float())
+        ctx.eps, ctx.shape = eps, tuple(refined.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d2, r2, lo2, le2, keep, coef = ctx.saved_tensors
+        dref = ops.boot_bce_grad(d2, r2, lo2, le2, keep, (coef * g).contiguous(), ctx.eps)
+        return None, dref.view(ctx.shape), None, None, None, None, None
+
+
 class PcmAttend(torch.autograd.Function):
     """sum_o softmax_o(act(<theta f_x, phi f_{x+o}>)/T) * cam_{x+o} — the DGL update_all of models.py:322-411."""
 

@@ -390,6 +390,25 @@ def masked_pool_bwd(x, mask, g, use_sigmoid=False, mode_gt0=False):
     return dx
 
 
+def boot_bce_sums(dense, refined, lobes, lesions, keep, eps=1e-7):
+    """[B,V] fp32 logits / masks, keep [B] -> double [7] (see dram_boot_bce_fwd)"""
+    B, V = refined.shape
+    sums = torch.empty(7, device=refined.device, dtype=torch.float64)
+    _lib.check(_L().dram_boot_bce_fwd(dense.data_ptr(), refined.data_ptr(), lobes.data_ptr(), lesions.data_ptr(),
+                                      keep.data_ptr(), sums.data_ptr(), B, V, float(eps), _stream()), "boot_bce_fwd")
+    return sums
+
+
+def boot_bce_grad(dense, refined, lobes, lesions, keep, coef, eps=1e-7):
+    """-> d loss / d refined [B,V] for loss = coef . sums[3:7]; coef: float32 [4] on the device"""
+    B, V = refined.shape
+    out = torch.empty_like(refined)
+    _lib.check(_L().dram_boot_bce_bwd(dense.data_ptr(), refined.data_ptr(), lobes.data_ptr(), lesions.data_ptr(),
+                                      keep.data_ptr(), coef.data_ptr(), out.data_ptr(), B, V, float(eps), _stream()),
+               "boot_bce_bwd")
+    return out
+
+
 def ram_activation(x, act):
     """act(x) elementwise: 1 = sigmoid, 2 = relu"""
     x = x.contiguous()

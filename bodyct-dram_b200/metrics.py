@@ -148,6 +148,15 @@ class IntRegRefineLoss(IntRegLoss):
 
     def compute_seg_loss(self, dense_outs, refined_dense_outs, images, lobes, lesions, scores, metas, obj, tag='fixed',
                          keep=None):
+        if self.refine_method != 'th':
+            raise NotImplementedError(f"Do not support refine method :{self.refine_method}!")
+        if keep is None:
+            keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in scores], dtype=torch.float32,
+                                device=dense_outs.device)
+        if os.environ.get("DRAM_FUSED_LOSS", "1") == "1":
+            # pseudo labels + bootstrapped BCE as one reduction kernel and one gradient kernel
+            return DF.BootBce.apply(dense_outs.detach(), refined_dense_outs, lobes, lesions, keep,
+                                    float(self.bootstrap_loss.smoothing), float(self.bootstrap_loss.eps))
         t = self.pseudo_labels(dense_outs, lobes, lesions, scores, keep)
         return self.bootstrap_loss(torch.sigmoid(refined_dense_outs), t, lobes > 0)
 

@@ -177,6 +177,18 @@ int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, 
 /* dx[b][v] = g[b] * f'(x) * m[b][v]   (g already divided by the mask count by the caller) */
 int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, float* dx, int B, long long V,
                          int use_sigmoid, int mode_gt0, void* stream);
+/* Segmentation term of IntRegRefineLoss in two passes (metrics.py:10-51 BootBinCrossEntropy over the thresholded pseudo
+ * labels of metrics.py:325-354): dense / refined are the RAM and refined-RAM logits [B][V], lobes / lesions the float
+ * masks, keep[b] = 0 zeroes the pseudo labels of sample b (ctss == 0, metrics.py:327-328).
+ * fwd: sums[0..6] (double, overwritten) = #outside, #inside, sum t*inside, sum nll*outside, sum nll*t*inside,
+ *      sum nll*(1-t)*inside, sum -log(pt_hat)*inside;  the caller forms the loss from these scalars (and all-reduces
+ *      sums[0..2] under data parallelism).
+ * bwd: drefined[b][v] = d loss / d refined given coef = (c_out, c_t, c_nt, c_boot) on the device with
+ *      loss = c_out*sums[3] + c_t*sums[4] + c_nt*sums[5] + c_boot*sums[6]. */
+int dram_boot_bce_fwd(const float* dense, const float* refined, const float* lobes, const float* lesions, const float* keep,
+                      double* sums, int B, long long V, float eps, void* stream);
+int dram_boot_bce_bwd(const float* dense, const float* refined, const float* lobes, const float* lesions, const float* keep,
+                      const float* coef, float* drefined, int B, long long V, float eps, void* stream);
 /* out = act(in) elementwise (0 identity, 1 sigmoid, 2 relu): job_runner.py:765 `probs = F.sigmoid(dense_outs)` */
 int dram_ram_activation(const float* in, float* out, long long n, int act, void* stream);
 /* Inference epilogue (job_runner.py:765-770 / 993-1004): trilinear-upsample one chunk's RAM [d][h][w] to the lobe crop

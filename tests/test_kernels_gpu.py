@@ -444,6 +444,37 @@ def test_masked_mean(use_sigmoid, gt0):
     assert_close(xg.grad, x.grad, TOL_F32, "masked mean bwd")
 
 
+def test_fused_boot_bce_matches_unfused_loss():
+    """dram_boot_bce_fwd/_bwd against the tensor-op BootBinCrossEntropy + pseudo_labels of metrics.py (same arithmetic as
+    the reference's metrics.py:10-51,325-354): value and gradient w.r.t. the refined logits, incl. a sample with
+    keep = 0, saturated logits (the eps clamp) and voxels outside every lobe."""
+    import metrics
+    from dram_native import functional as DF
+    torch.manual_seed(5)
+    B, S = 3, (6, 7, 8)
+    dense = (torch.randn(B, 1, *S) * 2).cuda()
+    refined = (torch.randn(B, 1, *S) * 3).cuda()
+    refined[0, 0, 0, 0, :4] = torch.tensor([40.0, -40.0, 17.0, -17.0])          # p saturates: pt hits the clamp
+    lobes = (torch.rand(B, 1, *S) > 0.3).float().cuda()
+    lesions = (torch.rand(B, 1, *S) > 0.5).float().cuda()
+    ctsses = ["3", "0", "5"]
+    loss_obj = metrics.IntRegRefineLoss()
+    keep = torch.tensor([1.0, 0.0, 1.0], device="cuda")
+    r1 = refined.clone().requires_grad_(True)
+    t = loss_obj.pseudo_labels(dense, lobes, lesions, ctsses, keep)
+    ref = loss_obj.bootstrap_loss(torch.sigmoid(r1), t, lobes > 0)
+    ref.backward()
+    r2 = refined.clone().requires_grad_(True)
+    got = DF.BootBce.apply(dense, r2, lobes, lesions, keep, 0.1, 1e-7)
+    got.backward()
+    assert abs(got.item() - ref.item()) <= 2e-6 * abs(ref.item()), (got.item(), ref.item())
+    assert_close(r2.grad, r1.grad, 2e-5, "d seg_loss / d refined")
+    # weighting by an upstream gradient
+    r3 = refined.clone().requires_grad_(True)
+    (DF.BootBce.apply(dense, r3, lobes, lesions, keep, 0.1, 1e-7) * 2.5).backward()
+    assert_close(r3.grad, 2.5 * r1.grad, 2e-5, "scaled gradient")
+
+
 def test_pooling_dense_features_matches_oracle():
     from oracle_import import O
     import models
