@@ -217,6 +217,37 @@ def test_full_size_chunk_against_oracle(att):
     print("full-size gradient check: worst parameter", worst)
 
 
+@pytest.mark.parametrize("size", [(20, 18, 22), (9, 12, 10)])
+def test_ragged_chunk_sizes_against_oracle(size):
+    """Sizes not divisible by 8: MaxPool3d floors odd extents and crop_concat_5d centre-crops the skip tensors with ceil
+    offsets (parts.py:37-46) — the path the reference only takes for unusual RESAMPLE_SIZEs.  Reference channel widths,
+    eval forward + one training-mode loss and backward against the CPU oracle."""
+    from oracle_import import O
+    import metrics
+    g, cfg, m, images, lobes, lesions, ctsses = _full_width_case(False, size, None, 2, seed=51)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    with torch.no_grad():
+        d_ref, r_ref = O.dc3d_forward(sd, images, cfg, False)
+        d, r = m(images.cuda(), lobes.cuda())
+    assert tuple(d.shape) == tuple(d_ref.shape)
+    assert rel_err(d, d_ref) <= 1e-3, rel_err(d, d_ref)
+    assert_close(m.pooling_dense_features(d, lobes.cuda()), O.masked_pool(d_ref, lobes), 1e-3, "pooled score")
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    d_ref, r_ref = O.dc3d_forward(sd, images, cfg, True)
+    rl_ref, sl_ref = O.int_reg_refine_loss(d_ref, r_ref, lobes, lesions, ctsses, g["freq_map"])
+    (2.0 * rl_ref + sl_ref).backward()
+    m.train()
+    rl, sl = metrics.IntRegRefineLoss(**g["loss_cfg"])(m, images.cuda(), lobes.cuda(), lesions.cuda(), ctsses,
+                                                       obj=Host(g["freq_map"]), metas={})
+    (2.0 * rl + sl).backward()
+    assert_close(rl, rl_ref, 1e-3, "reg loss")
+    assert_close(sl, sl_ref, 1e-3, "seg loss")
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
 def test_tensor_core_and_cuda_core_paths_agree_on_gradients(monkeypatch):
     """split-bf16 tcgen05 path vs fp32 CUDA-core path, same module / batch, no CPU involved (chunk 32^3)"""
     import metrics
