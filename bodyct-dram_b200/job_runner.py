@@ -314,10 +314,53 @@ class LesionSegTest(JobRunner):
         new_size = [int(np.ceil(s * sp / new_sp)) for s, sp in zip(arr_t.shape, spacing)]
         return ops.itk_resample(arr_t, new_size, mode, ratios=[new_sp / sp for sp in spacing])
 
-    def run(self):
-        """Process every `<uid>.npz` (keys: image int16, lobe uint8, spacing[, vessel]) under input_image_path."""
-        os.makedirs(os.path.join(self.output_path, self.task_name), exist_ok=True)
+    def archive_results(self, heatmap, pred, post_pred, meta):
+        """job_runner.py:857-890: `<out>/<task>/<uid>.mha` (lesion mask), `heatmap/<uid>.mha` (heat map windowed to uint8),
+        `post/<uid>.mha` (post-processed mask), all uint8 with the scan's origin / direction / original spacing."""
+        from utils import windowing, write_array_to_mha_itk
+        output_path = os.path.join(self.output_path, self.task_name)
+        post_path, heatmap_path = os.path.join(output_path, "post"), os.path.join(output_path, "heatmap")
+        for d in (output_path, post_path, heatmap_path):
+            os.makedirs(d, exist_ok=True)
+        geo = dict(type=np.uint8, origin=list(meta["origin"])[::-1], spacing=list(meta["original_spacing"])[::-1],
+                   direction=np.asarray(meta["direction"]).reshape(3, 3)[::-1].flatten().tolist())
+        write_array_to_mha_itk(output_path, [pred.astype(np.uint8)], [meta["uid"]], **geo)
+        write_array_to_mha_itk(heatmap_path, [windowing(heatmap, from_span=(0, 1)).astype(np.uint8)], [meta["uid"]], **geo)
+        write_array_to_mha_itk(post_path, [post_pred.astype(np.uint8)], [meta["uid"]], **geo)
+
+    def run_mha(self):
+        """The reference's file contract (job_runner.py:906-1067): every `<uid>.mha` scan under input_image_path with its
+        lobe mask `<uid>.mha` under input_lobe_path -> archive_results().  MetaImage I/O is utils.read_mha / write_mha."""
+        from utils import read_mha
         records = []
+        for path in sorted(glob.glob(os.path.join(self.scan_path, "*.mha"))):
+            uid = os.path.splitext(os.path.basename(path))[0]
+            if os.path.exists(os.path.join(self.output_path, self.task_name, uid + ".mha")):
+                self.logger.warning("We have already archived results for scan %s", uid)
+                continue
+            image, geo = read_mha(path)
+            lobe, _ = read_mha(os.path.join(self.lobe_path, uid + ".mha"))
+            start = time.time()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            spacing = [float(v) for v in geo["spacing"][::-1]]                      # ITK x-y-z -> z-y-x
+            scan_t = self.resample_to_working_grid(torch.from_numpy(image.astype(np.int16)).to(dev), spacing, "linear")
+            lobe_t = self.resample_to_working_grid(torch.from_numpy(lobe.astype(np.uint8)).to(dev), spacing, "nearest")
+            new_sp = [float(self.settings.TEST_RESAMPLE_SPACING)] * 3
+            out = self.run_scan(scan_t, lobe_t, new_sp, return_device=True)
+            back = lambda t, mode: ops_itk_back(t, image.shape, new_sp, spacing, mode).cpu().numpy()
+            meta = {"uid": uid, "origin": geo["origin"][::-1], "original_spacing": spacing,
+                    "direction": np.asarray(geo["direction"]).reshape(3, 3)[::-1].flatten().tolist()}
+            self.archive_results(back(out["heatmap"], "linear"), back(out["lesion"], "nearest"),
+                                 back(out["lesion_post"], "nearest"), meta)
+            records.append({"uid": uid, "seconds": time.time() - start, "ratio": float(out["ratio"].item())})
+            self.logger.info("Finished %s, in %.3f seconds.", uid, records[-1]["seconds"])
+        return records
+
+    def run(self):
+        """Process every `<uid>.mha` (reference contract, see run_mha) or `<uid>.npz` (keys: image int16, lobe uint8,
+        spacing[, vessel]) under input_image_path."""
+        os.makedirs(os.path.join(self.output_path, self.task_name), exist_ok=True)
+        records = self.run_mha() if self.lobe_path else []
         for path in sorted(glob.glob(os.path.join(self.scan_path, "*.npz"))):
             uid = os.path.splitext(os.path.basename(path))[0]
             target = os.path.join(self.output_path, self.task_name, uid + ".npz")

@@ -1,10 +1,12 @@
 """Host-side helpers the job runners and entry points need, mirroring the names in the reference's `dram/utils.py`
 (Settings :42-69, get_callable_by_name :280-283, windowing :189-198, find_crops :244-254, binary_cam :226-242,
-expand_dims/squeeze_dims :127-140, IOU/Dice :437-446, AverageMeter :98-114).  Pure numpy/Python — no SimpleITK,
+expand_dims/squeeze_dims :127-140, write_array_to_mha_itk :142-159, IOU/Dice :437-446, AverageMeter :98-114).  Pure numpy/Python — no SimpleITK,
 skimage or OpenCV; the GPU versions of windowing / resampling / Otsu live in libdram_b200 (dram_native.ops)."""
 import importlib
 import importlib.util
 import math
+import os
+import zlib
 
 import numpy as np
 
@@ -114,3 +116,73 @@ def IOU(predict, target, smooth):
 def Dice(predict, target, smooth):
     inter = np.sum(np.logical_and(predict, target))
     return (2. * inter + smooth) / (predict.sum() + target.sum() + smooth)
+
+
+# ------------------------------------------------------------------------------------------------ MetaImage (.mha) I/O
+# The reference writes its outputs with SimpleITK's ImageFileWriter (utils.py:142-159, compressed .mha) and reads scans /
+# lobe masks through SimpleITK.  SimpleITK is not a dependency here: MetaImage is a text header followed by (zlib-
+# compressed) little-endian voxels in x-fastest order, which numpy + zlib cover.  Arrays are z-y-x; spacing / origin are in
+# ITK's x-y-z order exactly as the reference hands them to SetSpacing / SetOrigin (callers reverse them,
+# job_runner.py:873-890); direction is the row-major 3x3 matrix.
+_MET_TYPES = {"MET_UCHAR": np.uint8, "MET_CHAR": np.int8, "MET_USHORT": np.uint16, "MET_SHORT": np.int16,
+              "MET_UINT": np.uint32, "MET_INT": np.int32, "MET_FLOAT": np.float32, "MET_DOUBLE": np.float64}
+_MET_NAMES = {np.dtype(v): k for k, v in _MET_TYPES.items()}
+
+
+def write_mha(path, arr, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), direction=None, compress=True,
+              orientation="RAI"):
+    arr = np.ascontiguousarray(arr)
+    if arr.ndim != 3 or arr.dtype not in _MET_NAMES:
+        raise ValueError(f"write_mha: need a 3-d array of a MetaImage element type, got {arr.dtype} {arr.shape}")
+    direction = np.eye(3).flatten().tolist() if direction is None else list(np.asarray(direction, np.float64).flatten())
+    data = arr.astype(arr.dtype.newbyteorder("<"), copy=False).tobytes()
+    if compress:
+        data = zlib.compress(data, 2)
+    fmt = lambda xs: " ".join(repr(float(x)) if float(x) != int(float(x)) else str(int(float(x))) for x in xs)
+    header = ["ObjectType = Image", "NDims = 3", "BinaryData = True", "BinaryDataByteOrderMSB = False",
+              f"CompressedData = {'True' if compress else 'False'}"]
+    if compress:
+        header.append(f"CompressedDataSize = {len(data)}")
+    header += [f"TransformMatrix = {fmt(direction)}", f"Offset = {fmt(origin)}", "CenterOfRotation = 0 0 0",
+               f"AnatomicalOrientation = {orientation}", f"ElementSpacing = {fmt(spacing)}",
+               f"DimSize = {arr.shape[2]} {arr.shape[1]} {arr.shape[0]}", f"ElementType = {_MET_NAMES[arr.dtype]}",
+               "ElementDataFile = LOCAL"]
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        f.write(data)
+
+
+def read_mha(path):
+    """-> (array z-y-x, {"spacing", "origin", "direction"} in ITK x-y-z order)"""
+    with open(path, "rb") as f:
+        raw = f.read()
+    meta, pos = {}, 0
+    while True:
+        end = raw.index(b"\n", pos)
+        key, _, val = raw[pos:end].decode("ascii", "replace").partition("=")
+        meta[key.strip()] = val.strip()
+        pos = end + 1
+        if key.strip() == "ElementDataFile":
+            break
+    if meta.get("ElementDataFile") != "LOCAL" or int(meta.get("NDims", 3)) != 3:
+        raise ValueError(f"read_mha: only 3-d images with local data are supported ({path})")
+    if meta.get("BinaryDataByteOrderMSB", "False") == "True" or meta.get("ElementByteOrderMSB", "False") == "True":
+        raise ValueError("read_mha: big-endian MetaImages are not supported")
+    dtype = _MET_TYPES[meta["ElementType"]]
+    nx, ny, nz = (int(v) for v in meta["DimSize"].split())
+    data = raw[pos:]
+    if meta.get("CompressedData", "False") == "True":
+        data = zlib.decompress(data)
+    arr = np.frombuffer(data, dtype=np.dtype(dtype).newbyteorder("<"), count=nx * ny * nz).reshape(nz, ny, nx).astype(dtype)
+    floats = lambda k, d: [float(v) for v in meta.get(k, d).split()]
+    return arr, {"spacing": floats("ElementSpacing", "1 1 1"), "origin": floats("Offset", meta.get("Position", "0 0 0")),
+                 "direction": floats("TransformMatrix", "1 0 0 0 1 0 0 0 1")}
+
+
+def write_array_to_mha_itk(target_path, arrs, names, type=np.int16, origin=[0.0, 0.0, 0.0],
+                           direction=np.eye(3, dtype=np.float64).flatten().tolist(), spacing=[1.0, 1.0, 1.0],
+                           orientation='RAI'):
+    """Same signature and files as utils.py:142-159: `<target_path>/<name>.mha`, compressed, one per array (z-y-x)."""
+    for arr, name in zip(arrs, names):
+        write_mha(os.path.join(target_path, '{}.mha'.format(name)), np.asarray(arr).astype(type), spacing, origin, direction,
+                  compress=True, orientation=orientation)

@@ -117,3 +117,23 @@ def test_utils_helpers():
     assert utils.find_crops(mask, (1.0, 0.7, 0.7), 5) == O.find_crops(mask, (1.0, 0.7, 0.7), 5)
     v = np.random.RandomState(1).rand(4000)
     assert abs(utils.binary_cam(v)[1] - O.binary_cam(v)) < 1e-12
+
+
+def test_metaimage_round_trip(tmp_path):
+    """utils.write_array_to_mha_itk (utils.py:142-159) / read_mha: voxels, element type and geometry survive, compressed
+    and uncompressed; the header is what ITK's MetaImageIO writes for a 3-d image."""
+    import utils
+    rs = np.random.RandomState(3)
+    for dtype in (np.uint8, np.int16, np.float32):
+        a = (rs.rand(5, 6, 7) * 200 - 50).astype(dtype)
+        utils.write_array_to_mha_itk(str(tmp_path), [a], ["vol"], type=dtype, origin=[1.5, -2.0, 3.25],
+                                     spacing=[0.7, 0.7, 1.25], direction=[0, 1, 0, 1, 0, 0, 0, 0, 1])
+        b, meta = utils.read_mha(str(tmp_path / "vol.mha"))
+        assert b.dtype == dtype and np.array_equal(a, b)
+        assert meta["spacing"] == [0.7, 0.7, 1.25] and meta["origin"] == [1.5, -2.0, 3.25]
+        assert meta["direction"] == [0, 1, 0, 1, 0, 0, 0, 0, 1]
+        head = open(tmp_path / "vol.mha", "rb").read(400).decode("latin1")
+        assert "DimSize = 7 6 5" in head and "CompressedData = True" in head and "ElementDataFile = LOCAL" in head
+        utils.write_mha(str(tmp_path / "raw.mha"), a, compress=False)
+        c, _ = utils.read_mha(str(tmp_path / "raw.mha"))
+        assert np.array_equal(a, c)

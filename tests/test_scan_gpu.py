@@ -134,3 +134,41 @@ def test_run_scan_matches_oracle(head):
     a, b = out["lesion_post"].astype(bool), ref["lesion_post"].astype(bool)
     assert (2.0 * (a & b).sum() + 1e-5) / (a.sum() + b.sum() + 1e-5) >= 0.999
     assert abs(out["ratio"] - ref["ratio"]) <= 1e-4 * abs(ref["ratio"])
+
+
+def test_run_reads_and_writes_metaimage(tmp_path):
+    """LesionSegTest.run() on the reference's file contract: <uid>.mha scan + lobe mask in, lesion / heat map / post .mha out
+    (job_runner.py:857-890), equal to run_scan on the same arrays resampled the same way."""
+    import job_runner
+    import utils
+    from oracle_import import O
+    from utils import Settings
+    g = torch.load(os.path.join(GOLDEN, "dc3dat_div16_16.pt"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = Settings(os.path.join(root, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    s.MODEL = dict(g["cfg"])
+    s.RESAMPLE_SIZE = (16, 16, 16)
+    scan, lobe, _, _ = O.synthetic_scan((40, 56, 48), (1.0, 0.8, 0.8), seed=7)
+    (tmp_path / "scans").mkdir(); (tmp_path / "lobes").mkdir()
+    geo = dict(origin=[-100.0, 20.5, 7.0], spacing=[0.8, 0.8, 1.0])             # ITK x-y-z
+    utils.write_array_to_mha_itk(str(tmp_path / "scans"), [scan], ["case1"], type=np.int16, **geo)
+    utils.write_array_to_mha_itk(str(tmp_path / "lobes"), [lobe], ["case1"], type=np.uint8, **geo)
+    runner = job_runner.LesionSegTest(str(tmp_path / "scans"), str(tmp_path / "lobes"), str(tmp_path / "out"), s, None)
+    runner.model.load_state_dict(g["state_dict"])
+    records = runner.run()
+    assert [r["uid"] for r in records] == ["case1"]
+    les, meta = utils.read_mha(str(tmp_path / "out" / "test" / "case1.mha"))
+    heat, _ = utils.read_mha(str(tmp_path / "out" / "test" / "heatmap" / "case1.mha"))
+    post, _ = utils.read_mha(str(tmp_path / "out" / "test" / "post" / "case1.mha"))
+    assert les.shape == scan.shape and les.dtype == np.uint8 and heat.shape == scan.shape and post.shape == scan.shape
+    assert meta["spacing"] == geo["spacing"] and meta["origin"] == geo["origin"]
+    dev = torch.device("cuda")
+    sp = [1.0, 0.8, 0.8]
+    scan_t = runner.resample_to_working_grid(torch.from_numpy(scan).to(dev), sp, "linear")
+    lobe_t = runner.resample_to_working_grid(torch.from_numpy(lobe).to(dev), sp, "nearest")
+    out = runner.run_scan(scan_t, lobe_t, [1.0, 1.0, 1.0], return_device=True)
+    ref_les = job_runner.ops_itk_back(out["lesion"], scan.shape, [1.0, 1.0, 1.0], sp, "nearest").cpu().numpy()
+    assert np.array_equal(les, ref_les)
+    ref_heat = job_runner.ops_itk_back(out["heatmap"], scan.shape, [1.0, 1.0, 1.0], sp, "linear").cpu().numpy()
+    assert np.array_equal(heat, utils.windowing(ref_heat, from_span=(0, 1)).astype(np.uint8))
+    assert runner.run() == []                                                    # already archived -> skipped
