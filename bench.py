@@ -190,7 +190,8 @@ def run_b200(args):
     from utils import Settings
 
     B = args.batch
-    settings = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref.py"))
+    att = args.model == "att"                       # BASELINE configs[2]: DC3DATGeneric (PCM lobe-graph attention head)
+    settings = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py" if att else "st_dram_ref.py"))
     settings.OPTIMIZER['lr'] = 1e-3                 # train.py default (train.py:33-34)
     settings.TRAIN_BATCH_SIZE = B
     torch.manual_seed(0)
@@ -286,6 +287,19 @@ def run_b200(args):
         del runner
         torch.cuda.empty_cache()
         extra = {"hbm_kernels": hbm_kernel_rooflines(peaks)}
+        if os.environ.get("DRAM_BWD_PRECISION", "bf16x3") != "bf16x2":
+            # the same step with the gradient operand of dgrad / wgrad carried as ONE bf16 plane (ops.grad_planes_three):
+            # reported next to the headline, never as it - the parity tolerances on gradients are stated for bf16x3
+            os.environ["DRAM_BWD_PRECISION"], os.environ["DRAM_CUDA_GRAPH"] = "bf16x2", "1"
+            torch.manual_seed(0)
+            r2 = job_runner.LesionSegChunkTrain(settings_module=settings)
+            ms2 = time_cuda(lambda: r2.train_step(dev_batch), args.steps, max(args.warmup, 3))
+            extra["train_bwd_bf16x2"] = {"metric": "train_lobe_chunks_per_s", "value": B / (ms2 / 1e3), "ms_per_step": ms2,
+                                         "note": "DRAM_BWD_PRECISION=bf16x2: dy as one bf16 plane x split weights / split "
+                                                 "layer input (2 MMAs per MAC in dgrad and wgrad); forward unchanged"}
+            os.environ["DRAM_BWD_PRECISION"] = "bf16x3"
+            del r2
+            torch.cuda.empty_cache()
         att = build_att_runner()
         m = att.model.eval()
         b5 = make_batch(5, seed=1, pinned=False)
@@ -309,10 +323,12 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32 elsewhere)",
         "data": "synthetic",
-        "config": {"workload": "DRAM training step: DC3D fwd + IntRegRefineLoss + bwd + Adam, synthetic 80^3 lobe chunks, "
-                               f"per-GPU batch {B} (BASELINE configs[1])",
+        "config": {"workload": f"DRAM training step: {'DC3DATGeneric (PCM attention head)' if att else 'DC3D'} fwd + "
+                               "IntRegRefineLoss + bwd + Adam, synthetic 80^3 lobe chunks, "
+                               f"per-GPU batch {B} (BASELINE configs[{2 if att else 1}])",
                    "per_gpu_batch": B, "global_batch": B * world, "chunk": list(CHUNK), "parallelism": f"dp{world}",
                    "precision_mode": os.environ.get("DRAM_PRECISION", "bf16x3"),
+                   "backward_precision": os.environ.get("DRAM_BWD_PRECISION", "bf16x3"),
                    "cuda_graph": graphed,
                    "l2": "no flush needed: ~13 GB of activations stream through the 126 MB L2 every step"},
         "clocks": clocks,
@@ -640,6 +656,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="train", choices=["train", "infer", "scan"],
                     help="train = BASELINE configs[1] (default, the driver's line); infer = chunk inference; scan = full-CT pipeline")
+    ap.add_argument("--model", default="dc3d", choices=["dc3d", "att"],
+                    help="train workload: dc3d = BASELINE configs[1]; att = DC3DATGeneric with the PCM head (configs[2])")
     ap.add_argument("--small", action="store_true", help="scan workload: 128x128x100 scan (quick check)")
     ap.add_argument("--no-extra", action="store_true", help="train workload: skip the extra inference / HBM-roofline figures")
     args = ap.parse_args()

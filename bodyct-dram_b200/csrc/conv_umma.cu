@@ -148,7 +148,7 @@ struct FwdParams {
   // kw-reuse mode (w3 = 1): one A box of (TW+2) x TH voxels per (kd,kh,channel block) serves the three kw taps.  The box is
   // loaded through a tensor map whose dimension order is (C,H,W,D,N), so shared-memory rows are ordered [w][h]: with
   // TH = 8 every w column is one 8-row / 1024-byte swizzle group and a kw shift is a 1024-byte-aligned descriptor offset.
-  int w3, a_plane_bytes, taps_per_stage, b_tap_bytes;
+  int w3, a_plane_bytes, taps_per_stage, b_tap_bytes, a_lo;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -163,9 +163,10 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                  tempty0 = smem_u32(bars + 2 * S + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool three = p.passes == 3;
+  const bool three = p.passes == 3;            // the weight operand has a lo plane
+  const bool a_lo = p.a_lo != 0;               // the activation operand has a lo plane (0: single-plane dy in dgrad)
   const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t offAlo = (uint32_t)p.a_plane_bytes, offBhi = (three ? 2u : 1u) * (uint32_t)p.a_plane_bytes,
+  const uint32_t offAlo = (uint32_t)p.a_plane_bytes, offBhi = (a_lo ? 2u : 1u) * (uint32_t)p.a_plane_bytes,
                  offBlo = offBhi + b_tile_bytes;
 
   if (threadIdx.x == 0) {
@@ -187,12 +188,13 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // whole warp converged, one elected lane issues (see elect_one)
     if (elect_one()) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
-      if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+      if (three) tma_prefetch_desc(&tmB_lo);
+      if (a_lo) tma_prefetch_desc(&tmA_lo);
     }
     {
       // bytes TMA will actually deliver: the A box has TW*TH*TD rows (<= 128), zero-filled halo included
       const uint32_t a_box_bytes = (uint32_t)((p.w3 ? (p.TW + 2) : p.TW) * p.TH * p.TD) * 128u;
-      const uint32_t stage_tx = (three ? 2u : 1u) * (a_box_bytes + (uint32_t)tps * b_tile_bytes);
+      const uint32_t stage_tx = (a_lo ? 2u : 1u) * a_box_bytes + (three ? 2u : 1u) * (uint32_t)tps * b_tile_bytes;
       uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
@@ -212,10 +214,10 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               mbar_expect_tx(fb, stage_tx);
               if (p.w3) {                                 // map dims (C,H,W,D,N); kw = 0 here, box starts at w0 - 1
                 tma_load_5d(sb, &tmA_hi, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
-                if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+                if (a_lo) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
               } else {
                 tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
-                if (three) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+                if (a_lo) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
               }
               for (int t = 0; t < tps; ++t) {
                 const uint32_t bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
@@ -250,14 +252,14 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             for (int t = 0; t < tps; ++t) {            // kw-reuse: tap t reads the halo box shifted by t columns = t*1024 B
               const uint32_t ao = (uint32_t)t * 1024u, bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
               const uint64_t a_hi = umma_desc(sb + ao, 16, 1024), b_hi = umma_desc(sb + offBhi + bo, 16, 1024);
-              const uint64_t a_lo = umma_desc(sb + offAlo + ao, 16, 1024);
+              const uint64_t a_lod = umma_desc(sb + offAlo + ao, 16, 1024);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {           // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
                 const uint64_t adv = (uint64_t)(k * 2);
                 const uint32_t accum = (kb | t | k) ? 1u : 0u;
                 if (three) {
                   umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
-                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                  if (a_lo) umma_bf16(d_tmem, a_lod + adv, b_hi + adv, idesc, 1u);
                 } else {
                   umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
                 }
@@ -345,7 +347,8 @@ struct Fwd2Params {
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
 };
 
-// MODE 0: one pass (bf16); 1: split-bf16 with the [B_hi | B_lo] N-concatenation (BN <= 64); 2: split-bf16, three N = BN MMAs
+// MODE 0: one pass (bf16); 1: split-bf16 with the [B_hi | B_lo] N-concatenation (BN <= 64); 2: split-bf16, three N = BN MMAs;
+// 3 / 4: as 1 / 2 with a SINGLE-plane A operand (dgrad with dy carried as one bf16 plane): A x [B_hi | B_lo], resp. A x B_hi, A x B_lo
 template <int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -353,7 +356,8 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const Fwd2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr bool three = MODE != 0, concat = MODE == 1;
+  constexpr bool three = MODE != 0 /* B has a lo plane */, a2 = (MODE == 1 || MODE == 2) /* A has a lo plane */,
+                 concat = (MODE == 1 || MODE == 3);
   const int SB = p.SB;
   uint8_t* smemB = smem + 2 * (size_t)p.a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)SB * p.b_stage_bytes);
@@ -381,10 +385,11 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ------------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
     if (elect_one()) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
-      if (three) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+      if (three) tma_prefetch_desc(&tmB_lo);
+      if (a2) tma_prefetch_desc(&tmA_lo);
     }
-    constexpr uint32_t planes = three ? 2u : 1u;
-    const uint32_t b_tx = planes * (uint32_t)p.BN * 128u;
+    constexpr uint32_t planes = a2 ? 2u : 1u;
+    const uint32_t b_tx = (three ? 2u : 1u) * (uint32_t)p.BN * 128u;
     uint32_t itA = 0, sB = 0, phB = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int nt = item % p.n_ntiles, pair = item / p.n_ntiles;
@@ -408,10 +413,10 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes, fa = fullA0 + 8 * sA;
             mbar_expect_tx(fa, a_tx);
             tma_load_5d(ab, &tmA_hi, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
-            if (three) tma_load_5d(ab + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
+            if (a2) tma_load_5d(ab + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
             if (ntile == 2) {
               tma_load_5d(ab + p.a_tile_bytes, &tmA_hi, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
-              if (three) tma_load_5d(ab + p.a_tile_bytes + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
+              if (a2) tma_load_5d(ab + p.a_tile_bytes + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
             }
           }
           __syncwarp();
@@ -474,13 +479,11 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t accum = (g | kw | k) ? 1u : 0u;
                 if (concat) {
                   umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);
-                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                  if (a2) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 } else {
                   umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
-                  if (three) {
-                    umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                  }
+                  if (three) umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                  if (a2) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
               }
             }
@@ -563,6 +566,8 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 //   MODE 0 (64-channel tiles): A = [W_hi ; W_lo] stacked on M; two MMAs per K step (x X_hi, x X_lo) give all FOUR split
 //            products (the lo*lo term comes for free); the epilogue adds accumulator rows co and co + 64.
 //   MODE 1 (128-channel tiles): A = W_hi or W_lo; three MMAs per K step (hi*hi, lo*hi, hi*lo) into the same accumulator.
+//   MODE 2 / 3: the same with a SINGLE-plane activation operand (dgrad with dy carried as one bf16 plane): MODE 2 is one
+//            MMA per K step ([W_hi ; W_lo] x X = exactly the two products), MODE 3 two (W_hi x X, W_lo x X).
 // Tile = 8(h) x TDD(d) x TW(w) = 256 voxels ((16,2) at 80^3, (8,4) at 40^3), same [w][d][h] row order and kw-shift trick
 // as k_conv_umma_fwd2; accumulator 128 lanes x 256 columns, double buffered (all 512 TMEM columns).
 struct Fwd3Params {
@@ -582,7 +587,8 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                  const Fwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int kXchgBytes = MODE == 0 ? 8192 : 0;     // 2 pairs x 2 parities x 2 directions x [8 columns][32 lanes] floats
+  constexpr bool stacked = (MODE == 0 || MODE == 2), x2 = MODE < 2;   // x2: the activation operand has a lo plane
+  constexpr int kXchgBytes = stacked ? 8192 : 0;     // 2 pairs x 2 parities x 2 directions x [8 columns][32 lanes] floats
   const int SW = p.SW;
   uint8_t* smemW = smem + 2 * (size_t)p.x_stage_bytes;
   float* xchg = reinterpret_cast<float*>(smemW + (size_t)SW * p.w_stage_bytes);
@@ -610,8 +616,8 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo); }
-    const uint32_t x_tx = 2u * (uint32_t)p.x_plane_bytes, w_tx = (uint32_t)p.w_stage_bytes;
+    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo); if (x2) tma_prefetch_desc(&tmX_lo); }
+    const uint32_t x_tx = (x2 ? 2u : 1u) * (uint32_t)p.x_plane_bytes, w_tx = (uint32_t)p.w_stage_bytes;
     uint32_t itX = 0, sW = 0, phW = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int ct = item % p.n_ctiles;
@@ -629,7 +635,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             const uint32_t xb = smemX_u + sX * (uint32_t)p.x_stage_bytes, fx = fullX0 + 8 * sX;
             mbar_expect_tx(fx, x_tx);
             tma_load_5d(xb, &tmX_hi, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
-            tma_load_5d(xb + p.x_plane_bytes, &tmX_lo, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
+            if (x2) tma_load_5d(xb + p.x_plane_bytes, &tmX_lo, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
           }
           __syncwarp();
 #pragma unroll
@@ -679,20 +685,15 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             const uint32_t wb = smemW_u + sW * (uint32_t)p.w_stage_bytes;
             const uint64_t x_hi = umma_desc(xb + (uint32_t)kw * kw_shift, 16, 1024);
             const uint64_t x_lo = umma_desc(xb + (uint32_t)p.x_plane_bytes + (uint32_t)kw * kw_shift, 16, 1024);
-            const uint64_t w_a = umma_desc(wb, 16, 1024);                                     // MODE 0: [W_hi ; W_lo]; MODE 1: W_hi
-            const uint64_t w_b = umma_desc(wb + ((uint32_t)p.w_stage_bytes >> 1), 16, 1024);  // MODE 1: W_lo
+            const uint64_t w_a = umma_desc(wb, 16, 1024);                                     // stacked: [W_hi ; W_lo]; plain: W_hi
+            const uint64_t w_b = umma_desc(wb + ((uint32_t)p.w_stage_bytes >> 1), 16, 1024);  // plain: W_lo
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
               const uint32_t accum = (g | kw | k) ? 1u : 0u;
-              if (MODE == 0) {
-                umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
-                umma_bf16(d_tmem, w_a + adv, x_lo + adv, idesc, 1u);
-              } else {
-                umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
-                umma_bf16(d_tmem, w_b + adv, x_hi + adv, idesc, 1u);
-                umma_bf16(d_tmem, w_a + adv, x_lo + adv, idesc, 1u);
-              }
+              umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
+              if (!stacked) umma_bf16(d_tmem, w_b + adv, x_hi + adv, idesc, 1u);
+              if (x2) umma_bf16(d_tmem, w_a + adv, x_lo + adv, idesc, 1u);
             }
             umma_commit(emptyW0 + 8 * sW);
             if (kw == 2) umma_commit(emptyX0 + 8 * sX);
@@ -728,7 +729,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
       if (prof) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
-      if (MODE == 1) {
+      if (!stacked) {
         const int co = ct * p.CT + q * 32 + lane;
         const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
         for (int c0 = 0; c0 < 256; c0 += 16) {
@@ -795,7 +796,7 @@ struct WgParams {
   float* ws;                                    // [slabs][n_mtiles][n_ntiles][128][BN]
   int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles, n_ntiles, BN;
   int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, chunks_per_slab;
-  int passes, stages, stage_bytes, tmem_cols, concat;
+  int passes, stages, stage_bytes, tmem_cols, concat, y_lo;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -810,7 +811,8 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
                  tempty0 = smem_u32(bars + 2 * S + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool three = p.passes == 3;
+  const bool three = p.passes == 3;             // X (layer input) has a lo plane
+  const bool y2 = p.y_lo != 0;                  // dY has a lo plane (0: gradient carried as one bf16 plane)
   const int nb = p.BN / 64;                                            // 64-channel blocks of the N operand
   const uint32_t a_bytes = 2u * kWgBlkBytes, b_bytes = (uint32_t)nb * kWgBlkBytes;
   const uint32_t offAlo = a_bytes, offBhi = three ? 2 * a_bytes : a_bytes, offBlo = offBhi + b_bytes;
@@ -832,7 +834,8 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
     // whole warp converged, one elected lane issues (see elect_one)
     if (elect_one()) {
       tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmY_hi);
-      if (three) { tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_lo); }
+      if (three) tma_prefetch_desc(&tmX_lo);
+      if (y2) tma_prefetch_desc(&tmY_lo);
     }
     {
       uint32_t s = 0, ph = 0;
@@ -842,7 +845,7 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
         const int slab = item / (p.n_ntiles * p.n_mtiles);
         const int mb0 = 2 * mt, mb1 = 2 * mt + 1;
         const bool has1 = mb1 < p.MB;
-        const uint32_t tx = (three ? 2u : 1u) * ((has1 ? 2u : 1u) * kWgBlkBytes + b_bytes);
+        const uint32_t tx = (three ? 2u : 1u) * (has1 ? 2u : 1u) * kWgBlkBytes + (y2 ? 2u : 1u) * b_bytes;
         const int tap0 = mb0 / p.CB, cb0 = mb0 % p.CB, tap1 = has1 ? mb1 / p.CB : 0, cb1 = has1 ? mb1 % p.CB : 0;
         const int kd0 = p.taps == 1 ? 0 : tap0 / 9 - p.pad, kh0 = p.taps == 1 ? 0 : (tap0 / 3) % 3 - p.pad, kw0 = p.taps == 1 ? 0 : tap0 % 3 - p.pad;
         const int kd1 = p.taps == 1 ? 0 : tap1 / 9 - p.pad, kh1 = p.taps == 1 ? 0 : (tap1 / 3) % 3 - p.pad, kw1 = p.taps == 1 ? 0 : tap1 % 3 - p.pad;
@@ -866,7 +869,7 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
             }
             for (int j = 0; j < nb; ++j) {
               tma_load_5d(sb + offBhi + j * kWgBlkBytes, &tmY_hi, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
-              if (three) tma_load_5d(sb + offBlo + j * kWgBlkBytes, &tmY_lo, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
+              if (y2) tma_load_5d(sb + offBlo + j * kWgBlkBytes, &tmY_lo, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
             }
           }
           __syncwarp();
@@ -902,10 +905,8 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
                 umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
               } else {
                 umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
-                if (three) {
-                  umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                  umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                }
+                if (y2) umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                if (three) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
               }
             }
             umma_commit(empty0 + 8 * s);
@@ -970,7 +971,7 @@ constexpr int kW3Stage = 4 * kW3XBox + 2 * kW3YBox;
 
 struct Wg3Params {
   float* ws;
-  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages, dfast;
+  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages, dfast, y_lo;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -1002,13 +1003,13 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
 
   if (warp == 0) {
     // whole warp converged, one elected lane issues (see elect_one)
-    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo); }
+    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); if (p.y_lo) tma_prefetch_desc(&tmY_lo); }
     {
       uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pair = item % p.n_pairs, slab = item / p.n_pairs;
         const int nsrc = (2 * pair + 1 < p.n_src) ? 2 : 1;
-        const uint32_t tx = 2u * (uint32_t)nsrc * kW3XBox + 2u * kW3YBox;
+        const uint32_t tx = 2u * (uint32_t)nsrc * kW3XBox + (p.y_lo ? 2u : 1u) * kW3YBox;
         const int s0 = 2 * pair, s1 = min(2 * pair + 1, p.n_src - 1);
         const int cb0 = s0 % p.CB, kh0 = (s0 / p.CB) % 3 - 1, kd0 = s0 / (3 * p.CB) - 1;
         const int cb1 = s1 % p.CB, kh1 = (s1 / p.CB) % 3 - 1, kd1 = s1 / (3 * p.CB) - 1;
@@ -1039,7 +1040,7 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
               tma_load_5d(sb + offXlo + kW3XBox, &tmX_lo, fb, cb1 * 64, h0 + kh1, w0 - 1, d0 + kd1, n0);
             }
             tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
-            tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
+            if (p.y_lo) tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -1076,7 +1077,7 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {           // 16 voxel rows (two w columns, 2048 B) per MMA
                   const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, k ? 1u : first);
+                  umma_bf16(d_tmem, a_hi + adv, b_hi + adv, p.y_lo ? idesc2 : idesc, k ? 1u : first);   // N = 128: [dY_hi | dY_lo]
                   umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
               }
@@ -1105,8 +1106,12 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         for (int c0 = 0; c0 < 64; c0 += 16) {
           uint32_t r[16], r2[16];
           tmem_ld16(taddr + c0, r);
-          tmem_ld16(taddr + 64 + c0, r2);
+          if (p.y_lo) tmem_ld16(taddr + 64 + c0, r2);
           tmem_ld_wait();
+          if (!p.y_lo) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r2[j] = 0u;                       // +0.0f
+          }
           if (valid || row < 64) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -1347,7 +1352,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
                          const float* shift, float* y, int N, int D, int H, int W, int Cin_pad, int Cout, int ksize,
                          void* stream) {
   DRAM_REQUIRE(x_hi && w_hi && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
-  DRAM_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "conv3d_umma_fwd: x_lo and w_lo must both be set (bf16x3) or both NULL (bf16)");
+  DRAM_REQUIRE(!(x_lo != nullptr && w_lo == nullptr), "conv3d_umma_fwd: x_lo needs w_lo (modes: both = bf16x3, w_lo only = single-plane activations x split weights, neither = bf16)");
   DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin_pad > 0 && Cin_pad % 64 == 0, "conv3d_umma_fwd: Cin_pad=%d must be a multiple of 64", Cin_pad);
@@ -1355,30 +1360,32 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
   // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
   const char* v3_env = getenv("DRAM_CONV_V3");
-  int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && Cin_pad <= 128)) ? 1 : 0);
+  int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && (Cin_pad <= 128 || !x_lo))) ? 1 : 0);
   if (use_v3 == 2) use_v3 = (Cout % 128 == 0) ? 1 : 0;       // experiment: 128-channel tiles only
-  if (use_v3 && x_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
+  if (use_v3 && w_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
       ((W % 16 == 0 && D % 2 == 0) || (W % 8 == 0 && D % 4 == 0))) {
     Fwd3Params q;
-    const int mode = (Cout % 128 == 0) ? 1 : 0;
+    const int plain = (Cout % 128 == 0) ? 1 : 0;
+    const int mode = plain + (x_lo ? 0 : 2);
     q.y = y; q.scale = scale; q.shift = shift;
-    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = mode ? 128 : 64; q.kblocks_c = Cin_pad / 64;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = plain ? 128 : 64; q.kblocks_c = Cin_pad / 64;
     if (W % 16 == 0 && D % 2 == 0) { q.TW = 16; q.TDD = 2; } else { q.TW = 8; q.TDD = 4; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
     q.n_vtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
     q.n_ctiles = Cout / q.CT;
     q.n_items = q.n_vtiles * q.n_ctiles;
     q.x_plane_bytes = (q.TW + 2) * q.TDD * 1024;
-    q.x_stage_bytes = 2 * q.x_plane_bytes;
-    q.w_stage_bytes = 2 * 128 * 128 / (mode ? 1 : 2);          // MODE 0: 64 hi + 64 lo rows; MODE 1: 128 + 128 rows
-    const int xchg = mode ? 0 : 8192;
+    q.x_stage_bytes = (x_lo ? 2 : 1) * q.x_plane_bytes;
+    q.w_stage_bytes = 2 * 128 * 128 / (plain ? 1 : 2);         // stacked: 64 hi + 64 lo rows; plain: 128 + 128 rows
+    const int xchg = plain ? 0 : 8192;
     q.SW = (227 * 1024 - 1024 - 512 - xchg - 2 * q.x_stage_bytes) / q.w_stage_bytes;
     if (q.SW > 6) q.SW = 6;
     DRAM_REQUIRE(q.SW >= 2, "conv3d_umma_fwd: channels-on-M pipeline does not fit in shared memory");
     CUtensorMap mX_hi, mX_lo, mW_hi, mW_lo;
     int rc3;
     if ((rc3 = make_volume_map_hdw(&mX_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3;
-    if ((rc3 = make_volume_map_hdw(&mX_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3;
+    if (x_lo) { if ((rc3 = make_volume_map_hdw(&mX_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3; }
+    else mX_lo = mX_hi;
     if ((rc3 = make_weight_map(&mW_hi, w_hi, 27ll * Cout, Cin_pad, q.CT))) return rc3;
     if ((rc3 = make_weight_map(&mW_lo, w_lo, 27ll * Cout, Cin_pad, q.CT))) return rc3;
     const size_t smem3 = 2 * (size_t)q.x_stage_bytes + (size_t)q.SW * q.w_stage_bytes + xchg + 1024 + 512;
@@ -1386,6 +1393,8 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     std::call_once(once3, [] {
       cudaFuncSetAttribute(k_conv_umma_fwd3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(k_conv_umma_fwd3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     const int grid3 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
     static long long* prof_buf3 = nullptr;
@@ -1393,7 +1402,9 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     if (want_prof3 && !prof_buf3) cudaMalloc(&prof_buf3, kNumSMs * 8 * sizeof(long long));
     q.prof = want_prof3 ? prof_buf3 : nullptr;
     if (mode == 0) k_conv_umma_fwd3<0><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
-    else k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    else if (mode == 1) k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    else if (mode == 2) k_conv_umma_fwd3<2><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    else k_conv_umma_fwd3<3><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
     DRAM_LAUNCH_CHECK();
     if (want_prof3) {
       long long h[kNumSMs * 8];
@@ -1410,8 +1421,8 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   if (allow_v2 && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) && Cout % 32 == 0) {
     Fwd2Params q;
     q.BN = Cout <= 64 ? Cout : (Cout % 128 == 0 ? 128 : (Cout % 96 == 0 ? 96 : (Cout % 64 == 0 ? 64 : 32)));
-    const int mode = !x_lo ? 0 : (q.BN <= 64 ? 1 : 2);
-    q.acc_cols = mode == 1 ? 2 * q.BN : q.BN;
+    const int mode = !w_lo ? 0 : ((q.BN <= 64 ? 1 : 2) + (x_lo ? 0 : 2));
+    q.acc_cols = (mode == 1 || mode == 3) ? 2 * q.BN : q.BN;
     q.tmem_cols = pow2_cols(4 * q.acc_cols);
     q.y = y; q.scale = scale; q.shift = shift;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64;
@@ -1423,7 +1434,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     q.a_plane_bytes = (q.TW + 2) * q.TDD * 1024;
     q.a_tile_bytes = (x_lo ? 2 : 1) * q.a_plane_bytes;
     q.a_stage_bytes = 2 * q.a_tile_bytes;
-    q.b_stage_bytes = (x_lo ? 2 : 1) * q.BN * 128;
+    q.b_stage_bytes = (w_lo ? 2 : 1) * q.BN * 128;
     const int smem_max = 227 * 1024;
     q.SB = (smem_max - 1024 - 512 - 2 * q.a_stage_bytes) / q.b_stage_bytes;
     if (q.SB > 8) q.SB = 8;
@@ -1432,18 +1443,17 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     int rc2;
     if ((rc2 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
     if ((rc2 = make_weight_map(&mB_hi, w_hi, 27ll * Cout, Cin_pad, q.BN))) return rc2;
-    if (x_lo) {
-      if ((rc2 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
-      if ((rc2 = make_weight_map(&mB_lo, w_lo, 27ll * Cout, Cin_pad, q.BN))) return rc2;
-    } else {
-      mA_lo = mA_hi; mB_lo = mB_hi;
-    }
+    mA_lo = mA_hi; mB_lo = mB_hi;
+    if (x_lo && (rc2 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
+    if (w_lo && (rc2 = make_weight_map(&mB_lo, w_lo, 27ll * Cout, Cin_pad, q.BN))) return rc2;
     const size_t smem2 = 2 * (size_t)q.a_stage_bytes + (size_t)q.SB * q.b_stage_bytes + 1024 + 512;
     static std::once_flag once2;
     std::call_once(once2, [] {
       cudaFuncSetAttribute(k_conv_umma_fwd2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(k_conv_umma_fwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(k_conv_umma_fwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_conv_umma_fwd2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     static long long* prof_buf = nullptr;
     static const bool want_prof = getenv("DRAM_CONV_PROF") != nullptr;
@@ -1452,7 +1462,9 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     const int grid2 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
     if (mode == 0) k_conv_umma_fwd2<0><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
     else if (mode == 1) k_conv_umma_fwd2<1><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
-    else k_conv_umma_fwd2<2><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    else if (mode == 2) k_conv_umma_fwd2<2><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    else if (mode == 3) k_conv_umma_fwd2<3><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    else k_conv_umma_fwd2<4><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
     DRAM_LAUNCH_CHECK();
     if (want_prof) {                         // diagnostics: per-CTA averages of the MMA thread's and one epilogue warp's cycle split
       long long h[kNumSMs * 8];
@@ -1479,27 +1491,25 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD);
   p.n_mtiles = N * p.tiles_d * p.tiles_h * p.tiles_w;
   p.n_ntiles = Cout / p.BN;
-  p.passes = x_lo ? 3 : 1;
+  p.passes = w_lo ? 3 : 1;
+  p.a_lo = x_lo ? 1 : 0;
   p.taps_per_stage = p.w3 ? 3 : 1;
   p.a_plane_bytes = p.w3 ? (p.TW + 2) * p.TH * 128 : kATileBytes;
-  p.b_tap_bytes = (x_lo ? 2 : 1) * p.BN * 128;
+  p.b_tap_bytes = (w_lo ? 2 : 1) * p.BN * 128;
   p.stage_bytes = (x_lo ? 2 : 1) * p.a_plane_bytes + p.taps_per_stage * p.b_tap_bytes;
   p.stages = (kSmemBudget - 1024) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
   DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_fwd: pipeline does not fit in shared memory");
-  p.acc_cols = (x_lo ? 2 : 1) * p.BN;
+  p.acc_cols = (w_lo ? 2 : 1) * p.BN;
   p.tmem_cols = pow2_cols(2 * p.acc_cols);
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc;
   const int abw = p.w3 ? p.TW + 2 : p.TW;
   if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
   if ((rc = make_weight_map(&tmB_hi, w_hi, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
-  if (x_lo) {
-    if ((rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
-    if ((rc = make_weight_map(&tmB_lo, w_lo, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
-  } else {
-    tmA_lo = tmA_hi; tmB_lo = tmB_hi;
-  }
+  tmA_lo = tmA_hi; tmB_lo = tmB_hi;
+  if (x_lo && (rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
+  if (w_lo && (rc = make_weight_map(&tmB_lo, w_lo, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(k_conv_umma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -1510,7 +1520,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   return DRAM_OK;
 }
 
-static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize, int passes) {
+static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize, int passes, int y_lo = 1) {
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
   p.CB = Cin_pad / 64; p.MB = p.taps * p.CB; p.n_mtiles = cdiv(p.MB, 2);
@@ -1537,10 +1547,11 @@ static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int 
   p.chunks_per_slab = cdiv(p.n_chunks, best);
   p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
   p.passes = passes;
-  p.stage_bytes = (passes == 3 ? 2 : 1) * (2 * kWgBlkBytes + (p.BN / 64) * kWgBlkBytes);
+  p.y_lo = (passes == 3 && y_lo) ? 1 : 0;
+  p.stage_bytes = (passes == 3 ? 2 : 1) * 2 * kWgBlkBytes + (p.y_lo ? 2 : 1) * (p.BN / 64) * kWgBlkBytes;
   p.stages = (kSmemBudget - 1024) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  p.concat = (passes == 3 && p.BN <= 128) ? 1 : 0;
+  p.concat = (passes == 3 && p.y_lo && p.BN <= 128) ? 1 : 0;
   p.tmem_cols = pow2_cols(2 * (p.concat ? 2 * p.BN : p.BN));
   return DRAM_OK;
 }
@@ -1603,20 +1614,22 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
                            void* workspace, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad,
                            int ksize, void* stream) {
   DRAM_REQUIRE(dy_hi && x_hi && dw && workspace && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_wgrad: bad arguments");
-  DRAM_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv3d_umma_wgrad: dy_lo and x_lo must both be set or both NULL");
+  DRAM_REQUIRE(!(dy_lo != nullptr && x_lo == nullptr), "conv3d_umma_wgrad: dy_lo needs x_lo (modes: both = bf16x3, x_lo only = single-plane gradient x split input, neither = bf16)");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_wgrad: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin > 0 && Cin_pad >= Cin && Cin_pad % 64 == 0 && Cout > 0 && Cout_pad >= Cout && Cout_pad % 64 == 0,
                "conv3d_umma_wgrad: channel pads must be multiples of 64 (Cin %d/%d, Cout %d/%d)", Cin, Cin_pad, Cout, Cout_pad);
-  if (wgrad_w3_ok(H, W, Cout_pad, ksize, dy_lo ? 3 : 1)) {
+  if (wgrad_w3_ok(H, W, Cout_pad, ksize, x_lo ? 3 : 1)) {
     Wg3Params q;
     wgrad_w3_plan(q, N, D, H, W, Cin_pad);
     q.ws = (float*)workspace;
+    q.y_lo = dy_lo ? 1 : 0;
     CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo;
     int rc3;
     if ((rc3 = make_volume_map(&mX_hi, x_hi, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
     if ((rc3 = make_volume_map(&mX_lo, x_lo, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
     if ((rc3 = make_volume_map(&mY_hi, dy_hi, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3;
-    if ((rc3 = make_volume_map(&mY_lo, dy_lo, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3;
+    if (dy_lo) { if ((rc3 = make_volume_map(&mY_lo, dy_lo, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3; }
+    else mY_lo = mY_hi;
     const size_t smem3 = (size_t)q.stages * kW3Stage + 1024 + 256;
     static std::once_flag once3;
     std::call_once(once3, [] { cudaFuncSetAttribute(k_conv_umma_wgrad_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -1629,7 +1642,7 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     return DRAM_OK;
   }
   WgParams p;
-  wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, dy_lo ? 3 : 1);
+  wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, x_lo ? 3 : 1, dy_lo ? 1 : 0);
   DRAM_REQUIRE(p.stages >= 2, "conv3d_umma_wgrad: pipeline does not fit in shared memory");
   DRAM_REQUIRE(p.tmem_cols <= 512, "conv3d_umma_wgrad: accumulator does not fit in TMEM");
   p.ws = (float*)workspace;
@@ -1637,12 +1650,9 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
   int rc;
   if ((rc = make_volume_map(&tmX_hi, x_hi, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
   if ((rc = make_volume_map(&tmY_hi, dy_hi, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
-  if (dy_lo) {
-    if ((rc = make_volume_map(&tmX_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
-    if ((rc = make_volume_map(&tmY_lo, dy_lo, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
-  } else {
-    tmX_lo = tmX_hi; tmY_lo = tmY_hi;
-  }
+  tmX_lo = tmX_hi; tmY_lo = tmY_hi;
+  if (x_lo && (rc = make_volume_map(&tmX_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  if (dy_lo && (rc = make_volume_map(&tmY_lo, dy_lo, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(k_conv_umma_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });

@@ -70,7 +70,7 @@ def conv_dgrad(dy, w, dys=None):
     """dx = conv(dy, flipped/transposed w).  `dys` = already split planes of dy (shared with wgrad)."""
     Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
     if ops.umma_ok_fwd(Cout, Cin, k):
-        dys = dys if dys is not None else ops.split_bf16(dy)
+        dys = dys if dys is not None else ops.split_bf16(dy, three=ops.grad_planes_three())
         w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_dgrad", lambda: ops.pack_weight_bf16(w.detach(), 1))
         return ops.conv_umma(dys, w_hi, w_lo, Cin, k)
     pack = WEIGHTS.get(w, "f32_dgrad", lambda: ops.pack_weight_f32(w.detach(), 1))
@@ -134,7 +134,7 @@ SIDE = _SideStream()
 def conv_wgrad(saved_in, dy, w, dys=None):
     Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
     if isinstance(saved_in, ops.SplitPlanes):
-        dys = dys if dys is not None else ops.split_bf16(dy)
+        dys = dys if dys is not None else ops.split_bf16(dy, three=ops.grad_planes_three())
         if SIDE.enabled() and not ops._lib.PROFILE.enabled:      # per-kernel event timing needs a single stream
             side = SIDE.fork()
             if side is not None:
@@ -295,7 +295,7 @@ class ConvBnRelu(torch.autograd.Function):
                     dbeta, dgamma = sums[:C].float(), sums[C:].float()
         saved_in = ctx.saved_planes if ctx.umma else x_plain
         if dys is None and (ctx.umma or (ctx.needs_input_grad[0] and ops.umma_ok_fwd(Cout, Cin, k))):
-            dys = ops.split_bf16(dy)
+            dys = ops.split_bf16(dy, three=ops.grad_planes_three())
         dx = conv_dgrad(dy, w, dys) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(saved_in, dy, w, dys) if ctx.needs_input_grad[3] else None
         dbias = dy.sum(dim=(0, 2, 3, 4)) if ctx.has_bias else None

@@ -79,6 +79,16 @@ def precision():
     return os.environ.get("DRAM_PRECISION", "bf16x3")
 
 
+def grad_planes_three():
+    """Does the GRADIENT operand of dgrad / wgrad (dy) carry a lo plane?  Default yes (three products, the parity mode every
+    gradient tolerance in tests/ is stated for).  DRAM_BWD_PRECISION=bf16x2 carries dy as ONE bf16 plane, multiplied with the
+    split weights (dgrad: dy*w_hi + dy*w_lo) and the split layer input (wgrad: x_hi*dy + x_lo*dy): exact products with the
+    bf16-rounded gradient (tests/test_kernels_gpu.py), ~6 ms of the 70 ms training step, per-parameter gradient error against
+    the fp32 CPU oracle 1e-3 -> 4e-3 at 32^3 and 5.0e-3 -> 5.6e-3 at 80^3 (tests/diag_bwd_x2.py).
+    Forward quantities are untouched either way."""
+    return precision() == "bf16x3" and os.environ.get("DRAM_BWD_PRECISION", "bf16x3") != "bf16x2"
+
+
 def _pad64(c):
     return (c + 63) // 64 * 64
 
@@ -268,7 +278,7 @@ def bn_relu_bwd_apply(da, y, scale, shift, mean, rstd, gamma, sums, count, pitch
 def bn_relu_bwd_apply_planes(da, pitch, wtop, y, scale, shift, mean, rstd, gamma, sums, count):
     """dy of the BatchNorm+ReLU backward as split planes (operand of dgrad / wgrad)"""
     N, C, D, H, W = y.shape
-    dys = alloc_planes((N, C, D, H, W))
+    dys = alloc_planes((N, C, D, H, W), three=grad_planes_three())
     _lib.check(_L().dram_bn_relu_bwd_apply_planes(da.data_ptr(), int(pitch), _p(wtop), y.data_ptr(), scale.data_ptr(),
                                                   shift.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count),
                                                   dys.hi.data_ptr(), _p(dys.lo), N * D * H * W, C, dys.Cpad, _stream()),
@@ -287,7 +297,7 @@ def bn_pool_bwd_reduce(ga, pitch, gp, y, scale, shift, mean, rstd):
 
 def bn_pool_bwd_apply_planes(ga, pitch, gp, y, scale, shift, mean, rstd, gamma, sums, count):
     N, C, D, H, W = y.shape
-    dys = alloc_planes((N, C, D, H, W))
+    dys = alloc_planes((N, C, D, H, W), three=grad_planes_three())
     _lib.check(_L().dram_bn_pool_bwd_apply_planes(_p(ga), int(pitch), _p(gp), y.data_ptr(), scale.data_ptr(),
                                                   shift.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count),
                                                   dys.hi.data_ptr(), _p(dys.lo), N, D, H, W, C, dys.Cpad, _stream()),

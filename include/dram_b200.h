@@ -60,8 +60,12 @@ int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack,
                            int N, int D, int H, int W, int Cin, int Cout, int ksize, void* stream);
 
 /* tcgen05 / TMEM / TMA implicit GEMM (sm_100a).  Operands are bf16 split planes, channels padded to a multiple of 64.
- *   x_hi/x_lo : [N][D][H][W][Cin_pad] bf16          (x_lo may be NULL => single-pass bf16 "fast" mode)
- *   w_hi/w_lo : [taps][Cout][Cin_pad] bf16 (K-major; mode as above, see dram_pack_weight_bf16)
+ *   x_hi/x_lo : [N][D][H][W][Cin_pad] bf16
+ *   w_hi/w_lo : [taps][Cout][Cin_pad] bf16 (K-major, see dram_pack_weight_bf16)
+ *   precision : x_lo && w_lo  -> split-bf16, x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (forward; parity mode)
+ *               !x_lo && w_lo -> single-plane activations x split weights, x*w_hi + x*w_lo (dgrad with the gradient
+ *                                carried as one bf16 plane: DRAM_BWD_PRECISION=bf16x2)
+ *               !x_lo && !w_lo -> single-pass bf16 ("fast" mode, reported only);  x_lo without w_lo is an error
  *   y         : [N][D][H][W][Cout] fp32 raw accumulators; if scale/shift != NULL the epilogue applies
  *               y = max(0, acc*scale[co] + shift[co])  (eval-mode folded BatchNorm + ReLU, parts.py:107-108)
  * Cout must be a multiple of 16.  K loop = taps x Cin_pad/64 stages of {A 128x64, B BNx64} fed by TMA (5-D tensor map
@@ -74,6 +78,8 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
                          int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, void* stream);
 /* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes
  *   dy_hi/dy_lo : [N][D][H][W][Cout_pad]   x_hi/x_lo : [N][D][H][W][Cin_pad]   (pads are multiples of 64)
+ *   precision: dy_lo && x_lo -> three products; !dy_lo && x_lo -> x_hi*dy + x_lo*dy (single-plane gradient,
+ *   DRAM_BWD_PRECISION=bf16x2); neither -> single pass;  dy_lo without x_lo is an error
  * partial sums over voxel ranges are written to `workspace` (dram_conv3d_umma_wgrad_workspace_bytes) and reduced
  * deterministically into dw in nn.Parameter layout [Cout][Cin][taps]. */
 size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize);

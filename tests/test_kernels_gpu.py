@@ -140,8 +140,14 @@ def test_conv_umma_forward_folded_bn_relu():
     assert_close(y, ref, TOL_X3, "conv_umma fwd + folded BN/ReLU epilogue")
 
 
+# gradient operand as ONE bf16 plane x split weights / split layer input (DRAM_BWD_PRECISION=bf16x2, ops.grad_planes_three):
+# dy is rounded to bf16 (2^-9 per element, unbiased), everything else keeps 16+ bits
+TOL_DY1 = 3e-3
+
+
 @pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES)
-def test_conv_umma_dgrad(N, Cin, Cout, S, k):
+@pytest.mark.parametrize("dy_planes", [2, 1])
+def test_conv_umma_dgrad(N, Cin, Cout, S, k, dy_planes):
     o = ops()
     if Cin % 16:
         pytest.skip("dgrad output channels must be a multiple of 16")
@@ -150,10 +156,13 @@ def test_conv_umma_dgrad(N, Cin, Cout, S, k):
     y = F.conv3d(x, w, None, padding=k // 2)
     dy = torch.randn_like(y)
     y.backward(dy)
-    dys = o.split_bf16(cuda_cl(dy), True)
+    dys = o.split_bf16(cuda_cl(dy), dy_planes == 2)
     w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 1, True)
     dx = o.conv_umma(dys, w_hi, w_lo, Cin, k)
-    assert_close(dx, x.grad, TOL_X3, "conv_umma dgrad")
+    assert_close(dx, x.grad, TOL_X3 if dy_planes == 2 else TOL_DY1, "conv_umma dgrad")
+    if dy_planes == 1:          # exactly the product with the bf16-rounded gradient: nothing else is lost
+        ref = torch.nn.grad.conv3d_input(x.shape, w, dy.bfloat16().float(), padding=k // 2)
+        assert_close(dx, ref, TOL_X3, "conv_umma dgrad vs bf16-rounded dy")
 
 
 @pytest.mark.parametrize("N,Cin,Cout,S,k", UMMA_CASES + [
@@ -171,6 +180,11 @@ def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
     y.backward(dy)
     dw = o.conv_umma_wgrad(o.split_bf16(cuda_cl(dy), three), o.split_bf16(cuda_cl(x), three), Cin, Cout, k)
     assert_close(dw, w.grad, TOL_X3 if three else TOL_BF16, "conv_umma wgrad")
+    if three:                   # single-plane gradient x split input (default backward)
+        dw1 = o.conv_umma_wgrad(o.split_bf16(cuda_cl(dy), False), o.split_bf16(cuda_cl(x), True), Cin, Cout, k)
+        assert_close(dw1, w.grad, TOL_DY1, "conv_umma wgrad, one-plane dy")
+        ref = torch.nn.grad.conv3d_weight(x, w.shape, dy.bfloat16().float(), padding=k // 2)
+        assert_close(dw1, ref, TOL_X3, "conv_umma wgrad vs bf16-rounded dy")
 
 
 def test_conv_umma_is_deterministic():
