@@ -9,8 +9,12 @@
 // T(x) = sqrt(#in-grid neighbours of x) for the 'scaled_dot_product*' merge types (models.py:274,277: the mailbox
 // degree, not the feature dim).  No graph structure is materialised: neighbours are address arithmetic.
 //
-// Data: f [B][V][Cf], cam/out [B][V] (V = D*H*W, channels-last), qk [B][V][2F] (theta|phi projections),
-// att [B][V][O] softmax weights (0 for absent neighbours) kept for the backward pass.
+// Data (R = B*V rows, V = D*H*W): f [R][Cf] channels-last, cam/out [R];
+//   qk    [2F][R]  theta|phi projections as PLANES (structure of arrays): a warp = 32 consecutive x of one grid row, so every
+//                  load of one feature of one neighbour offset is one coalesced 128-byte request (the [R][2F] rows of the
+//                  first version cost 16 L1 wavefronts per request - the kernels were LSU-bound at 2-4 % of HBM peak);
+//   stats [2][R]   running max m and normaliser l of the node's softmax, kept for the backward INSTEAD of the [R][O]
+//                  attention weights: a_{x,o} = exp(s_{x,o} - m_x) / l_x is recomputed from q_x and k_{x+o} (8 FMAs + 1 exp).
 #include "common.cuh"
 
 namespace dram {
@@ -45,256 +49,193 @@ __device__ __forceinline__ float temperature(const PcmGeom& g, int deg) {
   return mode == 1 ? sqrtf((float)deg) : (mode == 2 ? 0.01f : 1.f);
 }
 
-// qk[v][0:F] = theta f + b, qk[v][F:2F] = phi f + b
+// number of in-grid neighbours of (z,y,x) in closed form: with a_z = #{dz in {-1,+1} : z+dz in grid} etc. the stencil
+// {|dz|+|dy|+|dx| <= connectivity} has a_z+a_y+a_x members at L1 distance 1, a_z a_y + a_z a_x + a_y a_x at 2, a_z a_y a_x at 3
+__device__ __forceinline__ int degree_of(const PcmGeom& g, int z, int y, int x) {
+  const int az = (z > 0) + (z < g.D - 1), ay = (y > 0) + (y < g.H - 1), ax = (x > 0) + (x < g.W - 1);
+  const int conn = g.flags >> 8;
+  int deg = (g.flags >> 7) & 1;                               // self loop
+  deg += az + ay + ax;
+  if (conn >= 2) deg += az * ay + az * ax + ay * ax;
+  if (conn >= 3) deg += az * ay * ax;
+  return deg;
+}
+
+// The stencil as 27 fully unrolled candidates in build_offsets order (dz, dy, dx ascending): dz/dy/dx are compile-time
+// constants inside the body, membership is a warp-uniform test (indexing the by-value offset table would put it in local memory).
+#define PCM_FOR_EACH_OFFSET(g)                                                                                      \
+  _Pragma("unroll") for (int t_ = 0; t_ < 27; ++t_)                                                                 \
+    if (const int dz = t_ / 9 - 1, dy = (t_ / 3) % 3 - 1, dx = t_ % 3 - 1, l1_ = (dz != 0) + (dy != 0) + (dx != 0); \
+        l1_ == 0 ? (((g).flags >> 7) & 1) != 0 : l1_ <= ((g).flags >> 8))
+
+// qk[j][r] = theta f_r + b (j < F), phi f_r + b (F <= j < 2F).  A warp stages its 32 consecutive rows (32*Cf contiguous
+// floats) through shared memory with coalesced loads; a lane then walks its row at an odd pitch (conflict-free).
 __global__ void __launch_bounds__(256)
 k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const float* __restrict__ tb,
               const float* __restrict__ pw, const float* __restrict__ pb, float* __restrict__ qk, long long rows, int Cf, int F) {
-  __shared__ float sw[2 * kMaxF * kMaxCf];
-  __shared__ float sb[2 * kMaxF];
-  for (int i = threadIdx.x; i < F * Cf; i += blockDim.x) { sw[i] = tw[i]; sw[F * Cf + i] = pw[i]; }
-  for (int i = threadIdx.x; i < F; i += blockDim.x) { sb[i] = tb[i]; sb[F + i] = pb[i]; }
+  extern __shared__ float4 psm4[];
+  float* psm = reinterpret_cast<float*>(psm4);
+  const int Cfp = Cf | 1, J4 = (2 * F + 3) >> 2;    // outputs in groups of 4: the weights of one input channel are J4 float4
+  float* sw = psm;                                  // [Cf][4*J4]  (transposed, zero padded)
+  float* sb = sw + Cf * 4 * J4;                     // [4*J4]
+  float* st = sb + 4 * J4 + (threadIdx.x >> 5) * 32 * Cfp;   // this warp's [32][Cfp] tile
+  for (int i = threadIdx.x; i < Cf * 4 * J4; i += blockDim.x) {
+    const int c = i / (4 * J4), j = i - c * 4 * J4;
+    sw[i] = j < F ? tw[j * Cf + c] : (j < 2 * F ? pw[(j - F) * Cf + c] : 0.f);
+  }
+  for (int i = threadIdx.x; i < 4 * J4; i += blockDim.x) sb[i] = i < F ? tb[i] : (i < 2 * F ? pb[i - F] : 0.f);
   __syncthreads();
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
-    float acc[2 * kMaxF];
-#pragma unroll
-    for (int j = 0; j < 2 * kMaxF; ++j) acc[j] = j < 2 * F ? sb[j] : 0.f;
-    const float* fp = f + r * Cf;
-    for (int c = 0; c < Cf; ++c) {
-      float v = __ldg(fp + c);
-#pragma unroll
-      for (int j = 0; j < 2 * kMaxF; ++j)
-        if (j < 2 * F) acc[j] = fmaf(v, sw[j * Cf + c], acc[j]);
-    }
-    float* q = qk + r * 2 * F;
-#pragma unroll
-    for (int j = 0; j < 2 * kMaxF; ++j)
-      if (j < 2 * F) q[j] = acc[j];
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float* __restrict__ att,
-             float* __restrict__ out) {
-  const long long V = (long long)g.D * g.H * g.W;
-  const long long total = (long long)g.B * V;
-  const int F = g.F, O = g.O;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i % V, b = i / V;
-    int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    float q[kMaxF];
-#pragma unroll
-    for (int j = 0; j < kMaxF; ++j) q[j] = j < F ? qk[i * 2 * F + j] : 0.f;
-    float s[kMaxOff], c[kMaxOff];
-    int deg = 0;
-    for (int o = 0; o < O; ++o) {
-      long long nb;
-      if (nb_index(g, z, y, x, o, nb)) {
-        const float* kp = qk + (b * V + nb) * 2 * F + F;
-        float d = 0.f;
-#pragma unroll
-        for (int j = 0; j < kMaxF; ++j)
-          if (j < F) d = fmaf(q[j], __ldg(kp + j), d);
-        if (g.flags & 1) d = fmaxf(d, 0.f);
-        s[o] = d;
-        c[o] = __ldg(cam + b * V + nb);
-        ++deg;
-      } else {
-        s[o] = -INFINITY;
-        c[o] = 0.f;
-      }
-    }
-    float invT = 1.f / temperature(g, deg);
-    float mx = -INFINITY;
-    for (int o = 0; o < O; ++o) { s[o] *= invT; mx = fmaxf(mx, s[o]); }
-    float den = 0.f;
-    for (int o = 0; o < O; ++o) { s[o] = (s[o] == -INFINITY) ? 0.f : __expf(s[o] - mx); den += s[o]; }
-    float inv = deg > 0 ? 1.f / den : 0.f, acc = 0.f;
-    for (int o = 0; o < O; ++o) {
-      float a = s[o] * inv;
-      att[i * O + o] = a;
-      acc = fmaf(a, c[o], acc);
-    }
-    out[i] = acc;     // degree-0 nodes (1x1x1 grids) keep 0 like DGL's zero-filled result
-  }
-}
-
-// Inference variant (no attention weights kept): F = 8, online softmax in registers, neighbour keys as two float4 loads.
-// Warp-level sharing: consecutive lanes hold consecutive x of one grid row, so for the three offsets (dz,dy,-1|0|+1) the
-// key vector and the cam value of the (dz,dy) row are loaded ONCE per lane (at the lane's own x) and the x-1 / x+1
-// neighbours come from the adjacent lanes through __shfl_sync; only the lanes at a warp or row edge load them directly.
-__global__ void __launch_bounds__(256)
-k_pcm_attend_infer(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float* __restrict__ out) {
-  const long long V = (long long)g.D * g.H * g.W;
-  const long long total = (long long)g.B * V;
   const int lane = threadIdx.x & 31;
-  const int O = g.O;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long iters = (total + stride - 1) / stride;          // warp-uniform trip count: shuffles need converged warps
-  for (long long it = 0; it < iters; ++it) {
-    const long long i = first + it * stride;
-    const bool live = i < total;
-    const long long ii = live ? i : total - 1;
-    const long long v = ii % V, b = ii / V;
-    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    const float4* qp = reinterpret_cast<const float4*>(qk + ii * 16);
-    const float4 q0 = __ldg(qp), q1 = __ldg(qp + 1);
-    // lanes lane-1 / lane+1 hold x-1 / x+1 of the same row?
-    const int xl = __shfl_up_sync(0xffffffffu, x, 1), xr = __shfl_down_sync(0xffffffffu, x, 1);
-    const long long il = __shfl_up_sync(0xffffffffu, ii, 1), ir = __shfl_down_sync(0xffffffffu, ii, 1);
-    const bool left_ok = lane > 0 && xl == x - 1 && il == ii - 1;
-    const bool right_ok = lane < 31 && xr == x + 1 && ir == ii + 1;
-    int deg = 0;
-    for (int o = 0; o < O; ++o) {
-      int zz = z + g.off[o][0], yy = y + g.off[o][1], xx = x + g.off[o][2];
-      deg += (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? 1 : 0;
-    }
-    const float invT = 1.f / temperature(g, deg);
-    float m = -INFINITY, l = 0.f, acc = 0.f;
-    int cur_dz = 127, cur_dy = 127;
-    float4 kc0 = make_float4(0.f, 0.f, 0.f, 0.f), kc1 = kc0;
-    float cc = 0.f;
-    for (int o = 0; o < O; ++o) {
-      const int dz = g.off[o][0], dy = g.off[o][1], dx = g.off[o][2];
-      const int zz = z + dz, yy = y + dy, xx = x + dx;
-      const bool row_ok = zz >= 0 && zz < g.D && yy >= 0 && yy < g.H;
-      if (dz != cur_dz || dy != cur_dy) {                       // new (dz,dy) row: load key / cam at the lane's own x
-        cur_dz = dz; cur_dy = dy;
-        if (row_ok) {
-          const long long nb = b * V + ((long long)zz * g.H + yy) * g.W + x;
-          const float4* kp = reinterpret_cast<const float4*>(qk + nb * 16 + 8);
-          kc0 = __ldg(kp); kc1 = __ldg(kp + 1);
-          cc = __ldg(cam + nb);
-        }
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5, tiles = (rows + 31) >> 5;
+  for (long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < tiles; t += warps) {
+    const long long r0 = t << 5;
+    const int n = (int)(rows - r0 < 32 ? rows - r0 : 32);
+    const float* src = f + r0 * Cf;
+    __syncwarp();
+    for (int i = lane; i < n * Cf; i += 32) { const int r = i / Cf; st[r * Cfp + (i - r * Cf)] = __ldg(src + i); }
+    __syncwarp();
+    if (lane < n) {
+      float4 acc[kMaxF / 2];
+#pragma unroll
+      for (int j = 0; j < kMaxF / 2; ++j) acc[j] = j < J4 ? reinterpret_cast<const float4*>(sb)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* fp = st + lane * Cfp;
+      for (int c = 0; c < Cf; ++c) {
+        const float v = fp[c];
+        const float4* wc = reinterpret_cast<const float4*>(sw) + c * J4;
+#pragma unroll
+        for (int j = 0; j < kMaxF / 2; ++j)
+          if (j < J4) {
+            const float4 w4 = wc[j];
+            acc[j].x = fmaf(v, w4.x, acc[j].x); acc[j].y = fmaf(v, w4.y, acc[j].y);
+            acc[j].z = fmaf(v, w4.z, acc[j].z); acc[j].w = fmaf(v, w4.w, acc[j].w);
+          }
       }
-      // neighbour at x+dx of that row: own registers, an adjacent lane, or (edges) a direct load
-      float4 k0 = kc0, k1 = kc1;
-      float cv = cc;
-      if (dx != 0) {                                             // uniform across the warp (same offset table)
-        float4 s0, s1;
-        float sc;
-        if (dx < 0) {
-          s0.x = __shfl_up_sync(0xffffffffu, kc0.x, 1); s0.y = __shfl_up_sync(0xffffffffu, kc0.y, 1);
-          s0.z = __shfl_up_sync(0xffffffffu, kc0.z, 1); s0.w = __shfl_up_sync(0xffffffffu, kc0.w, 1);
-          s1.x = __shfl_up_sync(0xffffffffu, kc1.x, 1); s1.y = __shfl_up_sync(0xffffffffu, kc1.y, 1);
-          s1.z = __shfl_up_sync(0xffffffffu, kc1.z, 1); s1.w = __shfl_up_sync(0xffffffffu, kc1.w, 1);
-          sc = __shfl_up_sync(0xffffffffu, cc, 1);
-        } else {
-          s0.x = __shfl_down_sync(0xffffffffu, kc0.x, 1); s0.y = __shfl_down_sync(0xffffffffu, kc0.y, 1);
-          s0.z = __shfl_down_sync(0xffffffffu, kc0.z, 1); s0.w = __shfl_down_sync(0xffffffffu, kc0.w, 1);
-          s1.x = __shfl_down_sync(0xffffffffu, kc1.x, 1); s1.y = __shfl_down_sync(0xffffffffu, kc1.y, 1);
-          s1.z = __shfl_down_sync(0xffffffffu, kc1.z, 1); s1.w = __shfl_down_sync(0xffffffffu, kc1.w, 1);
-          sc = __shfl_down_sync(0xffffffffu, cc, 1);
-        }
-        const bool via_lane = dx < 0 ? left_ok : right_ok;
-        if (via_lane) { k0 = s0; k1 = s1; cv = sc; }
-        else if (row_ok && xx >= 0 && xx < g.W) {
-          const long long nb = b * V + ((long long)zz * g.H + yy) * g.W + xx;
-          const float4* kp = reinterpret_cast<const float4*>(qk + nb * 16 + 8);
-          k0 = __ldg(kp); k1 = __ldg(kp + 1);
-          cv = __ldg(cam + nb);
-        }
-      }
-      if (row_ok && xx >= 0 && xx < g.W) {
-        float d = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
-        if (g.flags & 1) d = fmaxf(d, 0.f);
-        const float sv = d * invT;
-        const float mn = fmaxf(m, sv);
-        const float corr = __expf(m - mn), e = __expf(sv - mn);     // m = -inf on the first neighbour -> corr = 0
-        l = l * corr + e;
-        acc = acc * corr + e * cv;
-        m = mn;
+      float* dst = qk + r0 + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxF / 2; ++j) {
+        if (4 * j + 0 < 2 * F) dst[(long long)(4 * j + 0) * rows] = acc[j].x;
+        if (4 * j + 1 < 2 * F) dst[(long long)(4 * j + 1) * rows] = acc[j].y;
+        if (4 * j + 2 < 2 * F) dst[(long long)(4 * j + 2) * rows] = acc[j].z;
+        if (4 * j + 3 < 2 * F) dst[(long long)(4 * j + 3) * rows] = acc[j].w;
       }
     }
-    if (live) out[i] = deg > 0 ? acc / l : 0.f;
   }
 }
 
-// backward pass 1 (per node x): dd[x][o] = d loss / d <q_x,k_{x+o}>,  dq[x] = sum_o dd_o k_{x+o}
+// forward: one thread per node, online softmax over the in-grid neighbours (no per-offset arrays).  SAVE: keep (m, l).
+template <int FT, bool SAVE>
 __global__ void __launch_bounds__(256)
-k_pcm_bwd_node(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float* __restrict__ att,
-               const float* __restrict__ dout, float* __restrict__ dd, float* __restrict__ dqk) {
-  const long long V = (long long)g.D * g.H * g.W;
-  const long long total = (long long)g.B * V;
-  const int F = g.F, O = g.O;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i % V, b = i / V;
-    int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    const float go = dout[i];
-    float q[kMaxF], dq[kMaxF];
+k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float* __restrict__ stats,
+             float* __restrict__ out) {
+  const long long V = (long long)g.D * g.H * g.W, R = (long long)g.B * V;
+  const int F = g.F;
+  const bool relu = g.flags & 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % V;
+    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
+    float q[FT];
 #pragma unroll
-    for (int j = 0; j < kMaxF; ++j) { q[j] = j < F ? qk[i * 2 * F + j] : 0.f; dq[j] = 0.f; }
-    float a[kMaxOff], da[kMaxOff];
-    long long nbs[kMaxOff];
-    int deg = 0;
-    float dot = 0.f;
-    for (int o = 0; o < O; ++o) {
-      a[o] = att[i * O + o];
-      if (nb_index(g, z, y, x, o, nbs[o])) {
-        da[o] = go * __ldg(cam + b * V + nbs[o]);
-        dot = fmaf(a[o], da[o], dot);
-        ++deg;
-      } else {
-        nbs[o] = -1;
-        da[o] = 0.f;
-      }
+    for (int j = 0; j < FT; ++j) q[j] = j < F ? __ldg(qk + (long long)j * R + i) : 0.f;
+    const int deg = degree_of(g, z, y, x);
+    const float invT = 1.f / temperature(g, deg);
+    const float* kbase = qk + (long long)F * R + i;
+    float m = -INFINITY, l = 0.f, acc = 0.f;
+    PCM_FOR_EACH_OFFSET(g) {
+      const int zz = z + dz, yy = y + dy, xx = x + dx;
+      if (zz < 0 || zz >= g.D || yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
+      const long long d_i = ((long long)dz * g.H + dy) * g.W + dx;
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < FT; ++j)
+        if (j < F) d = fmaf(q[j], __ldg(kbase + (long long)j * R + d_i), d);
+      if (relu) d = fmaxf(d, 0.f);
+      const float sv = d * invT, cv = __ldg(cam + i + d_i);
+      const float mn = fmaxf(m, sv);
+      const float corr = __expf(m - mn), e = __expf(sv - mn);      // m = -inf on the first neighbour -> corr = 0
+      l = l * corr + e;
+      acc = acc * corr + e * cv;
+      m = mn;
     }
-    float invT = 1.f / temperature(g, deg);
-    for (int o = 0; o < O; ++o) {
-      float r = 0.f;
-      if (nbs[o] >= 0) {
-        const float* kp = qk + (b * V + nbs[o]) * 2 * F + F;
-        float ds = a[o] * (da[o] - dot) * invT;
-        if (g.flags & 1) {
+    out[i] = deg > 0 ? acc / l : 0.f;     // degree-0 nodes (1x1x1 grids) keep 0 like DGL's zero-filled result
+    if (SAVE) { stats[i] = deg > 0 ? m : 0.f; stats[R + i] = deg > 0 ? l : 1.f; }
+  }
+}
+
+// backward, one thread per voxel i in both of its roles, nothing but (m, l) and the forward output s kept from the forward:
+//  node role   (i = x):  a_o = exp(s_o - m_x)/l_x,  ds_o = a_o (g_x cam_{x+o} - g_x s_x) / T_x [logit > 0],
+//                        dq_x = sum_o ds_o k_{x+o}
+//  gather role (i = y):  over the nodes x = y - o that list y as their neighbour o: the same a, ds from q_x, (m, l, g, s)_x and
+//                        the own k_y, cam_y:  dcam_y = sum g_x a,  dk_y = sum ds q_x
+// (sum_o a_o g cam_{x+o} = g_x s_x is the softmax-Jacobian dot product.)   dqk: [2F][R] planes like qk.
+template <int FT>
+__global__ void __launch_bounds__(256, FT <= 8 ? 2 : 1)
+k_pcm_bwd(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float* __restrict__ stats,
+          const float* __restrict__ s_out, const float* __restrict__ dout, float* __restrict__ dcam, float* __restrict__ dqk) {
+  const long long V = (long long)g.D * g.H * g.W, R = (long long)g.B * V;
+  const int F = g.F;
+  const bool relu = g.flags & 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % V;
+    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
+    float q[FT], k[FT], dq[FT], dk[FT];
+#pragma unroll
+    for (int j = 0; j < FT; ++j) {
+      q[j] = j < F ? __ldg(qk + (long long)j * R + i) : 0.f;
+      k[j] = j < F ? __ldg(qk + (long long)(F + j) * R + i) : 0.f;
+      dq[j] = 0.f; dk[j] = 0.f;
+    }
+    const int deg = degree_of(g, z, y, x);
+    const float invT = 1.f / temperature(g, deg);
+    const float go = __ldg(dout + i), m = __ldg(stats + i), il = 1.f / __ldg(stats + R + i), dot = go * __ldg(s_out + i);
+    const float cam_i = __ldg(cam + i);
+    float dc = 0.f;
+    PCM_FOR_EACH_OFFSET(g) {
+      const long long d_i = ((long long)dz * g.H + dy) * g.W + dx;
+      {   // node role: neighbour n = i + o
+        const int zz = z + dz, yy = y + dy, xx = x + dx;
+        if (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
+          float kn[FT];
           float d = 0.f;
 #pragma unroll
-          for (int j = 0; j < kMaxF; ++j)
-            if (j < F) d = fmaf(q[j], __ldg(kp + j), d);
-          if (!(d > 0.f)) ds = 0.f;
+          for (int j = 0; j < FT; ++j) {
+            kn[j] = j < F ? __ldg(qk + (long long)(F + j) * R + i + d_i) : 0.f;
+            d = fmaf(q[j], kn[j], d);
+          }
+          const bool dead = relu && !(d > 0.f);
+          if (relu) d = fmaxf(d, 0.f);
+          const float a = __expf(d * invT - m) * il;
+          const float ds = dead ? 0.f : a * (go * __ldg(cam + i + d_i) - dot) * invT;
+#pragma unroll
+          for (int j = 0; j < FT; ++j) dq[j] = fmaf(ds, kn[j], dq[j]);
         }
-        r = ds;
-#pragma unroll
-        for (int j = 0; j < kMaxF; ++j)
-          if (j < F) dq[j] = fmaf(ds, __ldg(kp + j), dq[j]);
       }
-      dd[i * O + o] = r;
-    }
+      {   // gather role: node n = i - o has i as its neighbour o
+        const int zz = z - dz, yy = y - dy, xx = x - dx;
+        if (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
+          const long long n = i - d_i;
+          float qn[FT];
+          float d = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxF; ++j)
-      if (j < F) dqk[i * 2 * F + j] = dq[j];
-  }
-}
-
-// backward pass 2 (per node y, gather over the nodes x = y - o that list y as neighbour o):
-//   dcam[y] = sum_o dout[x] att[x][o],   dk[y] = sum_o dd[x][o] q[x]
-__global__ void __launch_bounds__(256)
-k_pcm_bwd_gather(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ att, const float* __restrict__ dd,
-                 const float* __restrict__ dout, float* __restrict__ dcam, float* __restrict__ dqk) {
-  const long long V = (long long)g.D * g.H * g.W;
-  const long long total = (long long)g.B * V;
-  const int F = g.F, O = g.O;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i % V, b = i / V;
-    int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    float dk[kMaxF];
+          for (int j = 0; j < FT; ++j) {
+            qn[j] = j < F ? __ldg(qk + (long long)j * R + n) : 0.f;
+            d = fmaf(qn[j], k[j], d);
+          }
+          const bool dead = relu && !(d > 0.f);
+          if (relu) d = fmaxf(d, 0.f);
+          const float invTn = 1.f / temperature(g, degree_of(g, zz, yy, xx));
+          const float gn = __ldg(dout + n);
+          const float a = __expf(d * invTn - __ldg(stats + n)) / __ldg(stats + R + n);
+          dc = fmaf(gn, a, dc);
+          const float ds = dead ? 0.f : a * (gn * cam_i - gn * __ldg(s_out + n)) * invTn;
 #pragma unroll
-    for (int j = 0; j < kMaxF; ++j) dk[j] = 0.f;
-    float dc = 0.f;
-    for (int o = 0; o < O; ++o) {
-      int zz = z - g.off[o][0], yy = y - g.off[o][1], xx = x - g.off[o][2];
-      if (zz < 0 || zz >= g.D || yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
-      long long src = b * V + ((long long)zz * g.H + yy) * g.W + xx;
-      dc = fmaf(__ldg(dout + src), __ldg(att + src * O + o), dc);
-      float w = __ldg(dd + src * O + o);
-      const float* qp = qk + src * 2 * F;
-#pragma unroll
-      for (int j = 0; j < kMaxF; ++j)
-        if (j < F) dk[j] = fmaf(w, __ldg(qp + j), dk[j]);
+          for (int j = 0; j < FT; ++j) dk[j] = fmaf(ds, qn[j], dk[j]);
+        }
+      }
     }
     dcam[i] = dc;
 #pragma unroll
-    for (int j = 0; j < kMaxF; ++j)
-      if (j < F) dqk[i * 2 * F + F + j] = dk[j];
+    for (int j = 0; j < FT; ++j)
+      if (j < F) { dqk[(long long)j * R + i] = dq[j]; dqk[(long long)(F + j) * R + i] = dk[j]; }
   }
 }
 
@@ -306,8 +247,9 @@ k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, cons
                  int Cf, int F) {
   extern __shared__ float sm[];
   float* sf = sm;                                 // [kPcmChunk][Cf]
-  float* sg = sf + kPcmChunk * Cf;                // [kPcmChunk][2F]
-  float* sw = sg + kPcmChunk * 2 * F;             // [2F][Cf]
+  const int SG = 2 * F + 1;
+  float* sg = sf + kPcmChunk * Cf;                // [kPcmChunk][2F + 1]
+  float* sw = sg + kPcmChunk * SG;                // [2F][Cf]
   for (int i = threadIdx.x; i < F * Cf; i += blockDim.x) { sw[i] = tw[i]; sw[F * Cf + i] = pw[i]; }
   const int nout = 2 * F * (Cf + 1);              // outputs: for m in {theta,phi}: F*Cf weights then F biases
   float acc = 0.f;
@@ -324,18 +266,21 @@ k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, cons
     int n = (int)(rows - base < kPcmChunk ? rows - base : kPcmChunk);
     __syncthreads();
     for (int i = threadIdx.x; i < n * Cf; i += blockDim.x) sf[i] = f[base * Cf + i];
-    for (int i = threadIdx.x; i < n * 2 * F; i += blockDim.x) sg[i] = dqk[base * 2 * F + i];
+    for (int i = threadIdx.x; i < n * 2 * F; i += blockDim.x) {           // dqk planes [2F][rows] -> sg[r][SG], SG odd
+      const int jj = i / n, r = i - jj * n;
+      sg[r * SG + jj] = dqk[(long long)jj * rows + base + r];
+    }
     __syncthreads();
     if (owner) {
       for (int r = 0; r < n; ++r) {
-        float gq = sg[r * 2 * F + which * F + j];
+        float gq = sg[r * SG + which * F + j];
         acc = c >= 0 ? fmaf(gq, sf[r * Cf + c], acc) : acc + gq;
       }
     }
     for (int i = threadIdx.x; i < n * Cf; i += blockDim.x) {
       int r = i / Cf, cc = i % Cf;
       float d = 0.f;
-      for (int jj = 0; jj < 2 * F; ++jj) d = fmaf(sw[jj * Cf + cc], sg[r * 2 * F + jj], d);
+      for (int jj = 0; jj < 2 * F; ++jj) d = fmaf(sw[jj * Cf + cc], sg[r * SG + jj], d);
       df[base * Cf + i] = d;
     }
   }
@@ -350,7 +295,8 @@ static int pcm_geom(PcmGeom& g, int B, int D, int H, int W, int Cf, int F, int c
   DRAM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "pcm: bad grid");
   DRAM_REQUIRE(Cf > 0 && Cf <= kMaxCf && F > 0 && F <= kMaxF, "pcm: Cf=%d (<=%d) / F=%d (<=%d) unsupported", Cf, kMaxCf, F, kMaxF);
   DRAM_REQUIRE(connectivity >= 1 && connectivity <= 3, "pcm: connectivity %d unsupported", connectivity);
-  g.B = B; g.D = D; g.H = H; g.W = W; g.Cf = Cf; g.F = F; g.flags = flags;
+  g.B = B; g.D = D; g.H = H; g.W = W; g.Cf = Cf; g.F = F;
+  g.flags = (flags & 0x7f) | ((self_loop ? 1 : 0) << 7) | (connectivity << 8);   // degree_of reads bits 7 and 8+
   g.O = build_offsets(connectivity, self_loop, g.off);
   return DRAM_OK;
 }
@@ -363,7 +309,7 @@ int dram_pcm_num_offsets(int connectivity, int self_loop) {
 }
 
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
-                 const float* phi_b, float* qk, float* att, float* out, int B, int D, int H, int W, int Cf, int F,
+                 const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream) {
   DRAM_REQUIRE(f && cam && theta_w && theta_b && phi_w && phi_b && qk && out, "pcm_fwd: null pointer");
   PcmGeom g;
@@ -371,35 +317,39 @@ int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const f
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)B * D * H * W;
-  k_pcm_project<<<grid_for(rows, 256, 8), 256, 0, st>>>(f, theta_w, theta_b, phi_w, phi_b, qk, rows, Cf, F);
+  const int J4 = (2 * F + 3) / 4;
+  const size_t smem = sizeof(float) * ((size_t)Cf * 4 * J4 + 4 * J4 + (size_t)8 * 32 * (Cf | 1));
+  if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pcm_project<<<grid_for(rows, 256, 8), 256, smem, st>>>(f, theta_w, theta_b, phi_w, phi_b, qk, rows, Cf, F);
   DRAM_LAUNCH_CHECK();
-  if (att == nullptr && F == 8) {       // inference: no attention weights kept, warp-shuffle neighbour sharing
-    k_pcm_attend_infer<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, out);
+  const int grid = grid_for(rows, 256, 16);
+  if (F <= 8) {
+    if (stats) k_pcm_attend<8, true><<<grid, 256, 0, st>>>(g, qk, cam, stats, out);
+    else k_pcm_attend<8, false><<<grid, 256, 0, st>>>(g, qk, cam, nullptr, out);
   } else {
-    DRAM_REQUIRE(att != nullptr, "pcm_fwd: the attention-weight buffer may only be NULL for F == 8 (inference kernel)");
-    k_pcm_attend<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, att, out);
+    if (stats) k_pcm_attend<kMaxF, true><<<grid, 256, 0, st>>>(g, qk, cam, stats, out);
+    else k_pcm_attend<kMaxF, false><<<grid, 256, 0, st>>>(g, qk, cam, nullptr, out);
   }
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
 
 int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
-                 const float* att, const float* dout, float* dd_ws, float* dqk_ws, float* dcam, float* df,
+                 const float* stats, const float* s_out, const float* dout, float* dqk_ws, float* dcam, float* df,
                  double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
                  void* stream) {
-  DRAM_REQUIRE(f && cam && theta_w && phi_w && qk && att && dout && dd_ws && dqk_ws && dcam && df && dparams, "pcm_bwd: null pointer");
+  DRAM_REQUIRE(f && cam && theta_w && phi_w && qk && stats && s_out && dout && dqk_ws && dcam && df && dparams, "pcm_bwd: null pointer");
   PcmGeom g;
   int rc = pcm_geom(g, B, D, H, W, Cf, F, connectivity, self_loop, flags);
   if (rc) return rc;
   DRAM_REQUIRE(2 * F * (Cf + 1) <= 320, "pcm_bwd: 2F(Cf+1)=%d > 320 unsupported", 2 * F * (Cf + 1));
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)B * D * H * W;
-  k_pcm_bwd_node<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, cam, att, dout, dd_ws, dqk_ws);
-  DRAM_LAUNCH_CHECK();
-  k_pcm_bwd_gather<<<grid_for(rows, 256, 8), 256, 0, st>>>(g, qk, att, dd_ws, dout, dcam, dqk_ws);
+  if (F <= 8) k_pcm_bwd<8><<<grid_for(rows, 256, 16), 256, 0, st>>>(g, qk, cam, stats, s_out, dout, dcam, dqk_ws);
+  else k_pcm_bwd<kMaxF><<<grid_for(rows, 256, 16), 256, 0, st>>>(g, qk, cam, stats, s_out, dout, dcam, dqk_ws);
   DRAM_LAUNCH_CHECK();
   DRAM_CUDA(cudaMemsetAsync(dparams, 0, sizeof(double) * 2 * F * (Cf + 1), st));
-  size_t smem = sizeof(float) * ((size_t)kPcmChunk * Cf + (size_t)kPcmChunk * 2 * F + (size_t)2 * F * Cf);
+  size_t smem = sizeof(float) * ((size_t)kPcmChunk * Cf + (size_t)kPcmChunk * (2 * F + 1) + (size_t)2 * F * Cf);
   long long chunks = (rows + kPcmChunk - 1) / kPcmChunk;
   int grid = (int)(chunks < (long long)kNumSMs * 4 ? chunks : (long long)kNumSMs * 4);
   if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_bwd_params, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

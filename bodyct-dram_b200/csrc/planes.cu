@@ -553,6 +553,162 @@ k_merge_planes(const uint4* __restrict__ hi, const uint4* __restrict__ lo, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 1x1x1 conv on planes
+// The attention reshape heads (models.py:488-494, 564): Conv3d(C, 8, kernel_size=1) on a DETACHED decoder feature map that
+// exists only as planes.  HBM-bound: 4 B/element in, 32 B/voxel out.  LPR = Cpad/8 lanes share a voxel row (a lane owns
+// 8 channels: one 16-byte load per plane, the 8x8 weights of its channels in registers); a warp pass covers 32/LPR rows
+// with fully coalesced loads.  The 8 partial outputs are combined by a reduce-scatter over the row's lanes (4+2+1
+// shuffles: every lane ends with ONE output, lane sub holds output sub), so the store of a row is 32 contiguous bytes.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_pointwise8_planes_fwd(const uint4* __restrict__ hi, const uint4* __restrict__ lo, const float* __restrict__ w,
+                        const float* __restrict__ bias, float* __restrict__ y, long long rows, int Cin) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+  float wr[8][8];                                               // wr[j][c] = w[j][8*sub + c]
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[j][c] = (8 * sub + c < Cin) ? __ldg(w + j * Cin + 8 * sub + c) : 0.f;
+  const float b = bias ? __ldg(bias + (sub & 7)) : 0.f;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  constexpr int U = 4;                                           // warp passes in flight: 2*U 16-byte loads per lane
+  const long long rows_up = (rows + RPW - 1) / RPW * RPW;        // whole warps stay in the loop: the shuffles need them
+  for (long long r0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + rw; r0 < rows_up; r0 += warps * RPW * U) {
+    uint4 H[U], L[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + (long long)u * warps * RPW;
+      const bool live = r < rows;
+      H[u] = live ? __ldg(hi + r * LPR + sub) : zero;
+      L[u] = (live && lo) ? __ldg(lo + r * LPR + sub) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + (long long)u * warps * RPW;
+      if (r - rw >= rows_up) break;                              // warp-uniform
+      float v[8], p[8];
+      merge8(H[u], L[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a = fmaf(v[c], wr[j][c], a);
+        p[j] = a;
+      }
+      if (LPR == 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], 8);
+      }
+      float p4[4], p2[2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float send = (sub & 4) ? p[j] : p[j + 4], keep = (sub & 4) ? p[j + 4] : p[j];
+        p4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float send = (sub & 2) ? p4[j] : p4[j + 2], keep = (sub & 2) ? p4[j + 2] : p4[j];
+        p2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float send = (sub & 1) ? p2[0] : p2[1], keep = (sub & 1) ? p2[1] : p2[0];
+      const float out = keep + __shfl_xor_sync(0xffffffffu, send, 1) + b;
+      if (r < rows && sub < 8) y[r * 8 + sub] = out;
+    }
+  }
+}
+
+// weight / bias gradient of the same layer: dW[j][c] = sum_r dy[r][j] x[r][c], db[j] = sum_r dy[r][j].  Same lane layout;
+// a lane accumulates the 8x8 block of its channels over its rows, the block combines its warps through shared memory
+// and writes ONE partial [8*Cpad + 8] per block; k_pointwise8_reduce sums the partials in a fixed order (deterministic).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_pointwise8_planes_wgrad(const uint4* __restrict__ hi, const uint4* __restrict__ lo, const float* __restrict__ dy,
+                          float* __restrict__ partial, long long rows) {
+  constexpr int RPW = 32 / LPR, CP = LPR * 8, NOUT = 8 * CP + 8;
+  __shared__ float sm[8][NOUT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rw = lane / LPR;
+  float acc[8][8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    db[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  }
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int U = 4;                                           // rows in flight per lane: 4*U 16-byte loads
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (long long r0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + rw; r0 < rows; r0 += warps * RPW * U) {
+    uint4 H[U], L[U];
+    float4 G0[U], G1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + (long long)u * warps * RPW;
+      const bool live = r < rows;                                // dead rows contribute x = 0, dy = 0
+      H[u] = live ? __ldg(hi + r * LPR + sub) : zero;
+      L[u] = (live && lo) ? __ldg(lo + r * LPR + sub) : zero;
+      G0[u] = live ? __ldg(reinterpret_cast<const float4*>(dy + r * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      G1[u] = live ? __ldg(reinterpret_cast<const float4*>(dy + r * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      merge8(H[u], L[u], v);
+      const float g[8] = {G0[u].x, G0[u].y, G0[u].z, G0[u].w, G1[u].x, G1[u].y, G1[u].z, G1[u].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        db[j] += g[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(g[j], v[c], acc[j][c]);
+      }
+    }
+  }
+  // rows of one warp pass -> lanes sub, sub + LPR, ...: fold them onto rw == 0
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      db[j] += __shfl_xor_sync(0xffffffffu, db[j], off);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], off);
+    }
+  }
+  if (rw == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sm[warp][j * CP + 8 * sub + c] = acc[j][c];
+    if (sub == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm[warp][8 * CP + j] = db[j];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NOUT; e += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sm[wv][e];
+    partial[(long long)blockIdx.x * NOUT + e] = t;
+  }
+}
+
+// dw[j][c] (c < Cin) and db[j] from the per-block partials, summed in block order in double
+__global__ void k_pointwise8_reduce(const float* __restrict__ partial, int nblocks, int CP, int Cin, float* __restrict__ dw,
+                                    float* __restrict__ db) {
+  const int NOUT = 8 * CP + 8;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NOUT) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += (double)partial[(long long)b * NOUT + e];
+  if (e < 8 * CP) {
+    const int j = e / CP, c = e - j * CP;
+    if (c < Cin) dw[j * Cin + c] = (float)t;
+  } else if (db) {
+    db[e - 8 * CP] = (float)t;
+  }
+}
+
 }  // namespace dram
 
 using namespace dram;
@@ -675,6 +831,43 @@ int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void
 int dram_merge_planes(const void* hi, const void* lo, float* out, long long rows, int C, int Cpad, void* stream) {
   DRAM_REQUIRE(hi && out && rows > 0 && C > 0 && C % 8 == 0 && Cpad >= C && Cpad % 8 == 0, "merge_planes: bad arguments (C=%d Cpad=%d)", C, Cpad);
   k_merge_planes<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)hi, (const uint4*)lo, out, rows, C, Cpad);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static const int kPointwiseBlocks = kNumSMs * 2;
+
+int dram_pointwise8_planes_supported(int Cin_pad, int Cout) { return (Cout == 8 && (Cin_pad == 64 || Cin_pad == 128)) ? 1 : 0; }
+
+int dram_pointwise8_planes_fwd(const void* x_hi, const void* x_lo, const float* w, const float* bias, float* y, long long rows,
+                               int Cin, int Cin_pad, void* stream) {
+  DRAM_REQUIRE(x_hi && w && y && rows > 0, "pointwise8_planes_fwd: bad arguments");
+  DRAM_REQUIRE((Cin_pad == 64 || Cin_pad == 128) && Cin > 0 && Cin <= Cin_pad, "pointwise8_planes_fwd: Cin_pad %d unsupported (64 | 128)", Cin_pad);
+  const int lpr = Cin_pad / 8;
+  const int grid = grid_for((rows + (32 / lpr) - 1) / (32 / lpr) * 32, 256, 8);
+  if (lpr == 8)
+    k_pointwise8_planes_fwd<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x_hi, (const uint4*)x_lo, w, bias, y, rows, Cin);
+  else
+    k_pointwise8_planes_fwd<16><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x_hi, (const uint4*)x_lo, w, bias, y, rows, Cin);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+size_t dram_pointwise8_planes_wgrad_workspace_bytes(int Cin_pad) { return sizeof(float) * (size_t)kPointwiseBlocks * (8 * (size_t)Cin_pad + 8); }
+
+int dram_pointwise8_planes_wgrad(const void* x_hi, const void* x_lo, const float* dy, float* dw, float* dbias, void* workspace,
+                                 long long rows, int Cin, int Cin_pad, void* stream) {
+  DRAM_REQUIRE(x_hi && dy && dw && workspace && rows > 0, "pointwise8_planes_wgrad: bad arguments");
+  DRAM_REQUIRE((Cin_pad == 64 || Cin_pad == 128) && Cin > 0 && Cin <= Cin_pad, "pointwise8_planes_wgrad: Cin_pad %d unsupported (64 | 128)", Cin_pad);
+  const int lpr = Cin_pad / 8;
+  float* partial = (float*)workspace;
+  if (lpr == 8)
+    k_pointwise8_planes_wgrad<8><<<kPointwiseBlocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x_hi, (const uint4*)x_lo, dy, partial, rows);
+  else
+    k_pointwise8_planes_wgrad<16><<<kPointwiseBlocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x_hi, (const uint4*)x_lo, dy, partial, rows);
+  DRAM_LAUNCH_CHECK();
+  const int nout = 8 * Cin_pad + 8;
+  k_pointwise8_reduce<<<(nout + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, kPointwiseBlocks, Cin_pad, Cin, dw, dbias);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

@@ -198,9 +198,11 @@ class ConvBnRelu(torch.autograd.Function):
         # the backward writes dy straight to planes when both consumers (dgrad, wgrad) are tensor-core kernels
         planes_dy = umma and Cout % 8 == 0 and (ops.umma_ok_fwd(Cout, Cin, k) or not ctx.needs_input_grad[0])
         xs = x_real = None
+        pointwise = False
         if x_hi is not None:
             xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1])
-            if not umma:
+            pointwise = not umma and not ctx.needs_input_grad[0] and ops.pointwise8_ok(xs, Cout, k)
+            if not umma and not pointwise:
                 x_real = ops.merge_planes(xs)
         else:
             x_real = ops.to_cl(x, "conv input")
@@ -209,6 +211,8 @@ class ConvBnRelu(torch.autograd.Function):
                 xs = ops.split_bf16(x_real)
             w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_fwd", lambda: ops.pack_weight_bf16(w.detach(), 0))
             y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
+        elif pointwise:
+            y = ops.pointwise8_planes(xs, w, bias)       # reshape heads: straight from the planes, no fp32 copy of the input
         else:
             pack = WEIGHTS.get(w, "f32_fwd", lambda: ops.pack_weight_f32(w.detach(), 0))
             y = ops.conv_simt(x_real, pack, bias, Cout, k)
@@ -233,9 +237,10 @@ class ConvBnRelu(torch.autograd.Function):
             a, pooled = ops.bn_relu_apply(y, scale, shift, pool)
         ctx.training, ctx.pool, ctx.count, ctx.has_bias, ctx.umma = training, pool, count, bias is not None, umma
         ctx.planes_dy = planes_dy
-        ctx.saved_planes = xs if umma else None
+        ctx.pointwise = pointwise
+        ctx.saved_planes = xs if (umma or pointwise) else None
         ctx.save_for_backward(w, gamma, y, scale, shift, a if (pool and not planes_dy) else None, mean, rstd,
-                              None if umma else x_real)
+                              None if (umma or pointwise) else x_real)
         ctx.mark_non_differentiable(*[t for t in (a_hi, a_lo, p_hi, p_lo) if t is not None])
         return a, a_hi, a_lo, pooled, p_hi, p_lo
 
@@ -296,6 +301,9 @@ class ConvBnRelu(torch.autograd.Function):
         saved_in = ctx.saved_planes if ctx.umma else x_plain
         if dys is None and (ctx.umma or (ctx.needs_input_grad[0] and ops.umma_ok_fwd(Cout, Cin, k))):
             dys = ops.split_bf16(dy, three=ops.grad_planes_three())
+        if ctx.pointwise:
+            dw, dbias = ops.pointwise8_planes_wgrad(ctx.saved_planes, dy, ctx.has_bias)
+            return None, None, None, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
         dx = conv_dgrad(dy, w, dys) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(saved_in, dy, w, dys) if ctx.needs_input_grad[3] else None
         dbias = dy.sum(dim=(0, 2, 3, 4)) if ctx.has_bias else None
@@ -545,14 +553,14 @@ class PcmAttend(torch.autograd.Function):
         cam = cam.contiguous()
         tw, tb, pw, pb = tw.contiguous(), tb.contiguous(), pw.contiguous(), pb.contiguous()
         need_grad = keep_for_backward and any(ctx.needs_input_grad[:6])   # grad mode is off inside forward: the caller tells us
-        out, qk, att = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_att=need_grad)
+        out, qk, stats = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=need_grad)
         if need_grad:
-            ctx.save_for_backward(f, cam, tw, pw, qk, att)
+            ctx.save_for_backward(f, cam, tw, pw, qk, stats, out)
         ctx.cfg = (connectivity, self_loop, flags)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        f, cam, tw, pw, qk, att = ctx.saved_tensors
-        dcam, df, dtw, dtb, dpw, dpb = ops.pcm_bwd(f, cam, tw, pw, qk, att, g.contiguous(), *ctx.cfg)
+        f, cam, tw, pw, qk, stats, out = ctx.saved_tensors
+        dcam, df, dtw, dtb, dpw, dpb = ops.pcm_bwd(f, cam, tw, pw, qk, stats, out, g.contiguous(), *ctx.cfg)
         return dcam, df, dtw, dtb, dpw, dpb, None, None, None, None

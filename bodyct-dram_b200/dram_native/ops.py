@@ -256,6 +256,34 @@ def merge_planes(xs):
     return out
 
 
+def pointwise8_ok(xs, Cout, k):
+    """1x1x1 conv to 8 channels straight from planes (the attention reshape heads)"""
+    return k == 1 and isinstance(xs, SplitPlanes) and bool(_L().dram_pointwise8_planes_supported(int(xs.Cpad), int(Cout)))
+
+
+def pointwise8_planes(xs, w, bias):
+    """y [N,8,D,H,W] (channels-last) = Conv3d(C, 8, 1)(planes)"""
+    N, C, D, H, W = xs.shape
+    y = new_volume(N, 8, D, H, W, xs.hi.device)
+    wf = w.detach().reshape(8, C).contiguous()
+    _lib.PROFILE.note(bytes=float(N * D * H * W) * (4.0 * C + 32.0))
+    _lib.check(_L().dram_pointwise8_planes_fwd(xs.hi.data_ptr(), _p(xs.lo), wf.data_ptr(), _p(bias), y.data_ptr(),
+                                               N * D * H * W, C, xs.Cpad, _stream()), "pointwise8_planes_fwd")
+    return y
+
+
+def pointwise8_planes_wgrad(xs, dy, want_bias=True):
+    """-> (dw [8,C,1,1,1], dbias [8] | None) for the layer above; dy [N,8,D,H,W] channels-last fp32"""
+    N, C, D, H, W = xs.shape
+    dw = torch.empty((8, C, 1, 1, 1), device=dy.device, dtype=torch.float32)
+    db = torch.empty(8, device=dy.device, dtype=torch.float32) if want_bias else None
+    ws = torch.empty(_L().dram_pointwise8_planes_wgrad_workspace_bytes(int(xs.Cpad)), device=dy.device, dtype=torch.uint8)
+    _lib.PROFILE.note(bytes=float(N * D * H * W) * (4.0 * C + 32.0))
+    _lib.check(_L().dram_pointwise8_planes_wgrad(xs.hi.data_ptr(), _p(xs.lo), dy.data_ptr(), dw.data_ptr(), _p(db),
+                                                 ws.data_ptr(), N * D * H * W, C, xs.Cpad, _stream()), "pointwise8_planes_wgrad")
+    return dw, db
+
+
 def bn_relu_bwd_reduce(da, y, scale, shift, mean, rstd, pitch=0, wtop=None):
     """-> double sums [2C] (sum dz, sum dz*xhat); with wtop (fused RAM head, da = g [rows]): [3C+1], see the header"""
     N, C, D, H, W = y.shape
@@ -448,33 +476,30 @@ def pcm_num_offsets(connectivity, self_loop):
     return _L().dram_pcm_num_offsets(int(connectivity), int(bool(self_loop)))
 
 
-def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_att=True):
-    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk, att | None)"""
+def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=True):
+    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk planes [2F, B*V], softmax stats [2, B*V] | None)"""
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
-    O = pcm_num_offsets(connectivity, self_loop)
     V = D * H * W
-    keep_att = keep_att or F != 8
-    qk = torch.empty((B * V, 2 * F), device=f.device, dtype=torch.float32)
-    att = torch.empty((B * V, O), device=f.device, dtype=torch.float32) if keep_att else None
+    qk = torch.empty((2 * F, B * V), device=f.device, dtype=torch.float32)
+    stats = torch.empty((2, B * V), device=f.device, dtype=torch.float32) if keep_stats else None
     out = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     _lib.PROFILE.note(bytes=4.0 * B * V * (Cf + 2))
     _lib.check(_L().dram_pcm_fwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), tb.data_ptr(), pw.data_ptr(), pb.data_ptr(),
-                                 qk.data_ptr(), _p(att), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
+                                 qk.data_ptr(), _p(stats), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
                                  int(bool(self_loop)), int(flags), _stream()), "pcm_fwd")
-    return out, qk, att
+    return out, qk, stats
 
 
-def pcm_bwd(f, cam, tw, pw, qk, att, dout, connectivity, self_loop, flags):
+def pcm_bwd(f, cam, tw, pw, qk, stats, out, dout, connectivity, self_loop, flags):
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
-    dd = torch.empty_like(att)
     dqk = torch.empty_like(qk)
     dcam = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     df = new_volume(B, Cf, D, H, W, f.device)
     dparams = torch.empty(2 * F * (Cf + 1), device=f.device, dtype=torch.float64)
-    _lib.check(_L().dram_pcm_bwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), pw.data_ptr(), qk.data_ptr(), att.data_ptr(),
-                                 dout.data_ptr(), dd.data_ptr(), dqk.data_ptr(), dcam.data_ptr(), df.data_ptr(),
+    _lib.check(_L().dram_pcm_bwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), pw.data_ptr(), qk.data_ptr(), stats.data_ptr(),
+                                 out.data_ptr(), dout.data_ptr(), dqk.data_ptr(), dcam.data_ptr(), df.data_ptr(),
                                  dparams.data_ptr(), B, D, H, W, Cf, F, int(connectivity), int(bool(self_loop)),
                                  int(flags), _stream()), "pcm_bwd")
     dp = dparams.float()

@@ -148,6 +148,17 @@ int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void
 /* planes -> fp32 [rows][C]: materialises an activation for a consumer outside the tensor-core path */
 int dram_merge_planes(const void* hi, const void* lo /*nullable*/, float* out, long long rows, int C, int Cpad, void* stream);
 
+/* Conv3d(C, 8, kernel_size=1) on split planes - the attention reshape heads (models.py:488-494, applied at :564 to a
+ * detached decoder feature map).  x planes [rows][Cin_pad] bf16 (x_lo nullable), w [8][Cin] fp32 (nn.Conv3d layout),
+ * bias [8] (nullable), y [rows][8] fp32.  Supported: Cin_pad 64 | 128 (query dram_pointwise8_planes_supported). */
+int dram_pointwise8_planes_supported(int Cin_pad, int Cout);
+int dram_pointwise8_planes_fwd(const void* x_hi, const void* x_lo, const float* w, const float* bias, float* y, long long rows,
+                               int Cin, int Cin_pad, void* stream);
+/* dw [8][Cin], dbias [8] (nullable): overwritten; deterministic (per-block partials in `workspace`, fixed-order sum) */
+size_t dram_pointwise8_planes_wgrad_workspace_bytes(int Cin_pad);
+int dram_pointwise8_planes_wgrad(const void* x_hi, const void* x_lo, const float* dy, float* dw, float* dbias, void* workspace,
+                                 long long rows, int Cin, int Cin_pad, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ decoder glue
  * nn.Upsample(scale_factor=2, trilinear, align_corners=True) + crop_concat_5d: parts.py:149-153,37-46.
  * cat[..., 0:C1] = up(x) ; cat[..., C1:C1+C2] = skip centre-cropped with ceil offsets.  x: [N][d][h][w][C1],
@@ -214,15 +225,16 @@ int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, f
  * flags bit0: relu on logits; bits1-2: temperature (0 none, 1 sqrt(degree) — models.py:274-277, 2 = 0.01);
  * connectivity 1|2|3, self_loop 0|1. */
 int dram_pcm_num_offsets(int connectivity, int self_loop); /* O: 18 for (2, no self loop) */
-/* qk  [B][V][2F] (out): theta|phi projections;  att [B][V][O] (out): softmax weights, kept for the backward;
- * att == NULL (F == 8): inference kernel — online softmax in registers, x-neighbours shared through warp shuffles */
+/* R = B*V rows.  qk [2F][R] (out): theta|phi projections as planes (coalesced neighbour loads);
+ * stats [2][R] (out, may be NULL at inference): running max and normaliser of each node's softmax - what the backward keeps
+ * instead of the [R][O] attention weights (they are recomputed from qk) */
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
-                 const float* phi_b, float* qk, float* att, float* out, int B, int D, int H, int W, int Cf, int F,
+                 const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream);
-/* dd_ws [B][V][O], dqk_ws [B][V][2F]: scratch.  dcam [B][V], df [B][V][Cf]: overwritten.
+/* s_out: the forward's `out`.  dqk_ws [2F][R]: scratch.  dcam [R], df [R][Cf]: overwritten.
  * dparams double[2*F*(Cf+1)] = dtheta_w, dtheta_b, dphi_w, dphi_b: overwritten. */
 int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
-                 const float* att, const float* dout, float* dd_ws, float* dqk_ws, float* dcam, float* df,
+                 const float* stats, const float* s_out, const float* dout, float* dqk_ws, float* dcam, float* df,
                  double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
                  void* stream);
 

@@ -522,6 +522,65 @@ def test_ram_upsample_mask_scatter(act):
     assert abs(mx.item() - up.max().item()) <= 1e-5 * max(1.0, abs(up.max().item()))
 
 
+# ------------------------------------------------------------------------------------------------ 1x1x1 reshape heads on planes
+@pytest.mark.parametrize("N,C,S", [(2, 64, (5, 6, 7)), (1, 128, (4, 5, 9)), (3, 40, (3, 3, 3)), (1, 104, (2, 5, 31))])
+@pytest.mark.parametrize("three", [True, False])
+def test_pointwise8_planes(N, C, S, three):
+    """Conv3d(C, 8, 1) straight from split planes (models.py:488-494) and its weight / bias gradient"""
+    o = ops()
+    x = torch.randn(N, C, *S)
+    w, b = torch.randn(8, C, 1, 1, 1) / C ** 0.5, torch.randn(8)
+    xs = o.split_bf16(cuda_cl(x), three)
+    assert o.pointwise8_ok(xs, 8, 1) and not o.pointwise8_ok(xs, 16, 1) and not o.pointwise8_ok(xs, 8, 3)
+    xr = o.merge_planes(xs).cpu()                               # what the planes hold (== x to 2^-16 when three)
+    assert_close(xr, x, TOL_X3 if three else TOL_BF16, "planes")
+    ref = F.conv3d(xr, w, b)
+    y = o.pointwise8_planes(xs, w.cuda(), b.cuda())
+    assert_close(y, ref, TOL_F32, "pointwise8 fwd")
+    assert_close(o.pointwise8_planes(xs, w.cuda(), None), F.conv3d(xr, w), TOL_F32, "pointwise8 fwd, no bias")
+    dy = torch.randn_like(ref)
+    dw_ref = torch.nn.grad.conv3d_weight(xr, w.shape, dy)
+    dw, db = o.pointwise8_planes_wgrad(xs, cuda_cl(dy))
+    assert_close(dw, dw_ref, TOL_F32, "pointwise8 dw")
+    assert_close(db, dy.sum(dim=(0, 2, 3, 4)), TOL_F32, "pointwise8 dbias")
+    dw2, db2 = o.pointwise8_planes_wgrad(xs, cuda_cl(dy))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2), "pointwise8 wgrad must be deterministic"
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_reshape_head_unit_on_planes(training):
+    """[Conv3d(64, 8, 1) + bias -> BatchNorm3d -> ReLU] on a detached `Act` (planes) input: DC3DATGeneric._reshape_head"""
+    o, f = ops(), DF()
+    N, C, S = 2, 64, (6, 5, 8)
+    x = torch.randn(N, C, *S)
+    conv, bn = torch.nn.Conv3d(C, 8, 1), torch.nn.BatchNorm3d(8)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    bn.train(training)
+    rm, rv = bn.running_mean.clone().cuda(), bn.running_var.clone().cuda()
+    xs = o.split_bf16(cuda_cl(x), True)
+    xr = o.merge_planes(xs).cpu()
+    ref = F.relu(bn(conv(xr)))
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    act = f.Act(f._handle(xs.shape, "cuda"), xs)
+    wg, bg = conv.weight.detach().cuda().requires_grad_(True), conv.bias.detach().cuda().requires_grad_(True)
+    gg, beg = bn.weight.detach().cuda().requires_grad_(True), bn.bias.detach().cuda().requires_grad_(True)
+    from dram_native import lib
+    lib.PROFILE.reset()
+    got = f.conv_bn_relu(act.detach(), wg, bg, gg, beg, rm, rv, training, 0.1, 1e-5, 1, False)
+    assert lib.PROFILE.calls.get("dram_pointwise8_planes_fwd") == 1 and "dram_merge_planes" not in lib.PROFILE.calls
+    assert_close(got, ref, TOL_X3, "reshape head fwd")
+    got.backward(g.cuda())
+    assert lib.PROFILE.calls.get("dram_pointwise8_planes_wgrad") == 1
+    for t, r, name in ((wg, conv.weight, "dw"), (bg, conv.bias, "dbias"), (gg, bn.weight, "dgamma"), (beg, bn.bias, "dbeta")):
+        scale = max(r.grad.abs().max().item(), 1e-3 * conv.weight.grad.abs().max().item())
+        assert (t.grad.cpu() - r.grad).abs().max().item() <= 2e-4 * max(scale, 1e-6), f"reshape head {name}"
+    if training:
+        assert_close(rm, bn.running_mean, TOL_F32, "running mean")
+        assert_close(rv, bn.running_var, TOL_F32, "running var")
+
+
 # ------------------------------------------------------------------------------------------------ PCM stencil attention
 @pytest.mark.parametrize("merge,self_loop,conn,grid", [("scaled_dot_product_relu", False, 2, (6, 7, 8)), ("sm", True, 1, (5, 5, 5)),
                                                        ("scaled_dot_product", False, 3, (4, 6, 5)), ("smrelu", False, 2, (2, 1, 3)),
