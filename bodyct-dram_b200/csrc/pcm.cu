@@ -10,11 +10,14 @@
 // degree, not the feature dim).  No graph structure is materialised: neighbours are address arithmetic.
 //
 // Data (R = B*V rows, V = D*H*W): f [R][Cf] channels-last, cam/out [R];
-//   qk    [2F][R]  theta|phi projections as PLANES (structure of arrays): a warp = 32 consecutive x of one grid row, so every
-//                  load of one feature of one neighbour offset is one coalesced 128-byte request (the [R][2F] rows of the
-//                  first version cost 16 L1 wavefronts per request - the kernels were LSU-bound at 2-4 % of HBM peak);
-//   stats [2][R]   running max m and normaliser l of the node's softmax, kept for the backward INSTEAD of the [R][O]
-//                  attention weights: a_{x,o} = exp(s_{x,o} - m_x) / l_x is recomputed from q_x and k_{x+o} (8 FMAs + 1 exp).
+//   qk    [ceil(R/32)][2F][32]  theta|phi projections in blocks of 32 consecutive voxels (array of structures of arrays):
+//                  a warp = 32 consecutive x of one grid row, so one feature of one neighbour offset is one coalesced
+//                  128-byte request, and the 2F features of a voxel sit at COMPILE-TIME offsets (j*128 bytes) from one
+//                  address (the [R][2F] rows of the first version cost 16 L1 wavefronts per request, plain planes a
+//                  64-bit address computation per load);
+//   stats [R][4]   (m, 1/l, 1/T, s): running max and inverse normaliser of the node's softmax, its inverse temperature
+//                  and its output - what the backward keeps INSTEAD of the [R][O] attention weights:
+//                  a_{x,o} = exp(s_{x,o}/T_x - m_x) / l_x is recomputed from q_x and k_{x+o} (F FMAs + 1 exp).
 #include "common.cuh"
 
 namespace dram {
@@ -22,60 +25,79 @@ namespace dram {
 constexpr int kMaxOff = 27, kMaxF = 16, kMaxCf = 64;
 
 struct PcmGeom {
-  int B, D, H, W, Cf, F, O, flags;
-  signed char off[kMaxOff][3];
+  int B, D, H, W, Cf, F, O, flags;     // flags: bit0 relu, bits1-2 temperature mode, bit7 self loop, bits8+ connectivity
 };
 
-static int build_offsets(int connectivity, int self_loop, signed char off[kMaxOff][3]) {
+static int count_offsets(int connectivity, int self_loop) {
   int n = 0;
   for (int dz = -1; dz <= 1; ++dz)
     for (int dy = -1; dy <= 1; ++dy)
       for (int dx = -1; dx <= 1; ++dx) {
         int l1 = abs(dz) + abs(dy) + abs(dx);
-        bool take = (l1 == 0) ? (self_loop != 0) : (l1 <= connectivity);
-        if (take) { off[n][0] = (signed char)dz; off[n][1] = (signed char)dy; off[n][2] = (signed char)dx; ++n; }
+        n += (l1 == 0) ? (self_loop != 0) : (l1 <= connectivity);
       }
   return n;
 }
 
-__device__ __forceinline__ bool nb_index(const PcmGeom& g, int z, int y, int x, int o, long long& idx) {
-  int zz = z + g.off[o][0], yy = y + g.off[o][1], xx = x + g.off[o][2];
-  if (zz < 0 || zz >= g.D || yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) return false;
-  idx = ((long long)zz * g.H + yy) * g.W + xx;
-  return true;
-}
-__device__ __forceinline__ float temperature(const PcmGeom& g, int deg) {
-  int mode = (g.flags >> 1) & 3;
-  return mode == 1 ? sqrtf((float)deg) : (mode == 2 ? 0.01f : 1.f);
+// 1/T; mode 1 (scaled_dot_product*): T = sqrt(degree) -> one MUFU.RSQ (the forward and the backward use the same value)
+__device__ __forceinline__ float inv_temperature(int flags, int deg) {
+  const int mode = (flags >> 1) & 3;
+  return mode == 1 ? rsqrtf((float)deg) : (mode == 2 ? 100.f : 1.f);
 }
 
-// number of in-grid neighbours of (z,y,x) in closed form: with a_z = #{dz in {-1,+1} : z+dz in grid} etc. the stencil
+// number of in-grid neighbours in closed form: with a_z = #{dz in {-1,+1} : z+dz in grid} etc. the stencil
 // {|dz|+|dy|+|dx| <= connectivity} has a_z+a_y+a_x members at L1 distance 1, a_z a_y + a_z a_x + a_y a_x at 2, a_z a_y a_x at 3
-__device__ __forceinline__ int degree_of(const PcmGeom& g, int z, int y, int x) {
-  const int az = (z > 0) + (z < g.D - 1), ay = (y > 0) + (y < g.H - 1), ax = (x > 0) + (x < g.W - 1);
-  const int conn = g.flags >> 8;
-  int deg = (g.flags >> 7) & 1;                               // self loop
-  deg += az + ay + ax;
+__device__ __forceinline__ int degree_from(int flags, int az, int ay, int ax) {
+  const int conn = flags >> 8;
+  int deg = ((flags >> 7) & 1) + az + ay + ax;
   if (conn >= 2) deg += az * ay + az * ax + ay * ax;
   if (conn >= 3) deg += az * ay * ax;
   return deg;
 }
 
-// The stencil as 27 fully unrolled candidates in build_offsets order (dz, dy, dx ascending): dz/dy/dx are compile-time
-// constants inside the body, membership is a warp-uniform test (indexing the by-value offset table would put it in local memory).
-#define PCM_FOR_EACH_OFFSET(g)                                                                                      \
+// The stencil as 27 fully unrolled candidates in (dz, dy, dx) ascending order: dz/dy/dx are compile-time constants inside
+// the body, membership is a warp-uniform test (indexing a by-value offset table would put it in local memory).
+#define PCM_FOR_EACH_OFFSET(flags_)                                                                                 \
   _Pragma("unroll") for (int t_ = 0; t_ < 27; ++t_)                                                                 \
     if (const int dz = t_ / 9 - 1, dy = (t_ / 3) % 3 - 1, dx = t_ % 3 - 1, l1_ = (dz != 0) + (dy != 0) + (dx != 0); \
-        l1_ == 0 ? (((g).flags >> 7) & 1) != 0 : l1_ <= ((g).flags >> 8))
+        l1_ == 0 ? (((flags_) >> 7) & 1) != 0 : l1_ <= ((flags_) >> 8))
 
-// qk[j][r] = theta f_r + b (j < F), phi f_r + b (F <= j < 2F).  A warp stages its 32 consecutive rows (32*Cf contiguous
-// floats) through shared memory with coalesced loads; a lane then walks its row at an odd pitch (conflict-free).
+// per-thread position: one z-plane per blockIdx.y (b, z uniform), one 32-bit division for (y, x)
+struct PcmPos {
+  int i, x, y, z;               // i: global row index
+  bool zm, zp, ym, yp, xm, xp;  // neighbour at -1 / +1 along the axis is inside the grid
+  bool live;
+  __device__ __forceinline__ PcmPos(const PcmGeom& g) {
+    const int HW = g.H * g.W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    live = p < HW;
+    const int pp = live ? p : HW - 1;
+    z = blockIdx.y % g.D;
+    y = pp / g.W;
+    x = pp - y * g.W;
+    i = blockIdx.y * HW + pp;
+    zm = z > 0; zp = z < g.D - 1; ym = y > 0; yp = y < g.H - 1; xm = x > 0; xp = x < g.W - 1;
+  }
+  // neighbour (sz*dz, sz*dy, sz*dx), sz = +1 (x + o) or -1 (x - o), inside the grid?
+  template <int S>
+  __device__ __forceinline__ bool inside(int dz, int dy, int dx) const {
+    const int ez = S * dz, ey = S * dy, ex = S * dx;
+    return (ez < 0 ? zm : (ez > 0 ? zp : true)) && (ey < 0 ? ym : (ey > 0 ? yp : true)) && (ex < 0 ? xm : (ex > 0 ? xp : true));
+  }
+};
+
+template <int F>
+__device__ __forceinline__ const float* qk_at(const float* qk, int n) { return qk + (size_t)(n >> 5) * (2 * F * 32) + (n & 31); }
+
+// qk block layout: feature j (theta: j < F, phi: F <= j < 2F) of row r at [(r >> 5)][j][r & 31].  A warp stages its 32
+// consecutive rows (32*Cf contiguous floats) through shared memory with coalesced loads; a lane then walks its row at an
+// odd pitch (conflict-free); the weights of one input channel are J4 float4 broadcast reads.
 __global__ void __launch_bounds__(256)
 k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const float* __restrict__ tb,
               const float* __restrict__ pw, const float* __restrict__ pb, float* __restrict__ qk, long long rows, int Cf, int F) {
   extern __shared__ float4 psm4[];
   float* psm = reinterpret_cast<float*>(psm4);
-  const int Cfp = Cf | 1, J4 = (2 * F + 3) >> 2;    // outputs in groups of 4: the weights of one input channel are J4 float4
+  const int Cfp = Cf | 1, J4 = (2 * F + 3) >> 2;
   float* sw = psm;                                  // [Cf][4*J4]  (transposed, zero padded)
   float* sb = sw + Cf * 4 * J4;                     // [4*J4]
   float* st = sb + 4 * J4 + (threadIdx.x >> 5) * 32 * Cfp;   // this warp's [32][Cfp] tile
@@ -92,7 +114,10 @@ k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const f
     const int n = (int)(rows - r0 < 32 ? rows - r0 : 32);
     const float* src = f + r0 * Cf;
     __syncwarp();
-    for (int i = lane; i < n * Cf; i += 32) { const int r = i / Cf; st[r * Cfp + (i - r * Cf)] = __ldg(src + i); }
+    for (int i = lane, r = 0, c = lane; i < n * Cf; i += 32, c += 32) {
+      while (c >= Cf) { c -= Cf; ++r; }
+      st[r * Cfp + c] = __ldg(src + i);
+    }
     __syncwarp();
     if (lane < n) {
       float4 acc[kMaxF / 2];
@@ -110,181 +135,228 @@ k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const f
             acc[j].z = fmaf(v, w4.z, acc[j].z); acc[j].w = fmaf(v, w4.w, acc[j].w);
           }
       }
-      float* dst = qk + r0 + lane;
+      float* dst = qk + t * (2 * F * 32) + lane;
 #pragma unroll
       for (int j = 0; j < kMaxF / 2; ++j) {
-        if (4 * j + 0 < 2 * F) dst[(long long)(4 * j + 0) * rows] = acc[j].x;
-        if (4 * j + 1 < 2 * F) dst[(long long)(4 * j + 1) * rows] = acc[j].y;
-        if (4 * j + 2 < 2 * F) dst[(long long)(4 * j + 2) * rows] = acc[j].z;
-        if (4 * j + 3 < 2 * F) dst[(long long)(4 * j + 3) * rows] = acc[j].w;
+        if (4 * j + 0 < 2 * F) dst[(4 * j + 0) * 32] = acc[j].x;
+        if (4 * j + 1 < 2 * F) dst[(4 * j + 1) * 32] = acc[j].y;
+        if (4 * j + 2 < 2 * F) dst[(4 * j + 2) * 32] = acc[j].z;
+        if (4 * j + 3 < 2 * F) dst[(4 * j + 3) * 32] = acc[j].w;
       }
     }
   }
 }
 
-// forward: one thread per node, online softmax over the in-grid neighbours (no per-offset arrays).  SAVE: keep (m, l).
-template <int FT, bool SAVE>
+// forward: one thread per node; scores of the <= 26(+1) neighbours in registers, two-pass softmax.  SAVE: keep stats.
+template <int F, bool SAVE>
 __global__ void __launch_bounds__(256)
-k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float* __restrict__ stats,
+k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float4* __restrict__ stats,
              float* __restrict__ out) {
-  const long long V = (long long)g.D * g.H * g.W, R = (long long)g.B * V;
-  const int F = g.F;
-  const bool relu = g.flags & 1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const long long v = i % V;
-    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    float q[FT];
+  const PcmPos P(g);
+  const int W = g.W, HW = g.H * g.W, flags = g.flags;
+  const bool relu = flags & 1;
+  const float* qp = qk_at<F>(qk, P.i);
+  float q[F];
 #pragma unroll
-    for (int j = 0; j < FT; ++j) q[j] = j < F ? __ldg(qk + (long long)j * R + i) : 0.f;
-    const int deg = degree_of(g, z, y, x);
-    const float invT = 1.f / temperature(g, deg);
-    const float* kbase = qk + (long long)F * R + i;
-    float m = -INFINITY, l = 0.f, acc = 0.f;
-    PCM_FOR_EACH_OFFSET(g) {
-      const int zz = z + dz, yy = y + dy, xx = x + dx;
-      if (zz < 0 || zz >= g.D || yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
-      const long long d_i = ((long long)dz * g.H + dy) * g.W + dx;
+  for (int j = 0; j < F; ++j) q[j] = __ldg(qp + j * 32);
+  const int deg = degree_from(flags, P.zm + P.zp, P.ym + P.yp, P.xm + P.xp);
+  const float invT = inv_temperature(flags, deg);
+  float s[27], c[27];
+  float m = -INFINITY;
+  PCM_FOR_EACH_OFFSET(flags) {
+    float d = -INFINITY, cv = 0.f;
+    if (P.inside<1>(dz, dy, dx)) {
+      const int n = P.i + dz * HW + dy * W + dx;
+      const float* kp = qk_at<F>(qk, n) + F * 32;
+      d = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) d = fmaf(q[j], __ldg(kp + j * 32), d);
+      if (relu) d = fmaxf(d, 0.f);
+      d *= invT;
+      cv = __ldg(cam + n);
+    }
+    s[t_] = d; c[t_] = cv;
+    m = fmaxf(m, d);
+  }
+  float l = 0.f, acc = 0.f;
+  PCM_FOR_EACH_OFFSET(flags) {
+    const float e = __expf(s[t_] - m);                 // absent neighbour: exp(-inf) = 0
+    l += e;
+    acc = fmaf(e, c[t_], acc);
+  }
+  if (!P.live) return;
+  const bool any = deg > 0;                             // degree-0 nodes (1x1x1 grids) keep 0 like DGL's zero-filled result
+  const float il = any ? 1.f / l : 0.f, o = any ? acc * il : 0.f;
+  out[P.i] = o;
+  if (SAVE) stats[P.i] = make_float4(any ? m : 0.f, il, invT, o);
+}
+
+// backward, one thread per voxel i in both of its roles, nothing but `stats` kept from the forward:
+//  node role   (i = x):  a_o = exp(s_o/T_x - m_x)/l_x,  ds_o = a_o (g_x cam_{x+o} - g_x s_x) / T_x [logit > 0],
+//                        dq_x = sum_o ds_o k_{x+o}
+//  gather role (i = y):  over the nodes x = y - o that list y as their neighbour o: the same a, ds from q_x, stats_x, g_x and
+//                        the own k_y, cam_y:  dcam_y = sum g_x a,  dk_y = sum ds q_x
+// (sum_o a_o g cam_{x+o} = g_x s_x is the softmax-Jacobian dot product.)   dqk: blocks of 32 rows like qk.
+template <int F>
+__global__ void __launch_bounds__(256, F <= 8 ? 2 : 1)
+k_pcm_bwd(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float4* __restrict__ stats,
+          const float* __restrict__ dout, float* __restrict__ dcam, float* __restrict__ dqk) {
+  const PcmPos P(g);
+  const int W = g.W, HW = g.H * g.W, flags = g.flags;
+  const bool relu = flags & 1;
+  const float* qp = qk_at<F>(qk, P.i);
+  float q[F], k[F], dq[F], dk[F];
+#pragma unroll
+  for (int j = 0; j < F; ++j) { q[j] = __ldg(qp + j * 32); k[j] = __ldg(qp + (F + j) * 32); dq[j] = 0.f; dk[j] = 0.f; }
+  const float4 st = __ldg(stats + P.i);                 // m, 1/l, 1/T, s
+  const float go = __ldg(dout + P.i), cam_i = __ldg(cam + P.i);
+  const float dot = go * st.w;
+  float dc = 0.f;
+  PCM_FOR_EACH_OFFSET(flags) {
+    const int d_i = dz * HW + dy * W + dx;
+    if (P.inside<1>(dz, dy, dx)) {                      // node role: neighbour n = i + o
+      const int n = P.i + d_i;
+      const float* kp = qk_at<F>(qk, n) + F * 32;
+      float kn[F];
       float d = 0.f;
 #pragma unroll
-      for (int j = 0; j < FT; ++j)
-        if (j < F) d = fmaf(q[j], __ldg(kbase + (long long)j * R + d_i), d);
+      for (int j = 0; j < F; ++j) { kn[j] = __ldg(kp + j * 32); d = fmaf(q[j], kn[j], d); }
+      const bool dead = relu && !(d > 0.f);
       if (relu) d = fmaxf(d, 0.f);
-      const float sv = d * invT, cv = __ldg(cam + i + d_i);
-      const float mn = fmaxf(m, sv);
-      const float corr = __expf(m - mn), e = __expf(sv - mn);      // m = -inf on the first neighbour -> corr = 0
-      l = l * corr + e;
-      acc = acc * corr + e * cv;
-      m = mn;
+      const float a = __expf(fmaf(d, st.z, -st.x)) * st.y;
+      const float ds = dead ? 0.f : a * fmaf(go, __ldg(cam + n), -dot) * st.z;
+#pragma unroll
+      for (int j = 0; j < F; ++j) dq[j] = fmaf(ds, kn[j], dq[j]);
     }
-    out[i] = deg > 0 ? acc / l : 0.f;     // degree-0 nodes (1x1x1 grids) keep 0 like DGL's zero-filled result
-    if (SAVE) { stats[i] = deg > 0 ? m : 0.f; stats[R + i] = deg > 0 ? l : 1.f; }
+    if (P.inside<-1>(dz, dy, dx)) {                     // gather role: node n = i - o has i as its neighbour o
+      const int n = P.i - d_i;
+      const float* np = qk_at<F>(qk, n);
+      float qn[F];
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) { qn[j] = __ldg(np + j * 32); d = fmaf(qn[j], k[j], d); }
+      const bool dead = relu && !(d > 0.f);
+      if (relu) d = fmaxf(d, 0.f);
+      const float4 sn = __ldg(stats + n);
+      const float gn = __ldg(dout + n);
+      const float a = __expf(fmaf(d, sn.z, -sn.x)) * sn.y;
+      dc = fmaf(gn, a, dc);
+      const float ds = dead ? 0.f : a * gn * (cam_i - sn.w) * sn.z;
+#pragma unroll
+      for (int j = 0; j < F; ++j) dk[j] = fmaf(ds, qn[j], dk[j]);
+    }
   }
+  if (!P.live) return;
+  dcam[P.i] = dc;
+  float* dp = dqk + (size_t)(P.i >> 5) * (2 * F * 32) + (P.i & 31);
+#pragma unroll
+  for (int j = 0; j < F; ++j) { dp[j * 32] = dq[j]; dp[(F + j) * 32] = dk[j]; }
 }
 
-// backward, one thread per voxel i in both of its roles, nothing but (m, l) and the forward output s kept from the forward:
-//  node role   (i = x):  a_o = exp(s_o - m_x)/l_x,  ds_o = a_o (g_x cam_{x+o} - g_x s_x) / T_x [logit > 0],
-//                        dq_x = sum_o ds_o k_{x+o}
-//  gather role (i = y):  over the nodes x = y - o that list y as their neighbour o: the same a, ds from q_x, (m, l, g, s)_x and
-//                        the own k_y, cam_y:  dcam_y = sum g_x a,  dk_y = sum ds q_x
-// (sum_o a_o g cam_{x+o} = g_x s_x is the softmax-Jacobian dot product.)   dqk: [2F][R] planes like qk.
-template <int FT>
-__global__ void __launch_bounds__(256, FT <= 8 ? 2 : 1)
-k_pcm_bwd(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float* __restrict__ stats,
-          const float* __restrict__ s_out, const float* __restrict__ dout, float* __restrict__ dcam, float* __restrict__ dqk) {
-  const long long V = (long long)g.D * g.H * g.W, R = (long long)g.B * V;
-  const int F = g.F;
-  const bool relu = g.flags & 1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const long long v = i % V;
-    const int x = (int)(v % g.W), y = (int)((v / g.W) % g.H), z = (int)(v / ((long long)g.W * g.H));
-    float q[FT], k[FT], dq[FT], dk[FT];
-#pragma unroll
-    for (int j = 0; j < FT; ++j) {
-      q[j] = j < F ? __ldg(qk + (long long)j * R + i) : 0.f;
-      k[j] = j < F ? __ldg(qk + (long long)(F + j) * R + i) : 0.f;
-      dq[j] = 0.f; dk[j] = 0.f;
-    }
-    const int deg = degree_of(g, z, y, x);
-    const float invT = 1.f / temperature(g, deg);
-    const float go = __ldg(dout + i), m = __ldg(stats + i), il = 1.f / __ldg(stats + R + i), dot = go * __ldg(s_out + i);
-    const float cam_i = __ldg(cam + i);
-    float dc = 0.f;
-    PCM_FOR_EACH_OFFSET(g) {
-      const long long d_i = ((long long)dz * g.H + dy) * g.W + dx;
-      {   // node role: neighbour n = i + o
-        const int zz = z + dz, yy = y + dy, xx = x + dx;
-        if (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
-          float kn[FT];
-          float d = 0.f;
-#pragma unroll
-          for (int j = 0; j < FT; ++j) {
-            kn[j] = j < F ? __ldg(qk + (long long)(F + j) * R + i + d_i) : 0.f;
-            d = fmaf(q[j], kn[j], d);
-          }
-          const bool dead = relu && !(d > 0.f);
-          if (relu) d = fmaxf(d, 0.f);
-          const float a = __expf(d * invT - m) * il;
-          const float ds = dead ? 0.f : a * (go * __ldg(cam + i + d_i) - dot) * invT;
-#pragma unroll
-          for (int j = 0; j < FT; ++j) dq[j] = fmaf(ds, kn[j], dq[j]);
-        }
-      }
-      {   // gather role: node n = i - o has i as its neighbour o
-        const int zz = z - dz, yy = y - dy, xx = x - dx;
-        if (zz >= 0 && zz < g.D && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
-          const long long n = i - d_i;
-          float qn[FT];
-          float d = 0.f;
-#pragma unroll
-          for (int j = 0; j < FT; ++j) {
-            qn[j] = j < F ? __ldg(qk + (long long)j * R + n) : 0.f;
-            d = fmaf(qn[j], k[j], d);
-          }
-          const bool dead = relu && !(d > 0.f);
-          if (relu) d = fmaxf(d, 0.f);
-          const float invTn = 1.f / temperature(g, degree_of(g, zz, yy, xx));
-          const float gn = __ldg(dout + n);
-          const float a = __expf(d * invTn - __ldg(stats + n)) / __ldg(stats + R + n);
-          dc = fmaf(gn, a, dc);
-          const float ds = dead ? 0.f : a * (gn * cam_i - gn * __ldg(s_out + n)) * invTn;
-#pragma unroll
-          for (int j = 0; j < FT; ++j) dk[j] = fmaf(ds, qn[j], dk[j]);
-        }
-      }
-    }
-    dcam[i] = dc;
-#pragma unroll
-    for (int j = 0; j < FT; ++j)
-      if (j < F) { dqk[(long long)j * R + i] = dq[j]; dqk[(long long)(F + j) * R + i] = dk[j]; }
-  }
-}
-
-// backward pass 3: df = theta^T dq + phi^T dk; dparams += [dq (x) f, dq, dk (x) f, dk] reduced over all voxels
-constexpr int kPcmChunk = 128;
-__global__ void __launch_bounds__(320)
+// backward of the projections over chunks of 256 rows (dqk = [dq | dk] from k_pcm_bwd, G = 2F columns):
+//   df[r][c]  = sum_j W[j][c] dqk[r][j]              one thread per row, dqk row in registers, W as broadcast float4 reads;
+//                                                   rows leave through shared memory as one contiguous, coalesced block
+//   dW[j][c] += sum_r dqk[r][j] f[r][c], db[j] += sum_r dqk[r][j]
+//                                                   register tiles of 4 (j) x 4 (c) per thread over a [256][G] x [256][Cf+1]
+//                                                   pair of shared-memory tiles (f gets a column of ones for the bias);
+//                                                   the JG*CG tile owners form a row group, 256 / (JG*CG) groups split the rows
+__global__ void __launch_bounds__(256)
 k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, const float* __restrict__ pw,
                  const float* __restrict__ dqk, float* __restrict__ df, double* __restrict__ dparams, long long rows,
                  int Cf, int F) {
-  extern __shared__ float sm[];
-  float* sf = sm;                                 // [kPcmChunk][Cf]
-  const int SG = 2 * F + 1;
-  float* sg = sf + kPcmChunk * Cf;                // [kPcmChunk][2F + 1]
-  float* sw = sg + kPcmChunk * SG;                // [2F][Cf]
-  for (int i = threadIdx.x; i < F * Cf; i += blockDim.x) { sw[i] = tw[i]; sw[F * Cf + i] = pw[i]; }
-  const int nout = 2 * F * (Cf + 1);              // outputs: for m in {theta,phi}: F*Cf weights then F biases
-  float acc = 0.f;
-  int t = threadIdx.x;
-  int which = 0, j = 0, c = 0;
-  bool owner = t < nout;
-  if (owner) {
-    int per = F * (Cf + 1);
-    which = t / per;
-    int r = t % per;
-    if (r < F * Cf) { j = r / Cf; c = r % Cf; } else { j = r - F * Cf; c = -1; }
+  extern __shared__ float4 bsm4[];
+  float* bsm = reinterpret_cast<float*>(bsm4);
+  const int G = 2 * F, JG = (G + 3) >> 2, CG = (Cf + 4) >> 2;      // CG covers Cf + 1 columns
+  const int GP = 4 * JG + 4, CP = 4 * CG + 4;                       // row pitches (floats), multiples of 4
+  float* sf = bsm;                       // [256][CP]  f rows, column Cf = 1, rest 0
+  float* sg = sf + 256 * CP;             // [256][GP]  dqk rows
+  float* sw = sg + 256 * GP;             // [Cf][4*JG] W^T (theta | phi)
+  float* sd = sf;                        // df rows [256][Cf] reuse sf after the tile phase
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < Cf * 4 * JG; i += blockDim.x) {
+    const int c = i / (4 * JG), j = i - c * 4 * JG;
+    sw[i] = j < F ? tw[j * Cf + c] : (j < G ? pw[(j - F) * Cf + c] : 0.f);
   }
-  for (long long base = (long long)blockIdx.x * kPcmChunk; base < rows; base += (long long)gridDim.x * kPcmChunk) {
-    int n = (int)(rows - base < kPcmChunk ? rows - base : kPcmChunk);
+  const int NT = JG * CG, groups = 256 / NT;
+  const int grp = tid / NT, tt = tid - grp * NT, jg = tt / CG, cg = tt - jg * CG;
+  const bool owner = grp < groups;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const long long chunks = (rows + 255) >> 8;
+  for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    const long long base = ch << 8;
+    const int n = (int)(rows - base < 256 ? rows - base : 256);
+    __syncthreads();                                                // previous chunk's sd / sg readers are done
+    for (int i = tid; i < 256 * CP; i += blockDim.x) sf[i] = 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < n * Cf; i += blockDim.x) sf[i] = f[base * Cf + i];
-    for (int i = threadIdx.x; i < n * 2 * F; i += blockDim.x) {           // dqk planes [2F][rows] -> sg[r][SG], SG odd
-      const int jj = i / n, r = i - jj * n;
-      sg[r * SG + jj] = dqk[(long long)jj * rows + base + r];
+    for (int i = tid, r = 0, c = tid; i < n * Cf; i += 256, c += 256) {   // contiguous, coalesced
+      while (c >= Cf) { c -= Cf; ++r; }
+      sf[r * CP + c] = __ldg(f + base * Cf + i);
     }
+    float gr[2 * kMaxF];
+    if (tid < n) {
+      sf[tid * CP + Cf] = 1.f;
+      const float* gp = dqk + (size_t)((base + tid) >> 5) * (G * 32) + lane;     // base is a multiple of 32
+#pragma unroll
+      for (int j = 0; j < 2 * kMaxF; ++j) gr[j] = j < G ? __ldg(gp + j * 32) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2 * kMaxF; ++j) gr[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * kMaxF; ++j)
+      if (j < GP) sg[tid * GP + j] = gr[j];                         // rows >= n and columns >= G are zeros
     __syncthreads();
     if (owner) {
-      for (int r = 0; r < n; ++r) {
-        float gq = sg[r * SG + which * F + j];
-        acc = c >= 0 ? fmaf(gq, sf[r * Cf + c], acc) : acc + gq;
+      for (int r = grp; r < n; r += groups) {
+        const float4 gv = *reinterpret_cast<const float4*>(sg + r * GP + 4 * jg);
+        const float4 fv = *reinterpret_cast<const float4*>(sf + r * CP + 4 * cg);
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, fa[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], fa[b], acc[a][b]);
       }
     }
-    for (int i = threadIdx.x; i < n * Cf; i += blockDim.x) {
-      int r = i / Cf, cc = i % Cf;
-      float d = 0.f;
-      for (int jj = 0; jj < 2 * F; ++jj) d = fmaf(sw[jj * Cf + cc], sg[r * SG + jj], d);
-      df[base * Cf + i] = d;
+    __syncthreads();                                                // sf is free: df rows go there
+    if (tid < n) {
+      for (int c = 0; c < Cf; ++c) {
+        const float4* wc = reinterpret_cast<const float4*>(sw) + c * JG;
+        float d = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < kMaxF / 2; ++j4)
+          if (j4 < JG) {
+            const float4 w4 = wc[j4];
+            d = fmaf(w4.x, gr[4 * j4], d); d = fmaf(w4.y, gr[4 * j4 + 1], d);
+            d = fmaf(w4.z, gr[4 * j4 + 2], d); d = fmaf(w4.w, gr[4 * j4 + 3], d);
+          }
+        sd[tid * (Cf | 1) + c] = d;
+      }
+    }
+    __syncthreads();
+    for (int i = tid, r = 0, c = tid; i < n * Cf; i += 256, c += 256) {
+      while (c >= Cf) { c -= Cf; ++r; }
+      df[base * Cf + i] = sd[r * (Cf | 1) + c];
     }
   }
-  if (owner) atomicAdd(&dparams[t], (double)acc);
+  // tile owners -> dparams (double atomics: a few hundred adds per element)
+  if (owner) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int j = 4 * jg + a;
+      if (j >= G) continue;
+      const int which = j / F, jj = j - which * F;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = 4 * cg + b;
+        if (c < Cf) atomicAdd(&dparams[which * F * (Cf + 1) + jj * Cf + c], (double)acc[a][b]);
+        else if (c == Cf) atomicAdd(&dparams[which * F * (Cf + 1) + F * Cf + jj], (double)acc[a][b]);
+      }
+    }
+  }
 }
 
 }  // namespace dram
@@ -293,20 +365,21 @@ using namespace dram;
 
 static int pcm_geom(PcmGeom& g, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags) {
   DRAM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "pcm: bad grid");
-  DRAM_REQUIRE(Cf > 0 && Cf <= kMaxCf && F > 0 && F <= kMaxF, "pcm: Cf=%d (<=%d) / F=%d (<=%d) unsupported", Cf, kMaxCf, F, kMaxF);
+  DRAM_REQUIRE((long long)B * D * H * W < (1ll << 31) - 64 && (long long)B * D <= 65535, "pcm: grid too large (B*V < 2^31, B*D <= 65535)");
+  DRAM_REQUIRE(Cf > 0 && Cf <= kMaxCf, "pcm: Cf=%d (<=%d) unsupported", Cf, kMaxCf);
+  DRAM_REQUIRE(F == 4 || F == 8 || F == 16, "pcm: F=%d unsupported (4 | 8 | 16)", F);
   DRAM_REQUIRE(connectivity >= 1 && connectivity <= 3, "pcm: connectivity %d unsupported", connectivity);
   g.B = B; g.D = D; g.H = H; g.W = W; g.Cf = Cf; g.F = F;
-  g.flags = (flags & 0x7f) | ((self_loop ? 1 : 0) << 7) | (connectivity << 8);   // degree_of reads bits 7 and 8+
-  g.O = build_offsets(connectivity, self_loop, g.off);
+  g.flags = (flags & 0x7f) | ((self_loop ? 1 : 0) << 7) | (connectivity << 8);
+  g.O = count_offsets(connectivity, self_loop);
   return DRAM_OK;
 }
 
 extern "C" {
 
-int dram_pcm_num_offsets(int connectivity, int self_loop) {
-  signed char off[kMaxOff][3];
-  return build_offsets(connectivity, self_loop, off);
-}
+int dram_pcm_num_offsets(int connectivity, int self_loop) { return count_offsets(connectivity, self_loop); }
+
+size_t dram_pcm_qk_floats(long long rows, int F) { return (size_t)((rows + 31) / 32) * 32 * 2 * (size_t)F; }
 
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
@@ -322,38 +395,44 @@ int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const f
   if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_pcm_project<<<grid_for(rows, 256, 8), 256, smem, st>>>(f, theta_w, theta_b, phi_w, phi_b, qk, rows, Cf, F);
   DRAM_LAUNCH_CHECK();
-  const int grid = grid_for(rows, 256, 16);
-  if (F <= 8) {
-    if (stats) k_pcm_attend<8, true><<<grid, 256, 0, st>>>(g, qk, cam, stats, out);
-    else k_pcm_attend<8, false><<<grid, 256, 0, st>>>(g, qk, cam, nullptr, out);
-  } else {
-    if (stats) k_pcm_attend<kMaxF, true><<<grid, 256, 0, st>>>(g, qk, cam, stats, out);
-    else k_pcm_attend<kMaxF, false><<<grid, 256, 0, st>>>(g, qk, cam, nullptr, out);
-  }
+  const dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)(B * D));
+  float4* s4 = reinterpret_cast<float4*>(stats);
+#define PCM_ATTEND(FF)                                                                  \
+  do {                                                                                  \
+    if (stats) k_pcm_attend<FF, true><<<grid, 256, 0, st>>>(g, qk, cam, s4, out);       \
+    else k_pcm_attend<FF, false><<<grid, 256, 0, st>>>(g, qk, cam, nullptr, out);       \
+  } while (0)
+  if (F == 4) PCM_ATTEND(4);
+  else if (F == 8) PCM_ATTEND(8);
+  else PCM_ATTEND(16);
+#undef PCM_ATTEND
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
 
 int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
-                 const float* stats, const float* s_out, const float* dout, float* dqk_ws, float* dcam, float* df,
-                 double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
-                 void* stream) {
-  DRAM_REQUIRE(f && cam && theta_w && phi_w && qk && stats && s_out && dout && dqk_ws && dcam && df && dparams, "pcm_bwd: null pointer");
+                 const float* stats, const float* dout, float* dqk_ws, float* dcam, float* df, double* dparams, int B,
+                 int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags, void* stream) {
+  DRAM_REQUIRE(f && cam && theta_w && phi_w && qk && stats && dout && dqk_ws && dcam && df && dparams, "pcm_bwd: null pointer");
   PcmGeom g;
   int rc = pcm_geom(g, B, D, H, W, Cf, F, connectivity, self_loop, flags);
   if (rc) return rc;
-  DRAM_REQUIRE(2 * F * (Cf + 1) <= 320, "pcm_bwd: 2F(Cf+1)=%d > 320 unsupported", 2 * F * (Cf + 1));
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)B * D * H * W;
-  if (F <= 8) k_pcm_bwd<8><<<grid_for(rows, 256, 16), 256, 0, st>>>(g, qk, cam, stats, s_out, dout, dcam, dqk_ws);
-  else k_pcm_bwd<kMaxF><<<grid_for(rows, 256, 16), 256, 0, st>>>(g, qk, cam, stats, s_out, dout, dcam, dqk_ws);
+  const dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)(B * D));
+  const float4* s4 = reinterpret_cast<const float4*>(stats);
+  if (F == 4) k_pcm_bwd<4><<<grid, 256, 0, st>>>(g, qk, cam, s4, dout, dcam, dqk_ws);
+  else if (F == 8) k_pcm_bwd<8><<<grid, 256, 0, st>>>(g, qk, cam, s4, dout, dcam, dqk_ws);
+  else k_pcm_bwd<16><<<grid, 256, 0, st>>>(g, qk, cam, s4, dout, dcam, dqk_ws);
   DRAM_LAUNCH_CHECK();
   DRAM_CUDA(cudaMemsetAsync(dparams, 0, sizeof(double) * 2 * F * (Cf + 1), st));
-  size_t smem = sizeof(float) * ((size_t)kPcmChunk * Cf + (size_t)kPcmChunk * (2 * F + 1) + (size_t)2 * F * Cf);
-  long long chunks = (rows + kPcmChunk - 1) / kPcmChunk;
-  int grid = (int)(chunks < (long long)kNumSMs * 4 ? chunks : (long long)kNumSMs * 4);
+  const int JG = (2 * F + 3) / 4, CG = (Cf + 4) / 4;
+  DRAM_REQUIRE(JG * CG <= 256, "pcm_bwd: 2F=%d x Cf=%d tiles exceed one block", 2 * F, Cf);
+  const size_t smem = sizeof(float) * ((size_t)256 * (4 * CG + 4) + (size_t)256 * (4 * JG + 4) + (size_t)Cf * 4 * JG);
+  const long long chunks = (rows + 255) / 256;
+  const int pgrid = (int)(chunks < (long long)kNumSMs * 2 ? chunks : (long long)kNumSMs * 2);
   if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_bwd_params, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pcm_bwd_params<<<grid, 320, smem, st>>>(f, theta_w, phi_w, dqk_ws, df, dparams, rows, Cf, F);
+  k_pcm_bwd_params<<<pgrid, 256, smem, st>>>(f, theta_w, phi_w, dqk_ws, df, dparams, rows, Cf, F);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

@@ -623,7 +623,7 @@ k_pointwise8_planes_fwd(const uint4* __restrict__ hi, const uint4* __restrict__ 
 // a lane accumulates the 8x8 block of its channels over its rows, the block combines its warps through shared memory
 // and writes ONE partial [8*Cpad + 8] per block; k_pointwise8_reduce sums the partials in a fixed order (deterministic).
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_pointwise8_planes_wgrad(const uint4* __restrict__ hi, const uint4* __restrict__ lo, const float* __restrict__ dy,
                           float* __restrict__ partial, long long rows) {
   constexpr int RPW = 32 / LPR, CP = LPR * 8, NOUT = 8 * CP + 8;
@@ -637,7 +637,7 @@ k_pointwise8_planes_wgrad(const uint4* __restrict__ hi, const uint4* __restrict_
     for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
   }
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  constexpr int U = 4;                                           // rows in flight per lane: 4*U 16-byte loads
+  constexpr int U = 2;                                           // rows in flight per lane: 4*U 16-byte loads
   const uint4 zero = make_uint4(0, 0, 0, 0);
   for (long long r0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + rw; r0 < rows; r0 += warps * RPW * U) {
     uint4 H[U], L[U];

@@ -555,12 +555,12 @@ class PcmAttend(torch.autograd.Function):
         need_grad = keep_for_backward and any(ctx.needs_input_grad[:6])   # grad mode is off inside forward: the caller tells us
         out, qk, stats = ops.pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=need_grad)
         if need_grad:
-            ctx.save_for_backward(f, cam, tw, pw, qk, stats, out)
+            ctx.save_for_backward(f, cam, tw, pw, qk, stats)
         ctx.cfg = (connectivity, self_loop, flags)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        f, cam, tw, pw, qk, stats, out = ctx.saved_tensors
-        dcam, df, dtw, dtb, dpw, dpb = ops.pcm_bwd(f, cam, tw, pw, qk, stats, out, g.contiguous(), *ctx.cfg)
+        f, cam, tw, pw, qk, stats = ctx.saved_tensors
+        dcam, df, dtw, dtb, dpw, dpb = ops.pcm_bwd(f, cam, tw, pw, qk, stats, g.contiguous(), *ctx.cfg)
         return dcam, df, dtw, dtb, dpw, dpb, None, None, None, None

@@ -477,12 +477,13 @@ def pcm_num_offsets(connectivity, self_loop):
 
 
 def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=True):
-    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk planes [2F, B*V], softmax stats [2, B*V] | None)"""
+    """f CL volume [B,Cf,D,H,W]; cam [B,1,D,H,W] -> (out [B,1,D,H,W], qk (blocks of 32 voxels x 2F features),
+    softmax stats [B*V, 4] | None)"""
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
     V = D * H * W
-    qk = torch.empty((2 * F, B * V), device=f.device, dtype=torch.float32)
-    stats = torch.empty((2, B * V), device=f.device, dtype=torch.float32) if keep_stats else None
+    qk = torch.empty(_L().dram_pcm_qk_floats(B * V, F), device=f.device, dtype=torch.float32)
+    stats = torch.empty((B * V, 4), device=f.device, dtype=torch.float32) if keep_stats else None
     out = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     _lib.PROFILE.note(bytes=4.0 * B * V * (Cf + 2))
     _lib.check(_L().dram_pcm_fwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), tb.data_ptr(), pw.data_ptr(), pb.data_ptr(),
@@ -491,15 +492,16 @@ def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=T
     return out, qk, stats
 
 
-def pcm_bwd(f, cam, tw, pw, qk, stats, out, dout, connectivity, self_loop, flags):
+def pcm_bwd(f, cam, tw, pw, qk, stats, dout, connectivity, self_loop, flags):
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
     dqk = torch.empty_like(qk)
     dcam = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     df = new_volume(B, Cf, D, H, W, f.device)
     dparams = torch.empty(2 * F * (Cf + 1), device=f.device, dtype=torch.float64)
+    _lib.PROFILE.note(bytes=4.0 * B * D * H * W * (2 * Cf + 3))
     _lib.check(_L().dram_pcm_bwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), pw.data_ptr(), qk.data_ptr(), stats.data_ptr(),
-                                 out.data_ptr(), dout.data_ptr(), dqk.data_ptr(), dcam.data_ptr(), df.data_ptr(),
+                                 dout.data_ptr(), dqk.data_ptr(), dcam.data_ptr(), df.data_ptr(),
                                  dparams.data_ptr(), B, D, H, W, Cf, F, int(connectivity), int(bool(self_loop)),
                                  int(flags), _stream()), "pcm_bwd")
     dp = dparams.float()

@@ -192,6 +192,8 @@ class PCM(nn.Module):
             raise NotImplementedError(f"merge type {self.merge_type!r} is not on the B200 path {sorted(ops.MERGE_FLAGS)}")
         if self.k_size != 3 or self.p_enc_dim > 0 or self.g_ch != 1 or not isinstance(self.theta, nn.Linear):
             raise NotImplementedError("PCM on the B200 path needs k_size=3, p_enc_dim=0, g_ch=1 and f_dim>0")
+        if self.f_dim not in (4, 8, 16):
+            raise NotImplementedError(f"PCM on the B200 path is built for f_dim 4 | 8 | 16 (got {self.f_dim})")
 
     def forward(self, cam, f, args=None):
         self._check()

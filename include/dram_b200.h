@@ -225,18 +225,19 @@ int dram_ram_upsample_mask_scatter(const float* ram, const uint8_t* crop_mask, f
  * flags bit0: relu on logits; bits1-2: temperature (0 none, 1 sqrt(degree) — models.py:274-277, 2 = 0.01);
  * connectivity 1|2|3, self_loop 0|1. */
 int dram_pcm_num_offsets(int connectivity, int self_loop); /* O: 18 for (2, no self loop) */
-/* R = B*V rows.  qk [2F][R] (out): theta|phi projections as planes (coalesced neighbour loads);
- * stats [2][R] (out, may be NULL at inference): running max and normaliser of each node's softmax - what the backward keeps
- * instead of the [R][O] attention weights (they are recomputed from qk) */
+/* R = B*V rows.  qk (out, dram_pcm_qk_floats(R, F) floats): theta|phi projections in blocks of 32 consecutive voxels,
+ * [ceil(R/32)][2F][32] (coalesced neighbour loads, compile-time feature offsets).  F: 4 | 8 | 16.
+ * stats [R][4] (out, may be NULL at inference): (max, 1/normaliser, 1/T, output) of each node's softmax - what the backward
+ * keeps instead of the [R][O] attention weights (they are recomputed from qk) */
+size_t dram_pcm_qk_floats(long long rows, int F);
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream);
-/* s_out: the forward's `out`.  dqk_ws [2F][R]: scratch.  dcam [R], df [R][Cf]: overwritten.
+/* dqk_ws (dram_pcm_qk_floats floats): scratch.  dcam [R], df [R][Cf]: overwritten.
  * dparams double[2*F*(Cf+1)] = dtheta_w, dtheta_b, dphi_w, dphi_b: overwritten. */
 int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
-                 const float* stats, const float* s_out, const float* dout, float* dqk_ws, float* dcam, float* df,
-                 double* dparams, int B, int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags,
-                 void* stream);
+                 const float* stats, const float* dout, float* dqk_ws, float* dcam, float* df, double* dparams, int B,
+                 int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ scan pre/post-processing
  * What LesionSegTest.run / evaluate_scan do on the host around the model (job_runner.py:730-772, 951-1015), on the GPU.

@@ -582,14 +582,16 @@ def test_reshape_head_unit_on_planes(training):
 
 
 # ------------------------------------------------------------------------------------------------ PCM stencil attention
-@pytest.mark.parametrize("merge,self_loop,conn,grid", [("scaled_dot_product_relu", False, 2, (6, 7, 8)), ("sm", True, 1, (5, 5, 5)),
-                                                       ("scaled_dot_product", False, 3, (4, 6, 5)), ("smrelu", False, 2, (2, 1, 3)),
-                                                       ("scaled_dot_product_relu", False, 2, (3, 4, 64)),
-                                                       ("scaled_dot_product_relu", False, 2, (2, 3, 37))])
-def test_pcm_attention(merge, self_loop, conn, grid):
+@pytest.mark.parametrize("merge,self_loop,conn,grid,Fd", [
+    ("scaled_dot_product_relu", False, 2, (6, 7, 8), 8), ("sm", True, 1, (5, 5, 5), 8),
+    ("scaled_dot_product", False, 3, (4, 6, 5), 8), ("smrelu", False, 2, (2, 1, 3), 8),
+    ("scaled_dot_product_relu", False, 2, (3, 4, 64), 8), ("scaled_dot_product_relu", False, 2, (2, 3, 37), 8),
+    ("scaled_dot_product_relu", False, 2, (3, 20, 20), 8),          # plane larger than one 256-thread block
+    ("scaled_dot_product_relu", True, 3, (4, 5, 6), 4), ("smscaled", False, 2, (5, 4, 7), 16)])
+def test_pcm_attention(merge, self_loop, conn, grid, Fd):
     from oracle_import import O
     import models
-    B, Cf, Fd = 2, 17, 8
+    B, Cf = 2, 17
     torch.manual_seed(7)
     pcm = models.PCM(grid, Cf, 1, Fd, 0, 8, 1, 3, merge, self_loop, connectivity=conn, p_enc_dim=0)
     sd = {"attention_module." + k: v.detach().clone().requires_grad_(True) for k, v in pcm.state_dict().items()}
