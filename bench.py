@@ -418,8 +418,8 @@ def hbm_kernel_rooflines(peaks):
     heat = torch.zeros((SD, SH, SW), device="cuda")
     crop = ((20, 260), (30, 230), (40, 220))
     vc = 240 * 200 * 180
-    r1 = torch.randn(80, 80, 80, device="cuda")
-    ms = timed(lambda: ops.ram_upsample_label_scatter(r1, labels, 1, heat, crop, 1, 1.0))
+    r1 = ops.ram_activation(torch.randn(1, 1, 80, 80, 80, device="cuda"), 1)[0, 0]   # sigmoid first, as LesionSegTest.run does
+    ms = timed(lambda: ops.ram_upsample_label_scatter(r1, labels, 1, heat, crop, 0, 1.0))
     nbytes = 4.0 * V + 5.0 * vc
     out["ram_upsample_label_scatter"] = {"bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6,
                                          "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"],
@@ -549,6 +549,9 @@ def run_infer(args):
             "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd", "achieved": achieved, "peak": peaks["tflops_sustained"],
                          "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
                          "peak_source": peaks["source"]},
+            "kernels": {k.replace("dram_", ""): {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+                                                 **({"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} if v["flops"] else {})}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]},
             "cpu_baseline": cpu}))
     if world > 1:
         td.destroy_process_group()

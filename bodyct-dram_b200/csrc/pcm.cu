@@ -108,15 +108,22 @@ k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const f
   for (int i = threadIdx.x; i < 4 * J4; i += blockDim.x) sb[i] = i < F ? tb[i] : (i < 2 * F ? pb[i - F] : 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const unsigned inv_cf = (1u << 20) / (unsigned)Cf + 1u;          // i / Cf == (i * inv_cf) >> 20 for i < 32 * Cf
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5, tiles = (rows + 31) >> 5;
   for (long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < tiles; t += warps) {
     const long long r0 = t << 5;
     const int n = (int)(rows - r0 < 32 ? rows - r0 : 32);
     const float* src = f + r0 * Cf;
     __syncwarp();
-    for (int i = lane, r = 0, c = lane; i < n * Cf; i += 32, c += 32) {
-      while (c >= Cf) { c -= Cf; ++r; }
-      st[r * Cfp + c] = __ldg(src + i);
+    for (int i0 = lane; i0 < n * Cf; i0 += 32 * 6) {                 // 6 independent loads in flight, then their stores
+      float v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) v[u] = i0 + 32 * u < n * Cf ? __ldg(src + i0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < n * Cf) { const int r = (int)(((unsigned)i * inv_cf) >> 20); st[r * Cfp + (i - r * Cf)] = v[u]; }
+      }
     }
     __syncwarp();
     if (lane < n) {
@@ -149,7 +156,7 @@ k_pcm_project(const float* __restrict__ f, const float* __restrict__ tw, const f
 
 // forward: one thread per node; scores of the <= 26(+1) neighbours in registers, two-pass softmax.  SAVE: keep stats.
 template <int F, bool SAVE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, F <= 8 ? 3 : 2)
 k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, float4* __restrict__ stats,
              float* __restrict__ out) {
   const PcmPos P(g);
@@ -198,7 +205,7 @@ k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restr
 //                        the own k_y, cam_y:  dcam_y = sum g_x a,  dk_y = sum ds q_x
 // (sum_o a_o g cam_{x+o} = g_x s_x is the softmax-Jacobian dot product.)   dqk: blocks of 32 rows like qk.
 template <int F>
-__global__ void __launch_bounds__(256, F <= 8 ? 2 : 1)
+__global__ void __launch_bounds__(256, F <= 8 ? 3 : 1)
 k_pcm_bwd(const PcmGeom g, const float* __restrict__ qk, const float* __restrict__ cam, const float4* __restrict__ stats,
           const float* __restrict__ dout, float* __restrict__ dcam, float* __restrict__ dqk) {
   const PcmPos P(g);
@@ -262,7 +269,7 @@ k_pcm_bwd(const PcmGeom g, const float* __restrict__ qk, const float* __restrict
 //                                                   the JG*CG tile owners form a row group, 256 / (JG*CG) groups split the rows
 __global__ void __launch_bounds__(256)
 k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, const float* __restrict__ pw,
-                 const float* __restrict__ dqk, float* __restrict__ df, double* __restrict__ dparams, long long rows,
+                 const float* __restrict__ dqk, float* __restrict__ df, float* __restrict__ partial, long long rows,
                  int Cf, int F) {
   extern __shared__ float4 bsm4[];
   float* bsm = reinterpret_cast<float*>(bsm4);
@@ -273,6 +280,7 @@ k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, cons
   float* sw = sg + 256 * GP;             // [Cf][4*JG] W^T (theta | phi)
   float* sd = sf;                        // df rows [256][Cf] reuse sf after the tile phase
   const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned inv_cf = (1u << 20) / (unsigned)Cf + 1u;          // i / Cf == (i * inv_cf) >> 20 for i < 256 * Cf <= 2^14
   for (int i = tid; i < Cf * 4 * JG; i += blockDim.x) {
     const int c = i / (4 * JG), j = i - c * 4 * JG;
     sw[i] = j < F ? tw[j * Cf + c] : (j < G ? pw[(j - F) * Cf + c] : 0.f);
@@ -292,9 +300,15 @@ k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, cons
     __syncthreads();                                                // previous chunk's sd / sg readers are done
     for (int i = tid; i < 256 * CP; i += blockDim.x) sf[i] = 0.f;
     __syncthreads();
-    for (int i = tid, r = 0, c = tid; i < n * Cf; i += 256, c += 256) {   // contiguous, coalesced
-      while (c >= Cf) { c -= Cf; ++r; }
-      sf[r * CP + c] = __ldg(f + base * Cf + i);
+    for (int i0 = tid; i0 < n * Cf; i0 += 256 * 6) {                 // contiguous, coalesced, 6 loads in flight
+      float v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) v[u] = i0 + 256 * u < n * Cf ? __ldg(f + base * Cf + i0 + 256 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + 256 * u;
+        if (i < n * Cf) { const int r = (int)(((unsigned)i * inv_cf) >> 20); sf[r * CP + (i - r * Cf)] = v[u]; }
+      }
     }
     float gr[2 * kMaxF];
     if (tid < n) {
@@ -337,26 +351,43 @@ k_pcm_bwd_params(const float* __restrict__ f, const float* __restrict__ tw, cons
       }
     }
     __syncthreads();
-    for (int i = tid, r = 0, c = tid; i < n * Cf; i += 256, c += 256) {
-      while (c >= Cf) { c -= Cf; ++r; }
+    for (int i = tid; i < n * Cf; i += 256) {
+      const int r = (int)(((unsigned)i * inv_cf) >> 20), c = i - r * Cf;
       df[base * Cf + i] = sd[r * (Cf | 1) + c];
     }
   }
-  // tile owners -> dparams (double atomics: a few hundred adds per element)
+  // tile owners -> shared memory -> ONE partial [4*JG][4*CG] per block (row groups summed in order);
+  // k_pcm_params_reduce sums the blocks in a fixed order: deterministic
+  __syncthreads();
+  float* sp = bsm;                                                  // [groups][16*NT] <= 256*16 floats
   if (owner) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int j = 4 * jg + a;
-      if (j >= G) continue;
-      const int which = j / F, jj = j - which * F;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int c = 4 * cg + b;
-        if (c < Cf) atomicAdd(&dparams[which * F * (Cf + 1) + jj * Cf + c], (double)acc[a][b]);
-        else if (c == Cf) atomicAdd(&dparams[which * F * (Cf + 1) + F * Cf + jj], (double)acc[a][b]);
-      }
-    }
+      for (int b = 0; b < 4; ++b) sp[grp * (16 * NT) + (4 * jg + a) * (4 * CG) + 4 * cg + b] = acc[a][b];
   }
+  __syncthreads();
+  for (int e = tid; e < 16 * NT; e += 256) {
+    float t = 0.f;
+    for (int gI = 0; gI < groups; ++gI) t += sp[gI * (16 * NT) + e];
+    partial[(size_t)blockIdx.x * (16 * NT) + e] = t;
+  }
+}
+
+// dparams[which][F*Cf weights | F biases] (double) from the per-block tiles: one warp per output element, lanes stride
+// over the blocks, fixed-order shuffle tree
+__global__ void __launch_bounds__(256)
+k_pcm_params_reduce(const float* __restrict__ partial, int nparts, int Cf, int F, double* __restrict__ dparams) {
+  const int G = 2 * F, JG = (G + 3) >> 2, CG = (Cf + 4) >> 2;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= G * (Cf + 1)) return;
+  const int j = e / (Cf + 1), c = e - j * (Cf + 1);
+  double t = 0.0;
+  for (int p = lane; p < nparts; p += 32) t += (double)partial[(size_t)p * (16 * JG * CG) + j * (4 * CG) + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  const int which = j / F, jj = j - which * F;
+  if (lane == 0) dparams[which * F * (Cf + 1) + (c < Cf ? jj * Cf + c : F * Cf + jj)] = t;
 }
 
 }  // namespace dram
@@ -380,6 +411,13 @@ extern "C" {
 int dram_pcm_num_offsets(int connectivity, int self_loop) { return count_offsets(connectivity, self_loop); }
 
 size_t dram_pcm_qk_floats(long long rows, int F) { return (size_t)((rows + 31) / 32) * 32 * 2 * (size_t)F; }
+
+static const int kPcmParamBlocks = kNumSMs * 3;
+/* scratch of dram_pcm_bwd: the [dq | dk] blocks + one [4*JG][4*CG] tile of parameter-gradient partials per block */
+size_t dram_pcm_bwd_ws_floats(long long rows, int Cf, int F) {
+  const int JG = (2 * F + 3) / 4, CG = (Cf + 4) / 4;
+  return dram_pcm_qk_floats(rows, F) + (size_t)kPcmParamBlocks * (size_t)(16 * JG * CG);
+}
 
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
@@ -425,14 +463,17 @@ int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const f
   else if (F == 8) k_pcm_bwd<8><<<grid, 256, 0, st>>>(g, qk, cam, s4, dout, dcam, dqk_ws);
   else k_pcm_bwd<16><<<grid, 256, 0, st>>>(g, qk, cam, s4, dout, dcam, dqk_ws);
   DRAM_LAUNCH_CHECK();
-  DRAM_CUDA(cudaMemsetAsync(dparams, 0, sizeof(double) * 2 * F * (Cf + 1), st));
   const int JG = (2 * F + 3) / 4, CG = (Cf + 4) / 4;
   DRAM_REQUIRE(JG * CG <= 256, "pcm_bwd: 2F=%d x Cf=%d tiles exceed one block", 2 * F, Cf);
   const size_t smem = sizeof(float) * ((size_t)256 * (4 * CG + 4) + (size_t)256 * (4 * JG + 4) + (size_t)Cf * 4 * JG);
   const long long chunks = (rows + 255) / 256;
-  const int pgrid = (int)(chunks < (long long)kNumSMs * 2 ? chunks : (long long)kNumSMs * 2);
+  const int pgrid = (int)(chunks < (long long)kPcmParamBlocks ? chunks : (long long)kPcmParamBlocks);
+  float* partial = dqk_ws + dram_pcm_qk_floats(rows, F);
   if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_bwd_params, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pcm_bwd_params<<<pgrid, 256, smem, st>>>(f, theta_w, phi_w, dqk_ws, df, dparams, rows, Cf, F);
+  k_pcm_bwd_params<<<pgrid, 256, smem, st>>>(f, theta_w, phi_w, dqk_ws, df, partial, rows, Cf, F);
+  DRAM_LAUNCH_CHECK();
+  const int nout = 2 * F * (Cf + 1);
+  k_pcm_params_reduce<<<(nout * 32 + 255) / 256, 256, 0, st>>>(partial, pgrid, Cf, F, dparams);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

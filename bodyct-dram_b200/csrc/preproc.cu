@@ -119,43 +119,42 @@ k_itk_resample(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int
 }
 
 // ------------------------------------------------------------------------------------------------ RAM -> heat map
-// as k_ram_upsample_mask_scatter (ram.cu) but the lobe mask is read from the scan-sized label volume
+// as k_ram_upsample_mask_scatter (ram.cu) but the lobe mask is read from the scan-sized label volume.
+// Block = 32 (x) x 8 (y) threads, kScatterZ consecutive z per thread: a warp reads 32 consecutive labels and writes up to
+// 128 contiguous bytes of the heat map per z; the x / y interpolation set-up is shared by the thread's z steps; the eight
+// source taps come from the 2 MB chunk RAM (L1 / L2 resident).  Algorithmic HBM bytes: 1 (label) + 4 (heat) per crop voxel.
+constexpr int kScatterZ = 4;
 __global__ void __launch_bounds__(256)
 k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __restrict__ labels, int label,
                              float* __restrict__ heat, int d, int h, int w, int cd, int ch, int cw, int SH, int SW, int oz,
                              int oy, int ox, int act, float gain, float sz, float sy, float sx) {
-  // one thread = 4 consecutive x voxels of the crop: the z/y interpolation set-up and the 4 source rows are shared
-  const int cw4 = (cw + 3) >> 2;
-  const long long total = (long long)cd * ch * cw4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int X0 = (int)(i % cw4) << 2, Y = (int)((i / cw4) % ch), Z = (int)(i / ((long long)cw4 * ch));
-    const long long off = ((long long)(Z + oz) * SH + (Y + oy)) * SW + (X0 + ox);
-    bool in[4];
-    bool any = false;
+  const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y, Z0 = blockIdx.z * kScatterZ;
+  if (X >= cw || Y >= ch) return;
+  const Lerp lx = lerp_setup(X, sx, w), ly = lerp_setup(Y, sy, h);
+  const int o00 = ly.i0 * w + lx.i0, o01 = ly.i0 * w + lx.i1, o10 = ly.i1 * w + lx.i0, o11 = ly.i1 * w + lx.i1;
+  const long long col = (long long)(Y + oy) * SW + (X + ox);
+  uint8_t lab[kScatterZ];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { in[j] = (X0 + j < cw) && (labels[off + j] == label); any |= in[j]; }
-    if (!any) continue;
-    const Lerp lz = lerp_setup(Z, sz, d), ly = lerp_setup(Y, sy, h);
-    const float* r00 = ram + ((long long)lz.i0 * h + ly.i0) * w;
-    const float* r01 = ram + ((long long)lz.i0 * h + ly.i1) * w;
-    const float* r10 = ram + ((long long)lz.i1 * h + ly.i0) * w;
-    const float* r11 = ram + ((long long)lz.i1 * h + ly.i1) * w;
+  for (int k = 0; k < kScatterZ; ++k)
+    lab[k] = (Z0 + k < cd) ? labels[(long long)(Z0 + k + oz) * SH * SW + col] : (uint8_t)0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!in[j]) continue;
-      const Lerp lx = lerp_setup(X0 + j, sx, w);
-      float a00 = __ldg(r00 + lx.i0), b00 = __ldg(r00 + lx.i1), a01 = __ldg(r01 + lx.i0), b01 = __ldg(r01 + lx.i1);
-      float a10 = __ldg(r10 + lx.i0), b10 = __ldg(r10 + lx.i1), a11 = __ldg(r11 + lx.i0), b11 = __ldg(r11 + lx.i1);
-      if (act == 1) {
-        a00 = sigmoidf_(a00); b00 = sigmoidf_(b00); a01 = sigmoidf_(a01); b01 = sigmoidf_(b01);
-        a10 = sigmoidf_(a10); b10 = sigmoidf_(b10); a11 = sigmoidf_(a11); b11 = sigmoidf_(b11);
-      }
-      // same nesting as ATen's upsample_trilinear3d: d(h(w))
-      float v = lz.w0 * (ly.w0 * (lx.w0 * a00 + lx.w1 * b00) + ly.w1 * (lx.w0 * a01 + lx.w1 * b01)) +
-                lz.w1 * (ly.w0 * (lx.w0 * a10 + lx.w1 * b10) + ly.w1 * (lx.w0 * a11 + lx.w1 * b11));
-      if (act == 2) v = fmaxf(v, 0.f);
-      heat[off + j] = v * gain;
+  for (int k = 0; k < kScatterZ; ++k) {
+    const int Z = Z0 + k;
+    if (Z >= cd || lab[k] != label) continue;
+    const Lerp lz = lerp_setup(Z, sz, d);
+    const float* p0 = ram + (long long)lz.i0 * h * w;
+    const float* p1 = ram + (long long)lz.i1 * h * w;
+    float a00 = __ldg(p0 + o00), b00 = __ldg(p0 + o01), a01 = __ldg(p0 + o10), b01 = __ldg(p0 + o11);
+    float a10 = __ldg(p1 + o00), b10 = __ldg(p1 + o01), a11 = __ldg(p1 + o10), b11 = __ldg(p1 + o11);
+    if (act == 1) {
+      a00 = sigmoidf_(a00); b00 = sigmoidf_(b00); a01 = sigmoidf_(a01); b01 = sigmoidf_(b01);
+      a10 = sigmoidf_(a10); b10 = sigmoidf_(b10); a11 = sigmoidf_(a11); b11 = sigmoidf_(b11);
     }
+    // same nesting as ATen's upsample_trilinear3d: d(h(w))
+    float v = lz.w0 * (ly.w0 * (lx.w0 * a00 + lx.w1 * b00) + ly.w1 * (lx.w0 * a01 + lx.w1 * b01)) +
+              lz.w1 * (ly.w0 * (lx.w0 * a10 + lx.w1 * b10) + ly.w1 * (lx.w0 * a11 + lx.w1 * b11));
+    if (act == 2) v = fmaxf(v, 0.f);
+    heat[(long long)(Z + oz) * SH * SW + col] = v * gain;
   }
 }
 
@@ -254,7 +253,9 @@ int dram_ram_upsample_label_scatter(const float* ram, const uint8_t* labels, int
   DRAM_REQUIRE(ram && labels && heat && d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "ram_upsample_label_scatter: bad arguments");
   DRAM_REQUIRE(act >= 0 && act <= 2, "ram_upsample_label_scatter: act %d unknown", act);
   DRAM_REQUIRE(oz >= 0 && oy >= 0 && ox >= 0 && oz + cd <= SD && oy + ch <= SH && ox + cw <= SW, "ram_upsample_label_scatter: crop outside the scan");
-  k_ram_upsample_label_scatter<<<grid_for((long long)cd * ch * ((cw + 3) / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  DRAM_REQUIRE((cd + kScatterZ - 1) / kScatterZ <= 65535 && (ch + 7) / 8 <= 65535, "ram_upsample_label_scatter: crop too large");
+  const dim3 grid((unsigned)((cw + 31) / 32), (unsigned)((ch + 7) / 8), (unsigned)((cd + kScatterZ - 1) / kScatterZ));
+  k_ram_upsample_label_scatter<<<grid, dim3(32, 8, 1), 0, (cudaStream_t)stream>>>(
       ram, labels, label, heat, d, h, w, cd, ch, cw, SH, SW, oz, oy, ox, act, gain, ac_scale(d, cd), ac_scale(h, ch), ac_scale(w, cw));
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;

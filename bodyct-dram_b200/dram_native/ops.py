@@ -495,7 +495,7 @@ def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=T
 def pcm_bwd(f, cam, tw, pw, qk, stats, dout, connectivity, self_loop, flags):
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
-    dqk = torch.empty_like(qk)
+    dqk = torch.empty(_L().dram_pcm_bwd_ws_floats(B * D * H * W, Cf, F), device=f.device, dtype=torch.float32)
     dcam = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     df = new_volume(B, Cf, D, H, W, f.device)
     dparams = torch.empty(2 * F * (Cf + 1), device=f.device, dtype=torch.float64)

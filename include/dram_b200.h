@@ -233,8 +233,10 @@ size_t dram_pcm_qk_floats(long long rows, int F);
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream);
-/* dqk_ws (dram_pcm_qk_floats floats): scratch.  dcam [R], df [R][Cf]: overwritten.
- * dparams double[2*F*(Cf+1)] = dtheta_w, dtheta_b, dphi_w, dphi_b: overwritten. */
+/* dqk_ws (dram_pcm_bwd_ws_floats floats): scratch.  dcam [R], df [R][Cf]: overwritten.
+ * dparams double[2*F*(Cf+1)] = dtheta_w, dtheta_b, dphi_w, dphi_b: overwritten (per-block partials summed in a fixed
+ * order: deterministic). */
+size_t dram_pcm_bwd_ws_floats(long long rows, int Cf, int F);
 int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const float* phi_w, const float* qk,
                  const float* stats, const float* dout, float* dqk_ws, float* dcam, float* df, double* dparams, int B,
                  int D, int H, int W, int Cf, int F, int connectivity, int self_loop, int flags, void* stream);
