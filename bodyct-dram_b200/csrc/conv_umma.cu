@@ -143,6 +143,7 @@ struct FwdParams {
   const float* scale;
   const float* shift;
   int N, D, H, W, Cout, BN, kblocks_c, taps, pad;
+  int ksteps;   // K = 16 steps to issue per 64-channel block (< 4 only with ONE block whose upper channels are zero padding)
   int TW, TH, TD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles;
   int passes, stages, stage_bytes, tmem_cols, acc_cols;
   // kw-reuse mode (w3 = 1): one A box of (TW+2) x TH voxels per (kd,kh,channel block) serves the three kw taps.  The box is
@@ -255,6 +256,7 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               const uint64_t a_lod = umma_desc(sb + offAlo + ao, 16, 1024);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {           // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                if (k >= p.ksteps) break;             // all-zero padding channels: nothing to accumulate
                 const uint64_t adv = (uint64_t)(k * 2);
                 const uint32_t accum = (kb | t | k) ? 1u : 0u;
                 if (three) {
@@ -341,7 +343,7 @@ struct Fwd2Params {
   float* y;
   const float* scale;
   const float* shift;
-  int N, D, H, W, Cout, BN, kblocks_c;
+  int N, D, H, W, Cout, BN, kblocks_c, ksteps;
   int TW, TDD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles, n_items;
   int SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes, acc_cols, tmem_cols;
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
@@ -475,6 +477,7 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               const uint32_t d_tmem = d_set + (uint32_t)j * (uint32_t)p.acc_cols;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {          // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                if (k >= p.ksteps) break;            // all-zero padding channels: nothing to accumulate
                 const uint64_t adv = (uint64_t)(k * 2);
                 const uint32_t accum = (g | kw | k) ? 1u : 0u;
                 if (concat) {
@@ -574,7 +577,7 @@ struct Fwd3Params {
   float* y;
   const float* scale;
   const float* shift;
-  int N, D, H, W, Cout, CT, kblocks_c;
+  int N, D, H, W, Cout, CT, kblocks_c, ksteps;
   int TW, TDD, tiles_w, tiles_h, tiles_d, n_vtiles, n_ctiles, n_items;
   int SW, x_plane_bytes, x_stage_bytes, w_stage_bytes;
   long long* prof;   // DRAM_CONV_PROF diagnostics
@@ -689,6 +692,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             const uint64_t w_b = umma_desc(wb + ((uint32_t)p.w_stage_bytes >> 1), 16, 1024);  // plain: W_lo
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (k >= p.ksteps) break;              // all-zero padding channels: nothing to accumulate
               const uint64_t adv = (uint64_t)(k * 2);
               const uint32_t accum = (g | kw | k) ? 1u : 0u;
               umma_bf16(d_tmem, w_a + adv, x_hi + adv, idesc, accum);
@@ -1349,13 +1353,17 @@ int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo, int Cout, int 
 }
 
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* scale,
-                         const float* shift, float* y, int N, int D, int H, int W, int Cin_pad, int Cout, int ksize,
+                         const float* shift, float* y, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize,
                          void* stream) {
   DRAM_REQUIRE(x_hi && w_hi && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
   DRAM_REQUIRE(!(x_lo != nullptr && w_lo == nullptr), "conv3d_umma_fwd: x_lo needs w_lo (modes: both = bf16x3, w_lo only = single-plane activations x split weights, neither = bf16)");
   DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
   DRAM_REQUIRE(Cin_pad > 0 && Cin_pad % 64 == 0, "conv3d_umma_fwd: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  DRAM_REQUIRE(Cin > 0 && Cin <= Cin_pad, "conv3d_umma_fwd: Cin=%d must be in (0, Cin_pad=%d]", Cin, Cin_pad);
+  // channels [Cin, Cin_pad) are zeros in x and w: with a single 64-channel block the K = 16 steps that would only multiply
+  // padding are not issued (ds0.c1, Cin = 32: 2 of 4 steps)
+  const int ksteps = (Cin_pad == 64 && !getenv("DRAM_CONV_FULL_K")) ? (Cin + 15) / 16 : 4;
   // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
   // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
   // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
@@ -1368,7 +1376,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     const int plain = (Cout % 128 == 0) ? 1 : 0;
     const int mode = plain + (x_lo ? 0 : 2);
     q.y = y; q.scale = scale; q.shift = shift;
-    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = plain ? 128 : 64; q.kblocks_c = Cin_pad / 64;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = plain ? 128 : 64; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0 && D % 2 == 0) { q.TW = 16; q.TDD = 2; } else { q.TW = 8; q.TDD = 4; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
     q.n_vtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
@@ -1425,7 +1433,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     q.acc_cols = (mode == 1 || mode == 3) ? 2 * q.BN : q.BN;
     q.tmem_cols = pow2_cols(4 * q.acc_cols);
     q.y = y; q.scale = scale; q.shift = shift;
-    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
     q.n_mtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
@@ -1482,7 +1490,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   DRAM_REQUIRE(p.BN > 0, "conv3d_umma_fwd: Cout=%d must be a multiple of 16", Cout);
   p.y = y; p.scale = scale; p.shift = shift;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
-  p.kblocks_c = Cin_pad / 64; p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
+  p.kblocks_c = Cin_pad / 64; p.taps = ksize * ksize * ksize; p.pad = ksize / 2; p.ksteps = ksteps;
   // kw-reuse for the layers whose L2->smem fill rate is the bound (N tile <= 64: 125 B/cycle/SM needed, ~75-80 sustained)
   static const bool allow_w3 = getenv("DRAM_CONV_NO_W3") == nullptr;
   p.w3 = (allow_w3 && ksize == 3 && p.BN <= 64 && W % 16 == 0 && H % 8 == 0) ? 1 : 0;

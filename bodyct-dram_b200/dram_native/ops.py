@@ -166,7 +166,7 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None):
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
     _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")   # algorithmic (unpadded, 1 pass)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
-                                         y.data_ptr(), N, D, H, W, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
+                                         y.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
     return y
 
 
