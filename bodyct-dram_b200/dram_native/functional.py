@@ -183,6 +183,20 @@ def _grad_rows(g, name="grad"):
     return ops.to_cl(g, name), g.shape[1]
 
 
+def _bn_fold_cached(gamma, beta, running_mean, running_var, eps):
+    """eval-mode scale / shift of a BatchNorm, folded once per parameter state (inference calls it 16 times per forward)"""
+    key = (WEIGHTS.generation, eps) + tuple(v for t in (gamma, beta, running_mean, running_var) for v in (t.data_ptr(), t._version))
+    hit = getattr(running_mean, "_dram_fold", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
+    try:
+        running_mean._dram_fold = (key, val)
+    except AttributeError:
+        pass
+    return val
+
+
 class ConvBnRelu(torch.autograd.Function):
     """[Conv3d(bias optional) -> BatchNorm3d -> ReLU (-> MaxPool3d(2,2,0))]  — parts.py:103-110,184-196.
 
@@ -224,8 +238,11 @@ class ConvBnRelu(torch.autograd.Function):
             mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                        n_updates)
         else:
-            scale, shift = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
-            mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)      # only for dgamma/dbeta in eval mode
+            scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
+            if any(ctx.needs_input_grad):
+                mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)  # only for dgamma/dbeta in eval mode
+            else:
+                mean = rstd = None                                                  # inference: nothing is kept
         planes_out = bool(out_planes) and planes_enabled() and C % 8 == 0 and (planes_dy or not pool)
         a_hi = a_lo = p_hi = p_lo = pooled = None
         if planes_out:
@@ -368,8 +385,11 @@ class ConvBnReluRam(torch.autograd.Function):
             mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                        n_updates)
         else:
-            scale, shift = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
-            mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)
+            scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
+            if any(ctx.needs_input_grad):
+                mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)
+            else:
+                mean = rstd = None
         w2 = w_top.reshape(1, C).contiguous()
         ram = ops.ram_reduce(y, w2, b_top.contiguous(), scale, shift)
         ctx.training, ctx.count, ctx.saved_planes, ctx.wshape = training, count, xs, tuple(w_top.shape)

@@ -314,6 +314,70 @@ class LesionSegTest(JobRunner):
         new_size = [int(np.ceil(s * sp / new_sp)) for s, sp in zip(arr_t.shape, spacing)]
         return ops.itk_resample(arr_t, new_size, mode, ratios=[new_sp / sp for sp in spacing])
 
+    def scan_to_masks(self, scan_d, lobe_d, spacing):
+        """One scan at its ORIGINAL grid, already on the device -> (lesion, lesion_post) uint8 masks at the original grid and
+        the lesion ratio (device tensors): resample to the working grid, run_scan, resample back (job_runner.py:827-835,
+        942-1030)."""
+        new_sp = [float(self.settings.TEST_RESAMPLE_SPACING)] * 3
+        s_t = self.resample_to_working_grid(scan_d, spacing, "linear")
+        l_t = self.resample_to_working_grid(lobe_d, spacing, "nearest")
+        out = self.run_scan(s_t, l_t, new_sp, return_device=True)
+        shape = tuple(scan_d.shape)
+        return (ops_itk_back(out["lesion"], shape, new_sp, spacing, "nearest"),
+                ops_itk_back(out["lesion_post"], shape, new_sp, spacing, "nearest"), out["ratio"])
+
+    def run_scans(self, items):
+        """Pipelined full-CT inference over an iterable of (scan int16 [D,H,W], lobe uint8 [D,H,W], spacing) HOST tensors
+        (pinned memory makes the copies asynchronous): the upload of scan i+1 (copy stream) and the download of the masks
+        of scan i-1 (second copy stream, into two alternating pinned buffers) overlap the kernels of scan i, so a scan
+        costs max(compute, H2D, D2H) instead of their sum.  Yields (lesion, lesion_post, ratio) per scan; the yielded host
+        tensors are valid until the next result is requested."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_pipe", None) is None:                         # streams and pinned result buffers live with the runner
+            self._pipe = (torch.cuda.Stream(), torch.cuda.Stream(), [None, None])
+        up_s, down_s, bufs = self._pipe
+
+        def upload(item):
+            with torch.cuda.stream(up_s):
+                s_d, l_d = item[0].cuda(non_blocking=True), item[1].cuda(non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up_s)
+            return s_d, l_d, ev
+
+        def finish(p):
+            p[3].synchronize()
+            return p[0], p[1], float(p[2].item())
+
+        it = iter(items)
+        item = next(it, None)
+        up = upload(item) if item is not None else None
+        pending, k = None, 0
+        while item is not None:
+            (s_d, l_d, ev), spacing = up, item[2]
+            item = next(it, None)
+            up = upload(item) if item is not None else None              # next scan's H2D runs under this scan's kernels
+            cur.wait_event(ev)
+            s_d.record_stream(cur)
+            l_d.record_stream(cur)
+            les, post, ratio = self.scan_to_masks(s_d, l_d, spacing)
+            done = torch.cuda.Event()
+            done.record(cur)
+            if bufs[k] is None or bufs[k][0].shape != les.shape:
+                bufs[k] = (torch.empty(les.shape, dtype=les.dtype).pin_memory(), torch.empty(post.shape, dtype=post.dtype).pin_memory(),
+                           torch.empty((), dtype=torch.float32).pin_memory())
+            with torch.cuda.stream(down_s):
+                down_s.wait_event(done)
+                for dst, src in zip(bufs[k], (les, post, ratio)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(down_s)
+                dl = torch.cuda.Event()
+                dl.record(down_s)
+            if pending is not None:
+                yield finish(pending)
+            pending, k = (bufs[k][0], bufs[k][1], bufs[k][2], dl), k ^ 1
+        if pending is not None:
+            yield finish(pending)
+
     def archive_results(self, heatmap, pred, post_pred, meta):
         """job_runner.py:857-890: `<out>/<task>/<uid>.mha` (lesion mask), `heatmap/<uid>.mha` (heat map windowed to uint8),
         `post/<uid>.mha` (post-processed mask), all uint8 with the scan's origin / direction / original spacing."""

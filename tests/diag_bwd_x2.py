@@ -1,5 +1,8 @@
+"""Diagnostic (not a pytest file): per-parameter gradient error of the training step against the fp32 CPU oracle with the
+three-product backward (default) and with the single-plane gradient operand (DRAM_BWD_PRECISION=bf16x2).
+   python tests/diag_bwd_x2.py"""
 import os, sys, torch
-ROOT="/root/repo"
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("bodyct-dram_b200","oracle","tests"): sys.path.insert(0, os.path.join(ROOT,p))
 import dram_oracle as O, metrics, models
 from util import rel_err
@@ -19,13 +22,13 @@ def main(size,B,seed):
     d_ref, r_ref = O.dc3d_forward(sd, images, cfg, True)
     rl_ref, sl_ref = O.int_reg_refine_loss(d_ref, r_ref, lobes, lesions, ctsses, Host.ctss_frequency_map)
     (2 * rl_ref + sl_ref).backward()
-    for emu in ("0","1"):
-        os.environ["DRAM_EMULATE_BWD_X2"]=emu
+    for mode in ("bf16x3", "bf16x2"):
+        os.environ["DRAM_BWD_PRECISION"] = mode
         mm = models.DC3D(**cfg); mm.load_state_dict(sd0); mm = mm.cuda().train()
         rl, sl = metrics.IntRegRefineLoss()(mm, images.cuda(), lobes.cuda(), lesions.cuda(), ctsses, obj=Host(), metas={})
         (2 * rl + sl).backward()
         errs = sorted(((rel_err(p.grad, sd[k].grad), k) for k, p in mm.named_parameters()), reverse=True)
-        print(f"size {size} B {B} bwd_x2_emulated={emu}: worst", ", ".join(f"{k}:{e:.1e}" for e, k in errs[:4]), "| median %.2e" % errs[len(errs)//2][0], flush=True)
+        print(f"size {size} B {B} DRAM_BWD_PRECISION={mode}: worst", ", ".join(f"{k}:{e:.1e}" for e, k in errs[:4]), "| median %.2e" % errs[len(errs)//2][0], flush=True)
 main((32,32,32),2,21)
 main((48,48,48),2,5)
 main((80,80,80),1,33)

@@ -136,6 +136,37 @@ def test_run_scan_matches_oracle(head):
     assert abs(out["ratio"] - ref["ratio"]) <= 1e-4 * abs(ref["ratio"])
 
 
+def test_run_scans_pipeline_equals_one_scan_at_a_time():
+    """LesionSegTest.run_scans (uploads / downloads on side streams, overlapped with the kernels) returns, scan by scan,
+    exactly what the serial path (scan_to_masks) returns; scans of different sizes and spacings in one stream of work"""
+    from oracle_import import O
+    import job_runner
+    from utils import Settings
+    g = torch.load(os.path.join(GOLDEN, "dc3dat_div16_16.pt"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = Settings(os.path.join(root, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    s.MODEL = dict(g["cfg"])
+    s.RESAMPLE_SIZE = (16, 16, 16)
+    runner = job_runner.LesionSegTest(None, None, None, s, None)
+    runner.model.load_state_dict(g["state_dict"])
+    items = []
+    for seed, shape, sp in ((1, (40, 56, 48), (1.0, 1.0, 1.0)), (2, (36, 64, 64), (1.0, 0.8, 0.8)), (3, (40, 56, 48), (1.0, 1.0, 1.0)),
+                            (4, (30, 48, 40), (1.5, 1.0, 1.0))):
+        scan, lobe, _, _ = O.synthetic_scan(shape, sp, seed=seed)
+        items.append((torch.from_numpy(scan).pin_memory(), torch.from_numpy(lobe).pin_memory(), [float(v) for v in sp]))
+    serial = []
+    for scan_h, lobe_h, sp in items:
+        les, post, ratio = runner.scan_to_masks(scan_h.cuda(), lobe_h.cuda(), sp)
+        serial.append((les.cpu().clone(), post.cpu().clone(), float(ratio.item())))
+    n = 0
+    for (les, post, ratio), (rl, rp, rr) in zip(runner.run_scans(items), serial):
+        assert les.shape == rl.shape and torch.equal(les, rl) and torch.equal(post, rp), f"scan {n}: masks differ"
+        assert ratio == rr
+        n += 1
+    assert n == len(items)
+    assert list(runner.run_scans([])) == []
+
+
 def test_run_reads_and_writes_metaimage(tmp_path):
     """LesionSegTest.run() on the reference's file contract: <uid>.mha scan + lobe mask in, lesion / heat map / post .mha out
     (job_runner.py:857-890), equal to run_scan on the same arrays resampled the same way."""
