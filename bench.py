@@ -30,6 +30,16 @@ FWD_GFLOP_PER_CHUNK = 924.61           # SURVEY §8d, 2*MAC over the 14 convs + 
 TRAIN_GFLOP_PER_CHUNK = 2772.96        # fwd + dgrad + wgrad, no dgrad for layer 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the run's ONE stdout line"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -163,7 +173,7 @@ def run_reference(args):
         return
     v, s_per_step, threads = cpu_train_chunks_per_s(args.steps, args.warmup, batch=1)
     sample = f"{args.steps} timed training steps of batch 1 (80^3 chunk) after {args.warmup} warm-up, torch CPU fp32"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "train_lobe_chunks_per_s", "value": v, "unit": "chunks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -351,7 +361,7 @@ def run_b200(args):
         "extra": extra,
         "loss": final_loss,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         td.destroy_process_group()
 
@@ -534,7 +544,7 @@ def run_infer(args):
             v, dt, threads = cpu_infer_chunks_per_s(True, 1)
             cpu = {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port",
                    "sample": f"1 eval forward of DC3DATGeneric + pooling, batch 1, 80^3 chunk ({dt:.1f} s), torch CPU fp32 oracle"}
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "infer_lobe_chunks_per_s", "value": world * B * args.steps / (ms.item() / 1e3), "unit": "chunks/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item() / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -643,7 +653,7 @@ def run_scan(args):
                    "sample": f"model part only: one of the scan's 5 lobe chunks through the CPU oracle ({dt:.1f} s) x 5; the "
                              "reference additionally spends CPU time in SimpleITK resampling and numpy masking"}
         s_per_scan = ms.item() / 1e3 / args.steps
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "seconds_per_ct_scan", "value": s_per_scan / world, "unit": "s/scan (wall time per scan of the whole job)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item() / args.steps,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -661,6 +671,12 @@ def run_scan(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the duration of the run (NCCL prints
+    # its version banner and debug lines to fd 1 from native code) and the line is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
