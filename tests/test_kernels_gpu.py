@@ -187,6 +187,19 @@ def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
         assert_close(dw1, ref, TOL_X3, "conv_umma wgrad vs bf16-rounded dy")
 
 
+@pytest.mark.parametrize("Cin,Cout,S", [(32, 64, (16, 16, 16)), (24, 64, (8, 8, 16)), (32, 64, (5, 5, 5)), (16, 32, (8, 8, 8))])
+def test_conv_umma_skips_only_zero_padding(monkeypatch, Cin, Cout, S):
+    """With one 64-channel K block the MMAs over the all-zero channel padding are not issued: same bits as issuing them"""
+    o = ops()
+    x, w = torch.randn(2, Cin, *S), torch.randn(Cout, Cin, 3, 3, 3) * 0.1
+    xs = o.split_bf16(cuda_cl(x), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    y = o.conv_umma(xs, w_hi, w_lo, Cout, 3)
+    assert_close(y, F.conv3d(x, w, None, padding=1), TOL_X3, "conv_umma fwd, padded K block")
+    monkeypatch.setenv("DRAM_CONV_FULL_K", "1")
+    assert torch.equal(y, o.conv_umma(xs, w_hi, w_lo, Cout, 3))
+
+
 def test_conv_umma_is_deterministic():
     o = ops()
     x, w = torch.randn(2, 64, 8, 8, 8), torch.randn(64, 64, 3, 3, 3) * 0.05
