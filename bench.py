@@ -627,6 +627,12 @@ def run_scan(args):
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         td.all_reduce(ms, op=td.ReduceOp.MAX)
+    lib.PROFILE.reset()                                  # per-kernel CUDA events of one more scan (outside the timed region)
+    lib.PROFILE.enabled = True
+    one_scan(scan_d, lobe_d, False)
+    torch.cuda.synchronize()
+    lib.PROFILE.enabled = False
+    prof = lib.PROFILE.summary()
     # end to end through the public API: LesionSegTest.run_scans over PINNED HOST scans (upload of scan i+1 and download
     # of the masks of scan i-1 overlap the kernels of scan i); every scan's H2D and D2H is inside the timed region
     for _ in runner.run_scans([(scan_h, lobe_h, spacing)] * 2):
@@ -665,6 +671,8 @@ def run_scan(args):
                     "h2d_bytes_per_step": int(scan_h.numel() * 2 + lobe_h.numel()), "d2h_bytes_per_step": int(2 * lobe_h.numel() + 4),
                     "api": "LesionSegTest.run_scans (pipelined copies)", "single_scan_latency_s": e2e_single},
             "gpu_launches": launches, "cpu_baseline": cpu,
+            "kernels": {k.replace("dram_", ""): {"calls_per_scan": v["calls"], "ms_per_scan": v["ms"]}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:16]},
             "roofline": None}))
     if world > 1:
         td.destroy_process_group()

@@ -118,6 +118,69 @@ k_itk_resample(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int
   }
 }
 
+// Same arithmetic, 4 consecutive output voxels of the FLAT output array per thread (an aligned 4-element store; the
+// group may straddle a row end, so the row set-up is redone when x wraps): one 32-bit division pair per 4 outputs, the
+// z / y part of the interpolation shared by the group.  Used when the output has < 2^31 voxels and a 16-byte aligned base.
+template <typename T> struct alignas(4 * sizeof(T)) Vec4 { T v[4]; };
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_itk_resample_v4(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, float rz,
+                  float ry, float rx) {
+  const unsigned total = (unsigned)D * H * W, HW = (unsigned)H * W;
+  const unsigned groups = (total + 3) >> 2;
+  for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+    const unsigned i0 = g << 2;
+    int Z = (int)(i0 / HW);
+    const unsigned rem = i0 - (unsigned)Z * HW;
+    int Y = (int)(rem / (unsigned)W), X = (int)(rem - (unsigned)Y * W);
+    Vec4<T> out;
+    bool fresh = true;
+    // row state: nearest -> (row pointer, inside); linear -> four row pointers + z/y weights
+    const T *r00 = src, *r01 = src, *r10 = src, *r11 = src;
+    float wz1 = 0.f, wy1 = 0.f;
+    bool row_in = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j >= total) { out.v[j] = (T)0; continue; }
+      if (fresh) {
+        fresh = false;
+        if (MODE == 1) {
+          row_in = true;
+          const int zn = itk_nearest(Z, rz, d, row_in), yn = itk_nearest(Y, ry, h, row_in);
+          r00 = src + ((long long)zn * h + yn) * w;
+        } else {
+          const Axis az = itk_axis(Z, rz, d), ay = itk_axis(Y, ry, h);
+          row_in = az.inside && ay.inside;
+          wz1 = az.w1; wy1 = ay.w1;
+          r00 = src + ((long long)az.i0 * h + ay.i0) * w; r01 = src + ((long long)az.i0 * h + ay.i1) * w;
+          r10 = src + ((long long)az.i1 * h + ay.i0) * w; r11 = src + ((long long)az.i1 * h + ay.i1) * w;
+        }
+      }
+      if (MODE == 1) {
+        bool in = row_in;
+        const int xn = itk_nearest(X, rx, w, in);
+        out.v[j] = in ? r00[xn] : (T)0;
+      } else {
+        const Axis ax = itk_axis(X, rx, w);
+        // the same sum, in the same order, as k_itk_resample: k = 4*zbit + 2*ybit + xbit ascending
+        const float wz[2] = {1.f - wz1, wz1}, wy[2] = {1.f - wy1, wy1}, wx[2] = {1.f - ax.w1, ax.w1};
+        const T* rows[4] = {r00, r01, r10, r11};
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          acc += (wz[k >> 2] * wy[(k >> 1) & 1] * wx[k & 1]) * (float)rows[k >> 1][(k & 1) ? ax.i1 : ax.i0];
+        out.v[j] = (row_in && ax.inside) ? cast_out<T>(acc) : (T)0;
+      }
+      if (++X == W) { X = 0; fresh = true; if (++Y == H) { Y = 0; ++Z; } }
+    }
+    if (i0 + 3 < total) {
+      *reinterpret_cast<Vec4<T>*>(dst + i0) = out;
+    } else {
+      for (int j = 0; j < 4 && i0 + j < total; ++j) dst[i0 + j] = out.v[j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RAM -> heat map
 // as k_ram_upsample_mask_scatter (ram.cu) but the lobe mask is read from the scan-sized label volume.
 // Block = 32 (x) x 8 (y) threads, kScatterZ consecutive z per thread: a warp reads 32 consecutive labels and writes up to
@@ -238,6 +301,21 @@ int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w
   DRAM_REQUIRE(src && dst && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1), "itk_resample: bad arguments");
   DRAM_REQUIRE(rz > 0.f && ry > 0.f && rx > 0.f, "itk_resample: index ratios must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((long long)D * H * W < (1ll << 31) - 4 && ((uintptr_t)dst % 16) == 0 && !getenv("DRAM_RESAMPLE_SCALAR")) {
+    const int g4 = grid_for(((long long)D * H * W + 3) / 4, 256, 16);
+#define ITK_V4(T)                                                                                                        \
+  do {                                                                                                                   \
+    if (mode == 0) k_itk_resample_v4<T, 0><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, rz, ry, rx);     \
+    else k_itk_resample_v4<T, 1><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, rz, ry, rx);               \
+  } while (0)
+    if (dtype == 0) ITK_V4(float);
+    else if (dtype == 1) ITK_V4(short);
+    else if (dtype == 2) ITK_V4(uint8_t);
+    else DRAM_REQUIRE(false, "itk_resample: dtype %d unknown (0 f32, 1 i16, 2 u8)", dtype);
+#undef ITK_V4
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   int grid = grid_for((long long)D * H * W, 256, 16);
   if (dtype == 0) k_itk_resample<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
   else if (dtype == 1) k_itk_resample<short><<<grid, 256, 0, st>>>((const short*)src, (short*)dst, d, h, w, D, H, W, rz, ry, rx, mode);

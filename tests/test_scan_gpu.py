@@ -48,7 +48,7 @@ def test_lobe_chunk_preprocess(chunk):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.int16, np.uint8])
 @pytest.mark.parametrize("mode", ["linear", "nearest"])
-@pytest.mark.parametrize("src,dst", [((20, 24, 18), (10, 16, 18)), ((9, 10, 11), (20, 31, 15))])
+@pytest.mark.parametrize("src,dst", [((20, 24, 18), (10, 16, 18)), ((9, 10, 11), (20, 31, 15)), ((12, 14, 10), (7, 9, 11))])
 def test_itk_resample(dtype, mode, src, dst):
     from oracle_import import O
     rng = np.random.RandomState(3)
@@ -63,6 +63,20 @@ def test_itk_resample(dtype, mode, src, dst):
     else:                                                       # truncating cast: at most 1 LSB on rounding ties
         diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int16, torch.uint8])
+@pytest.mark.parametrize("mode", ["linear", "nearest"])
+def test_itk_resample_vector_kernel_equals_scalar_kernel(monkeypatch, dtype, mode):
+    """4 outputs per thread with aligned vector stores (groups straddle row ends; ragged tail) == one output per thread"""
+    torch.manual_seed(5)
+    for src, dst, ratios in (((23, 30, 26), (17, 21, 23), None), ((16, 20, 22), (16, 29, 31), (1.0, 0.7, 0.7)), ((5, 6, 7), (3, 3, 3), None)):
+        a = (torch.rand(src) * 300 - 100).to(dtype).cuda() if dtype != torch.uint8 else torch.randint(0, 6, src, dtype=torch.uint8).cuda()
+        monkeypatch.delenv("DRAM_RESAMPLE_SCALAR", raising=False)
+        fast = ops().itk_resample(a, dst, mode, ratios=ratios)
+        monkeypatch.setenv("DRAM_RESAMPLE_SCALAR", "1")
+        slow = ops().itk_resample(a, dst, mode, ratios=ratios)
+        assert torch.equal(fast, slow), (src, dst)
 
 
 def test_itk_resample_fixed_spacing_round_trip_sizes():
