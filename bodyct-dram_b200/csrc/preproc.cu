@@ -7,20 +7,52 @@ namespace dram {
 
 // ------------------------------------------------------------------------------------------------ lobe bounding boxes
 // utils.find_crops (utils.py:244-254) for all labels at once: out[l][0..2] = min z,y,x; out[l][3..5] = max z,y,x (inclusive)
+// A thread reads 4 labels as one aligned word of the flat volume and skips all-background words (most of a chest CT);
+// only words that hold a label pay for coordinates (one 32-bit division pair per word) and update the thread's own
+// register boxes (the label loop is unrolled: no dynamic register indexing); shared / global atomics once per thread / block.
+template <int NL>
 __global__ void __launch_bounds__(256)
 k_label_bboxes(const uint8_t* __restrict__ labels, int D, int H, int W, int nlabels, int* __restrict__ out) {
   __shared__ int smin[8][3], smax[8][3];                       // labels 1..7 supported per launch
   for (int i = threadIdx.x; i < 8 * 3; i += blockDim.x) { (&smin[0][0])[i] = 0x7fffffff; (&smax[0][0])[i] = -1; }
   __syncthreads();
-  const long long total = (long long)D * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int l = labels[i];
-    if (l >= 1 && l <= nlabels) {
-      int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
-      atomicMin(&smin[l][0], z); atomicMin(&smin[l][1], y); atomicMin(&smin[l][2], x);
-      atomicMax(&smax[l][0], z); atomicMax(&smax[l][1], y); atomicMax(&smax[l][2], x);
+  int mn[NL][3], mx[NL][3];
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mn[l][a] = 0x7fffffff; mx[l][a] = -1; }
+  const unsigned total = (unsigned)D * H * W, HW = (unsigned)H * W, words = (total + 3) >> 2;
+  const unsigned* lw = reinterpret_cast<const unsigned*>(labels);
+  for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < words; g += gridDim.x * blockDim.x) {
+    const unsigned i0 = g << 2;
+    unsigned word;
+    if (i0 + 3 < total) word = __ldg(lw + g);
+    else {
+      word = 0;
+      for (int j = 0; j < 4 && i0 + j < total; ++j) word |= (unsigned)labels[i0 + j] << (8 * j);
+    }
+    if (word == 0) continue;
+    int z = (int)(i0 / HW);
+    const unsigned rem = i0 - (unsigned)z * HW;
+    int y = (int)(rem / (unsigned)W), x = (int)(rem - (unsigned)y * W);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int lab = (int)((word >> (8 * j)) & 0xffu);
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+        if (lab == l + 1 && l < nlabels) {
+          mn[l][0] = min(mn[l][0], z); mn[l][1] = min(mn[l][1], y); mn[l][2] = min(mn[l][2], x);
+          mx[l][0] = max(mx[l][0], z); mx[l][1] = max(mx[l][1], y); mx[l][2] = max(mx[l][2], x);
+        }
+      if (++x == W) { x = 0; if (++y == H) { y = 0; ++z; } }
     }
   }
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+    if (mx[l][0] >= 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { atomicMin(&smin[l + 1][a], mn[l][a]); atomicMax(&smax[l + 1][a], mx[l][a]); }
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < 8 * 3; i += blockDim.x) {
     int l = i / 3, a = i % 3;
@@ -225,46 +257,83 @@ k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __res
 // histogram of uint8(window(v, lo, hi) * 255) over voxels with labels > 0  (utils.binary_cam utils.py:226-242);
 // integer-exact: the uint8 conversion is the same truncation numpy's astype performs
 template <typename T>
+__device__ __forceinline__ int hist_bin(T raw, float lo, float hi) {
+  // numpy evaluates the windowing in the array's float type: float32 for the heat map, float64 for the int16 scan
+  if (sizeof(T) == 4) {
+    float x = (float)raw;
+    x = fminf(fmaxf(x, lo), hi);
+    return (int)(((x - lo) / (hi - lo)) * 255.0f) & 255;
+  }
+  double x = (double)raw;
+  x = x < lo ? (double)lo : (x > hi ? (double)hi : x);
+  return (int)(((x - (double)lo) / ((double)hi - (double)lo)) * 255.0) & 255;
+}
+// a thread reads 4 labels as one word and skips all-background words before touching the values
+template <typename T>
 __global__ void __launch_bounds__(256)
 k_masked_hist_u8(const T* __restrict__ v, const uint8_t* __restrict__ labels, long long n, float lo, float hi,
                  unsigned int* __restrict__ hist) {
   __shared__ unsigned int sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
-  // numpy evaluates the windowing in the array's float type: float32 for the heat map, float64 for the int16 scan
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (labels[i] == 0) continue;
-    int bin;
-    if (sizeof(T) == 4) {
-      float x = (float)v[i];
-      x = fminf(fmaxf(x, lo), hi);
-      bin = (int)(((x - lo) / (hi - lo)) * 255.0f);
-    } else {
-      double x = (double)v[i];
-      x = x < lo ? (double)lo : (x > hi ? (double)hi : x);
-      bin = (int)(((x - (double)lo) / ((double)hi - (double)lo)) * 255.0);
-    }
-    atomicAdd(&sh[bin & 255], 1u);
+  const long long words = n >> 2;
+  const unsigned* lw = reinterpret_cast<const unsigned*>(labels);
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < words; g += (long long)gridDim.x * blockDim.x) {
+    const unsigned word = __ldg(lw + g);
+    if (word == 0) continue;
+    const Vec4<T> raw = *reinterpret_cast<const Vec4<T>*>(v + (g << 2));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((word >> (8 * j)) & 0xffu) atomicAdd(&sh[hist_bin<T>(raw.v[j], lo, hi)], 1u);
   }
+  for (long long i = (words << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (labels[i] != 0) atomicAdd(&sh[hist_bin<T>(v[i], lo, hi)], 1u);
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // lesion = heat > th;  post = lesion && (window(scan) > th2) && !vessel      (job_runner.py:1009-1015)
+__device__ __forceinline__ void threshold_voxel(float hv, short sv, uint8_t vv, float thf, double th2, double lo, double hi,
+                                                double span, bool has_post, uint8_t& les_o, uint8_t& post_o) {
+  const bool les = hv > thf;               // numpy compares the float32 heat map against th cast to float32
+  les_o = les ? 1 : 0;
+  post_o = 0;
+  if (has_post && les) {                   // the float64 windowing only where the lesion mask is set
+    double x = (double)sv;
+    x = x < lo ? lo : (x > hi ? hi : x);
+    post_o = (((x - lo) / span > th2) && !(vv > 0)) ? 1 : 0;
+  }
+}
+// 4 voxels per thread: float4 / short4 / uchar4 loads, uchar4 stores
 __global__ void __launch_bounds__(256)
 k_threshold_masks(const float* __restrict__ heat, const short* __restrict__ scan, const uint8_t* __restrict__ vessel,
                   long long n, double th, double th2, float win_lo, float win_hi, uint8_t* __restrict__ lesion,
                   uint8_t* __restrict__ post) {
-  const double span = (double)win_hi - (double)win_lo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    bool les = heat[i] > (float)th;          // numpy compares the float32 heat map against th cast to float32
-    lesion[i] = les ? 1 : 0;
-    if (post) {
-      double x = (double)scan[i];
-      x = x < win_lo ? (double)win_lo : (x > win_hi ? (double)win_hi : x);
-      bool keep = les && ((x - (double)win_lo) / span > th2) && !(vessel && vessel[i] > 0);
-      post[i] = keep ? 1 : 0;
+  const double lo = (double)win_lo, hi = (double)win_hi, span = hi - lo;
+  const float thf = (float)th;
+  const bool has_post = post != nullptr;
+  const long long words = n >> 2;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < words; g += (long long)gridDim.x * blockDim.x) {
+    const float4 h4 = __ldg(reinterpret_cast<const float4*>(heat) + g);
+    const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+    Vec4<short> sv = {{0, 0, 0, 0}};
+    Vec4<uint8_t> vv = {{0, 0, 0, 0}};
+    if (has_post) {
+      sv = *(reinterpret_cast<const Vec4<short>*>(scan) + g);
+      if (vessel) vv = *(reinterpret_cast<const Vec4<uint8_t>*>(vessel) + g);
     }
+    Vec4<uint8_t> lo4, po4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) threshold_voxel(hv[j], sv.v[j], vv.v[j], thf, th2, lo, hi, span, has_post, lo4.v[j], po4.v[j]);
+    *(reinterpret_cast<Vec4<uint8_t>*>(lesion) + g) = lo4;
+    if (has_post) *(reinterpret_cast<Vec4<uint8_t>*>(post) + g) = po4;
+  }
+  for (long long i = (words << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t l, p;
+    threshold_voxel(heat[i], has_post ? scan[i] : (short)0, (has_post && vessel) ? vessel[i] : (uint8_t)0, thf, th2, lo, hi, span,
+                    has_post, l, p);
+    lesion[i] = l;
+    if (has_post) post[i] = p;
   }
 }
 
@@ -279,7 +348,10 @@ int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, i
   cudaStream_t st = (cudaStream_t)stream;
   k_bbox_init<<<1, 64, 0, st>>>(out, (nlabels + 1) * 6);
   DRAM_LAUNCH_CHECK();
-  k_label_bboxes<<<grid_for((long long)D * H * W, 256 * 8, 8), 256, 0, st>>>(labels, D, H, W, nlabels, out);
+  DRAM_REQUIRE((long long)D * H * W < (1ll << 31) - 4 && ((uintptr_t)labels % 4) == 0, "label_bboxes: volume too large or label base not 4-byte aligned");
+  const int grid = grid_for(((long long)D * H * W + 3) / 4, 256 * 4, 8);
+  if (nlabels <= 5) k_label_bboxes<5><<<grid, 256, 0, st>>>(labels, D, H, W, nlabels, out);
+  else k_label_bboxes<7><<<grid, 256, 0, st>>>(labels, D, H, W, nlabels, out);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
@@ -344,7 +416,8 @@ int dram_masked_hist_u8(const void* values, int dtype, const uint8_t* labels, lo
   DRAM_REQUIRE(values && labels && hist && n > 0 && hi > lo, "masked_hist_u8: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   DRAM_CUDA(cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), st));
-  int grid = grid_for(n, 256 * 8, 8);
+  DRAM_REQUIRE(((uintptr_t)values % 16) == 0 && ((uintptr_t)labels % 4) == 0, "masked_hist_u8: values must be 16-byte, labels 4-byte aligned");
+  int grid = grid_for((n + 3) / 4, 256 * 4, 8);
   if (dtype == 0) k_masked_hist_u8<float><<<grid, 256, 0, st>>>((const float*)values, labels, n, lo, hi, hist);
   else if (dtype == 1) k_masked_hist_u8<short><<<grid, 256, 0, st>>>((const short*)values, labels, n, lo, hi, hist);
   else DRAM_REQUIRE(false, "masked_hist_u8: dtype %d unknown (0 f32, 1 i16)", dtype);
@@ -356,7 +429,9 @@ int dram_threshold_masks(const float* heat, const short* scan, const uint8_t* ve
                          float win_lo, float win_hi, uint8_t* lesion, uint8_t* post, void* stream) {
   DRAM_REQUIRE(heat && lesion && n > 0, "threshold_masks: bad arguments");
   DRAM_REQUIRE(!post || (scan && win_hi > win_lo), "threshold_masks: post mask needs the scan and a window");
-  k_threshold_masks<<<grid_for(n, 256 * 4, 8), 256, 0, (cudaStream_t)stream>>>(heat, scan, vessel, n, th, th2, win_lo, win_hi, lesion, post);
+  DRAM_REQUIRE(((uintptr_t)heat % 16) == 0 && ((uintptr_t)lesion % 4) == 0 && (!post || (((uintptr_t)post % 4) == 0 && ((uintptr_t)scan % 8) == 0)) &&
+                   (!vessel || ((uintptr_t)vessel % 4) == 0), "threshold_masks: volumes must be allocation-aligned (16 B)");
+  k_threshold_masks<<<grid_for((n + 3) / 4, 256 * 2, 8), 256, 0, (cudaStream_t)stream>>>(heat, scan, vessel, n, th, th2, win_lo, win_hi, lesion, post);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
