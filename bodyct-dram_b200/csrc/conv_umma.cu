@@ -138,8 +138,36 @@ __device__ __forceinline__ uint32_t umma_idesc(int n, int a_mn_major, int b_mn_m
 constexpr int kFwdThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kATileBytes = 128 * 128;    // 128 voxel rows x 64 bf16
 
+// fp32 -> (hi, lo) bf16 split, the same rounding as planes.cu's split2 (round to nearest even, lo = bf16(v - hi))
+__device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+// 16 consecutive channels of one voxel -> 32 bytes per plane
+__device__ __forceinline__ void store_planes16(uint16_t* hi, uint16_t* lo, const float (&v)[16]) {
+  uint32_t H[8], L[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint16_t h0, l0, h1, l1;
+    split1(v[2 * j], h0, l0);
+    split1(v[2 * j + 1], h1, l1);
+    H[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    L[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  }
+  reinterpret_cast<uint4*>(hi)[0] = make_uint4(H[0], H[1], H[2], H[3]);
+  reinterpret_cast<uint4*>(hi)[1] = make_uint4(H[4], H[5], H[6], H[7]);
+  if (lo) {
+    reinterpret_cast<uint4*>(lo)[0] = make_uint4(L[0], L[1], L[2], L[3]);
+    reinterpret_cast<uint4*>(lo)[1] = make_uint4(L[4], L[5], L[6], L[7]);
+  }
+}
+
 struct FwdParams {
   float* y;
+  uint16_t* o_hi;   // eval mode: folded BatchNorm + ReLU output written as bf16 split planes [rows][Cout] instead of y
+  uint16_t* o_lo;
   const float* scale;
   const float* shift;
   int N, D, H, W, Cout, BN, kblocks_c, taps, pad;
@@ -310,9 +338,14 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
             }
           }
+          if (p.o_hi) {
+            const long long po = out - p.y + c0;                 // element offset is the same in y and in the planes
+            store_planes16(p.o_hi + po, p.o_lo ? p.o_lo + po : nullptr, v);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -341,6 +374,8 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // issues hi*hi, hi*lo, lo*hi as three N = BN MMAs into the same columns.
 struct Fwd2Params {
   float* y;
+  uint16_t* o_hi;   // eval mode: folded BatchNorm + ReLU output written as bf16 split planes [rows][Cout] instead of y
+  uint16_t* o_lo;
   const float* scale;
   const float* shift;
   int N, D, H, W, Cout, BN, kblocks_c, ksteps;
@@ -543,9 +578,14 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               v[jj] = fmaxf(fmaf(v[jj], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
             }
           }
+          if (p.o_hi) {
+            const long long po = out - p.y + c0;
+            store_planes16(p.o_hi + po, p.o_lo ? p.o_lo + po : nullptr, v);
+          } else {
 #pragma unroll
-          for (int jj = 0; jj < 16; jj += 4)
-            *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+            for (int jj = 0; jj < 16; jj += 4)
+              *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -575,6 +615,8 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // as k_conv_umma_fwd2; accumulator 128 lanes x 256 columns, double buffered (all 512 TMEM columns).
 struct Fwd3Params {
   float* y;
+  uint16_t* o_hi;   // eval mode: folded BatchNorm + ReLU output written as bf16 split planes [rows][Cout] instead of y
+  uint16_t* o_lo;
   const float* scale;
   const float* shift;
   int N, D, H, W, Cout, CT, kblocks_c, ksteps;
@@ -749,7 +791,15 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             for (int j = 0; j < 8; ++j) {
               float v = __uint_as_float(r[gi * 8 + j]);
               if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
-              out[j * hstride] = v;                    // 32 lanes = 32 consecutive channels of one voxel: 128 B
+              if (p.o_hi) {                            // planes: 32 lanes = 64 contiguous bytes per plane
+                const long long po = (out - p.y) + j * hstride;
+                uint16_t hh, ll;
+                split1(v, hh, ll);
+                p.o_hi[po] = hh;
+                if (p.o_lo) p.o_lo[po] = ll;
+              } else {
+                out[j * hstride] = v;                  // 32 lanes = 32 consecutive channels of one voxel: 128 B
+              }
             }
           }
         }
@@ -776,7 +826,15 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
           for (int j = 0; j < 8; ++j) {
             float v = __uint_as_float(upper ? r[j + 8] : r[j]) + rcv[j * 32 + lane];
             if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
-            out[j * hstride] = v;
+            if (p.o_hi) {
+              const long long po = (out - p.y) + j * hstride;
+              uint16_t hh, ll;
+              split1(v, hh, ll);
+              p.o_hi[po] = hh;
+              if (p.o_lo) p.o_lo[po] = ll;
+            } else {
+              out[j * hstride] = v;
+            }
           }
         }
       }
@@ -1353,9 +1411,13 @@ int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo, int Cout, int 
 }
 
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* scale,
-                         const float* shift, float* y, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize,
-                         void* stream) {
-  DRAM_REQUIRE(x_hi && w_hi && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
+                         const float* shift, float* y, void* out_hi, void* out_lo, int N, int D, int H, int W, int Cin, int Cin_pad,
+                         int Cout, int ksize, void* stream) {
+  DRAM_REQUIRE(x_hi && w_hi && (y || out_hi) && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
+  DRAM_REQUIRE(!out_hi || (scale && Cout % 64 == 0), "conv3d_umma_fwd: plane output needs scale/shift (eval mode) and Cout %% 64 == 0 (no channel padding)");
+  DRAM_REQUIRE(out_hi || !out_lo, "conv3d_umma_fwd: out_lo without out_hi");
+  // with plane output the kernels never dereference y: it only serves as the base of the element offset
+  if (!y) y = reinterpret_cast<float*>(uintptr_t(1) << 40);
   DRAM_REQUIRE(!(x_lo != nullptr && w_lo == nullptr), "conv3d_umma_fwd: x_lo needs w_lo (modes: both = bf16x3, w_lo only = single-plane activations x split weights, neither = bf16)");
   DRAM_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3d_umma_fwd: scale and shift must come together");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_fwd: kernel size %d unsupported", ksize);
@@ -1375,7 +1437,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     Fwd3Params q;
     const int plain = (Cout % 128 == 0) ? 1 : 0;
     const int mode = plain + (x_lo ? 0 : 2);
-    q.y = y; q.scale = scale; q.shift = shift;
+    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = plain ? 128 : 64; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0 && D % 2 == 0) { q.TW = 16; q.TDD = 2; } else { q.TW = 8; q.TDD = 4; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
@@ -1432,7 +1494,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     const int mode = !w_lo ? 0 : ((q.BN <= 64 ? 1 : 2) + (x_lo ? 0 : 2));
     q.acc_cols = (mode == 1 || mode == 3) ? 2 * q.BN : q.BN;
     q.tmem_cols = pow2_cols(4 * q.acc_cols);
-    q.y = y; q.scale = scale; q.shift = shift;
+    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
@@ -1488,7 +1550,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   FwdParams p;
   p.BN = pick_bn(Cout);
   DRAM_REQUIRE(p.BN > 0, "conv3d_umma_fwd: Cout=%d must be a multiple of 16", Cout);
-  p.y = y; p.scale = scale; p.shift = shift;
+  p.y = y; p.scale = scale; p.shift = shift; p.o_hi = (uint16_t*)out_hi; p.o_lo = (uint16_t*)out_lo;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
   p.kblocks_c = Cin_pad / 64; p.taps = ksize * ksize * ksize; p.pad = ksize / 2; p.ksteps = ksteps;
   // kw-reuse for the layers whose L2->smem fill rate is the bound (N tile <= 64: 125 B/cycle/SM needed, ~75-80 sustained)

@@ -197,6 +197,11 @@ def _bn_fold_cached(gamma, beta, running_mean, running_var, eps):
     return val
 
 
+# Grad mode is always off INSIDE autograd.Function.forward and ctx.needs_input_grad reflects requires_grad of the parameters
+# whatever the mode: the wrappers record the caller's grad mode here right before .apply (single-threaded, SURVEY 8b).
+_GRAD_OFF = [False]
+
+
 class ConvBnRelu(torch.autograd.Function):
     """[Conv3d(bias optional) -> BatchNorm3d -> ReLU (-> MaxPool3d(2,2,0))]  — parts.py:103-110,184-196.
 
@@ -224,6 +229,13 @@ class ConvBnRelu(torch.autograd.Function):
             if xs is None:
                 xs = ops.split_bf16(x_real)
             w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_fwd", lambda: ops.pack_weight_bf16(w.detach(), 0))
+            if (not training and not pool and bool(out_planes) and planes_enabled() and Cout % 64 == 0
+                    and _GRAD_OFF[0] and os.environ.get("DRAM_EVAL_EPILOGUE", "1") == "1"):
+                # inference: folded BatchNorm + ReLU in the convolution's epilogue, written as the next layer's planes
+                scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
+                ap = ops.conv_umma(xs, w_hi, w_lo, Cout, k, scale, shift, out_planes=True)
+                ctx.mark_non_differentiable(ap.hi, *([ap.lo] if ap.lo is not None else []))
+                return _handle(ap.shape, ap.hi.device), ap.hi, ap.lo, None, None, None
             y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
         elif pointwise:
             y = ops.pointwise8_planes(xs, w, bias)       # reshape heads: straight from the planes, no fp32 copy of the input
@@ -239,7 +251,7 @@ class ConvBnRelu(torch.autograd.Function):
                                                        n_updates)
         else:
             scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
-            if any(ctx.needs_input_grad):
+            if not _GRAD_OFF[0]:
                 mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)  # only for dgamma/dbeta in eval mode
             else:
                 mean = rstd = None                                                  # inference: nothing is kept
@@ -341,6 +353,7 @@ def conv_bn_relu(x, w, bias, gamma, beta, running_mean, running_var, training, m
                  out_planes=False):
     """One [conv -> BN -> ReLU (-> pool)] unit on a tensor or an `Act`; returns tensors, or `Act`s when out_planes is set
     and the shape allows it.  With pool: (a, pooled)."""
+    _GRAD_OFF[0] = not torch.is_grad_enabled()
     a, a_hi, a_lo, p, p_hi, p_lo = ConvBnRelu.apply(*_unwrap(x), w, bias, gamma, beta, running_mean, running_var, training,
                                                     momentum, eps, n_updates, pool, out_planes)
     if pool:
@@ -386,7 +399,7 @@ class ConvBnReluRam(torch.autograd.Function):
                                                        n_updates)
         else:
             scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
-            if any(ctx.needs_input_grad):
+            if not _GRAD_OFF[0]:
                 mean, rstd = running_mean.clone(), torch.rsqrt(running_var + eps)
             else:
                 mean = rstd = None
@@ -421,6 +434,7 @@ def ram_fusable(w, w_top, bias):
 
 
 def conv_bn_relu_ram(x, w, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates, w_top, b_top):
+    _GRAD_OFF[0] = not torch.is_grad_enabled()
     return ConvBnReluRam.apply(*_unwrap(x), w, gamma, beta, running_mean, running_var, training, momentum, eps, n_updates,
                                w_top, b_top)
 

@@ -160,13 +160,23 @@ def pack_weight_bf16(w, mode, three=None):
     return hi, lo, Kpad
 
 
-def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None):
-    """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32."""
+def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=False):
+    """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32, or (with
+    out_planes, eval mode: scale / shift = folded BatchNorm) the ReLU'd activation as SplitPlanes, no fp32 tensor written."""
     N, Cin, D, H, W = xs.shape
-    y = new_volume(N, Cout, D, H, W, xs.hi.device)
     _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")   # algorithmic (unpadded, 1 pass)
+    if out_planes:
+        if scale is None or Cout % 64:
+            raise _lib.DramLibraryError("conv_umma: plane output needs folded BatchNorm scale/shift and Cout % 64 == 0")
+        out = alloc_planes((N, Cout, D, H, W), three=xs.lo is not None)
+        _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), scale.data_ptr(),
+                                             shift.data_ptr(), None, out.hi.data_ptr(), _p(out.lo), N, D, H, W, Cin, xs.Cpad,
+                                             Cout, ksize, _stream()), "conv3d_umma_fwd")
+        return out
+    y = new_volume(N, Cout, D, H, W, xs.hi.device)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
-                                         y.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
+                                         y.data_ptr(), None, None, N, D, H, W, Cin, xs.Cpad, Cout, ksize, _stream()),
+               "conv3d_umma_fwd")
     return y
 
 

@@ -68,6 +68,8 @@ int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack,
  *               !x_lo && !w_lo -> single-pass bf16 ("fast" mode, reported only);  x_lo without w_lo is an error
  *   y         : [N][D][H][W][Cout] fp32 raw accumulators; if scale/shift != NULL the epilogue applies
  *               y = max(0, acc*scale[co] + shift[co])  (eval-mode folded BatchNorm + ReLU, parts.py:107-108)
+ *   out_hi/lo : optional (needs scale/shift, Cout % 64 == 0): that activation is written as bf16 split planes
+ *               [N][D][H][W][Cout] - the next convolution's operand - instead of y (inference: no fp32 round trip)
  * Cin = real input channels; channels [Cin, Cin_pad) of x and w are zeros (with one 64-channel block the K = 16 steps that
  * would only multiply that padding are not issued).
  * Cout must be a multiple of 16.  K loop = taps x Cin_pad/64 stages of {A 128x64, B BNx64} fed by TMA (5-D tensor map
@@ -76,7 +78,8 @@ int dram_split_bf16(const float* x, void* hi, void* lo /*nullable*/, long long r
 int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo /*nullable*/, int Cout, int Cin, int Cin_pad,
                           int ksize, int mode, void* stream);
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
-                         const float* scale /*nullable*/, const float* shift /*nullable*/, float* y,
+                         const float* scale /*nullable*/, const float* shift /*nullable*/, float* y /*nullable with out_hi*/,
+                         void* out_hi /*nullable*/, void* out_lo /*nullable*/,
                          int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, void* stream);
 /* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes
  *   dy_hi/dy_lo : [N][D][H][W][Cout_pad]   x_hi/x_lo : [N][D][H][W][Cin_pad]   (pads are multiples of 64)

@@ -200,6 +200,32 @@ def test_conv_umma_skips_only_zero_padding(monkeypatch, Cin, Cout, S):
     assert torch.equal(y, o.conv_umma(xs, w_hi, w_lo, Cout, 3))
 
 
+@pytest.mark.parametrize("N,Cin,Cout,S", [(2, 64, 64, (16, 16, 16)),      # channels-on-M kernel, stacked 64-channel tile
+                                          (1, 64, 128, (8, 16, 16)),     # channels-on-M kernel, 128-channel tile
+                                          (1, 192, 64, (16, 16, 16)),    # tile-pair kernel
+                                          (2, 128, 256, (5, 5, 5)),      # generic kernel, ragged tiles
+                                          (1, 256, 512, (10, 10, 10))])
+@pytest.mark.parametrize("three", [True, False])
+def test_conv_umma_eval_epilogue_writes_planes(N, Cin, Cout, S, three):
+    """inference epilogue: folded BatchNorm + ReLU written as split planes == conv -> bn_relu_apply_planes, bit for bit"""
+    o = ops()
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, 3, 3, 3) * (2.0 / (27 * Cin)) ** 0.5
+    scale, shift = (torch.rand(Cout) + 0.5).cuda(), torch.randn(Cout).cuda()
+    xs = o.split_bf16(cuda_cl(x), three)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, three)
+    y = o.conv_umma(xs, w_hi, w_lo, Cout, 3)
+    ref, _ = o.bn_relu_apply_planes(y, scale, shift, False)
+    got = o.conv_umma(xs, w_hi, w_lo, Cout, 3, scale, shift, out_planes=True)
+    assert got.Cpad == ref.Cpad == Cout and tuple(got.shape) == tuple(ref.shape)
+    assert torch.equal(got.hi.view(torch.int16), ref.hi.view(torch.int16)), "hi plane"
+    if three:
+        assert torch.equal(got.lo.view(torch.int16), ref.lo.view(torch.int16)), "lo plane"
+    else:
+        assert got.lo is None
+    assert_close(o.merge_planes(got), F.relu(F.conv3d(x, w, None, padding=1) * scale.cpu().view(1, -1, 1, 1, 1) + shift.cpu().view(1, -1, 1, 1, 1)),
+                 TOL_X3 if three else TOL_BF16, "eval epilogue vs torch")
+
+
 def test_conv_umma_is_deterministic():
     o = ops()
     x, w = torch.randn(2, 64, 8, 8, 8), torch.randn(64, 64, 3, 3, 3) * 0.05
