@@ -635,7 +635,7 @@ def run_scan(args):
     prof = lib.PROFILE.summary()
     # end to end through the public API: LesionSegTest.run_scans over PINNED HOST scans (upload of scan i+1 and download
     # of the masks of scan i-1 overlap the kernels of scan i); every scan's H2D and D2H is inside the timed region
-    for _ in runner.run_scans([(scan_h, lobe_h, spacing)] * 2):
+    for _ in runner.run_scans([(scan_h, lobe_h, spacing)] * max(args.steps, 3)):     # warm-up: slots, pinned buffers, allocator pools
         pass
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -337,6 +337,14 @@ k_threshold_masks(const float* __restrict__ heat, const short* __restrict__ scan
   }
 }
 
+// small result read-back without the copy engines: the kernel stores straight into PINNED host memory (unified virtual
+// addressing: the host pointer is valid on the device), so a 1 KB histogram does not queue behind a bulk D2H transfer of
+// another stream (LesionSegTest.run_scans downloads the previous scan's masks while this scan computes).
+__global__ void k_store_to_host(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int nwords) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
 }  // namespace dram
 
 using namespace dram;
@@ -432,6 +440,19 @@ int dram_threshold_masks(const float* heat, const short* scan, const uint8_t* ve
   DRAM_REQUIRE(((uintptr_t)heat % 16) == 0 && ((uintptr_t)lesion % 4) == 0 && (!post || (((uintptr_t)post % 4) == 0 && ((uintptr_t)scan % 8) == 0)) &&
                    (!vessel || ((uintptr_t)vessel % 4) == 0), "threshold_masks: volumes must be allocation-aligned (16 B)");
   k_threshold_masks<<<grid_for((n + 3) / 4, 256 * 2, 8), 256, 0, (cudaStream_t)stream>>>(heat, scan, vessel, n, th, th2, win_lo, win_hi, lesion, post);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_store_to_host(const void* src, void* dst_pinned_host, int nbytes, void* stream) {
+  DRAM_REQUIRE(src && dst_pinned_host && nbytes > 0 && nbytes % 4 == 0 && nbytes <= (1 << 20), "store_to_host: 4..1 MiB, multiple of 4 bytes");
+  DRAM_REQUIRE(((uintptr_t)src % 4) == 0 && ((uintptr_t)dst_pinned_host % 4) == 0, "store_to_host: unaligned pointers");
+  cudaPointerAttributes attr;
+  DRAM_CUDA(cudaPointerGetAttributes(&attr, dst_pinned_host));
+  DRAM_REQUIRE(attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr, "store_to_host: destination is not pinned (device-mapped) host memory");
+  const int nwords = nbytes / 4;
+  k_store_to_host<<<(nwords + 255) / 256 > 64 ? 64 : (nwords + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned*)src, (unsigned*)attr.devicePointer, nwords);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

@@ -223,7 +223,7 @@ class LesionSegTest(JobRunner):
         """utils.find_crops for the 5 lobes; one 120-byte device->host read per scan."""
         from dram_native import ops
         import math
-        boxes = ops.label_bboxes(lobe_t, 5).cpu().numpy()
+        boxes = ops.read_small(ops.label_bboxes(lobe_t, 5)).numpy()
         crops = {}
         for label in range(1, 6):
             mn, mx = boxes[label, :3], boxes[label, 3:]
@@ -270,7 +270,7 @@ class LesionSegTest(JobRunner):
         from utils import otsu_threshold_from_histogram
 
         def otsu(values, lo, hi, scaler):
-            hist = ops.masked_hist_u8(values, lobe_t, lo, hi).cpu().numpy().astype(np.int64)     # 1 KB device->host
+            hist = ops.read_small(ops.masked_hist_u8(values, lobe_t, lo, hi)).numpy().astype(np.int64)   # 1 KB, no copy engine
             if hist.sum() == 0:
                 raise ValueError("empty array encountered! cam_probs.size == 0.")
             if np.count_nonzero(hist) < 2:
@@ -333,13 +333,29 @@ class LesionSegTest(JobRunner):
         costs max(compute, H2D, D2H) instead of their sum.  Yields (lesion, lesion_post, ratio) per scan; the yielded host
         tensors are valid until the next result is requested."""
         cur = torch.cuda.current_stream()
-        if getattr(self, "_pipe", None) is None:                         # streams and pinned result buffers live with the runner
-            self._pipe = (torch.cuda.Stream(), torch.cuda.Stream(), [None, None])
-        up_s, down_s, bufs = self._pipe
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if getattr(self, "_pipe", None) is None:     # streams, two device input slots, two pinned result slots: live with the runner
+            self._pipe = {"up": torch.cuda.Stream(), "down": torch.cuda.Stream(), "out": [None, None],
+                          "in": [None, None], "in_free": [None, None]}
+        P = self._pipe
+        up_s, down_s, bufs = P["up"], P["down"], P["out"]
 
-        def upload(item):
+        def upload(item, slot):
+            """host scan -> persistent device slot (no per-scan allocation); the slot is reused only after the scan that
+            read it last has finished"""
+            scan_h, lobe_h = item[0], item[1]
+            n = scan_h.numel()
+            if P["in"][slot] is None or P["in"][slot][0].numel() < n:
+                P["in"][slot] = (torch.empty(n, dtype=torch.int16, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+                P["in_free"][slot] = None
+                cur.synchronize()                                      # fresh storage: visible to the copy stream
+            s_d = P["in"][slot][0][:n].view(scan_h.shape)
+            l_d = P["in"][slot][1][:n].view(lobe_h.shape)
             with torch.cuda.stream(up_s):
-                s_d, l_d = item[0].cuda(non_blocking=True), item[1].cuda(non_blocking=True)
+                if P["in_free"][slot] is not None:
+                    up_s.wait_event(P["in_free"][slot])
+                s_d.copy_(scan_h, non_blocking=True)
+                l_d.copy_(lobe_h, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(up_s)
             return s_d, l_d, ev
@@ -350,18 +366,19 @@ class LesionSegTest(JobRunner):
 
         it = iter(items)
         item = next(it, None)
-        up = upload(item) if item is not None else None
+        slot = 0
+        up = upload(item, slot) if item is not None else None
         pending, k = None, 0
         while item is not None:
-            (s_d, l_d, ev), spacing = up, item[2]
+            (s_d, l_d, ev), spacing, this_slot = up, item[2], slot
             item = next(it, None)
-            up = upload(item) if item is not None else None              # next scan's H2D runs under this scan's kernels
+            slot ^= 1
+            up = upload(item, slot) if item is not None else None      # next scan's H2D runs under this scan's kernels
             cur.wait_event(ev)
-            s_d.record_stream(cur)
-            l_d.record_stream(cur)
             les, post, ratio = self.scan_to_masks(s_d, l_d, spacing)
             done = torch.cuda.Event()
             done.record(cur)
+            P["in_free"][this_slot] = done
             if bufs[k] is None or bufs[k][0].shape != les.shape:
                 bufs[k] = (torch.empty(les.shape, dtype=les.dtype).pin_memory(), torch.empty(post.shape, dtype=post.dtype).pin_memory(),
                            torch.empty((), dtype=torch.float32).pin_memory())

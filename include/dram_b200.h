@@ -252,6 +252,10 @@ int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const f
 /* utils.find_crops (utils.py:244-254) for all labels at once: out[l*6 + {0,1,2}] = min z,y,x, out[l*6 + {3,4,5}] = max
  * z,y,x (inclusive) for l in 1..nlabels (<= 7); empty labels keep min = INT_MAX, max = -1.  out: int[(nlabels+1)*6]. */
 int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, int* out, void* stream);
+/* Read back a SMALL device result (bounding boxes, a histogram) with a kernel that stores into pinned, device-mapped host
+ * memory instead of a cudaMemcpy: the copy engines stay free for the bulk transfers of neighbouring scans (run_scans).
+ * The caller synchronises the stream (or an event) before reading dst.  nbytes: multiple of 4, <= 1 MiB. */
+int dram_store_to_host(const void* src, void* dst_pinned_host, int nbytes, void* stream);
 /* job_runner.py:961-984: crop [cz,cz+cd)x[cy,cy+ch)x[cx,cx+cw), voxels outside `label` -> pad_value (-2048), Windowing
  * (data_transforms.py:37-54) to [0,1], Resample('fixed_size') (data_transforms.py:170-175, ITK identity-transform
  * resample: index o -> o*in/out, linear for the image, nearest for the mask) to the chunk grid (d,h,w). */

@@ -150,6 +150,17 @@ def test_run_scan_matches_oracle(head):
     assert abs(out["ratio"] - ref["ratio"]) <= 1e-4 * abs(ref["ratio"])
 
 
+def test_read_small_goes_through_pinned_memory():
+    """small results are stored into pinned host memory by a kernel (no cudaMemcpy): same values as .cpu(); misuse is loud"""
+    from dram_native import lib
+    o = ops()
+    for t in (torch.arange(36, dtype=torch.int32, device="cuda").view(6, 6), torch.randint(0, 1 << 20, (256,), dtype=torch.int32, device="cuda"),
+              torch.randn(1000, device="cuda")):
+        assert torch.equal(o.read_small(t), t.cpu())
+    with pytest.raises(lib.DramLibraryError):                       # pageable destination
+        lib.check(lib.load().dram_store_to_host(torch.zeros(4, device="cuda").data_ptr(), torch.zeros(4).data_ptr(), 16, 0), "store_to_host")
+
+
 def test_run_scans_pipeline_equals_one_scan_at_a_time():
     """LesionSegTest.run_scans (uploads / downloads on side streams, overlapped with the kernels) returns, scan by scan,
     exactly what the serial path (scan_to_masks) returns; scans of different sizes and spacings in one stream of work"""
