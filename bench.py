@@ -167,20 +167,40 @@ def cpu_train_chunks_per_s(steps, warmup, batch=1, threads=None):
     return batch * steps / dt, dt / steps, threads
 
 
+TRAIN_WORKLOAD = ("DRAM training step: DC3D fwd + IntRegRefineLoss + bwd + Adam, synthetic 80^3 lobe chunks, "
+                  "per-GPU batch {B} (BASELINE configs[1])")
+INFER_WORKLOAD = ("DC3DATGeneric eval forward (U-Net + RAM head + PCM refinement) + per-lobe pooling on the 5 lobe chunks of "
+                  "one scan, 80^3, batch 5 per GPU")
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port: /root/reference does not exist on the GPU box), all
+    host threads, on this arm's metric / unit / config; every step is a bounded sample of the workload (one chunk)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, s_per_step, threads = cpu_train_chunks_per_s(args.steps, args.warmup, batch=1)
-    sample = f"{args.steps} timed training steps of batch 1 (80^3 chunk) after {args.warmup} warm-up, torch CPU fp32"
+    if args.workload == "train":
+        v, s_per_step, threads = cpu_train_chunks_per_s(args.steps, args.warmup, batch=1)
+        metric, unit, hib, ms = "train_lobe_chunks_per_s", "chunks/s", True, s_per_step * 1e3
+        workload = TRAIN_WORKLOAD.format(B=args.batch)
+        sample = f"{args.steps} timed training steps of batch 1 (one 80^3 chunk per step) after {args.warmup} warm-up, torch CPU fp32"
+    elif args.workload == "infer":
+        v, dt, threads = cpu_infer_chunks_per_s(True, 1)
+        metric, unit, hib, ms, workload = "infer_lobe_chunks_per_s", "chunks/s", True, dt * 1e3, INFER_WORKLOAD
+        sample = "1 eval forward of DC3DATGeneric + pooling, batch 1 (one 80^3 chunk), torch CPU fp32"
+    else:
+        _, dt, threads = cpu_infer_chunks_per_s(True, 1)
+        v, metric, unit, hib, ms = 5.0 * dt, "seconds_per_ct_scan", "s/scan (wall time per scan of the whole job)", False, 5.0 * dt * 1e3
+        workload = "process_pipeline full-CT inference, synthetic scan 400x512x512 @ (1.0,0.7,0.7) mm + 5-lobe mask, one scan per step per GPU"
+        sample = ("model part only: one of the scan's 5 lobe chunks through the CPU oracle x 5; the reference additionally "
+                  "spends CPU time in SimpleITK resampling and numpy masking")
     emit(json.dumps({
-        "impl": "reference", "metric": "train_lobe_chunks_per_s", "value": v, "unit": "chunks/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": hib,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DRAM training step (DC3D fwd + IntRegRefineLoss + bwd + Adam), 80^3 lobe chunks, "
-                               "CPU arm runs batch 1 per step", "chunk": list(CHUNK)},
-        "cpu_baseline": {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload, "chunk": list(CHUNK), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
@@ -333,9 +353,9 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32 elsewhere)",
         "data": "synthetic",
-        "config": {"workload": f"DRAM training step: {'DC3DATGeneric (PCM attention head)' if att else 'DC3D'} fwd + "
-                               "IntRegRefineLoss + bwd + Adam, synthetic 80^3 lobe chunks, "
-                               f"per-GPU batch {B} (BASELINE configs[{2 if att else 1}])",
+        "config": {"workload": TRAIN_WORKLOAD.format(B=B) if not att else
+                               "DRAM training step: DC3DATGeneric (PCM attention head) fwd + IntRegRefineLoss + bwd + Adam, "
+                               f"synthetic 80^3 lobe chunks, per-GPU batch {B} (BASELINE configs[2])",
                    "per_gpu_batch": B, "global_batch": B * world, "chunk": list(CHUNK), "parallelism": f"dp{world}",
                    "precision_mode": os.environ.get("DRAM_PRECISION", "bf16x3"),
                    "backward_precision": os.environ.get("DRAM_BWD_PRECISION", "bf16x3"),
@@ -549,8 +569,7 @@ def run_infer(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item() / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32 elsewhere)", "data": "synthetic",
-            "config": {"workload": "DC3DATGeneric eval forward (U-Net + RAM head + PCM refinement) + per-lobe pooling on the "
-                                   "5 lobe chunks of one scan, 80^3, batch 5 per GPU", "per_gpu_batch": B, "chunk": list(CHUNK),
+            "config": {"workload": INFER_WORKLOAD, "per_gpu_batch": B, "chunk": list(CHUNK),
                        "l2": "activations (~5 GB per batch) stream through L2"},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e.item(), "unit": "chunks/s",

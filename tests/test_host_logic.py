@@ -137,3 +137,29 @@ def test_metaimage_round_trip(tmp_path):
         utils.write_mha(str(tmp_path / "raw.mha"), a, compress=False)
         c, _ = utils.read_mha(str(tmp_path / "raw.mha"))
         assert np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("workload", ["train", "infer"])
+def test_bench_reference_arm_prints_one_json_line(workload):
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): exactly ONE stdout line, the contract's
+    keys, the metric / unit / workload string of the B200 arm, no GPU needed"""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import bench
+    if workload == "train":
+        assert d["metric"] == "train_lobe_chunks_per_s" and d["config"]["workload"] == bench.TRAIN_WORKLOAD.format(B=8)
+    else:
+        assert d["metric"] == "infer_lobe_chunks_per_s" and d["config"]["workload"] == bench.INFER_WORKLOAD
