@@ -337,6 +337,46 @@ k_threshold_masks(const float* __restrict__ heat, const short* __restrict__ scan
   }
 }
 
+// lesion ratio of a scan (job_runner.py:772): sum of the heat map over voxels with a lobe label, and their count.
+// 4 voxels per thread, all-background words skipped; per-block partials in double, summed in block order (deterministic).
+__global__ void __launch_bounds__(256)
+k_labelled_sum(const float* __restrict__ v, const uint8_t* __restrict__ labels, long long n, double* __restrict__ partial) {
+  float s = 0.f;
+  unsigned cnt = 0;
+  const long long words = n >> 2;
+  const unsigned* lw = reinterpret_cast<const unsigned*>(labels);
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < words; g += (long long)gridDim.x * blockDim.x) {
+    const unsigned word = __ldg(lw + g);
+    if (word == 0) continue;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(v) + g);
+    if (word & 0x000000ffu) { s += x.x; ++cnt; }
+    if (word & 0x0000ff00u) { s += x.y; ++cnt; }
+    if (word & 0x00ff0000u) { s += x.z; ++cnt; }
+    if (word & 0xff000000u) { s += x.w; ++cnt; }
+  }
+  for (long long i = (words << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (labels[i]) { s += v[i]; ++cnt; }
+  __shared__ double sh[2][8];
+  double ds = (double)s, dc = (double)cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dc += __shfl_xor_sync(0xffffffffu, dc, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ds; sh[1][threadIdx.x >> 5] = dc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; c += sh[1][w]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = c;
+  }
+}
+__global__ void k_labelled_sum_finish(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  double a = 0.0, c = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 32) { a += partial[2 * b]; c += partial[2 * b + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if (threadIdx.x == 0) { out[0] = a; out[1] = c; }
+}
+
 // small result read-back without the copy engines: the kernel stores straight into PINNED host memory (unified virtual
 // addressing: the host pointer is valid on the device), so a 1 KB histogram does not queue behind a bulk D2H transfer of
 // another stream (LesionSegTest.run_scans downloads the previous scan's masks while this scan computes).
@@ -453,6 +493,20 @@ int dram_store_to_host(const void* src, void* dst_pinned_host, int nbytes, void*
   const int nwords = nbytes / 4;
   k_store_to_host<<<(nwords + 255) / 256 > 64 ? 64 : (nwords + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       (const unsigned*)src, (unsigned*)attr.devicePointer, nwords);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+static const int kLabelledSumBlocks = kNumSMs * 4;
+size_t dram_labelled_sum_workspace_bytes(void) { return sizeof(double) * 2 * (size_t)kLabelledSumBlocks; }
+
+int dram_labelled_sum(const float* values, const uint8_t* labels, long long n, double* out2, void* workspace, void* stream) {
+  DRAM_REQUIRE(values && labels && out2 && workspace && n > 0, "labelled_sum: bad arguments");
+  DRAM_REQUIRE(((uintptr_t)values % 16) == 0 && ((uintptr_t)labels % 4) == 0, "labelled_sum: values must be 16-byte, labels 4-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_labelled_sum<<<kLabelledSumBlocks, 256, 0, st>>>(values, labels, n, (double*)workspace);
+  DRAM_LAUNCH_CHECK();
+  k_labelled_sum_finish<<<1, 32, 0, st>>>((const double*)workspace, kLabelledSumBlocks, out2);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

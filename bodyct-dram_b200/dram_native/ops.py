@@ -600,6 +600,18 @@ def masked_hist_u8(values, labels, lo, hi):
     return hist
 
 
+def labelled_mean(values, labels):
+    """mean of `values` (fp32) over voxels with labels > 0 (0 when there are none) -> 0-dim fp32 device tensor"""
+    _req(labels, "labels", torch.uint8)
+    if values.dtype != torch.float32 or not values.is_contiguous() or values.numel() != labels.numel():
+        raise _lib.DramLibraryError("labelled_mean: values must be a contiguous float32 tensor of the labels' size")
+    out = torch.empty(2, device=values.device, dtype=torch.float64)
+    ws = torch.empty(_L().dram_labelled_sum_workspace_bytes(), device=values.device, dtype=torch.uint8)
+    _lib.check(_L().dram_labelled_sum(values.data_ptr(), labels.data_ptr(), values.numel(), out.data_ptr(), ws.data_ptr(),
+                                      _stream()), "labelled_sum")
+    return (out[0] / out[1].clamp_min(1.0)).float()
+
+
 def threshold_masks(heat, th, scan=None, vessel=None, th2=0.0, window=(-1150.0, 350.0), want_post=True):
     lesion = torch.empty(heat.shape, device=heat.device, dtype=torch.uint8)
     post = torch.empty_like(lesion) if (want_post and scan is not None) else None

@@ -298,8 +298,8 @@ class LesionSegTest(JobRunner):
                 _, dense = self.model(imgs, msks)
                 self.paste(dense, msks, lobe_t, crops, heat)
             lesion, post, th, th2 = self.postprocess(heat, scan_t, lobe_t, vessel_t)
-            inside = (lobe_t > 0)
-            ratio = (heat * inside).sum() / inside.sum().clamp_min(1)       # job_runner.py:772
+            from dram_native import ops
+            ratio = ops.labelled_mean(heat, lobe_t)                         # job_runner.py:772, one pass over heat + labels
         out = {"heatmap": heat, "lesion": lesion, "lesion_post": post, "threshold": th, "threshold_post": th2,
                "ratio": ratio, "crops": crops}
         if not return_device:

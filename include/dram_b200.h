@@ -252,6 +252,10 @@ int dram_pcm_bwd(const float* f, const float* cam, const float* theta_w, const f
 /* utils.find_crops (utils.py:244-254) for all labels at once: out[l*6 + {0,1,2}] = min z,y,x, out[l*6 + {3,4,5}] = max
  * z,y,x (inclusive) for l in 1..nlabels (<= 7); empty labels keep min = INT_MAX, max = -1.  out: int[(nlabels+1)*6]. */
 int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, int* out, void* stream);
+/* job_runner.py:772 lesion ratio: out2[0] = sum of values over voxels with labels > 0, out2[1] = their count (doubles);
+ * deterministic (per-block partials in `workspace`, dram_labelled_sum_workspace_bytes(), summed in block order) */
+size_t dram_labelled_sum_workspace_bytes(void);
+int dram_labelled_sum(const float* values, const uint8_t* labels, long long n, double* out2, void* workspace, void* stream);
 /* Read back a SMALL device result (bounding boxes, a histogram) with a kernel that stores into pinned, device-mapped host
  * memory instead of a cudaMemcpy: the copy engines stay free for the bulk transfers of neighbouring scans (run_scans).
  * The caller synchronises the stream (or an event) before reading dst.  nbytes: multiple of 4, <= 1 MiB. */

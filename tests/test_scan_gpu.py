@@ -150,6 +150,20 @@ def test_run_scan_matches_oracle(head):
     assert abs(out["ratio"] - ref["ratio"]) <= 1e-4 * abs(ref["ratio"])
 
 
+@pytest.mark.parametrize("shape", [(40, 56, 48), (7, 9, 11), (3, 5, 2)])
+def test_labelled_mean(shape):
+    """lesion ratio (job_runner.py:772): mean of the heat map over the lobe voxels, deterministic"""
+    torch.manual_seed(11)
+    heat = torch.rand(shape, device="cuda")
+    labels = (torch.rand(shape, device="cuda") > 0.6).to(torch.uint8) * torch.randint(1, 6, shape, device="cuda", dtype=torch.uint8)
+    inside = labels > 0
+    ref = (heat.double() * inside).sum() / inside.sum().clamp_min(1)
+    got = ops().labelled_mean(heat, labels)
+    assert got.dtype == torch.float32 and abs(got.item() - ref.item()) <= 1e-6 * max(ref.item(), 1e-6)
+    assert ops().labelled_mean(heat, labels).item() == got.item()
+    assert ops().labelled_mean(heat, torch.zeros_like(labels)).item() == 0.0
+
+
 def test_read_small_goes_through_pinned_memory():
     """small results are stored into pinned host memory by a kernel (no cudaMemcpy): same values as .cpu(); misuse is loud"""
     from dram_native import lib
