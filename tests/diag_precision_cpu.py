@@ -89,5 +89,98 @@ def main():
             print(f"{bn_state:28s} {mode:8s} {e_ram:13.2e} {e_pool:13.2e} {dice:24.5f}", flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "grad"):
     main()
+
+
+# ------------------------------------------------------------------------------------------------ gradients
+# Second part (python tests/diag_precision_cpu.py grad [size] [batch]): per-parameter gradient error of the training step
+# for the backward modes of the library and for TF32 operands everywhere - what the reference itself computes on a GPU
+# with PyTorch's default torch.backends.cudnn.allow_tf32 = True (convolutions in TF32, 10-bit mantissas).
+def _tf32(t):
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class RoundedConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, padding, fwd, bwd):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (padding, bwd, b is not None)
+        if fwd == "fp32":
+            return _conv3d(x, w, b, padding=padding)
+        if fwd == "tf32":
+            return _conv3d(_tf32(x), _tf32(w), b, padding=padding)
+        xh, xl = _split(x, torch.bfloat16)
+        wh, wl = _split(w, torch.bfloat16)
+        return _conv3d(xh, wh, b, padding=padding) + _conv3d(xh, wl, None, padding=padding) + _conv3d(xl, wh, None, padding=padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        padding, bwd, has_b = ctx.cfg
+        gi = lambda g, ww: torch.nn.grad.conv3d_input(x.shape, ww, g, padding=padding)
+        gw = lambda xx, g: torch.nn.grad.conv3d_weight(xx, w.shape, g, padding=padding)
+        if bwd == "fp32":
+            dx, dw = gi(dy, w), gw(x, dy)
+        elif bwd == "tf32":
+            dx, dw = gi(_tf32(dy), _tf32(w)), gw(_tf32(x), _tf32(dy))
+        else:
+            xh, xl = _split(x, torch.bfloat16)
+            wh, wl = _split(w, torch.bfloat16)
+            gh, gl = _split(dy, torch.bfloat16)
+            if bwd == "bf16x3":
+                dx = gi(gh, wh) + gi(gh, wl) + gi(gl, wh)
+                dw = gw(xh, gh) + gw(xh, gl) + gw(xl, gh)
+            else:                                            # bf16x2: the gradient operand as one bf16 plane
+                dx = gi(gh, wh) + gi(gh, wl)
+                dw = gw(xh, gh) + gw(xl, gh)
+        db = dy.sum(dim=(0, 2, 3, 4)) if has_b else None
+        return (dx if ctx.needs_input_grad[0] else None), dw, db, None, None, None
+
+
+def grad_main():
+    size = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    cfg = dict(n_layers=3, in_ch_list=[1, 64, 128, 256, 768, 384, 192], base_ch_list=[32, 64, 128, 256, 256, 128, 64],
+               end_ch_list=[64, 128, 256, 512, 256, 128, 64], kernel_sizes=[(3, 3)] * 7, stacking=3,
+               padding_list=[(1, 1)] * 7, checkpoint_layers=[0, 1, 0, 1, 0, 1, 0], dropout=0.0, upsample_ksize=(3, 3, 3),
+               upsample_sf=(2, 2, 2), out_ch=1)
+    torch.set_num_threads(os.cpu_count())
+    modes = [("fp32", "fp32")]
+
+    def conv(x, w, b=None, *a, padding=0, **k):
+        if w.shape[1] == 1 or w.shape[2] == 1:
+            return _conv3d(x, w, b, *a, padding=padding, **k)
+        return RoundedConv.apply(x, w, b, padding, *modes[0])
+
+    O.F.conv3d = conv
+    torch.manual_seed(0)
+    m = models.DC3D(**cfg)
+    m.init(models.HeNorm(mode="fan_in"))
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    images, lobes, lesions, ctsses = O.synthetic_batch(B, (size,) * 3, seed=1)
+    freq = {k: 1.0 / 6 for k in range(6)}
+    print(f"DC3D training step (IntRegRefineLoss), {B} x {size}^3; per-parameter gradient error ||g - g_fp32|| / ||g_fp32||")
+    ref = None
+    for fwd, bwd, label in (("fp32", "fp32", "fp32"), ("bf16x3", "bf16x3", "library default: bf16x3 forward + bf16x3 backward"),
+                            ("bf16x3", "bf16x2", "DRAM_BWD_PRECISION=bf16x2: bf16x3 forward + one-plane gradient"),
+                            ("tf32", "tf32", "TF32 operands everywhere (the reference on a GPU, cudnn.allow_tf32)")):
+        modes[0] = (fwd, bwd)
+        sd = {k: v.clone() for k, v in sd0.items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+        d, r = O.dc3d_forward(sd, images, cfg, True)
+        rl, sl = O.int_reg_refine_loss(d, r, lobes, lesions, ctsses, freq)
+        (2.0 * rl + sl).backward()
+        g = {k: v.grad.detach().clone() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+        if ref is None:
+            ref = g
+            continue
+        errs = sorted(((g[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-30)).item() for k in ref)
+        print(f"{label:72s} median {errs[len(errs) // 2]:.2e}  90% {errs[int(len(errs) * 0.9)]:.2e}  worst {errs[-1]:.2e}", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "grad":
+    grad_main()
