@@ -184,17 +184,10 @@ def _grad_rows(g, name="grad"):
 
 
 def _bn_fold_cached(gamma, beta, running_mean, running_var, eps):
-    """eval-mode scale / shift of a BatchNorm, folded once per parameter state (inference calls it 16 times per forward)"""
-    key = (WEIGHTS.generation, eps) + tuple(v for t in (gamma, beta, running_mean, running_var) for v in (t.data_ptr(), t._version))
-    hit = getattr(running_mean, "_dram_fold", None)
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    val = ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
-    try:
-        running_mean._dram_fold = (key, val)
-    except AttributeError:
-        pass
-    return val
+    """eval-mode scale / shift of a BatchNorm.  Deliberately NOT cached: the running statistics are updated in place by
+    kernels (also from a replayed CUDA graph, where no Python runs), so no host-side key can tell a stale fold from a fresh
+    one; the fold is one tiny launch."""
+    return ops.bn_fold_eval(gamma, beta, running_mean, running_var, eps)
 
 
 # Grad mode is always off INSIDE autograd.Function.forward and ctx.needs_input_grad reflects requires_grad of the parameters
