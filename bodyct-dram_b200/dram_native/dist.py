@@ -11,7 +11,7 @@ the single-process reference run on the GLOBAL batch, hence three kinds of excha
 import torch
 import torch.distributed as td
 
-_STATE = {"group": None, "sync_bn": True}
+_STATE = {"group": None, "sync_bn": True, "reducer": None}
 
 
 def configure(group=None, sync_bn=True):
@@ -28,6 +28,30 @@ def rank():
 
 def active():
     return world_size() > 1
+
+
+def shard(items):
+    """This rank's share of a (sorted) work list: items[rank::world] — scans / lobe batches shard with no collective."""
+    items = list(items)
+    return items[rank()::world_size()] if active() else items
+
+
+def all_gather_object(obj):
+    """-> [obj of rank 0, obj of rank 1, ...] (small host objects: validation results)"""
+    if not active():
+        return [obj]
+    out = [None] * world_size()
+    td.all_gather_object(out, obj, group=_STATE["group"])
+    return out
+
+
+def check_uniform_batch(shape_key):
+    """Every rank must step the same batch shape: `allreduce_stats` multiplies the local voxel count by the world size
+    instead of exchanging it, and a shape change re-captures the step's CUDA graph (NCCL calls inside) on every rank.
+    One small host-side gather per NEW shape; raises on a mismatch (use drop_last=True loaders under data parallelism)."""
+    keys = all_gather_object(tuple(shape_key))
+    if any(k != keys[0] for k in keys):
+        raise RuntimeError(f"data parallel training needs the same batch shape on every rank, got {keys}")
 
 
 def all_reduce_(t):
@@ -55,85 +79,131 @@ def allreduce_sums(sums):
 
 
 class GradReducer:
-    """Bucketed asynchronous gradient all-reduce (SUM) driven by post-accumulate-grad hooks.
+    """Gradient all-reduce (SUM) over ONE flat fp32 buffer that the parameters' `.grad` tensors are views of.
 
-    Parameters are packed, in REVERSE registration order (the order backward produces them), into flat buckets of
-    ~bucket_mb; when the last gradient of a bucket has been accumulated the bucket is copied into its flat buffer and
-    an async all_reduce is issued; `finish()` waits and scatters the sums back into `.grad`.
-    `scale`: the reference's loss terms are batch SUMS / global means formed before backward, so the correct reduction
-    is a plain SUM (scale=1); pass 1/world_size for mean semantics."""
+    Layout: parameters in REVERSE registration order (the order backward produces them), split into contiguous buckets of
+    ~bucket_mb.  The tensor-core wgrad kernels write `dw` straight into the buffer (`grad_view`, handed to autograd, which
+    adopts the tensor as `.grad` without a copy); any gradient that arrives in other storage is copied in once by the
+    post-accumulate-grad hook and `.grad` is re-pointed at the view.  Nothing is packed or unpacked around the all-reduce
+    (round 1 moved every gradient through two `copy_` kernels: ~170 launches per step).
+    overlap=True: a bucket's async all_reduce is issued as soon as its last gradient exists (NCCL runs under the rest of the
+    backward pass); overlap=False (default, DRAM_GRAD_OVERLAP=0): one all_reduce over the whole buffer in `finish()` —
+    the persistent one-CTA-per-SM convolution kernels leave NCCL no SM to run on concurrently, so the overlap mostly costs
+    them a second wave.
+    `scale`: the reference's loss terms are batch SUMS / global means formed before backward, so the correct reduction is
+    a plain SUM (scale=1); pass 1/world_size for mean semantics."""
 
-    def __init__(self, params, bucket_mb=16.0, scale=1.0):
+    def __init__(self, params, bucket_mb=16.0, scale=1.0, overlap=None):
+        import os
         self.params = [p for p in params if p.requires_grad]
         self.scale = scale
-        self.buckets = []
-        cur, cur_bytes = [], 0
+        self.overlap = (os.environ.get("DRAM_GRAD_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
+        self.slot, self.buckets, self.owner = {}, [], {}
+        off, start, cur = 0, 0, []
         for p in reversed(self.params):
+            self.slot[id(p)] = (off, p.numel())
+            self.owner[id(p)] = len(self.buckets)
             cur.append(p)
-            cur_bytes += p.numel() * 4
-            if cur_bytes >= bucket_mb * (1 << 20):
-                self.buckets.append(cur)
-                cur, cur_bytes = [], 0
+            off += (p.numel() + 3) // 4 * 4                       # 16-byte aligned views (vector stores in the kernels)
+            if (off - start) * 4 >= bucket_mb * (1 << 20):
+                self.buckets.append((start, off, cur))
+                start, cur = off, []
         if cur:
-            self.buckets.append(cur)
-        self.owner = {}
-        for bi, b in enumerate(self.buckets):
-            for p in b:
-                self.owner[p] = bi
-        self.flat = [None] * len(self.buckets)
-        self.pending = [0] * len(self.buckets)
+            self.buckets.append((start, off, cur))
+        self.total = off
+        self.flat = None
+        self.by_ptr = {}
         self.work = []
         self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        _STATE["reducer"] = self
         self.reset()
 
+    def _ensure(self):
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.zeros(self.total, device=dev, dtype=torch.float32)
+            self.by_ptr = {p.data_ptr(): p for p in self.params}
+        return self.flat
+
+    def view(self, p):
+        off, n = self.slot[id(p)]
+        return self._ensure()[off:off + n].view_as(p)
+
+    def grad_view(self, w):
+        """Storage for a freshly computed gradient of parameter `w` (looked up by address: autograd hands the Functions a
+        different Python object), or None when `w` is not reduced here or already holds a gradient (accumulation)."""
+        if not active() or not self.params:
+            return None
+        self._ensure()
+        p = self.by_ptr.get(w.data_ptr())
+        if p is None or p.grad is not None or tuple(p.shape) != tuple(w.shape):
+            return None
+        return self.view(p)
+
     def reset(self):
-        self.pending = [len(b) for b in self.buckets]
+        self.pending = [len(b[2]) for b in self.buckets]
+        self.seen = set()
         self.work = []
+
+    def _adopt(self, p):
+        v = self.view(p)
+        if p.grad is None:
+            v.zero_()
+        elif p.grad.data_ptr() != v.data_ptr():
+            v.copy_(p.grad)
+        else:
+            return
+        p.grad = v
 
     def _hook(self, p):
         if not active():
             return
-        bi = self.owner[p]
+        self._adopt(p)
+        self.seen.add(id(p))
+        bi = self.owner[id(p)]
         self.pending[bi] -= 1
-        if self.pending[bi] == 0:
+        if self.pending[bi] == 0 and self.overlap:
             self._launch(bi)
 
     def _launch(self, bi):
         from . import functional as _F
-        _F.SIDE.join()                    # weight gradients are produced on the side stream (functional._SideStream)
-        b = self.buckets[bi]
-        n = sum(p.numel() for p in b)
-        if self.flat[bi] is None or self.flat[bi].numel() != n or self.flat[bi].device != b[0].device:
-            self.flat[bi] = torch.empty(n, device=b[0].device, dtype=torch.float32)
-        flat, off = self.flat[bi], 0
-        for p in b:
-            k = p.numel()
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
-            flat[off:off + k].copy_(g.reshape(-1))
-            off += k
-        self.work.append((bi, td.all_reduce(flat, op=td.ReduceOp.SUM, group=_STATE["group"], async_op=True)))
+        _F.SIDE.join()                    # weight gradients may be produced on the side stream (functional._SideStream)
+        start, end, _ = self.buckets[bi]
+        self.pending[bi] = -1
+        self.work.append(td.all_reduce(self._ensure()[start:end], op=td.ReduceOp.SUM, group=_STATE["group"], async_op=True))
 
     def finish(self):
-        """Wait for every bucket and write the reduced gradients back.  Call after loss.backward()."""
+        """All-reduce what has not been launched yet, wait, leave the sums in `.grad`.  Call after loss.backward()."""
         if active():
-            for bi in range(len(self.buckets)):          # parameters that never received a gradient this step
-                if self.pending[bi] > 0:
-                    self._launch(bi)
-            for bi, w in self.work:
+            for p in self.params:                          # parameters that never received a gradient this step: zeros
+                if id(p) not in self.seen:
+                    self._adopt(p)
+            if self.overlap:
+                for bi in range(len(self.buckets)):
+                    if self.pending[bi] >= 0:
+                        self._launch(bi)
+            else:
+                from . import functional as _F
+                _F.SIDE.join()
+                self.work.append(td.all_reduce(self._ensure(), op=td.ReduceOp.SUM, group=_STATE["group"], async_op=True))
+            for w in self.work:
                 w.wait()
-                flat, off = self.flat[bi], 0
-                for p in self.buckets[bi]:
-                    k = p.numel()
-                    g = flat[off:off + k].view_as(p)
-                    if self.scale != 1.0:
-                        g = g * self.scale
-                    if p.grad is None:
-                        p.grad = g.clone()
-                    else:
-                        p.grad.copy_(g)
-                    off += k
+            if self.scale != 1.0:
+                self.flat.mul_(self.scale)
         self.reset()
 
     def remove(self):
         for h in self.hooks:
             h.remove()
+        if _STATE.get("reducer") is self:
+            _STATE["reducer"] = None
+
+
+def grad_out(w, shape=None):
+    """Tensor a backward kernel should write the gradient of parameter `w` into: its slice of the data-parallel flat
+    gradient buffer when there is one (no copy before the all-reduce), else fresh memory."""
+    r = _STATE.get("reducer")
+    v = r.grad_view(w) if r is not None else None
+    if v is not None:
+        return v
+    return torch.empty(tuple(w.shape) if shape is None else shape, device=w.device, dtype=torch.float32)

@@ -135,12 +135,16 @@ def conv_wgrad(saved_in, dy, w, dys=None):
     Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
     if isinstance(saved_in, ops.SplitPlanes):
         dys = dys if dys is not None else ops.split_bf16(dy, three=ops.grad_planes_three())
-        if SIDE.enabled() and not ops._lib.PROFILE.enabled:      # per-kernel event timing needs a single stream
+        # an existing .grad means AccumulateGrad will `+=` this result on the main stream before the end-of-backward join:
+        # stay on one stream then (gradient accumulation); likewise while per-kernel events are being recorded
+        if SIDE.enabled() and not ops._lib.PROFILE.enabled and w.grad is None:
             side = SIDE.fork()
             if side is not None:
                 SIDE.keep.append((dys, saved_in))
-                return ops.conv_umma_wgrad(dys, saved_in, Cin, Cout, k, stream=side.cuda_stream, keep=SIDE.keep)
-        return ops.conv_umma_wgrad(dys, saved_in, Cin, Cout, k)
+                return ops.conv_umma_wgrad(dys, saved_in, Cin, Cout, k, stream=side.cuda_stream, keep=SIDE.keep,
+                                           out=ddist.grad_out(w))
+        # data parallel: dw is written straight into the flat all-reduce buffer (dist.GradReducer.grad_view)
+        return ops.conv_umma_wgrad(dys, saved_in, Cin, Cout, k, out=ddist.grad_out(w) if ddist.active() else None)
     return ops.conv_simt_wgrad(saved_in, dy, k)
 
 

@@ -180,7 +180,7 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
     return y
 
 
-def conv_umma_wgrad(dys, xs, Cin, Cout, ksize, stream=None, keep=None):
+def conv_umma_wgrad(dys, xs, Cin, Cout, ksize, stream=None, keep=None, out=None):
     """dys / xs: SplitPlanes of dy and of the layer input -> dw [Cout, Cin, k, k, k] fp32.
     `stream`: raw cudaStream_t to enqueue on (default: the current stream); memory is always allocated on the current
     stream.  `keep`: list that receives the workspace so the caller can keep it alive until that stream is joined."""
@@ -189,7 +189,7 @@ def conv_umma_wgrad(dys, xs, Cin, Cout, ksize, stream=None, keep=None):
     if nbytes == 0:
         raise _lib.DramLibraryError("conv3d_umma_wgrad: unsupported shape")
     ws = torch.empty(nbytes // 4, device=xs.hi.device, dtype=torch.float32)
-    dw = torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
+    dw = out if out is not None else torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
     _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")
     _lib.check(_L().dram_conv3d_umma_wgrad(dys.hi.data_ptr(), _p(dys.lo), xs.hi.data_ptr(), _p(xs.lo), dw.data_ptr(),
                                            ws.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize,

@@ -47,7 +47,9 @@ def pooling_dense_features(dense_outs, lungs, pooling_method='avg'):
     """models.py:37-49 — per-lobe masked average of the RAM: sum(dense * lobe) / sum(lobe) per (sample, channel)."""
     B, C = dense_outs.shape[0], dense_outs.shape[1]
     if pooling_method == 'global_max':
-        raise NotImplementedError("global_max pooling is not on the B200 path")
+        # models.py:42-43 (F.adaptive_max_pool3d(dense_outs, 1)); no shipped settings file selects it: a plain reduction
+        # over the channels-last volume, gradient to the arg-max voxel like the reference's
+        return torch.amax(dense_outs.reshape(B, C, -1), dim=2)
     if pooling_method == 'global_avg':
         lungs = torch.ones_like(dense_outs[:, :1])
     x = ops.to_ncdhw(dense_outs).reshape(B * C, -1)

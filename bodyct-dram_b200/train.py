@@ -1,6 +1,13 @@
-"""Training entry point — same CLI as the reference's `dram/train.py` (2 positionals + 3 options, train.py:27-43).
-Data loading from the institute's .mha archive is out of scope: batches come from `--synthetic N` steps of the
-synthetic generator, or from a caller-supplied loader via `run_training_job(..., loader=...)`."""
+"""Training entry point — same CLI as the reference's `dram/train.py` (2 positionals + 3 options, train.py:27-43) and the
+same flow: Settings(--smp) -> overrides -> `get_callable_by_name(JOB_RUNNER_CLS)(settings_module=settings).run()`.
+
+Data loading from the institute's .mha archive is out of scope: batches come from `--synthetic N` synthetic
+steps per epoch, or from a caller-supplied `loader_factory` via `run_training_job(..., loader_factory=...)`.
+
+Data parallel (new functionality): launched under `torchrun --nproc-per-node N train.py ...` the process
+group is initialised from RANK / LOCAL_RANK / WORLD_SIZE (NCCL), every rank owns one GPU and draws its own shard of the
+data; gradients, BatchNorm statistics and the loss normalisers are all-reduced inside the step (dram_native/dist.py), so
+the replicas hold identical weights after every step."""
 import argparse
 import os
 import sys
@@ -27,30 +34,52 @@ def synthetic_loader(steps, batch_size, size=(80, 80, 80), seed=0):
                "meta": {"cle": [str(i % 6) for i in range(batch_size)]}}
 
 
-def run_training_job(pretrain, lr, batch_size, smp, ckp_path, loader=None, synthetic_steps=0):
+def init_distributed():
+    """One process per GPU under torchrun: NCCL process group from the environment; no-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or not torch.distributed.is_available() or torch.distributed.is_initialized():
+        return world
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world
+
+
+def run_training_job(pretrain, lr, batch_size, smp, ckp_path, loader=None, synthetic_steps=0, loader_factory=None,
+                     val_dataset=None, epochs=None):
+    """train.py:11-24.  Returns the runner after `run()` (or after one pass over an explicit `loader`)."""
+    init_distributed()
     settings = Settings(smp)
     settings.OPTIMIZER['lr'] = lr
     settings.TRAIN_BATCH_SIZE = batch_size
     settings.RELOAD_CHECKPOINT = bool(pretrain)
     settings.RELOAD_CHECKPOINT_PATH = ckp_path
-    runner = get_callable_by_name(settings.JOB_RUNNER_CLS)(settings_module=settings)
-    if settings.RELOAD_CHECKPOINT:
-        runner.reload_model_from_cache(ckp_path)
-    if loader is None and synthetic_steps > 0:
-        loader = synthetic_loader(synthetic_steps, batch_size, tuple(settings.RESAMPLE_SIZE))
+    settings.SYNTHETIC_STEPS = synthetic_steps
+    if epochs is not None:
+        settings.NUM_EPOCHS = epochs
+    runner_cls = get_callable_by_name(settings.JOB_RUNNER_CLS)
+    runner = runner_cls(settings_module=settings, loader_factory=loader_factory, val_dataset=val_dataset)
     if loader is not None:
-        return runner.train(loader)
+        runner.train(loader)
+    else:
+        runner.run()
     return runner
 
 
 if __name__ == "__main__":
     parser = argparse.ArgumentParser()
-    parser.add_argument('pretrain', type=int, nargs='?', default=0, help="reload a checkpoint before training")
-    parser.add_argument('lr', type=float, nargs='?', default=1e-3, help="learning rate")
-    parser.add_argument('--batch_size', type=int, default=1)
-    parser.add_argument('--smp', type=str, default=os.path.join(HERE, "exp_settings", "st_dram_ref.py"))
-    parser.add_argument('--ckp_path', type=str, default=None)
-    parser.add_argument('--synthetic', type=int, default=0, help="run N steps on synthetic lobe chunks")
+    parser.add_argument('pretrain', type=int, nargs='?', default=0, help="if use pretrained model.")
+    parser.add_argument('lr', type=float, nargs='?', default=1e-3, help="set up learning rate.")
+    parser.add_argument('--batch_size', type=int, nargs='?', default=1)
+    parser.add_argument('--smp', type=str, nargs='?', default=os.path.join(HERE, "exp_settings", "st_dram_ref.py"))
+    parser.add_argument('--ckp_path', type=str, default=None, help='set checkpoint path.')
+    parser.add_argument('--synthetic', type=int, default=0, help="synthetic lobe-chunk batches per epoch (no dataset on this path)")
+    parser.add_argument('--epochs', type=int, default=None, help="override settings.NUM_EPOCHS")
     args = parser.parse_args()
     torch.backends.cudnn.benchmark = True
-    print(run_training_job(args.pretrain, args.lr, args.batch_size, args.smp, args.ckp_path, synthetic_steps=args.synthetic))
+    torch.backends.cudnn.deterministic = True
+    r = run_training_job(args.pretrain, args.lr, args.batch_size, args.smp, args.ckp_path, synthetic_steps=args.synthetic,
+                         epochs=args.epochs)
+    print({"epoch": r.epoch_n, "iteration": r.current_iteration, **r.metrics})
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

@@ -52,11 +52,51 @@ def _worker(rank, world, port, q):
     gref, = torch.autograd.grad(ref, p_ref)
     out["loss_ok"] = bool(abs(tot.item() - ref.item()) < 1e-5 * abs(ref.item()))
     out["loss_grad_ok"] = bool((gmine - gref[sl]).abs().max() < 1e-6 * gref.abs().max())
+    # --- work sharding of the inference entry points: every item exactly once, no collective on the data path
+    items = [f"case{i}" for i in range(7)]
+    mine = ddist.shard(items)
+    every = ddist.all_gather_object(mine)
+    out["shard_ok"] = sorted(u for part in every for u in part) == items and mine == items[rank::world]
+    try:
+        ddist.check_uniform_batch(((2, 16, 16, 16),) * 3)
+        out["uniform_ok"] = True
+    except RuntimeError:
+        out["uniform_ok"] = False
+    try:
+        ddist.check_uniform_batch(((2 + rank, 16, 16, 16),) * 3)
+        out["ragged_raises"] = False
+    except RuntimeError:
+        out["ragged_raises"] = True
+    # --- LesionSegTest.run_mha: the sorted scan list is sharded rank::world, already archived scans are skipped
+    import job_runner
+    from utils import Settings
+    tmp = os.environ["DRAM_TEST_TMP"]
+    s = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref_att.py"))
+    runner = job_runner.LesionSegTest(os.path.join(tmp, "scans"), os.path.join(tmp, "lobes"), os.path.join(tmp, "out"), s, None,
+                                      build_model=False)
+
+    def fake_process(path):                      # stands in for the GPU work: archive a marker under the scan's uid
+        uid = os.path.splitext(os.path.basename(path))[0]
+        os.makedirs(os.path.join(tmp, "out", "test"), exist_ok=True)
+        with open(os.path.join(tmp, "out", "test", uid + ".mha"), "x") as f:          # "x": fails if written twice
+            f.write(str(rank))
+        return {"uid": uid, "seconds": 0.0, "ratio": 0.0}
+
+    runner._process_mha = fake_process
+    recs = runner.run_mha()
+    td.barrier()
+    done = sorted(os.listdir(os.path.join(tmp, "out", "test")))
+    out["run_mha_ok"] = done == [f"s{i}.mha" for i in range(5)] and [r["uid"] for r in recs] == [f"s{i}" for i in range(5)][rank::world]
+    out["rerun_skips"] = runner.run_mha() == []
     q.put((rank, out))
     td.destroy_process_group()
 
 
-def test_data_parallel_host_logic_world_size_2():
+def test_data_parallel_host_logic_world_size_2(tmp_path):
+    os.makedirs(tmp_path / "scans")
+    for i in range(5):
+        (tmp_path / "scans" / f"s{i}.mha").write_text("")
+    os.environ["DRAM_TEST_TMP"] = str(tmp_path)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)

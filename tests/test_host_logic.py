@@ -163,3 +163,14 @@ def test_bench_reference_arm_prints_one_json_line(workload):
         assert d["metric"] == "train_lobe_chunks_per_s" and d["config"]["workload"] == bench.TRAIN_WORKLOAD.format(B=8)
     else:
         assert d["metric"] == "infer_lobe_chunks_per_s" and d["config"]["workload"] == bench.INFER_WORKLOAD
+
+
+def test_process_pipeline_refuses_to_run_without_a_checkpoint(tmp_path):
+    """a missing best.pth must not silently run the pipeline on random weights; default folders are the reference's"""
+    import inspect
+    import process_pipeline
+    sig = inspect.signature(process_pipeline.main)
+    assert sig.parameters["input_lobe_path"].default == "/input/images/pulmonary-lobes/"      # process_pipeline.py:14-16
+    assert sig.parameters["output_path"].default == "/output/images/"
+    with pytest.raises(RuntimeError, match="does not exist"):
+        process_pipeline.main(str(tmp_path), str(tmp_path), str(tmp_path / "out"), algorithm_path=str(tmp_path))
