@@ -249,10 +249,10 @@ def reg_loss(dense, lobes, lesions, ctsses, freq_map, band_width=1e-2):
     rub = (lesions * lobes).reshape(B, -1).sum(-1) / lobes.reshape(B, -1).sum(-1)
     inside = (lobes > 0).to(dense.dtype)
     pred = (probs * inside).reshape(B, -1).sum(-1) / inside.reshape(B, -1).sum(-1)
-    tg = interval_targets(ctsses, rub, band_width)
+    tg = interval_targets(ctsses, rub, band_width).to(dense.device)
     K = (0.5 * (tg[:, 1] - tg[:, 0])) ** 2
     unhinge = (pred - (tg[:, 1] + tg[:, 0]) / 2.0) ** 2 - K
-    w = torch.tensor([freq_map[int(float(c))] for c in ctsses], dtype=torch.float32).clamp(0.2, 0.8)
+    w = torch.tensor([freq_map[int(float(c))] for c in ctsses], dtype=torch.float32).clamp(0.2, 0.8).to(dense.device)
     return (torch.clamp_min(unhinge, 0.0) / w).sum()
 
 
@@ -260,7 +260,7 @@ def pseudo_labels(dense, lobes, lesions, ctsses):
     """IntRegRefineLoss.compute_seg_loss metrics.py:333-354 + threshold_postprocessing :325-329."""
     pred = (torch.sigmoid(dense.detach()) > 0.5) & (lobes != 0)
     t = (pred & (lesions > 0)).to(dense.dtype)
-    keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in ctsses], dtype=dense.dtype)
+    keep = torch.tensor([0.0 if float(c) < 1e-7 else 1.0 for c in ctsses], dtype=dense.dtype, device=dense.device)
     return t * keep.view(-1, 1, 1, 1, 1)
 
 

@@ -4,8 +4,20 @@ per kernel launches, summed time, share of the summed kernel time and mean DRAM 
 usage: summarize_launches.py launches.csv out.md out.json"""
 import collections
 import csv
+import hashlib
 import json
+import os
 import sys
+
+
+def source_sha():
+    """fingerprint of the kernel sources the capture belongs to (bench.py compares it with the current sources and flags a
+    stale `roofline.traffic`)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for f in ("conv_umma.cu", "planes.cu", "elementwise.cu"):
+        h.update(open(os.path.join(root, "bodyct-dram_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main(src, out_md, out_json):
