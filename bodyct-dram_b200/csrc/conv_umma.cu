@@ -1034,11 +1034,32 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
 constexpr int kW3XBox = 10 * 8 * 128;           // one halo box: 10 w-columns x 8 h-rows x 128 B
 constexpr int kW3YBox = 8 * 8 * 128;            // one dY tile
 constexpr int kW3Stage = 4 * kW3XBox + 2 * kW3YBox;
+constexpr int kW3Window = 8;                    // chunks a single-source item may run ahead of the item it follows
 
 struct Wg3Params {
   float* ws;
-  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, chunks_per_slab, stages, dfast, y_lo;
+  int* prog;      // [n_items] chunks issued so far per work item (pacing of the single-source items, see below)
+  int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, spg, stages, dfast, y_lo;
 };
+
+// Chunk schedule of the kw-reuse wgrad.  The voxel chunks are split over `n_slabs` slabs (split-K); a work item is
+// (slab, source pair) and item i runs on CTA i % gridDim.x.  Round 1 gave every slab a CONTIGUOUS range of chunks: ~10-30
+// slabs were in flight at once, each streaming its own region, and the neighbouring (w,h) columns of a slab (halo re-use)
+// were a whole column of chunks x all live slabs apart — far beyond the L2.  ncu: 2.4-2.6x the operand bytes from DRAM.
+// Now the slabs of a GROUP (`spg` consecutive slabs ~ one wave of CTAs) INTERLEAVE over the group's contiguous range:
+// slab r of the group takes chunks r, r + spg, r + 2 spg, ...  All CTAs of a wave sweep one common front through the
+// volume, so the dY tile shared by the pairs of a slab, the kd-1/kd/kd+1 planes shared by its sources and the w/h halos
+// shared with the neighbouring slabs are all a few chunk steps apart.
+struct Wg3Range { int first, step, count; };
+__device__ __forceinline__ Wg3Range wg3_range(const Wg3Params& p, int slab) {
+  const int g = slab / p.spg, s0 = g * p.spg, s1 = min(s0 + p.spg, p.n_slabs);
+  const int lo = (int)((long long)p.n_chunks * s0 / p.n_slabs), hi = (int)((long long)p.n_chunks * s1 / p.n_slabs);
+  Wg3Range r;
+  r.step = s1 - s0;
+  r.first = lo + (slab - s0);
+  r.count = r.first < hi ? (hi - r.first + r.step - 1) / r.step : 0;
+  return r;
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
@@ -1079,10 +1100,29 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         const int s0 = 2 * pair, s1 = min(2 * pair + 1, p.n_src - 1);
         const int cb0 = s0 % p.CB, kh0 = (s0 / p.CB) % 3 - 1, kd0 = s0 / (3 * p.CB) - 1;
         const int cb1 = s1 % p.CB, kh1 = (s1 / p.CB) % 3 - 1, kd1 = s1 / (3 * p.CB) - 1;
-        const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
-        for (int ch = c_begin; ch < c_end; ++ch) {
+        const Wg3Range rg = wg3_range(p, slab);
+        // Pacing.  With an odd number of sources the last pair of a slab has ONE source: 2 MMA tiles per chunk instead of 3,
+        // so its CTA runs 1.5x faster than its slab mates and reads dY and its X planes from DRAM long before they do — the
+        // lines are evicted again by the time the others arrive (measured: +1 x dY + 1.25 x X[source] per launch).  It now
+        // follows the pair before it: that item publishes its chunk count, this one stays at most kW3Window chunks ahead.
+        // The followed item has a lower index (same or earlier wave) and never waits itself; the wait is bounded, so a CTA
+        // that is not resident yet can only cost locality, never progress.
+        const bool paced = (p.n_src & 1) && pair == p.n_pairs - 1 && p.n_pairs > 1;
+        const bool paces = (p.n_src & 1) && pair == p.n_pairs - 2;
+        volatile int* prog = p.prog;
+        bool pacing = paced;
+        for (int k = 0; k < rg.count; ++k) {
+          const int ch = rg.first + k * rg.step;
+          if (paces && (k & 3) == 0 && lane == 0) prog[item] = k;
+          if (pacing && (k & 3) == 0) {
+            uint32_t spins = 0;
+            while (prog[item - 1] + kW3Window < k) {
+              __nanosleep(128);
+              if (++spins > (1u << 14)) { pacing = false; break; }
+            }
+          }
           // chunk order: depth fastest.  The kd = 0,1,2 sources of a chunk read planes d-1, d, d+1; walking d first puts
-          // their re-use one or two chunks apart (L2 hits) instead of a whole plane of chunks apart (3x the DRAM reads).
+          // their re-use one or two chunks of the common front apart (L2 hits) instead of a whole plane of chunks apart.
           int t = ch, w0, h0, d0, n0;
           if (p.dfast) {
             d0 = t % p.D; t /= p.D;
@@ -1111,6 +1151,7 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
+        if (paces && lane == 0) prog[item] = 0x3fffffff;        // done: the follower runs free
       }
     }
   } else if (warp == 1) {
@@ -1122,7 +1163,7 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
         const int pair = item % p.n_pairs, slab = item / p.n_pairs;
         const int ntiles = (2 * pair + 1 < p.n_src) ? 3 : 2;
-        const int c_begin = slab * p.chunks_per_slab, c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        const int c_begin = 0, c_end = wg3_range(p, slab).count;
         mbar_wait(tempty, (icount & 1) ^ 1);
         tc_fence_after();
         for (int ch = c_begin; ch < c_end; ++ch) {
@@ -1660,8 +1701,10 @@ static void wgrad_w3_plan(Wg3Params& p, int N, int D, int H, int W, int Cin_pad)
     const double cost = worst * (1.0 + 0.002 * sl);
     if (cost < best_cost) { best_cost = cost; best = sl; }
   }
-  p.chunks_per_slab = cdiv(p.n_chunks, best);
-  p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
+  p.n_slabs = cdiv(p.n_chunks, cdiv(p.n_chunks, best));
+  // slabs per interleave group = the slabs one wave of CTAs holds (wg3_range); DRAM_WGRAD_SPG=1 restores contiguous slabs
+  p.spg = cdiv(kNumSMs, p.n_pairs);
+  { const char* e = getenv("DRAM_WGRAD_SPG"); if (e && atoi(e) > 0) p.spg = atoi(e); }
   p.stages = (kSmemBudget - 1024) / kW3Stage;
   { const char* e = getenv("DRAM_WGRAD_ORDER"); p.dfast = e ? atoi(e) : 1; }
 }

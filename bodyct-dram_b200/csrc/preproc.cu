@@ -67,141 +67,162 @@ __global__ void k_bbox_init(int* out, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ ITK-style resampling
-// SimpleITK ResampleImageFilter with identity transform / same origin (utils.py:414-434): output index o maps to the
-// continuous input index o * (in/out) (no half-pixel shift); linear = 8-tap with neighbours clamped at the last
-// sample; nearest = round-half-up.  Restated from the published ITK semantics (SimpleITK 1.1.0 is not vendored).
-// A continuous index outside [-0.5, n - 0.5) is outside the ITK buffer: the output voxel takes the default value 0.
-struct Axis { int i0, i1; float w1; bool inside; };
-__device__ __forceinline__ Axis itk_axis(int o, float ratio, int n) {
-  float c = (float)o * ratio;
-  int i0 = (int)floorf(c);
-  Axis a;
-  a.inside = c < (float)n - 0.5f;
-  a.w1 = c - (float)i0;
-  a.i0 = min(max(i0, 0), n - 1);
-  a.i1 = min(i0 + 1, n - 1);
+// SimpleITK ResampleImageFilter with identity transform / identity direction / shared origin (utils.py:414-434,
+// data_transforms.py:170-175), computed the way ITK 4.13 computes it — in DOUBLE, operation by operation, so that integer
+// and float32 outputs are bit-identical to the float64 oracle (oracle/dram_oracle.py::itk_resample, which restates the ITK
+// classes, not this kernel):
+//   coordinates   itk::ImageBase::TransformIndexToPhysicalPoint / TransformPhysicalPointToContinuousIndex:
+//                   cidx = (1 / spacing_in) * (spacing_out * index)            (y, z)
+//                 itk::ResampleImageFilter::LinearThreadedGenerateData, along a scanline of `size` pixels (x):
+//                   alpha = i / double(size); cidx = start + alpha * (end - start), start/end = mapped indices 0 and `size`
+//   inside test   itk::InterpolateImageFunction::IsInsideBuffer: -0.5 <= cidx < n - 0.5, else the default value 0
+//   linear        itk::LinearInterpolateImageFunction::EvaluateOptimized: base = floor(cidx) clamped to 0, distance = cidx - base,
+//                 neighbours beyond the last index fall back to the base sample, nested lerps a + (b - a) * d over x, y, z
+//   nearest       itk::NearestNeighborInterpolateImageFunction: floor(cidx + 0.5)
+//   output cast   ResampleImageFilter::CastPixelWithBoundsChecking: clamp + static_cast (truncation for integers)
+// Every double operation is an explicit round-to-nearest intrinsic: the compiler must not contract a*b+c into an FMA.
+struct AxisD { int i0, i1; double dist; bool inside; };
+__device__ __forceinline__ AxisD itk_axis(double c, int n) {
+  AxisD a;
+  a.inside = (c >= -0.5) && (c < (double)n - 0.5);
+  int b = (int)floor(c);
+  if (b < 0) b = 0;
+  double dist = __dsub_rn(c, (double)b);
+  a.dist = dist > 0.0 ? dist : 0.0;
+  a.i0 = min(b, n - 1);
+  a.i1 = min(b + 1, n - 1);
   return a;
 }
-__device__ __forceinline__ int itk_nearest(int o, float ratio, int n, bool& inside) {
-  float c = (float)o * ratio;
-  inside = inside && (c < (float)n - 0.5f);
-  int i = (int)floorf(c + 0.5f);
+__device__ __forceinline__ int itk_nearest(double c, int n, bool& inside) {
+  inside = inside && (c >= -0.5) && (c < (double)n - 0.5);
+  const int i = (int)floor(__dadd_rn(c, 0.5));
   return min(max(i, 0), n - 1);
 }
+// y / z: the mapped index itself; x: ITK's per-scanline start/end interpolation
+__device__ __forceinline__ double itk_cidx(int i, double inv_in, double sp_out) { return __dmul_rn(inv_in, __dmul_rn(sp_out, (double)i)); }
+__device__ __forceinline__ double itk_cidx_line(int i, int size, double inv_in, double sp_out) {
+  const double start = __dmul_rn(inv_in, __dmul_rn(sp_out, 0.0));
+  const double end = __dmul_rn(inv_in, __dmul_rn(sp_out, (double)size));
+  const double alpha = __ddiv_rn((double)i, (double)size);
+  return __dadd_rn(start, __dmul_rn(alpha, __dsub_rn(end, start)));
+}
+__device__ __forceinline__ double itk_lerp(double a, double b, double d) { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), d)); }
 
-// one lobe chunk: crop [cz..cz+cd) x ... of the scan, blank voxels outside `label` to pad_value, window to [0,1],
-// linear-resample to (d,h,w); mask = nearest-resampled (labels == label) as float {0,1}   (job_runner.py:961-984)
+struct ItkGeom { double inv_z, inv_y, inv_x, out_z, out_y, out_x; };   // 1 / input spacing, output spacing (z, y, x)
+
+// one lobe chunk: crop [cz..cz+cd) x ... of the scan, blank voxels outside `label` to pad_value, window to [0,1] in float32
+// (Windowing, data_transforms.py:37-54: numpy float32 arithmetic), linear-resample to (d,h,w); mask = nearest-resampled
+// (labels == label) as float {0,1}   (job_runner.py:961-984)
 __global__ void __launch_bounds__(256)
 k_lobe_chunk_preprocess(const short* __restrict__ scan, const uint8_t* __restrict__ labels, int SH, int SW, int label,
                         int cz, int cy, int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value,
-                        float* __restrict__ img, float* __restrict__ msk, int d, int h, int w) {
+                        float* __restrict__ img, float* __restrict__ msk, int d, int h, int w, ItkGeom g) {
   const long long total = (long long)d * h * w;
-  const float rz = (float)cd / d, ry = (float)ch / h, rx = (float)cw / w;
   const float span = win_hi - win_lo;              // numpy divides (utils.py:197), keep the same rounding
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % w), Y = (int)((i / w) % h), Z = (int)(i / ((long long)w * h));
-    Axis az = itk_axis(Z, rz, cd), ay = itk_axis(Y, ry, ch), ax = itk_axis(X, rx, cw);
-    float acc = 0.f;
+    const int X = (int)(i % w), Y = (int)((i / w) % h), Z = (int)(i / ((long long)w * h));
+    const double c_z = itk_cidx(Z, g.inv_z, g.out_z), c_y = itk_cidx(Y, g.inv_y, g.out_y), c_x = itk_cidx_line(X, w, g.inv_x, g.out_x);
+    const AxisD az = itk_axis(c_z, cd), ay = itk_axis(c_y, ch), ax = itk_axis(c_x, cw);
+    double v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      int zi = ((k & 4) ? az.i1 : az.i0) + cz, yi = ((k & 2) ? ay.i1 : ay.i0) + cy, xi = ((k & 1) ? ax.i1 : ax.i0) + cx;
-      float wt = ((k & 4) ? az.w1 : 1.f - az.w1) * ((k & 2) ? ay.w1 : 1.f - ay.w1) * ((k & 1) ? ax.w1 : 1.f - ax.w1);
-      long long off = ((long long)zi * SH + yi) * SW + xi;
-      float v = (labels[off] == label) ? (float)scan[off] : pad_value;
-      v = fminf(fmaxf(v, win_lo), win_hi);
-      acc += wt * ((v - win_lo) / span);
+      const int zi = ((k & 4) ? az.i1 : az.i0) + cz, yi = ((k & 2) ? ay.i1 : ay.i0) + cy, xi = ((k & 1) ? ax.i1 : ax.i0) + cx;
+      const long long off = ((long long)zi * SH + yi) * SW + xi;
+      float t = (labels[off] == label) ? (float)scan[off] : pad_value;
+      t = fminf(fmaxf(t, win_lo), win_hi);
+      v[k] = (double)__fdiv_rn(__fsub_rn(t, win_lo), span);
     }
+    const double lo = itk_lerp(itk_lerp(v[0], v[1], ax.dist), itk_lerp(v[2], v[3], ax.dist), ay.dist);
+    const double hi = itk_lerp(itk_lerp(v[4], v[5], ax.dist), itk_lerp(v[6], v[7], ax.dist), ay.dist);
     bool in = az.inside && ay.inside && ax.inside;
-    img[i] = in ? acc : 0.f;
-    int zn = itk_nearest(Z, rz, cd, in) + cz, yn = itk_nearest(Y, ry, ch, in) + cy, xn = itk_nearest(X, rx, cw, in) + cx;
-    msk[i] = (in && labels[((long long)zn * SH + yn) * SW + xn] == label) ? 1.f : 0.f;
+    img[i] = in ? (float)itk_lerp(lo, hi, az.dist) : 0.f;
+    bool inn = true;
+    const int zn = itk_nearest(c_z, cd, inn) + cz, yn = itk_nearest(c_y, ch, inn) + cy, xn = itk_nearest(c_x, cw, inn) + cx;
+    msk[i] = (inn && labels[((long long)zn * SH + yn) * SW + xn] == label) ? 1.f : 0.f;
   }
 }
 
 // generic volume resample (scan <-> working grid): T in {short, uint8, float}; linear (mode 0) or nearest (mode 1)
 template <typename T>
-__device__ __forceinline__ T cast_out(float v);
-template <> __device__ __forceinline__ float cast_out<float>(float v) { return v; }
-template <> __device__ __forceinline__ short cast_out<short>(float v) { return (short)fminf(fmaxf(v, -32768.f), 32767.f); }        // trunc
-template <> __device__ __forceinline__ uint8_t cast_out<uint8_t>(float v) { return (uint8_t)fminf(fmaxf(v, 0.f), 255.f); }
+__device__ __forceinline__ T cast_out(double v);
+template <> __device__ __forceinline__ float cast_out<float>(double v) { return (float)v; }                       // round to nearest
+template <> __device__ __forceinline__ short cast_out<short>(double v) { return (short)(int)fmin(fmax(v, -32768.0), 32767.0); }   // trunc
+template <> __device__ __forceinline__ uint8_t cast_out<uint8_t>(double v) { return (uint8_t)(int)fmin(fmax(v, 0.0), 255.0); }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_itk_resample(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, float rz, float ry,
-               float rx, int mode) {
+k_itk_resample(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, ItkGeom g, int mode) {
   const long long total = (long long)D * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % W), Y = (int)((i / W) % H), Z = (int)(i / ((long long)W * H));
+    const int X = (int)(i % W), Y = (int)((i / W) % H), Z = (int)(i / ((long long)W * H));
+    const double c_z = itk_cidx(Z, g.inv_z, g.out_z), c_y = itk_cidx(Y, g.inv_y, g.out_y), c_x = itk_cidx_line(X, W, g.inv_x, g.out_x);
     if (mode == 1) {
       bool in = true;
-      int zn = itk_nearest(Z, rz, d, in), yn = itk_nearest(Y, ry, h, in), xn = itk_nearest(X, rx, w, in);
+      const int zn = itk_nearest(c_z, d, in), yn = itk_nearest(c_y, h, in), xn = itk_nearest(c_x, w, in);
       dst[i] = in ? src[((long long)zn * h + yn) * w + xn] : (T)0;
     } else {
-      Axis az = itk_axis(Z, rz, d), ay = itk_axis(Y, ry, h), ax = itk_axis(X, rx, w);
-      float acc = 0.f;
+      const AxisD az = itk_axis(c_z, d), ay = itk_axis(c_y, h), ax = itk_axis(c_x, w);
+      double v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        int zi = (k & 4) ? az.i1 : az.i0, yi = (k & 2) ? ay.i1 : ay.i0, xi = (k & 1) ? ax.i1 : ax.i0;
-        float wt = ((k & 4) ? az.w1 : 1.f - az.w1) * ((k & 2) ? ay.w1 : 1.f - ay.w1) * ((k & 1) ? ax.w1 : 1.f - ax.w1);
-        acc += wt * (float)src[((long long)zi * h + yi) * w + xi];
-      }
-      dst[i] = (az.inside && ay.inside && ax.inside) ? cast_out<T>(acc) : (T)0;
+      for (int k = 0; k < 8; ++k)
+        v[k] = (double)src[((long long)((k & 4) ? az.i1 : az.i0) * h + ((k & 2) ? ay.i1 : ay.i0)) * w + ((k & 1) ? ax.i1 : ax.i0)];
+      const double lo = itk_lerp(itk_lerp(v[0], v[1], ax.dist), itk_lerp(v[2], v[3], ax.dist), ay.dist);
+      const double hi = itk_lerp(itk_lerp(v[4], v[5], ax.dist), itk_lerp(v[6], v[7], ax.dist), ay.dist);
+      dst[i] = (az.inside && ay.inside && ax.inside) ? cast_out<T>(itk_lerp(lo, hi, az.dist)) : (T)0;
     }
   }
 }
 
 // Same arithmetic, 4 consecutive output voxels of the FLAT output array per thread (an aligned 4-element store; the
 // group may straddle a row end, so the row set-up is redone when x wraps): one 32-bit division pair per 4 outputs, the
-// z / y part of the interpolation shared by the group.  Used when the output has < 2^31 voxels and a 16-byte aligned base.
+// z / y part of the interpolation set-up shared by the group.  Used when the output has < 2^31 voxels and a 16-byte aligned base.
 template <typename T> struct alignas(4 * sizeof(T)) Vec4 { T v[4]; };
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
-k_itk_resample_v4(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, float rz,
-                  float ry, float rx) {
+k_itk_resample_v4(const T* __restrict__ src, T* __restrict__ dst, int d, int h, int w, int D, int H, int W, ItkGeom g) {
   const unsigned total = (unsigned)D * H * W, HW = (unsigned)H * W;
   const unsigned groups = (total + 3) >> 2;
-  for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
-    const unsigned i0 = g << 2;
+  for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const unsigned i0 = gi << 2;
     int Z = (int)(i0 / HW);
     const unsigned rem = i0 - (unsigned)Z * HW;
     int Y = (int)(rem / (unsigned)W), X = (int)(rem - (unsigned)Y * W);
     Vec4<T> out;
     bool fresh = true;
-    // row state: nearest -> (row pointer, inside); linear -> four row pointers + z/y weights
+    // row state: nearest -> (row pointer, inside); linear -> four row pointers + z/y distances
     const T *r00 = src, *r01 = src, *r10 = src, *r11 = src;
-    float wz1 = 0.f, wy1 = 0.f;
+    double dz = 0.0, dy = 0.0;
     bool row_in = true;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (i0 + j >= total) { out.v[j] = (T)0; continue; }
       if (fresh) {
         fresh = false;
+        const double c_z = itk_cidx(Z, g.inv_z, g.out_z), c_y = itk_cidx(Y, g.inv_y, g.out_y);
         if (MODE == 1) {
           row_in = true;
-          const int zn = itk_nearest(Z, rz, d, row_in), yn = itk_nearest(Y, ry, h, row_in);
+          const int zn = itk_nearest(c_z, d, row_in), yn = itk_nearest(c_y, h, row_in);
           r00 = src + ((long long)zn * h + yn) * w;
         } else {
-          const Axis az = itk_axis(Z, rz, d), ay = itk_axis(Y, ry, h);
+          const AxisD az = itk_axis(c_z, d), ay = itk_axis(c_y, h);
           row_in = az.inside && ay.inside;
-          wz1 = az.w1; wy1 = ay.w1;
+          dz = az.dist; dy = ay.dist;
           r00 = src + ((long long)az.i0 * h + ay.i0) * w; r01 = src + ((long long)az.i0 * h + ay.i1) * w;
           r10 = src + ((long long)az.i1 * h + ay.i0) * w; r11 = src + ((long long)az.i1 * h + ay.i1) * w;
         }
       }
+      const double c_x = itk_cidx_line(X, W, g.inv_x, g.out_x);
       if (MODE == 1) {
         bool in = row_in;
-        const int xn = itk_nearest(X, rx, w, in);
+        const int xn = itk_nearest(c_x, w, in);
         out.v[j] = in ? r00[xn] : (T)0;
       } else {
-        const Axis ax = itk_axis(X, rx, w);
-        // the same sum, in the same order, as k_itk_resample: k = 4*zbit + 2*ybit + xbit ascending
-        const float wz[2] = {1.f - wz1, wz1}, wy[2] = {1.f - wy1, wy1}, wx[2] = {1.f - ax.w1, ax.w1};
-        const T* rows[4] = {r00, r01, r10, r11};
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          acc += (wz[k >> 2] * wy[(k >> 1) & 1] * wx[k & 1]) * (float)rows[k >> 1][(k & 1) ? ax.i1 : ax.i0];
-        out.v[j] = (row_in && ax.inside) ? cast_out<T>(acc) : (T)0;
+        const AxisD ax = itk_axis(c_x, w);
+        const double lo = itk_lerp(itk_lerp((double)r00[ax.i0], (double)r00[ax.i1], ax.dist),
+                                   itk_lerp((double)r01[ax.i0], (double)r01[ax.i1], ax.dist), dy);
+        const double hi = itk_lerp(itk_lerp((double)r10[ax.i0], (double)r10[ax.i1], ax.dist),
+                                   itk_lerp((double)r11[ax.i0], (double)r11[ax.i1], ax.dist), dy);
+        out.v[j] = (row_in && ax.inside) ? cast_out<T>(itk_lerp(lo, hi, dz)) : (T)0;
       }
       if (++X == W) { X = 0; fresh = true; if (++Y == H) { Y = 0; ++Z; } }
     }
@@ -405,28 +426,34 @@ int dram_label_bboxes(const uint8_t* labels, int D, int H, int W, int nlabels, i
 }
 
 int dram_lobe_chunk_preprocess(const short* scan, const uint8_t* labels, int SD, int SH, int SW, int label, int cz, int cy,
-                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, float* img,
-                               float* msk, int d, int h, int w, void* stream) {
+                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, double sp_z,
+                               double sp_y, double sp_x, float* img, float* msk, int d, int h, int w, void* stream) {
   DRAM_REQUIRE(scan && labels && img && msk && d > 0 && h > 0 && w > 0 && cd > 0 && ch > 0 && cw > 0, "lobe_chunk_preprocess: bad arguments");
   DRAM_REQUIRE(cz >= 0 && cy >= 0 && cx >= 0 && cz + cd <= SD && cy + ch <= SH && cx + cw <= SW, "lobe_chunk_preprocess: crop outside the scan");
   DRAM_REQUIRE(win_hi > win_lo, "lobe_chunk_preprocess: empty window");
+  DRAM_REQUIRE(sp_z > 0.0 && sp_y > 0.0 && sp_x > 0.0, "lobe_chunk_preprocess: spacing must be positive");
+  // Resample('fixed_size'), data_transforms.py:170-175: require_spacing = spacing * (current_size / size), in double
+  const ItkGeom g = {1.0 / sp_z, 1.0 / sp_y, 1.0 / sp_x, sp_z * ((double)cd / (double)d), sp_y * ((double)ch / (double)h),
+                     sp_x * ((double)cw / (double)w)};
   k_lobe_chunk_preprocess<<<grid_for((long long)d * h * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      scan, labels, SH, SW, label, cz, cy, cx, cd, ch, cw, win_lo, win_hi, pad_value, img, msk, d, h, w);
+      scan, labels, SH, SW, label, cz, cy, cx, cd, ch, cw, win_lo, win_hi, pad_value, img, msk, d, h, w, g);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
 
-int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, float rz, float ry,
-                      float rx, int mode, void* stream) {
+int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, double in_sp_z,
+                      double in_sp_y, double in_sp_x, double out_sp_z, double out_sp_y, double out_sp_x, int mode, void* stream) {
   DRAM_REQUIRE(src && dst && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1), "itk_resample: bad arguments");
-  DRAM_REQUIRE(rz > 0.f && ry > 0.f && rx > 0.f, "itk_resample: index ratios must be positive");
+  DRAM_REQUIRE(in_sp_z > 0.0 && in_sp_y > 0.0 && in_sp_x > 0.0 && out_sp_z > 0.0 && out_sp_y > 0.0 && out_sp_x > 0.0,
+               "itk_resample: spacings must be positive");
+  const ItkGeom g = {1.0 / in_sp_z, 1.0 / in_sp_y, 1.0 / in_sp_x, out_sp_z, out_sp_y, out_sp_x};
   cudaStream_t st = (cudaStream_t)stream;
   if ((long long)D * H * W < (1ll << 31) - 4 && ((uintptr_t)dst % 16) == 0 && !getenv("DRAM_RESAMPLE_SCALAR")) {
     const int g4 = grid_for(((long long)D * H * W + 3) / 4, 256, 16);
-#define ITK_V4(T)                                                                                                        \
-  do {                                                                                                                   \
-    if (mode == 0) k_itk_resample_v4<T, 0><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, rz, ry, rx);     \
-    else k_itk_resample_v4<T, 1><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, rz, ry, rx);               \
+#define ITK_V4(T)                                                                                                  \
+  do {                                                                                                             \
+    if (mode == 0) k_itk_resample_v4<T, 0><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, g);        \
+    else k_itk_resample_v4<T, 1><<<g4, 256, 0, st>>>((const T*)src, (T*)dst, d, h, w, D, H, W, g);                  \
   } while (0)
     if (dtype == 0) ITK_V4(float);
     else if (dtype == 1) ITK_V4(short);
@@ -437,9 +464,9 @@ int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w
     return DRAM_OK;
   }
   int grid = grid_for((long long)D * H * W, 256, 16);
-  if (dtype == 0) k_itk_resample<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
-  else if (dtype == 1) k_itk_resample<short><<<grid, 256, 0, st>>>((const short*)src, (short*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
-  else if (dtype == 2) k_itk_resample<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, d, h, w, D, H, W, rz, ry, rx, mode);
+  if (dtype == 0) k_itk_resample<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, d, h, w, D, H, W, g, mode);
+  else if (dtype == 1) k_itk_resample<short><<<grid, 256, 0, st>>>((const short*)src, (short*)dst, d, h, w, D, H, W, g, mode);
+  else if (dtype == 2) k_itk_resample<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, d, h, w, D, H, W, g, mode);
   else DRAM_REQUIRE(false, "itk_resample: dtype %d unknown (0 f32, 1 i16, 2 u8)", dtype);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;

@@ -551,8 +551,9 @@ def label_bboxes(labels, nlabels=5):
     return out
 
 
-def lobe_chunk_preprocess(scan, labels, label, crop, window, pad_value, img_out, msk_out):
-    """scan int16 / labels uint8 [SD,SH,SW]; crop = ((z0,z1),(y0,y1),(x0,x1)); writes img_out/msk_out [d,h,w] fp32."""
+def lobe_chunk_preprocess(scan, labels, label, crop, window, pad_value, img_out, msk_out, spacing=(1.0, 1.0, 1.0)):
+    """scan int16 / labels uint8 [SD,SH,SW] with voxel `spacing` (z,y,x); crop = ((z0,z1),(y0,y1),(x0,x1)); writes
+    img_out/msk_out [d,h,w] fp32."""
     _req(scan, "scan", torch.int16)
     _req(labels, "labels", torch.uint8)
     SD, SH, SW = scan.shape
@@ -560,21 +561,25 @@ def lobe_chunk_preprocess(scan, labels, label, crop, window, pad_value, img_out,
     d, h, w = img_out.shape
     _lib.check(_L().dram_lobe_chunk_preprocess(scan.data_ptr(), labels.data_ptr(), SD, SH, SW, int(label), z0, y0, x0,
                                                z1 - z0, y1 - y0, x1 - x0, float(window[0]), float(window[1]),
-                                               float(pad_value), img_out.data_ptr(), msk_out.data_ptr(), d, h, w, _stream()),
+                                               float(pad_value), float(spacing[0]), float(spacing[1]), float(spacing[2]),
+                                               img_out.data_ptr(), msk_out.data_ptr(), d, h, w, _stream()),
                "lobe_chunk_preprocess")
 
 
-def itk_resample(src, new_size, mode="linear", ratios=None):
-    """Volume resample with ITK identity-transform semantics; ratios default to in/out ('fixed_size')."""
+def itk_resample(src, new_size, mode="linear", in_spacing=None, out_spacing=None):
+    """Volume resample with SimpleITK ResampleImageFilter semantics (identity transform, shared origin): `src` has voxel
+    spacing in_spacing (z,y,x; default 1), the result has `new_size` voxels of out_spacing (default: Resample('fixed_size'),
+    in_spacing * in_size / out_size, data_transforms.py:170-175).  Bit-identical to the float64 oracle."""
     if src.dtype not in _DTYPE_CODE or not src.is_cuda or not src.is_contiguous():
         raise _lib.DramLibraryError("itk_resample: need a contiguous CUDA tensor of dtype float32 / int16 / uint8")
     d, h, w = src.shape
     D, H, W = (int(s) for s in new_size)
-    if ratios is None:
-        ratios = (d / D, h / H, w / W)
+    isp = [1.0, 1.0, 1.0] if in_spacing is None else [float(v) for v in in_spacing]
+    osp = [s * (float(n_in) / float(n_out)) for s, n_in, n_out in zip(isp, (d, h, w), (D, H, W))] if out_spacing is None \
+        else [float(v) for v in out_spacing]
     dst = torch.empty((D, H, W), device=src.device, dtype=src.dtype)
     _lib.check(_L().dram_itk_resample(src.data_ptr(), dst.data_ptr(), _DTYPE_CODE[src.dtype], d, h, w, D, H, W,
-                                      float(ratios[0]), float(ratios[1]), float(ratios[2]), 0 if mode == "linear" else 1,
+                                      isp[0], isp[1], isp[2], osp[0], osp[1], osp[2], 0 if mode == "linear" else 1,
                                       _stream()), "itk_resample")
     return dst
 

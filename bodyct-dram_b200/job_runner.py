@@ -144,7 +144,7 @@ class _ScanPipeline:
                                  for a in range(3))
         return crops
 
-    def preprocess(self, scan_t, lobe_t, crops):
+    def preprocess(self, scan_t, lobe_t, crops, spacing=(1.0, 1.0, 1.0)):
         from dram_native import ops
         size = tuple(self.settings.RESAMPLE_SIZE)
         n = len(crops)
@@ -152,7 +152,8 @@ class _ScanPipeline:
         msks = torch.empty((n, 1) + size, device=scan_t.device, dtype=torch.float32)
         window = (self.settings.WINDOWING_MIN, self.settings.WINDOWING_MAX)
         for i, (label, crop) in enumerate(crops.items()):
-            ops.lobe_chunk_preprocess(scan_t, lobe_t, label, crop, window, self.settings.PAD_VALUE, imgs[i, 0], msks[i, 0])
+            ops.lobe_chunk_preprocess(scan_t, lobe_t, label, crop, window, self.settings.PAD_VALUE, imgs[i, 0], msks[i, 0],
+                                      spacing)
         return imgs, msks
 
     def paste(self, dense, msks, lobe_t, crops, heat):
@@ -205,7 +206,7 @@ class _ScanPipeline:
             crops = self.lobe_crops(lobe_t, spacing)
             heat = torch.zeros(scan_t.shape, device=dev, dtype=torch.float32)
             if crops:
-                imgs, msks = self.preprocess(scan_t, lobe_t, crops)
+                imgs, msks = self.preprocess(scan_t, lobe_t, crops, spacing)
                 _, dense = self.model(imgs, msks)
                 self.paste(dense, msks, lobe_t, crops, heat)
             from dram_native import ops
@@ -225,8 +226,8 @@ class _ScanPipeline:
         """Resample('fixed_spacing', TEST_RESAMPLE_SPACING) of a whole scan (job_runner.py:827-835)."""
         from dram_native import ops
         new_sp = float(self.settings.TEST_RESAMPLE_SPACING)
-        new_size = [int(np.ceil(s * sp / new_sp)) for s, sp in zip(arr_t.shape, spacing)]
-        return ops.itk_resample(arr_t, new_size, mode, ratios=[new_sp / sp for sp in spacing])
+        new_size = [int(np.ceil(s * (sp / new_sp))) for s, sp in zip(arr_t.shape, spacing)]     # utils.py:369-371
+        return ops.itk_resample(arr_t, new_size, mode, in_spacing=spacing, out_spacing=[new_sp] * 3)
 
     def scan_to_masks(self, scan_d, lobe_d, spacing):
         """One scan at its ORIGINAL grid, already on the device -> (lesion, lesion_post) uint8 masks at the original grid and
@@ -615,5 +616,5 @@ class LesionSegTest(JobRunner, _ScanPipeline):
 def ops_itk_back(t, original_size, spacing, original_spacing, mode):
     """resample a working-grid volume back to the scan's original grid (job_runner.py:1017-1030)."""
     from dram_native import ops
-    return ops.itk_resample(t.contiguous(), tuple(int(s) for s in original_size), mode,
-                            ratios=[o / s for o, s in zip(original_spacing, spacing)])
+    return ops.itk_resample(t.contiguous(), tuple(int(s) for s in original_size), mode, in_spacing=spacing,
+                            out_spacing=original_spacing)

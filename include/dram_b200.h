@@ -261,16 +261,23 @@ int dram_labelled_sum(const float* values, const uint8_t* labels, long long n, d
  * The caller synchronises the stream (or an event) before reading dst.  nbytes: multiple of 4, <= 1 MiB. */
 int dram_store_to_host(const void* src, void* dst_pinned_host, int nbytes, void* stream);
 /* job_runner.py:961-984: crop [cz,cz+cd)x[cy,cy+ch)x[cx,cx+cw), voxels outside `label` -> pad_value (-2048), Windowing
- * (data_transforms.py:37-54) to [0,1], Resample('fixed_size') (data_transforms.py:170-175, ITK identity-transform
- * resample: index o -> o*in/out, linear for the image, nearest for the mask) to the chunk grid (d,h,w). */
+ * (data_transforms.py:37-54, float32) to [0,1], Resample('fixed_size') (data_transforms.py:170-175: SimpleITK resample with
+ * require_spacing = spacing * crop_size / chunk_size, linear for the image, nearest for the mask) to the chunk grid (d,h,w).
+ * sp_* = spacing of the scan grid (z, y, x).  Coordinates and interpolation in double exactly as ITK 4.13 computes them
+ * (see dram_itk_resample): bit-identical to the float64 oracle. */
 int dram_lobe_chunk_preprocess(const short* scan, const uint8_t* labels, int SD, int SH, int SW, int label, int cz, int cy,
-                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, float* img,
-                               float* msk, int d, int h, int w, void* stream);
-/* utils.resample (utils.py:414-434) of a whole volume [d][h][w] -> [D][H][W]; output index o reads the continuous input
- * index o*r (r = new_spacing/old_spacing per axis; = in/out for a fixed-size resample); outside the ITK buffer -> 0.
- * dtype 0 = f32, 1 = i16 (truncating cast), 2 = u8; mode 0 = linear, 1 = nearest (round half up). */
-int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, float rz, float ry,
-                      float rx, int mode, void* stream);
+                               int cx, int cd, int ch, int cw, float win_lo, float win_hi, float pad_value, double sp_z,
+                               double sp_y, double sp_x, float* img, float* msk, int d, int h, int w, void* stream);
+/* utils.resample (utils.py:414-434) -> SimpleITK ResampleImageFilter (identity transform, identity direction, shared
+ * origin, default value 0, output pixel type = input pixel type) of a whole volume [d][h][w] with spacing in_sp_* onto the
+ * grid [D][H][W] with spacing out_sp_* (z, y, x).  Restates ITK 4.13 in double, operation by operation: continuous index =
+ * (1/in_sp) * (out_sp * index) (ImageBase::TransformIndexToPhysicalPoint / TransformPhysicalPointToContinuousIndex), along x
+ * through ResampleImageFilter::LinearThreadedGenerateData's start + (i/size) * (end - start); outside [-0.5, n-0.5) -> 0;
+ * LinearInterpolateImageFunction::EvaluateOptimized nested lerps in double; NearestNeighbor = floor(c + 0.5);
+ * CastPixelWithBoundsChecking (clamp + truncating cast for integers, round-to-nearest for f32).
+ * dtype 0 = f32, 1 = i16, 2 = u8; mode 0 = linear, 1 = nearest. */
+int dram_itk_resample(const void* src, void* dst, int dtype, int d, int h, int w, int D, int H, int W, double in_sp_z,
+                      double in_sp_y, double in_sp_x, double out_sp_z, double out_sp_y, double out_sp_x, int mode, void* stream);
 /* dram_ram_upsample_mask_scatter with the mask read from the scan-sized label volume (labels == label) */
 int dram_ram_upsample_label_scatter(const float* ram, const uint8_t* labels, int label, float* heat, int d, int h, int w,
                                     int cd, int ch, int cw, int SD, int SH, int SW, int oz, int oy, int ox, int act,

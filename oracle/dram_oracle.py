@@ -310,51 +310,102 @@ def find_crops(mask, spacing, border):
     return tuple(sl)
 
 
-def itk_resample(arr, new_size, interpolator="linear", ratios=None):
+def itk_continuous_indices(in_size, out_size, in_spacing, out_spacing):
+    """Continuous INPUT index of every output index along each axis, as ITK's ResampleImageFilter computes it for an
+    identity transform, identity direction and a shared origin — in float64, following (not fitted to any kernel):
+
+      * itk::ImageBase::TransformIndexToPhysicalPoint:            point = spacing_out * index  (+ origin)
+      * itk::ImageBase::TransformPhysicalPointToContinuousIndex:  cidx  = (1 / spacing_in) * (point - origin)
+      * itk::ResampleImageFilter::LinearThreadedGenerateData (the path taken for a linear — here identity — transform):
+        per output scanline (ITK x = our LAST axis) the continuous index of the line's first pixel (`startIndex`) and of
+        index `start + size` (`endIndex`) are mapped as above, and pixel i of the line gets
+            alpha = i / double(size);  inputIndex = startIndex + alpha * (endIndex - startIndex)
+        so the y / z components (equal at both ends of a line) are the mapped values themselves.
+
+    ITK version: SimpleITK 1.1.0 (requirements.in:33) bundles ITK 4.13; `sitk.GetImageFromArray` gives origin 0 and identity
+    direction (utils.py:418-419), the matrix inverse of diag(spacing) is taken as 1/spacing.  Parity unpinned (no SimpleITK
+    in this image).  Axes are (z, y, x); returns three float64 arrays."""
+    in_spacing = [float(v) for v in in_spacing]
+    out_spacing = [float(v) for v in out_spacing]
+    inv = [1.0 / v for v in in_spacing]
+    cz = inv[0] * (out_spacing[0] * np.arange(out_size[0], dtype=np.float64))
+    cy = inv[1] * (out_spacing[1] * np.arange(out_size[1], dtype=np.float64))
+    start = inv[2] * (out_spacing[2] * 0.0)
+    end = inv[2] * (out_spacing[2] * float(out_size[2]))
+    alpha = np.arange(out_size[2], dtype=np.float64) / float(out_size[2])
+    cx = start + alpha * (end - start)
+    return [cz, cy, cx]
+
+
+def fixed_size_spacing(in_size, out_size, spacing=(1.0, 1.0, 1.0)):
+    """Resample('fixed_size') data_transforms.py:170-175: require_spacing = spacing * (current_size / size), float64."""
+    ratios = np.asarray(in_size, dtype=np.float64) / np.asarray(out_size, dtype=np.float64)
+    return (np.asarray(spacing, dtype=np.float64) * ratios).tolist()
+
+
+def itk_resample(arr, new_size, interpolator="linear", in_spacing=None, out_spacing=None):
     """SimpleITK ResampleImageFilter as used by utils.resample utils.py:414-434 (+ resample_sitk_image :299-384) and
-    Resample('fixed_size') data_transforms.py:170-175: identity transform, same origin, fill 0.
-    Output index i maps to the continuous input index i*r with r = new_spacing/old_spacing (= in/out for 'fixed_size';
-    pixel-centre origin, NO half-pixel shift).  Indices >= n-0.5 are outside the ITK buffer -> 0.
-    Linear: float32 8-tap, neighbours beyond the last sample clamped.  Nearest: round-half-up.
-    (SimpleITK 1.1.0 is not vendored: parity unpinned.)"""
-    if ratios is None and tuple(arr.shape) == tuple(new_size):
+    Resample('fixed_size') data_transforms.py:170-175: identity transform, same origin, default pixel value 0, output pixel
+    type = input pixel type.  An INDEPENDENT float64 restatement of the ITK 4.13 classes (see itk_continuous_indices for the
+    coordinate part):
+
+      * itk::InterpolateImageFunction::IsInsideBuffer: a continuous index outside [-0.5, n - 0.5) on any axis -> default 0;
+      * itk::LinearInterpolateImageFunction::EvaluateOptimized (3-D): base = floor(cidx) clamped to the first index,
+        distance = cidx - base (a non-positive distance means "no interpolation on this axis"), neighbours beyond the last
+        index fall back to the base sample; values are combined in RealType = double as nested lerps x, then y, then z:
+            vx00 = v000 + (v100 - v000) * dx;  vxx0 = vx00 + (vx10 - vx00) * dy;  out = vxx0 + (vxx1 - vxx0) * dz
+        (every special-case branch of the ITK function equals this expression with dx/dy/dz = 0 or equal neighbours);
+      * itk::NearestNeighborInterpolateImageFunction: index = Math::RoundHalfIntegerUp(cidx) = floor(cidx + 0.5);
+      * itk::ResampleImageFilter::CastPixelWithBoundsChecking: clamp to the output type's range, then static_cast —
+        truncation toward zero for integer pixels, round-to-nearest for float32.
+
+    in_spacing / out_spacing (z, y, x) default to Resample('fixed_size'): in = 1, out = in * in_size / out_size."""
+    arr = np.asarray(arr)
+    if in_spacing is None and out_spacing is None and tuple(arr.shape) == tuple(new_size):
         return arr                                                              # utils.py:415-417
-    ratios = [np.float32(n_in) / np.float32(n_out) for n_in, n_out in zip(arr.shape, new_size)] if ratios is None else ratios
-    coords = [np.arange(n_out, dtype=np.float32) * np.float32(r) for n_out, r in zip(new_size, ratios)]
-    inside = [c < np.float32(n) - np.float32(0.5) for c, n in zip(coords, arr.shape)]
+    in_spacing = [1.0, 1.0, 1.0] if in_spacing is None else in_spacing
+    out_spacing = fixed_size_spacing(arr.shape, new_size, in_spacing) if out_spacing is None else out_spacing
+    coords = itk_continuous_indices(arr.shape, new_size, in_spacing, out_spacing)
+    inside = [(c >= -0.5) & (c < n - 0.5) for c, n in zip(coords, arr.shape)]
     inside3 = inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
     if interpolator == "nearest":
-        idx = [np.clip(np.floor(c + np.float32(0.5)).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
+        idx = [np.clip(np.floor(c + 0.5).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
         out = arr[np.ix_(*idx)].copy()
         out[~inside3] = 0
         return out
-    i0 = [np.clip(np.floor(c).astype(np.int64), 0, n - 1) for c, n in zip(coords, arr.shape)]
-    i1 = [np.clip(np.floor(c).astype(np.int64) + 1, 0, n - 1) for c, n in zip(coords, arr.shape)]
-    w1 = [(c - np.floor(c)).astype(np.float32) for c in coords]
-    src = arr.astype(np.float32)
-    out = np.zeros(tuple(new_size), dtype=np.float32)
-    for k in range(8):                                                          # same tap order / fp32 math as the kernel
-        iz = i1[0] if k & 4 else i0[0]
-        iy = i1[1] if k & 2 else i0[1]
-        ix = i1[2] if k & 1 else i0[2]
-        wz = w1[0] if k & 4 else np.float32(1) - w1[0]
-        wy = w1[1] if k & 2 else np.float32(1) - w1[1]
-        wx = w1[2] if k & 1 else np.float32(1) - w1[2]
-        wt = (wz[:, None, None] * wy[None, :, None]) * wx[None, None, :]
-        out += wt * src[np.ix_(iz, iy, ix)]
-    out[~inside3] = 0
+    base = [np.maximum(np.floor(c).astype(np.int64), 0) for c in coords]
+    dist = [np.maximum(c - b.astype(np.float64), 0.0) for c, b in zip(coords, base)]
+    i0 = [np.minimum(b, n - 1) for b, n in zip(base, arr.shape)]                  # only reached when outside the buffer
+    i1 = [np.minimum(b + 1, n - 1) for b, n in zip(base, arr.shape)]              # beyond the last index -> the base sample
+    src = arr.astype(np.float64)
+    dz, dy, dx = dist[0][:, None, None], dist[1][None, :, None], dist[2][None, None, :]
+
+    def g(zi, yi, xi):
+        return src[np.ix_(zi, yi, xi)]
+
+    def lerp_x(zi, yi):
+        a = g(zi, yi, i0[2])
+        return a + (g(zi, yi, i1[2]) - a) * dx
+
+    def lerp_xy(zi):
+        a = lerp_x(zi, i0[1])
+        return a + (lerp_x(zi, i1[1]) - a) * dy
+
+    lo = lerp_xy(i0[0])
+    out = lo + (lerp_xy(i1[0]) - lo) * dz
+    out[~inside3] = 0.0
     if np.issubdtype(arr.dtype, np.integer):
         info = np.iinfo(arr.dtype)
-        return np.trunc(np.clip(out, info.min, info.max)).astype(arr.dtype)     # ITK static_cast: truncation
-    return out
+        return np.trunc(np.clip(out, info.min, info.max)).astype(arr.dtype)     # static_cast: truncation toward zero
+    return out.astype(arr.dtype)
 
 
 def resample_to_spacing(arr, spacing, new_spacing, interpolator="linear"):
     """Resample('fixed_spacing') data_transforms.py:76-83 + resample_sitk_image utils.py:369-371:
-    new_size = ceil(size * spacing / new_spacing), index ratio = new_spacing / spacing."""
+    new_size = ceil(size * spacing / new_spacing), output spacing = new_spacing."""
     spacing, new_spacing = np.asarray(spacing, np.float64), np.asarray(new_spacing, np.float64)
     new_size = np.ceil(np.asarray(arr.shape) * (spacing / new_spacing)).astype(int)
-    return itk_resample(arr, tuple(new_size), interpolator, ratios=[np.float32(a / b) for a, b in zip(new_spacing, spacing)])
+    return itk_resample(arr, tuple(new_size), interpolator, in_spacing=spacing.tolist(), out_spacing=new_spacing.tolist())
 
 
 def threshold_otsu_u8(values_u8):
@@ -390,8 +441,8 @@ def preprocess_lobe_chunk(scan, lobe, label, spacing, window, chunk_size=(80, 80
     scan_chunk = scan[sl].copy()
     scan_chunk[lobe_chunk == 0] = pad_value
     img = windowing(scan_chunk.astype(np.int16).astype(np.float32), from_span=window, to_span=(0, 1))
-    img = itk_resample(img.astype(np.float32), chunk_size, "linear")
-    msk = itk_resample(lobe_chunk.astype(np.uint8), chunk_size, "nearest")
+    img = itk_resample(img.astype(np.float32), chunk_size, "linear", in_spacing=spacing)
+    msk = itk_resample(lobe_chunk.astype(np.uint8), chunk_size, "nearest", in_spacing=spacing)
     return sl, lobe_chunk, img.astype(np.float32), msk.astype(np.float32)
 
 

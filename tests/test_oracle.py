@@ -121,3 +121,20 @@ def test_infer_scan_heads():
     assert out["heatmap"][lobe > 0].max() > 0
     lit = O.infer_scan(fn, scan, lobe, spacing, window=(-1000, -300), chunk_size=(8, 8, 8), head="literal")
     assert (lit["heatmap"] == 0).all()        # the shipped out_ch=1 head zeroes every heat map
+
+
+def test_itk_resample_known_answers_from_the_itk_definitions():
+    """Hand-derived vectors for the float64 ITK restatement: index i of an N -> 2N 'fixed_size' resample reads the continuous
+    index i/2; ITK's buffer ends at n - 0.5 (IsInsideBuffer is half-open), so the last output sample takes the default 0;
+    integer outputs are static_cast (truncation toward zero), nearest is round-half-up."""
+    a = np.array([0, 10, 20, 30], dtype=np.float32).reshape(1, 1, 4)
+    assert O.itk_resample(a, (1, 1, 8), "linear").ravel().tolist() == [0, 5, 10, 15, 20, 25, 30, 0]
+    b = np.array([-5, 0, 5, -10], dtype=np.int16).reshape(1, 1, 4)
+    assert O.itk_resample(b, (1, 1, 8), "linear").ravel().tolist() == [-5, -2, 0, 2, 5, -2, -10, 0]      # -2.5 -> -2, 2.5 -> 2
+    assert O.itk_resample(b, (1, 1, 8), "nearest").ravel().tolist() == [-5, 0, 0, 5, 5, -10, -10, 0]       # 0.5 -> 1, 1.5 -> 2, 2.5 -> 3
+    c = np.arange(6, dtype=np.float32).reshape(1, 1, 6)                                                    # 6 -> 4: cidx = 1.5 i
+    assert O.itk_resample(c, (1, 1, 4), "linear").ravel().tolist() == [0.0, 1.5, 3.0, 4.5]
+    # anisotropic spacing, fixed_spacing mode: new_size = ceil(size * spacing / new_spacing)
+    d = np.arange(5, dtype=np.float32).reshape(5, 1, 1)
+    r = O.resample_to_spacing(d, (1.5, 1.0, 1.0), (1.0, 1.0, 1.0), "linear")
+    assert r.shape == (8, 1, 1) and np.allclose(r.ravel()[:7], np.arange(7) / 1.5, atol=1e-12) and r.ravel()[7] == 0.0   # 7/1.5 = 4.67 >= 4.5

@@ -41,28 +41,25 @@ def test_lobe_chunk_preprocess(chunk):
         img = torch.empty(chunk, device="cuda")
         msk = torch.empty(chunk, device="cuda")
         crop = tuple((s.start, s.stop) for s in sl)
-        ops().lobe_chunk_preprocess(scan_t, lobe_t, label, crop, (-1000, -700), -2048, img, msk)
+        ops().lobe_chunk_preprocess(scan_t, lobe_t, label, crop, (-1000, -700), -2048, img, msk, spacing)
         assert torch.equal(msk.cpu(), torch.from_numpy(msk_ref)), "nearest-resampled lobe mask must be bit-exact"
-        assert (img.cpu() - torch.from_numpy(img_ref)).abs().max().item() <= 2e-6
+        assert torch.equal(img.cpu(), torch.from_numpy(img_ref)), "the kernel follows ITK's double arithmetic operation by operation: bit-exact vs the float64 oracle"
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.int16, np.uint8])
 @pytest.mark.parametrize("mode", ["linear", "nearest"])
 @pytest.mark.parametrize("src,dst", [((20, 24, 18), (10, 16, 18)), ((9, 10, 11), (20, 31, 15)), ((12, 14, 10), (7, 9, 11))])
 def test_itk_resample(dtype, mode, src, dst):
+    """vs the float64 restatement of ITK's ResampleImageFilter / LinearInterpolate / NearestNeighbor (the
+    oracle is written from the ITK definitions in double, the kernel must match it BIT-EXACTLY for every dtype)"""
     from oracle_import import O
     rng = np.random.RandomState(3)
-    a = (rng.rand(*src) * 200 - 50).astype(dtype) if dtype != np.uint8 else rng.randint(0, 6, size=src).astype(np.uint8)
-    ref = O.itk_resample(a, dst, mode)
-    got = ops().itk_resample(torch.from_numpy(a).cuda(), dst, mode).cpu().numpy()
-    assert got.shape == ref.shape and got.dtype == ref.dtype
-    if mode == "nearest":
-        assert np.array_equal(got, ref)
-    elif dtype == np.float32:
-        assert np.abs(got - ref).max() <= 1e-4
-    else:                                                       # truncating cast: at most 1 LSB on rounding ties
-        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
-        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    a = (rng.rand(*src) * 200 - 50).astype(dtype) if dtype != np.uint8 else rng.randint(0, 256, size=src).astype(np.uint8)
+    for in_sp in (None, (1.0, 0.7, 0.7), (2.5, 0.68359375, 0.68359375)):
+        ref = O.itk_resample(a, dst, mode, in_spacing=in_sp)
+        got = ops().itk_resample(torch.from_numpy(a).cuda(), dst, mode, in_spacing=in_sp).cpu().numpy()
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert np.array_equal(got, ref), (dtype, mode, in_sp, np.abs(got.astype(np.float64) - ref.astype(np.float64)).max())
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.int16, torch.uint8])
@@ -70,24 +67,30 @@ def test_itk_resample(dtype, mode, src, dst):
 def test_itk_resample_vector_kernel_equals_scalar_kernel(monkeypatch, dtype, mode):
     """4 outputs per thread with aligned vector stores (groups straddle row ends; ragged tail) == one output per thread"""
     torch.manual_seed(5)
-    for src, dst, ratios in (((23, 30, 26), (17, 21, 23), None), ((16, 20, 22), (16, 29, 31), (1.0, 0.7, 0.7)), ((5, 6, 7), (3, 3, 3), None)):
+    for src, dst, osp in (((23, 30, 26), (17, 21, 23), None), ((16, 20, 22), (16, 29, 31), (1.0, 0.7, 0.7)), ((5, 6, 7), (3, 3, 3), None)):
         a = (torch.rand(src) * 300 - 100).to(dtype).cuda() if dtype != torch.uint8 else torch.randint(0, 6, src, dtype=torch.uint8).cuda()
         monkeypatch.delenv("DRAM_RESAMPLE_SCALAR", raising=False)
-        fast = ops().itk_resample(a, dst, mode, ratios=ratios)
+        fast = ops().itk_resample(a, dst, mode, out_spacing=osp)
         monkeypatch.setenv("DRAM_RESAMPLE_SCALAR", "1")
-        slow = ops().itk_resample(a, dst, mode, ratios=ratios)
+        slow = ops().itk_resample(a, dst, mode, out_spacing=osp)
         assert torch.equal(fast, slow), (src, dst)
 
 
-def test_itk_resample_fixed_spacing_round_trip_sizes():
+@pytest.mark.parametrize("mode,dtype", [("linear", np.int16), ("nearest", np.uint8), ("linear", np.float32)])
+def test_itk_resample_fixed_spacing_and_back(mode, dtype):
+    """Resample('fixed_spacing') of a scan to the 1 mm working grid (job_runner.py:827-835) and the resample back to the
+    original grid (job_runner.py:1017-1030): sizes and every voxel equal to the float64 ITK restatement"""
     from oracle_import import O
     rng = np.random.RandomState(4)
-    a = rng.randint(-1000, 400, size=(20, 30, 30)).astype(np.int16)
-    ref = O.resample_to_spacing(a, (1.5, 0.7, 0.7), (1.0, 1.0, 1.0), "linear")
-    new_size = ref.shape
-    got = ops().itk_resample(torch.from_numpy(a).cuda(), new_size, "linear", ratios=[1.0 / 1.5, 1.0 / 0.7, 1.0 / 0.7]).cpu().numpy()
-    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
-    assert new_size == (30, 21, 21) and diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    a = rng.randint(-1000, 400, size=(20, 30, 30)).astype(dtype) if dtype != np.uint8 else rng.randint(0, 6, size=(20, 30, 30)).astype(np.uint8)
+    sp = (1.5, 0.7, 0.7)
+    ref = O.resample_to_spacing(a, sp, (1.0, 1.0, 1.0), mode)
+    assert ref.shape == (30, 21, 21)
+    got = ops().itk_resample(torch.from_numpy(a).cuda(), ref.shape, mode, in_spacing=sp, out_spacing=(1.0, 1.0, 1.0))
+    assert np.array_equal(got.cpu().numpy(), ref)
+    back_ref = O.itk_resample(ref, a.shape, mode, in_spacing=(1.0, 1.0, 1.0), out_spacing=sp)
+    back = ops().itk_resample(got, a.shape, mode, in_spacing=(1.0, 1.0, 1.0), out_spacing=sp)
+    assert np.array_equal(back.cpu().numpy(), back_ref)
 
 
 def test_masked_histogram_and_thresholds_are_integer_exact():
