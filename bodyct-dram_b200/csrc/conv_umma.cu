@@ -383,7 +383,43 @@ struct Fwd2Params {
   int TW, TDD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles, n_items;
   int SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes, acc_cols, tmem_cols;
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
+  float* stat;       // training: BatchNorm partial sums of y, [n_mtiles * 4][2][Cout] (row = M tile x epilogue warp), or NULL
 };
+
+// Column sums over the 32 lanes of a warp for 32 values per lane: after the five exchange rounds lane l holds the total
+// of element l (fixed tree, deterministic).  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? x[i] : x[i + 16], keep = up ? x[i + 16] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? x[i] : x[i + 8], keep = up ? x[i + 8] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? x[i] : x[i + 4], keep = up ? x[i + 4] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? x[i] : x[i + 2], keep = up ? x[i + 2] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? x[0] : x[1], keep = up ? x[1] : x[0];
+    x[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return x[0];
+}
 
 // MODE 0: one pass (bf16); 1: split-bf16 with the [B_hi | B_lo] N-concatenation (BN <= 64); 2: split-bf16, three N = BN MMAs;
 // 3 / 4: as 1 / 2 with a SINGLE-plane A operand (dgrad with dy carried as one bf16 plane): A x [B_hi | B_lo], resp. A x B_hi, A x B_lo
@@ -573,6 +609,17 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
             v[jj] = concat ? __uint_as_float(r[jj]) + __uint_as_float(r2[jj]) : __uint_as_float(r[jj]);
+          if (p.stat) {
+            // BatchNorm batch statistics of the raw output (parts.py:19, train mode) as a by-product of the epilogue: per
+            // channel sum and sum of squares over this warp's 32 voxel rows, one partial row per (M tile, warp); the
+            // partial rows are combined in double by k_bn_partials_reduce — no separate pass over y
+            float x[32];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) { x[jj] = v[jj]; x[jj + 16] = v[jj] * v[jj]; }
+            const float tot = warp_transpose_sum32(x, lane);
+            const long long row = (long long)(2 * pair + j) * 4 + q;
+            p.stat[(row * 2 + (lane >> 4)) * p.Cout + nt * p.BN + c0 + (lane & 15)] = tot;
+          }
           if (p.scale) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
@@ -625,6 +672,7 @@ struct Fwd3Params {
   int TW, TDD, tiles_w, tiles_h, tiles_d, n_vtiles, n_ctiles, n_items;
   int SW, x_plane_bytes, x_stage_bytes, w_stage_bytes;
   long long* prof;   // DRAM_CONV_PROF diagnostics
+  float* stat;       // training: BatchNorm partial sums of y, [rows][2][Cout]; rows = n_vtiles (x 2 warps in the stacked modes)
 };
 
 template <int MODE>
@@ -780,6 +828,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
       if (!stacked) {
         const int co = ct * p.CT + q * 32 + lane;
         const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+        float s1 = 0.f, s2 = 0.f;            // BatchNorm partial sums: a thread owns a channel, no cross-thread reduction
         for (int c0 = 0; c0 < 256; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
@@ -793,6 +842,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float v = __uint_as_float(r[gi * 8 + j]);
+              s1 += v; s2 = fmaf(v, v, s2);
               if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
               if (p.o_hi) {                            // planes: 32 lanes = 64 contiguous bytes per plane
                 const long long po = oo + j * hstride;
@@ -806,12 +856,18 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             }
           }
         }
+        if (p.stat) {
+          float* sp = p.stat + (long long)(item / p.n_ctiles) * 2 * p.Cout + co;
+          sp[0] = s1;
+          sp[p.Cout] = s2;
+        }
       } else {
         // rows 0..63 hold W_hi * X, rows 64..127 hold W_lo * X for the same channels: warps q and q+2 form a pair, each
         // owns one of the two 8-voxel groups of every 16 columns and receives the partner's values through shared memory
         const int pair = q & 1, upper = q >> 1;
         const int co = ct * p.CT + pair * 32 + lane;
         const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+        float s1 = 0.f, s2 = 0.f;            // this warp's half of the tile's voxels (partial row = 2 * voxel tile + upper)
         for (int c0 = 0; c0 < 256; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
@@ -829,6 +885,7 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v = __uint_as_float(upper ? r[j + 8] : r[j]) + rcv[j * 32 + lane];
+            s1 += v; s2 = fmaf(v, v, s2);
             if (p.scale) v = fmaxf(fmaf(v, sc, sh), 0.f);
             if (p.o_hi) {
               const long long po = oo + j * hstride;
@@ -840,6 +897,11 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
               out[j * hstride] = v;
             }
           }
+        }
+        if (p.stat) {
+          float* sp = p.stat + ((long long)(item / p.n_ctiles) * 2 + upper) * 2 * p.Cout + co;
+          sp[0] = s1;
+          sp[p.Cout] = s2;
         }
       }
       tc_fence_before();
@@ -861,9 +923,21 @@ constexpr int kWgBlkBytes = kWgKV * 128;        // one 64-voxel x 64-channel MN-
 struct WgParams {
   float* ws;                                    // [slabs][n_mtiles][n_ntiles][128][BN]
   int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles, n_ntiles, BN;
-  int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, chunks_per_slab;
+  int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, spg;
   int passes, stages, stage_bytes, tmem_cols, concat, y_lo;
 };
+// slab -> chunks first, first + step, ... (count of them): the slabs of a group of `spg` consecutive slabs (about one wave of
+// CTAs) interleave over the group's contiguous chunk range, so that all CTAs in flight read neighbouring chunks (see Wg3Params)
+struct WgRange { int first, step, count; };
+__device__ __forceinline__ WgRange wg_range(int n_chunks, int n_slabs, int spg, int slab) {
+  const int g = slab / spg, s0 = g * spg, s1 = min(s0 + spg, n_slabs);
+  const int lo = (int)((long long)n_chunks * s0 / n_slabs), hi = (int)((long long)n_chunks * s1 / n_slabs);
+  WgRange r;
+  r.step = s1 - s0;
+  r.first = lo + (slab - s0);
+  r.count = r.first < hi ? (hi - r.first + r.step - 1) / r.step : 0;
+  return r;
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
@@ -915,10 +989,9 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
         const int tap0 = mb0 / p.CB, cb0 = mb0 % p.CB, tap1 = has1 ? mb1 / p.CB : 0, cb1 = has1 ? mb1 % p.CB : 0;
         const int kd0 = p.taps == 1 ? 0 : tap0 / 9 - p.pad, kh0 = p.taps == 1 ? 0 : (tap0 / 3) % 3 - p.pad, kw0 = p.taps == 1 ? 0 : tap0 % 3 - p.pad;
         const int kd1 = p.taps == 1 ? 0 : tap1 / 9 - p.pad, kh1 = p.taps == 1 ? 0 : (tap1 / 3) % 3 - p.pad, kw1 = p.taps == 1 ? 0 : tap1 % 3 - p.pad;
-        const int c_begin = slab * p.chunks_per_slab;
-        const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
-        for (int ch = c_begin; ch < c_end; ++ch) {
-          int t = ch;                                // depth fastest (see k_conv_umma_wgrad_w3)
+        const WgRange rg = wg_range(p.n_chunks, p.n_slabs, p.spg, slab);
+        for (int k = 0; k < rg.count; ++k) {
+          int t = rg.first + k * rg.step;            // depth fastest (see k_conv_umma_wgrad_w3)
           const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
           const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
           const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
@@ -949,8 +1022,7 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
       uint32_t s = 0, ph = 0, tcount = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         const int slab = item / (p.n_ntiles * p.n_mtiles);
-        const int c_begin = slab * p.chunks_per_slab;
-        const int c_end = min(c_begin + p.chunks_per_slab, p.n_chunks);
+        const int c_begin = 0, c_end = wg_range(p.n_chunks, p.n_slabs, p.spg, slab).count;
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         tc_fence_after();
@@ -1050,16 +1122,8 @@ struct Wg3Params {
 // slab r of the group takes chunks r, r + spg, r + 2 spg, ...  All CTAs of a wave sweep one common front through the
 // volume, so the dY tile shared by the pairs of a slab, the kd-1/kd/kd+1 planes shared by its sources and the w/h halos
 // shared with the neighbouring slabs are all a few chunk steps apart.
-struct Wg3Range { int first, step, count; };
-__device__ __forceinline__ Wg3Range wg3_range(const Wg3Params& p, int slab) {
-  const int g = slab / p.spg, s0 = g * p.spg, s1 = min(s0 + p.spg, p.n_slabs);
-  const int lo = (int)((long long)p.n_chunks * s0 / p.n_slabs), hi = (int)((long long)p.n_chunks * s1 / p.n_slabs);
-  Wg3Range r;
-  r.step = s1 - s0;
-  r.first = lo + (slab - s0);
-  r.count = r.first < hi ? (hi - r.first + r.step - 1) / r.step : 0;
-  return r;
-}
+typedef WgRange Wg3Range;
+__device__ __forceinline__ Wg3Range wg3_range(const Wg3Params& p, int slab) { return wg_range(p.n_chunks, p.n_slabs, p.spg, slab); }
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
@@ -1407,16 +1471,23 @@ static void pick_fwd_tile(int D, int H, int W, int& TW, int& TH, int& TD) {
       if (eff > best + 1e-9 || (eff > best - 1e-9 && (tw > TW || (tw == TW && th > TH)))) { best = eff; TW = tw; TH = th; TD = td; }
     }
 }
-// K chunk (TW,TH,TD,TN) with product exactly 64 (powers of two), minimising zero-filled rows
+// K chunk (TW,TH,TD,TN) with product exactly 64 (powers of two): least zero-filled rows first, then the most COMPACT box —
+// smallest halo volume TN*(TW+2)*(TH+2)*(TD+2), i.e. the 27 shifted boxes of a chunk and the boxes of the neighbouring chunks
+// overlap as much as possible in L2.  (Round 1 broke ties by the largest TW and ended up with 8(w) x 1 x 1 voxels x 8 SAMPLES
+// at the 40^3 level: every chunk touched eight volumes, the kh / kd neighbours of a row were hundreds of chunk steps away
+// and us1.c0 read 4.1x its operands from DRAM; 4 x 4 x 4 voxels of one sample now.)
 static void pick_wgrad_chunk(int N, int D, int H, int W, int& TW, int& TH, int& TD, int& TN) {
-  double best = 1e300;
+  double best = 1e300, best_halo = 1e300;
   TW = 64; TH = TD = TN = 1;
   for (int tw = 1; tw <= 64; tw *= 2)
     for (int th = 1; tw * th <= 64; th *= 2)
       for (int td = 1; tw * th * td <= 64; td *= 2) {
         int tn = 64 / (tw * th * td);
         double vol = (double)cdiv(W, tw) * tw * cdiv(H, th) * th * (double)cdiv(D, td) * td * cdiv(N, tn) * tn;
-        if (vol < best - 0.5 || (vol < best + 0.5 && tw > TW)) { best = vol; TW = tw; TH = th; TD = td; TN = tn; }
+        double halo = (double)tn * (tw + 2) * (th + 2) * (td + 2);
+        if (vol < best - 0.5 || (vol < best + 0.5 && halo < best_halo - 0.5)) {
+          best = vol; best_halo = halo; TW = tw; TH = th; TD = td; TN = tn;
+        }
       }
 }
 static int pick_bn(int Cout) {
@@ -1428,6 +1499,57 @@ static int pick_bn(int Cout) {
 static int pow2_cols(int c) { int v = 32; while (v < c) v *= 2; return v; }
 
 constexpr int kSmemBudget = 200 * 1024;
+
+// which forward / dgrad kernel runs a layer (shared by the launcher and by the query for the BatchNorm partial rows)
+enum { kFwdGeneric = 0, kFwdPairs = 2, kFwdChannelsOnM = 3 };
+static int fwd_kernel_kind(int D, int H, int W, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
+  // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
+  // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
+  // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
+  const char* v3_env = getenv("DRAM_CONV_V3");
+  int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && (Cin_pad <= 128 || !x_lo))) ? 1 : 0);
+  if (use_v3 == 2) use_v3 = (Cout % 128 == 0) ? 1 : 0;       // experiment: 128-channel tiles only
+  if (use_v3 && w_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
+      ((W % 16 == 0 && D % 2 == 0) || (W % 8 == 0 && D % 4 == 0)))
+    return kFwdChannelsOnM;
+  // weight-sharing tile pairs (k_conv_umma_fwd2) wherever the volume tiles into 8(h) x TDD(d) x TW(w) boxes
+  static const bool allow_v2 = getenv("DRAM_CONV_NO_V2") == nullptr;
+  if (allow_v2 && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) && Cout % 32 == 0) return kFwdPairs;
+  return kFwdGeneric;
+}
+// rows of the BatchNorm partial-sum buffer [rows][2][Cout] the kernel's epilogue fills (0: this kernel has no such epilogue)
+static long long fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
+  const int kind = fwd_kernel_kind(D, H, W, Cin_pad, Cout, ksize, x_lo, w_lo);
+  if (kind == kFwdChannelsOnM) {
+    const int TW = (W % 16 == 0 && D % 2 == 0) ? 16 : 8, TDD = (W % 16 == 0 && D % 2 == 0) ? 2 : 4;
+    const long long vt = (long long)N * (D / TDD) * (H / 8) * (W / TW);
+    return (Cout % 128 == 0) ? vt : 2 * vt;
+  }
+  if (kind == kFwdPairs) {
+    const int TW = (W % 16 == 0) ? 16 : 8, TDD = (W % 16 == 0) ? 1 : 2;
+    return 4ll * N * (D / TDD) * (H / 8) * (W / TW);
+  }
+  return 0;
+}
+
+// sums[c] = sum over rows of partial[row][0][c], sums[C + c] = ... [1][c], in double, fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+k_bn_partials_reduce(const float* __restrict__ partial, long long rows, int C, double* __restrict__ sums) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;                   // column of the [rows][2C] matrix
+  double a = 0.0;
+  if (col < 2 * C)
+    for (long long r = wp; r < rows; r += 8) a += (double)__ldg(partial + r * 2 * C + col);
+  sh[wp][lane] = a;
+  __syncthreads();
+  if (wp == 0 && col < 2 * C) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][lane];
+    sums[col] = t;
+  }
+}
 
 }  // namespace dram
 
@@ -1455,9 +1577,21 @@ int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo, int Cout, int 
   return DRAM_OK;
 }
 
+long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin_pad <= 0 || Cin_pad % 64 || Cout <= 0) return 0;
+  return fwd_stat_rows(N, D, H, W, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
+}
+
+int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* stream) {
+  DRAM_REQUIRE(partials && sums && rows > 0 && C > 0, "bn_stats_from_partials: bad arguments");
+  k_bn_partials_reduce<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, rows, C, sums);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* scale,
-                         const float* shift, float* y, void* out_hi, void* out_lo, int N, int D, int H, int W, int Cin, int Cin_pad,
-                         int Cout, int ksize, void* stream) {
+                         const float* shift, float* y, void* out_hi, void* out_lo, float* bn_partials, int N, int D, int H,
+                         int W, int Cin, int Cin_pad, int Cout, int ksize, void* stream) {
   DRAM_REQUIRE(x_hi && w_hi && (y || out_hi) && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
   DRAM_REQUIRE(!out_hi || (scale && Cout % 64 == 0), "conv3d_umma_fwd: plane output needs scale/shift (eval mode) and Cout %% 64 == 0 (no channel padding)");
   DRAM_REQUIRE(out_hi || !out_lo, "conv3d_umma_fwd: out_lo without out_hi");
@@ -1469,18 +1603,15 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   // channels [Cin, Cin_pad) are zeros in x and w: with a single 64-channel block the K = 16 steps that would only multiply
   // padding are not issued (ds0.c1, Cin = 32: 2 of 4 steps)
   const int ksteps = (Cin_pad == 64 && !getenv("DRAM_CONV_FULL_K")) ? (Cin + 15) / 16 : 4;
-  // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
-  // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
-  // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
-  const char* v3_env = getenv("DRAM_CONV_V3");
-  int use_v3 = v3_env ? atoi(v3_env) : ((Cout % 128 == 0 || (Cout == 64 && (Cin_pad <= 128 || !x_lo))) ? 1 : 0);
-  if (use_v3 == 2) use_v3 = (Cout % 128 == 0) ? 1 : 0;       // experiment: 128-channel tiles only
-  if (use_v3 && w_lo && ksize == 3 && H % 8 == 0 && Cout % 64 == 0 &&
-      ((W % 16 == 0 && D % 2 == 0) || (W % 8 == 0 && D % 4 == 0))) {
+  const int kind = fwd_kernel_kind(D, H, W, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr);
+  DRAM_REQUIRE(!bn_partials || (!scale && fwd_stat_rows(N, D, H, W, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr) > 0),
+               "conv3d_umma_fwd: bn_partials needs a raw (no scale/shift) output and a kernel with the statistics epilogue "
+               "(dram_conv3d_umma_fwd_stat_rows > 0)");
+  if (kind == kFwdChannelsOnM) {
     Fwd3Params q;
     const int plain = (Cout % 128 == 0) ? 1 : 0;
     const int mode = plain + (x_lo ? 0 : 2);
-    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo;
+    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo; q.stat = bn_partials;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.CT = plain ? 128 : 64; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0 && D % 2 == 0) { q.TW = 16; q.TDD = 2; } else { q.TW = 8; q.TDD = 4; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
@@ -1529,15 +1660,13 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     }
     return DRAM_OK;
   }
-  // weight-sharing tile pairs (k_conv_umma_fwd2) wherever the volume tiles into 8(h) x TDD(d) x TW(w) boxes
-  static const bool allow_v2 = getenv("DRAM_CONV_NO_V2") == nullptr;
-  if (allow_v2 && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) && Cout % 32 == 0) {
+  if (kind == kFwdPairs) {
     Fwd2Params q;
     q.BN = Cout <= 64 ? Cout : (Cout % 128 == 0 ? 128 : (Cout % 96 == 0 ? 96 : (Cout % 64 == 0 ? 64 : 32)));
     const int mode = !w_lo ? 0 : ((q.BN <= 64 ? 1 : 2) + (x_lo ? 0 : 2));
     q.acc_cols = (mode == 1 || mode == 3) ? 2 * q.BN : q.BN;
     q.tmem_cols = pow2_cols(4 * q.acc_cols);
-    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo;
+    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo; q.stat = bn_partials;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
     if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
     q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
@@ -1657,8 +1786,9 @@ static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int 
     const double score = eff - 0.003 * sl;
     if (score > best_score) { best_score = score; best = sl; }
   }
-  p.chunks_per_slab = cdiv(p.n_chunks, best);
-  p.n_slabs = cdiv(p.n_chunks, p.chunks_per_slab);
+  p.n_slabs = cdiv(p.n_chunks, cdiv(p.n_chunks, best));
+  p.spg = cdiv(kNumSMs, tiles);
+  { const char* e = getenv("DRAM_WGRAD_SPG"); if (e && atoi(e) > 0) p.spg = atoi(e); }
   p.passes = passes;
   p.y_lo = (passes == 3 && y_lo) ? 1 : 0;
   p.stage_bytes = (passes == 3 ? 2 : 1) * 2 * kWgBlkBytes + (p.y_lo ? 2 : 1) * (p.BN / 64) * kWgBlkBytes;
@@ -1717,7 +1847,7 @@ size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Ci
   if (wgrad_w3_ok(H, W, Cout_pad, ksize, 3)) {
     Wg3Params q;
     wgrad_w3_plan(q, N, D, H, W, Cin_pad);
-    w3 = (size_t)q.n_slabs * q.n_pairs * 3 * 128 * 64 * sizeof(float);
+    w3 = (size_t)q.n_slabs * q.n_pairs * (3 * 128 * 64 * sizeof(float) + sizeof(int)) + 16;   // partial tiles + pacing counters
   }
   WgParams p;
   wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, 3);
@@ -1737,6 +1867,7 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     Wg3Params q;
     wgrad_w3_plan(q, N, D, H, W, Cin_pad);
     q.ws = (float*)workspace;
+    q.prog = (int*)(q.ws + (size_t)q.n_slabs * q.n_pairs * 3 * 128 * 64);        // uninitialised on purpose (see the kernel)
     q.y_lo = dy_lo ? 1 : 0;
     CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo;
     int rc3;

@@ -222,6 +222,7 @@ class ConvBnRelu(torch.autograd.Function):
                 x_real = ops.merge_planes(xs)
         else:
             x_real = ops.to_cl(x, "conv input")
+        sums = None
         if umma:
             if xs is None:
                 xs = ops.split_bf16(x_real)
@@ -233,7 +234,7 @@ class ConvBnRelu(torch.autograd.Function):
                 ap = ops.conv_umma(xs, w_hi, w_lo, Cout, k, scale, shift, out_planes=True)
                 ctx.mark_non_differentiable(ap.hi, *([ap.lo] if ap.lo is not None else []))
                 return _handle(ap.shape, ap.hi.device), ap.hi, ap.lo, None, None, None
-            y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
+            y, sums = ops.conv_umma(xs, w_hi, w_lo, Cout, k, want_stats=True) if training else (ops.conv_umma(xs, w_hi, w_lo, Cout, k), None)
         elif pointwise:
             y = ops.pointwise8_planes(xs, w, bias)       # reshape heads: straight from the planes, no fp32 copy of the input
         else:
@@ -242,7 +243,8 @@ class ConvBnRelu(torch.autograd.Function):
         N, C, D, H, W = y.shape
         count = N * D * H * W
         if training:
-            sums = ops.bn_stats(y)
+            if sums is None:                       # kernels without the statistics epilogue (CUDA-core layers, ragged tiles)
+                sums = ops.bn_stats(y)
             count = ddist.allreduce_stats(sums, count)
             mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                        n_updates)
@@ -386,11 +388,12 @@ class ConvBnReluRam(torch.autograd.Function):
         xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]) if x_hi is not None else \
             ops.split_bf16(ops.to_cl(x, "conv input"))
         w_hi, w_lo, _ = WEIGHTS.get(w, "bf16_fwd", lambda: ops.pack_weight_bf16(w.detach(), 0))
-        y = ops.conv_umma(xs, w_hi, w_lo, Cout, k)
+        y, sums = ops.conv_umma(xs, w_hi, w_lo, Cout, k, want_stats=True) if training else (ops.conv_umma(xs, w_hi, w_lo, Cout, k), None)
         N, C, D, H, W = y.shape
         count = N * D * H * W
         if training:
-            sums = ops.bn_stats(y)
+            if sums is None:
+                sums = ops.bn_stats(y)
             count = ddist.allreduce_stats(sums, count)
             mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                        n_updates)

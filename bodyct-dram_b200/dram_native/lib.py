@@ -19,9 +19,9 @@ def parse_header(path=HEADER):
     src = re.sub(r"//[^\n]*", " ", src)
     src = re.sub(r"^\s*#.*$", " ", src, flags=re.M)
     protos = {}
-    for m in re.finditer(r"\b(const\s+char\s*\*|int|size_t)\s+(dram_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(const\s+char\s*\*|long\s+long|int|size_t)\s+(dram_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        restype = ctypes.c_char_p if "char" in ret else _CTYPES[ret.strip()]
+        restype = ctypes.c_char_p if "char" in ret else _CTYPES[" ".join(ret.split())]
         argtypes = []
         if args and args != "void":
             for a in args.split(","):
@@ -41,7 +41,7 @@ class DramLibraryError(RuntimeError):
 
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim); memsets are not counted
-KERNELS_PER_CALL = {"dram_version": 0, "dram_sm_arch": 0, "dram_last_error": 0, "dram_device_check": 0,
+KERNELS_PER_CALL = {"dram_conv3d_umma_fwd_stat_rows": 0, "dram_version": 0, "dram_sm_arch": 0, "dram_last_error": 0, "dram_device_check": 0,
                     "dram_pcm_num_offsets": 0, "dram_pcm_qk_floats": 0, "dram_labelled_sum_workspace_bytes": 0, "dram_labelled_sum": 2, "dram_pcm_bwd_ws_floats": 0, "dram_conv3d_umma_wgrad_workspace_bytes": 0,
                     "dram_upsample2x_concat_fwd": 2, "dram_upsample2x_concat_planes": 2, "dram_upsample2x_concat_bwd": 1, "dram_conv3d_umma_wgrad": 2,
                     "dram_pcm_fwd": 2, "dram_pcm_bwd": 3, "dram_pointwise8_planes_supported": 0,

@@ -160,9 +160,11 @@ def pack_weight_bf16(w, mode, three=None):
     return hi, lo, Kpad
 
 
-def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=False):
+def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=False, want_stats=False):
     """xs: SplitPlanes of the input volume; weights packed by pack_weight_bf16 -> CL volume [N,Cout,D,H,W] fp32, or (with
-    out_planes, eval mode: scale / shift = folded BatchNorm) the ReLU'd activation as SplitPlanes, no fp32 tensor written."""
+    out_planes, eval mode: scale / shift = folded BatchNorm) the ReLU'd activation as SplitPlanes, no fp32 tensor written.
+    want_stats (train mode): -> (y, sums | None); sums = double [2*Cout] (sum y, sum y^2 per channel) accumulated in the
+    convolution's epilogue when the kernel that runs this shape supports it (None otherwise: use bn_stats(y))."""
     N, Cin, D, H, W = xs.shape
     _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")   # algorithmic (unpadded, 1 pass)
     if out_planes:
@@ -170,14 +172,25 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
             raise _lib.DramLibraryError("conv_umma: plane output needs folded BatchNorm scale/shift and Cout % 64 == 0")
         out = alloc_planes((N, Cout, D, H, W), three=xs.lo is not None)
         _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), scale.data_ptr(),
-                                             shift.data_ptr(), None, out.hi.data_ptr(), _p(out.lo), N, D, H, W, Cin, xs.Cpad,
-                                             Cout, ksize, _stream()), "conv3d_umma_fwd")
+                                             shift.data_ptr(), None, out.hi.data_ptr(), _p(out.lo), None, N, D, H, W, Cin,
+                                             xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
         return out
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
+    partials, rows = None, 0
+    if want_stats and scale is None and os.environ.get("DRAM_BN_EPILOGUE", "1") == "1":
+        rows = _L().dram_conv3d_umma_fwd_stat_rows(N, D, H, W, xs.Cpad, Cout, ksize, int(xs.lo is not None), int(w_lo is not None))
+        if rows > 0:
+            partials = torch.empty((rows, 2, Cout), device=xs.hi.device, dtype=torch.float32)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
-                                         y.data_ptr(), None, None, N, D, H, W, Cin, xs.Cpad, Cout, ksize, _stream()),
-               "conv3d_umma_fwd")
-    return y
+                                         y.data_ptr(), None, None, _p(partials), N, D, H, W, Cin, xs.Cpad, Cout, ksize,
+                                         _stream()), "conv3d_umma_fwd")
+    if not want_stats:
+        return y
+    if partials is None:
+        return y, None
+    sums = torch.empty(2 * Cout, device=y.device, dtype=torch.float64)
+    _lib.check(_L().dram_bn_stats_from_partials(partials.data_ptr(), rows, Cout, sums.data_ptr(), _stream()), "bn_stats_from_partials")
+    return y, sums
 
 
 def conv_umma_wgrad(dys, xs, Cin, Cout, ksize, stream=None, keep=None, out=None):

@@ -128,6 +128,33 @@ def test_conv_umma_forward(N, Cin, Cout, S, k, three):
     assert_close(y, ref, TOL_X3 if three else TOL_BF16, "conv_umma fwd")
 
 
+@pytest.mark.parametrize("N,Cin,Cout,S", [
+    (2, 64, 128, (8, 8, 16)),       # channels-on-M, 128-channel tiles: a thread owns a channel
+    (2, 32, 64, (8, 8, 16)),        # channels-on-M, stacked 64-channel tiles: two warps share a channel
+    (1, 64, 64, (16, 40, 40)),      # channels-on-M, (TW,TDD) = (8,4)
+    (2, 192, 64, (3, 16, 32)),      # weight-sharing tile pairs (us2.c0 shape class): warp transpose-reduce, odd tile count
+    (2, 128, 256, (10, 10, 10)),    # ragged tiles: no statistics epilogue -> None, the caller runs bn_stats
+])
+def test_conv_umma_forward_bn_statistics_epilogue(N, Cin, Cout, S):
+    """train-mode BatchNorm sums (sum y, sum y^2 per channel) from the convolution's epilogue == sums of the stored y"""
+    o = ops()
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, 3, 3, 3) * (2.0 / (Cin * 27)) ** 0.5
+    xs = o.split_bf16(cuda_cl(x), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    y, sums = o.conv_umma(xs, w_hi, w_lo, Cout, 3, want_stats=True)
+    assert torch.equal(y, o.conv_umma(xs, w_hi, w_lo, Cout, 3)), "the statistics epilogue must not change y"
+    if S == (10, 10, 10):
+        assert sums is None
+        return
+    assert sums is not None and sums.dtype == torch.float64 and sums.shape == (2 * Cout,)
+    yd = y.double()
+    ref = torch.cat([yd.sum(dim=(0, 2, 3, 4)), (yd * yd).sum(dim=(0, 2, 3, 4))])
+    scale = torch.cat([yd.abs().sum(dim=(0, 2, 3, 4)), (yd * yd).sum(dim=(0, 2, 3, 4))])      # fp32 partials of <= 256 values each
+    assert ((sums - ref).abs() <= 1e-5 * scale).all(), ((sums - ref).abs() / scale).max().item()
+    assert ((sums - o.bn_stats(y)).abs() <= 1e-5 * scale).all()
+    assert torch.equal(sums, o.conv_umma(xs, w_hi, w_lo, Cout, 3, want_stats=True)[1]), "fixed summation order: deterministic"
+
+
 def test_conv_umma_forward_folded_bn_relu():
     o = ops()
     N, Cin, Cout, S = 1, 64, 64, (8, 8, 8)
