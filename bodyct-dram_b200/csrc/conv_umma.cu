@@ -1532,23 +1532,44 @@ static long long fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout
   return 0;
 }
 
-// sums[c] = sum over rows of partial[row][0][c], sums[C + c] = ... [1][c], in double, fixed order (deterministic)
+// sums[c] = sum over rows of partial[row][0][c], sums[C + c] = ... [1][c], in double, in a fixed order (deterministic):
+// level 1, grid (column blocks of 32, kStatChunks row chunks): a warp owns a column block, its lanes the columns, the 8 warps
+// of a block stride the chunk's rows -> ws[chunk][2C]; level 2 adds the chunks per column.
+constexpr int kStatChunks = 192;
 __global__ void __launch_bounds__(256)
-k_bn_partials_reduce(const float* __restrict__ partial, long long rows, int C, double* __restrict__ sums) {
+k_bn_partials_reduce(const float* __restrict__ partial, long long rows, int C, double* __restrict__ ws) {
   __shared__ double sh[8][32];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;                   // column of the [rows][2C] matrix
+  const long long rpc = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * rpc, r1 = r0 + rpc < rows ? r0 + rpc : rows;
   double a = 0.0;
-  if (col < 2 * C)
-    for (long long r = wp; r < rows; r += 8) a += (double)__ldg(partial + r * 2 * C + col);
+  if (col < 2 * C) {
+    const float* p = partial + col;
+    long long r = r0 + wp;
+    for (; r + 24 < r1; r += 32) {                          // four independent loads in flight
+      const float v0 = __ldg(p + r * 2 * C), v1 = __ldg(p + (r + 8) * 2 * C), v2 = __ldg(p + (r + 16) * 2 * C),
+                  v3 = __ldg(p + (r + 24) * 2 * C);
+      a += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; r < r1; r += 8) a += (double)__ldg(p + r * 2 * C);
+  }
   sh[wp][lane] = a;
   __syncthreads();
   if (wp == 0 && col < 2 * C) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sh[k][lane];
-    sums[col] = t;
+    ws[(long long)blockIdx.y * 2 * C + col] = t;
   }
+}
+__global__ void __launch_bounds__(128)
+k_bn_partials_finish(const double* __restrict__ ws, int chunks, int C, double* __restrict__ sums) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= 2 * C) return;
+  double t = 0.0;
+  for (int k = 0; k < chunks; ++k) t += ws[(long long)k * 2 * C + col];
+  sums[col] = t;
 }
 
 }  // namespace dram
@@ -1582,9 +1603,15 @@ long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin_pad
   return fwd_stat_rows(N, D, H, W, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
 }
 
-int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* stream) {
-  DRAM_REQUIRE(partials && sums && rows > 0 && C > 0, "bn_stats_from_partials: bad arguments");
-  k_bn_partials_reduce<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, rows, C, sums);
+size_t dram_bn_stats_from_partials_workspace_bytes(int C) { return C > 0 ? sizeof(double) * 2 * (size_t)C * kStatChunks : 0; }
+
+int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* workspace, void* stream) {
+  DRAM_REQUIRE(partials && sums && workspace && rows > 0 && C > 0, "bn_stats_from_partials: bad arguments");
+  const int chunks = rows < kStatChunks ? (int)rows : kStatChunks;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_bn_partials_reduce<<<dim3((2 * C + 31) / 32, chunks), 256, 0, st>>>(partials, rows, C, (double*)workspace);
+  DRAM_LAUNCH_CHECK();
+  k_bn_partials_finish<<<(2 * C + 127) / 128, 128, 0, st>>>((const double*)workspace, chunks, C, sums);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

@@ -506,6 +506,115 @@ k_up2x_planes_blocked(const uint4* __restrict__ xh, const uint4* __restrict__ xl
   }
 }
 
+// Sliding-window variant (the default): a thread owns one (n, ky, kx, 8-channel group) COLUMN of 2x2x2 output blocks and
+// walks it along z.  The x/y-interpolated source planes kz-1, kz, kz+1 (4 outputs x 8 channels each) stay in registers, so
+// every step loads and x/y-interpolates ONE new source plane (9 row loads instead of 27, 30 FMAs per channel instead of 90)
+// and then blends the three planes along z.  Same weights (lerp_setup, 3-tap form with exact zeros) and the same per-axis
+// order x -> y -> z as k_up2x_planes_blocked.  `zseg` blocks per thread: each segment start pays two extra planes.
+__device__ __forceinline__ void up2x_plane(const uint4* __restrict__ xh, const uint4* __restrict__ xl, long long zbase, int w,
+                                           const int (&yi)[3], const int (&xi)[3], int pg1, int g, const float (&wy)[2][3],
+                                           const float (&wx)[2][3], float (&u)[4][8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[i][c] = 0.f;
+#pragma unroll
+  for (int ty = 0; ty < 3; ++ty) {
+    uint4 A[3], B[3];
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) {
+      const long long row = (zbase + yi[ty]) * w + xi[tx];
+      A[tx] = __ldg(xh + row * pg1 + g);
+      B[tx] = xl ? __ldg(xl + row * pg1 + g) : make_uint4(0, 0, 0, 0);
+    }
+    float t0[8], t1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t0[c] = t1[c] = 0.f;
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) {
+      float v[8];
+      merge8(A[tx], B[tx], v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { t0[c] = fmaf(wx[0][tx], v[c], t0[c]); t1[c] = fmaf(wx[1][tx], v[c], t1[c]); }
+    }
+#pragma unroll
+    for (int jy = 0; jy < 2; ++jy)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        u[jy * 2 + 0][c] = fmaf(wy[jy][ty], t0[c], u[jy * 2 + 0][c]);
+        u[jy * 2 + 1][c] = fmaf(wy[jy][ty], t1[c], u[jy * 2 + 1][c]);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_up2x_planes_zslide(const uint4* __restrict__ xh, const uint4* __restrict__ xl, uint4* __restrict__ ch_,
+                     uint4* __restrict__ cl, int N, int d, int h, int w, int C1, int P1, int Pc, float sz, float sy, float sx,
+                     int zseg, int nseg) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const int groups = C1 / 8, pg1 = P1 / 8, pgc = Pc / 8;
+  const long long cols = (long long)N * nseg * h * w;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long dcol = ((long long)gridDim.x * blockDim.x) / groups;     // launch: total threads % groups == 0
+  const int g = (int)(tid % groups);
+  for (long long b = tid / groups; b < cols; b += dcol) {
+    unsigned r = (unsigned)b;
+    const int kx = (int)(r % (unsigned)w); r /= (unsigned)w;
+    const int ky = (int)(r % (unsigned)h); r /= (unsigned)h;
+    const int seg = (int)(r % (unsigned)nseg);
+    const int n = (int)(r / (unsigned)nseg);
+    const int kz0 = seg * zseg, kz1 = min(kz0 + zseg, d);
+    float wy[2][3], wx[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const Lerp ly = lerp_setup(2 * ky + j, sy, h), lx = lerp_setup(2 * kx + j, sx, w);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        wy[j][t] = (ly.i0 == ky - 1 + t ? ly.w0 : 0.f) + (ly.i1 == ky - 1 + t ? ly.w1 : 0.f);
+        wx[j][t] = (lx.i0 == kx - 1 + t ? lx.w0 : 0.f) + (lx.i1 == kx - 1 + t ? lx.w1 : 0.f);
+      }
+    }
+    int xi[3], yi[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      xi[t] = min(max(kx - 1 + t, 0), w - 1);
+      yi[t] = min(max(ky - 1 + t, 0), h - 1);
+    }
+    const long long nbase = (long long)n * d;
+    float P0[4][8], P1_[4][8], P2[4][8];
+    up2x_plane(xh, xl, (nbase + max(kz0 - 1, 0)) * h, w, yi, xi, pg1, g, wy, wx, P1_);     // becomes P0 in the first step
+    up2x_plane(xh, xl, (nbase + kz0) * h, w, yi, xi, pg1, g, wy, wx, P2);                  // becomes P1
+    for (int kz = kz0; kz < kz1; ++kz) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { P0[i][c] = P1_[i][c]; P1_[i][c] = P2[i][c]; }
+      up2x_plane(xh, xl, (nbase + min(kz + 1, d - 1)) * h, w, yi, xi, pg1, g, wy, wx, P2);
+      float wz[2][3];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const Lerp lz = lerp_setup(2 * kz + j, sz, d);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) wz[j][t] = (lz.i0 == kz - 1 + t ? lz.w0 : 0.f) + (lz.i1 == kz - 1 + t ? lz.w1 : 0.f);
+      }
+#pragma unroll
+      for (int jz = 0; jz < 2; ++jz)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float o[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = fmaf(wz[jz][2], P2[i][c], fmaf(wz[jz][1], P1_[i][c], wz[jz][0] * P0[i][c]));
+          const int Z = 2 * kz + jz, Y = 2 * ky + (i >> 1), X = 2 * kx + (i & 1);
+          const long long row = (((long long)n * D + Z) * H + Y) * W + X;
+          uint4 Hh, Ll;
+          split8(o, Hh, Ll);
+          ch_[row * pgc + g] = Hh;
+          if (cl) cl[row * pgc + g] = Ll;
+        }
+    }
+  }
+}
+
 // cat[..., C1:C1+C2] = skip (centre crop), cat[..., C1+C2:Pc] = 0: 16-byte chunks, one thread per (voxel, chunk)
 __global__ void __launch_bounds__(256)
 k_skip_copy_planes(const uint4* __restrict__ sh_, const uint4* __restrict__ sl, uint4* __restrict__ ch_, uint4* __restrict__ cl,
@@ -810,9 +919,23 @@ int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void
   static const bool blocked = getenv("DRAM_UP2X_SIMPLE") == nullptr;
   if (blocked) {
     cudaStream_t st = (cudaStream_t)stream;
-    k_up2x_planes_blocked<<<grid_fixed_group((long long)N * d * h * w, C1 / 8, 128, 64), 128, 0, st>>>(
-        (const uint4*)x_hi, (const uint4*)x_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d, h, w, C1, P1, Pc, ac_scale(d, D),
-        ac_scale(h, H), ac_scale(w, W));
+    static const bool zslide = getenv("DRAM_UP2X_BLOCKED") == nullptr;
+    if (zslide) {
+      // z segments: enough columns for ~4 waves of 128-thread blocks, at least 8 blocks of z per thread
+      const long long cols1 = (long long)N * h * w * (C1 / 8);
+      int nseg = (int)((4ll * kNumSMs * 8 * 128 + cols1 - 1) / cols1);
+      if (nseg > d / 8) nseg = d / 8;
+      if (nseg < 1) nseg = 1;
+      const int zseg = (d + nseg - 1) / nseg;
+      nseg = (d + zseg - 1) / zseg;
+      k_up2x_planes_zslide<<<grid_fixed_group((long long)N * nseg * h * w, C1 / 8, 128, 64), 128, 0, st>>>(
+          (const uint4*)x_hi, (const uint4*)x_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d, h, w, C1, P1, Pc, ac_scale(d, D),
+          ac_scale(h, H), ac_scale(w, W), zseg, nseg);
+    } else {
+      k_up2x_planes_blocked<<<grid_fixed_group((long long)N * d * h * w, C1 / 8, 128, 64), 128, 0, st>>>(
+          (const uint4*)x_hi, (const uint4*)x_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, d, h, w, C1, P1, Pc, ac_scale(d, D),
+          ac_scale(h, H), ac_scale(w, W));
+    }
     DRAM_LAUNCH_CHECK();
     k_skip_copy_planes<<<grid_for((long long)N * D * H * W * ((Pc - C1) / 8), 256), 256, 0, st>>>(
         (const uint4*)skip_hi, (const uint4*)skip_lo, (uint4*)cat_hi, (uint4*)cat_lo, N, D, H, W, C1, Ds, Hs, Ws, C2, P2, Pc,

@@ -189,7 +189,9 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
     if partials is None:
         return y, None
     sums = torch.empty(2 * Cout, device=y.device, dtype=torch.float64)
-    _lib.check(_L().dram_bn_stats_from_partials(partials.data_ptr(), rows, Cout, sums.data_ptr(), _stream()), "bn_stats_from_partials")
+    ws = torch.empty(_L().dram_bn_stats_from_partials_workspace_bytes(Cout), device=y.device, dtype=torch.uint8)
+    _lib.check(_L().dram_bn_stats_from_partials(partials.data_ptr(), rows, Cout, sums.data_ptr(), ws.data_ptr(), _stream()),
+               "bn_stats_from_partials")
     return y, sums
 
 

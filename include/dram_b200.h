@@ -85,9 +85,11 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
  * bn_partials != NULL (raw output only) the epilogue also writes per-channel partial sums of y and y*y,
  * [rows][2][Cout] floats, rows = dram_conv3d_umma_fwd_stat_rows(...) (one row per output tile and epilogue warp; 0 = the
  * kernel that runs this shape has no such epilogue: use dram_bn_stats).  dram_bn_stats_from_partials adds the rows up in
- * double in a fixed order -> sums[0..C) = sum y, sums[C..2C) = sum y*y, what dram_bn_finalize takes. */
+ * double in a fixed order (two levels; workspace of dram_bn_stats_from_partials_workspace_bytes(C) bytes) ->
+ * sums[0..C) = sum y, sums[C..2C) = sum y*y, what dram_bn_finalize takes. */
 long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo);
-int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* stream);
+size_t dram_bn_stats_from_partials_workspace_bytes(int C);
+int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* workspace, void* stream);
 /* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes
  *   dy_hi/dy_lo : [N][D][H][W][Cout_pad]   x_hi/x_lo : [N][D][H][W][Cin_pad]   (pads are multiples of 64)
  *   precision: dy_lo && x_lo -> three products; !dy_lo && x_lo -> x_hi*dy + x_lo*dy (single-plane gradient,

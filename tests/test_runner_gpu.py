@@ -106,8 +106,10 @@ def test_scheduler_step_reaches_the_captured_graph(monkeypatch):
         finals[mode] = (moved, {k: v.detach().clone() for k, v in runner.model.named_parameters()})
     # two Adam steps at lr 1e-4 move a weight by at most ~2e-4 (+ slack); at the stale 1e-3 they would move it ~2e-3
     assert finals["1"][0] < 1e-3 and finals["0"][0] < 1e-3, (finals["0"][0], finals["1"][0])
+    # graph and eager runs differ only by summation order; Adam turns a ~0 gradient's last-bit noise into a step of up to lr,
+    # so the bound is the step budget of the six updates (4 x 1e-3 + 2 x 1e-4), not rounding error
     for k, v in finals["0"][1].items():
-        assert (finals["1"][1][k] - v).abs().max().item() <= 3e-3, k
+        assert (finals["1"][1][k] - v).abs().max().item() <= 5e-3, k
 
 
 def test_pooling_global_max_and_avg():
