@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libdram_b200.so")
-SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_umma.cu", "ram.cu", "pcm.cu", "preproc.cu", "planes.cu"]
+SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_umma.cu", "ram.cu", "pcm.cu", "preproc.cu", "planes.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
              ]
 

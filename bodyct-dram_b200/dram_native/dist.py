@@ -11,7 +11,7 @@ the single-process reference run on the GLOBAL batch, hence three kinds of excha
 import torch
 import torch.distributed as td
 
-_STATE = {"group": None, "sync_bn": True, "reducer": None}
+_STATE = {"group": None, "sync_bn": True, "reducer": None, "peer": None}
 
 
 def configure(group=None, sync_bn=True):
@@ -54,8 +54,92 @@ def check_uniform_batch(shape_key):
         raise RuntimeError(f"data parallel training needs the same batch shape on every rank, got {keys}")
 
 
+class PeerGroup:
+    """NVLink peer-memory mailboxes for the step's small exchanges (csrc/peer.cu): every rank allocates a mailbox with
+    cudaMalloc, exports it through CUDA IPC, and maps every other rank's mailbox.  One kernel per exchange: push to all
+    peers, signal, wait, reduce in rank order.  `DRAM_PEER=0` (or a failed IPC mapping) keeps the NCCL path."""
+
+    def __init__(self):
+        import ctypes
+        from . import lib as _lib
+        self._lib, self._ct = _lib, ctypes
+        L = _lib.load()
+        self.rank, self.world = rank(), world_size()
+        if self.world > L.dram_peer_max_ranks():
+            raise RuntimeError(f"peer mailboxes are built for <= {L.dram_peer_max_ranks()} ranks of one node")
+        mine = ctypes.c_void_p()
+        _lib.check(L.dram_peer_alloc(ctypes.byref(mine)), "peer_alloc")
+        self.mine = mine
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(L.dram_peer_export(mine, handle), "peer_export")
+        handles = [None] * self.world
+        td.all_gather_object(handles, bytes(handle), group=_STATE["group"])
+        self.opened = []
+        ptrs = []
+        for q, h in enumerate(handles):
+            if q == self.rank:
+                ptrs.append(mine.value)
+                continue
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            p = ctypes.c_void_p()
+            _lib.check(L.dram_peer_open(buf, ctypes.byref(p)), f"peer_open(rank {q})")
+            self.opened.append(p)
+            ptrs.append(p.value)
+        self.boxes = (ctypes.c_void_p * self.world)(*ptrs)
+        self.max_doubles = L.dram_peer_max_doubles()
+        td.barrier(group=_STATE["group"])
+
+    def _arr(self, *ptrs):
+        return (self._ct.c_void_p * len(ptrs))(*ptrs)
+
+    def all_reduce_(self, t, out=None):
+        """SUM of a small contiguous float64 CUDA tensor over the ranks (in place unless `out`)."""
+        out = t if out is None else out
+        self._lib.check(self._lib.load().dram_peer_allreduce_f64(self.boxes, self._arr(t.data_ptr()), self._arr(out.data_ptr()),
+                                                                 t.numel(), self.rank, self.world, 1,
+                                                                 torch.cuda.current_stream().cuda_stream), "peer_allreduce_f64")
+        return out
+
+    def bn_finalize(self, sums, count, gamma, beta, running_mean, running_var, momentum, eps, n_updates):
+        """global BatchNorm statistics + finalize in one kernel -> (mean, rstd, scale, shift, global count)"""
+        C = sums.numel() // 2
+        gsums = torch.empty(2 * C + 1, device=sums.device, dtype=torch.float64)
+        o = torch.empty((4, C), device=sums.device, dtype=torch.float32)
+        p = lambda x: 0 if x is None else x.data_ptr()
+        cnt = (self._ct.c_double * 1)(float(count))
+        self._lib.check(self._lib.load().dram_bn_finalize_peer(
+            self.boxes, self._arr(sums.data_ptr()), cnt, self._arr(gsums.data_ptr()), self.rank, self.world, 1,
+            self._arr(p(gamma)), self._arr(p(beta)), self._arr(p(running_mean)), self._arr(p(running_var)), float(momentum),
+            float(eps), int(n_updates), self._arr(o[0].data_ptr()), self._arr(o[1].data_ptr()), self._arr(o[2].data_ptr()),
+            self._arr(o[3].data_ptr()), C, torch.cuda.current_stream().cuda_stream), "bn_finalize_peer")
+        return o[0], o[1], o[2], o[3]
+
+
+def init_peer():
+    """Set up the peer mailboxes once per process (NCCL backend, all ranks on one node); returns the group or None."""
+    import os
+    if _STATE.get("peer") is not None or not active() or os.environ.get("DRAM_PEER", "1") != "1":
+        return _STATE.get("peer")
+    if td.get_backend(_STATE["group"]) != "nccl" or not torch.cuda.is_available():
+        return None
+    try:
+        _STATE["peer"] = PeerGroup()
+    except Exception as e:                                   # noqa: BLE001  (no IPC between the ranks: NCCL does the exchanges)
+        import logging
+        logging.getLogger("dram.dist").warning("peer mailboxes unavailable (%s): BatchNorm / loss exchanges go through NCCL", e)
+        _STATE["peer"] = None
+    return _STATE["peer"]
+
+
+def peer():
+    return _STATE.get("peer") if (active() and _STATE["sync_bn"]) else None
+
+
 def all_reduce_(t):
     if active():
+        pg = _STATE.get("peer")
+        if pg is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= pg.max_doubles:
+            return pg.all_reduce_(t)
         td.all_reduce(t, op=td.ReduceOp.SUM, group=_STATE["group"])
     return t
 
@@ -73,6 +157,9 @@ def allreduce_sums(sums):
     """Global copy of the BatchNorm backward sums (the local ones stay intact: they are this rank's dgamma/dbeta)."""
     if not (active() and _STATE["sync_bn"]):
         return sums
+    pg = _STATE.get("peer")
+    if pg is not None and sums.is_cuda and sums.is_contiguous() and sums.numel() <= pg.max_doubles:
+        return pg.all_reduce_(sums, out=torch.empty_like(sums))      # one kernel, the local sums stay untouched
     g = sums.clone()
     all_reduce_(g)
     return g

@@ -245,9 +245,16 @@ class ConvBnRelu(torch.autograd.Function):
         if training:
             if sums is None:                       # kernels without the statistics epilogue (CUDA-core layers, ragged tiles)
                 sums = ops.bn_stats(y)
-            count = ddist.allreduce_stats(sums, count)
-            mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
-                                                       n_updates)
+            pg = ddist.peer()
+            if pg is not None and sums.numel() < pg.max_doubles:
+                # data parallel: the statistics exchange over NVLink peer memory and the finalize are ONE kernel
+                mean, rstd, scale, shift = pg.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                                          n_updates)
+                count = float(count) * ddist.world_size()
+            else:
+                count = ddist.allreduce_stats(sums, count)
+                mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum,
+                                                           eps, n_updates)
         else:
             scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
             if not _GRAD_OFF[0]:
@@ -394,9 +401,16 @@ class ConvBnReluRam(torch.autograd.Function):
         if training:
             if sums is None:
                 sums = ops.bn_stats(y)
-            count = ddist.allreduce_stats(sums, count)
-            mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
-                                                       n_updates)
+            pg = ddist.peer()
+            if pg is not None and sums.numel() < pg.max_doubles:
+                # data parallel: the statistics exchange over NVLink peer memory and the finalize are ONE kernel
+                mean, rstd, scale, shift = pg.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                                          n_updates)
+                count = float(count) * ddist.world_size()
+            else:
+                count = ddist.allreduce_stats(sums, count)
+                mean, rstd, scale, shift = ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum,
+                                                           eps, n_updates)
         else:
             scale, shift = _bn_fold_cached(gamma, beta, running_mean, running_var, eps)
             if not _GRAD_OFF[0]:

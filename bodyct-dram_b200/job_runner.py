@@ -60,6 +60,7 @@ class JobRunner:
         self.scheduler = get_callable_by_name(sched_cfg.pop('method'))(self.optimizer, **sched_cfg)
         self.reducer = ddist.GradReducer(self.model.parameters()) if ddist.active() else None
         if ddist.active():                                   # replicas start from rank 0's weights
+            ddist.init_peer()                                # NVLink mailboxes for the BatchNorm / loss-normaliser exchanges
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 torch.distributed.broadcast(t.data, src=0)
             self._weights_changed()

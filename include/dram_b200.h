@@ -300,6 +300,34 @@ int dram_masked_hist_u8(const void* values, int dtype, const uint8_t* labels, lo
 int dram_threshold_masks(const float* heat, const short* scan, const uint8_t* vessel, long long n, double th, double th2,
                          float win_lo, float win_hi, uint8_t* lesion, uint8_t* post, void* stream);
 
+/* ---- cross-GPU exchanges of the data-parallel step over NVLink peer memory (new functionality: the reference has no
+ * distributed code).  Parity target = the single-process reference on the GLOBAL batch, so every train-mode
+ * nn.BatchNorm3d (parts.py:19) needs all ranks' batch statistics, forward and backward, and IntRegRefineLoss needs the
+ * batch-global normalisers of metrics.py:30,37,42,48.  Each rank owns a mailbox (dram_peer_alloc) that every other rank maps
+ * through CUDA IPC (dram_peer_export -> 64-byte handle -> dram_peer_open); one call = ONE kernel: push the payload into every
+ * mailbox, release a flag, wait for every peer's flag, sum in rank order (bit-identical on all ranks).  `mailboxes` is a HOST
+ * array of `world` device pointers (entry `rank` = the own mailbox); all ranks must issue the same sequence of calls.
+ * nvirt = 1 in production.  nvirt = world plays ALL ranks as the blocks of one launch on one GPU (in/out/... are host arrays
+ * of nvirt per-rank pointers) - the single-GPU test of the protocol. */
+size_t dram_peer_mailbox_bytes(void);
+int dram_peer_max_doubles(void);
+int dram_peer_max_ranks(void);
+int dram_peer_alloc(void** mailbox);
+int dram_peer_free(void* mailbox);
+int dram_peer_export(const void* mailbox, void* handle64);
+int dram_peer_open(const void* handle64, void** mailbox);
+int dram_peer_close(void* mailbox);
+/* out[r][i] = sum over ranks q (in order) of in_q[i], n <= dram_peer_max_doubles(); out may alias in */
+int dram_peer_allreduce_f64(void* const* mailboxes, const double* const* in, double* const* out, int n, int rank, int world,
+                            int nvirt, void* stream);
+/* dram_bn_finalize on the GLOBAL statistics, fused with their exchange: payload = local (sum y [C], sum y^2 [C]) + the local
+ * element count counts[r]; sums_out[r] receives the global [2C+1]; then mean / rstd / scale / shift and the running-statistic
+ * update exactly as dram_bn_finalize (unbiased variance with the GLOBAL count). */
+int dram_bn_finalize_peer(void* const* mailboxes, const double* const* sums_in, const double* counts, double* const* sums_out,
+                          int rank, int world, int nvirt, const float* const* gamma, const float* const* beta,
+                          float* const* running_mean, float* const* running_var, float momentum, float eps, int n_updates,
+                          float* const* mean, float* const* rstd, float* const* scale, float* const* shift, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     td.init_process_group("nccl")
+    if os.environ.get("DRAM_PEER", "1") == "1":
+        assert ddist.init_peer() is not None, "peer mailboxes (CUDA IPC over NVLink) could not be set up"
     att = len(sys.argv) > 1 and sys.argv[1] == "att"
     cfg = dict(n_layers=3, in_ch_list=[1, 64, 128, 256, 768, 384, 192], base_ch_list=[32, 64, 128, 256, 256, 128, 64],
                end_ch_list=[64, 128, 256, 512, 256, 128, 64], kernel_sizes=[(3, 3)] * 7, stacking=3,

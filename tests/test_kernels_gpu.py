@@ -681,3 +681,70 @@ def test_pcm_attention(merge, self_loop, conn, grid, Fd):
     for name, p in pcm.named_parameters():
         ref = sd["attention_module." + name].grad
         assert (p.grad.cpu() - ref).abs().max().item() <= 2e-4 * scale, f"pcm d{name}"
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory exchanges
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_allreduce_protocol_all_ranks_played_on_one_gpu(world):
+    """csrc/peer.cu with nvirt = world: block b of ONE launch plays rank b, the "peer" mailboxes are buffers of this GPU.
+    Covers the push / flag / wait / rank-ordered reduce protocol, slot reuse over many calls and the fused BatchNorm finalize
+    (the multi-process NVLink path runs the same kernel with nvirt = 1: tests/dp_parity.py under torchrun)."""
+    import ctypes
+    from dram_native import lib
+    L = lib.load()
+    o = ops()
+    boxes = []
+    for _ in range(world):
+        p = ctypes.c_void_p()
+        lib.check(L.dram_peer_alloc(ctypes.byref(p)), "peer_alloc")
+        boxes.append(p)
+    box_arr = (ctypes.c_void_p * world)(*[b.value for b in boxes])
+    arr = lambda ts: (ctypes.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(7)
+    try:
+        for call in range(11):                                            # > 2 x slots: every slot is reused
+            n = [5, 1040, 64, 129][call % 4]
+            ins = [torch.randn(n, device="cuda", dtype=torch.float64) for _ in range(world)]
+            outs = [torch.empty(n, device="cuda", dtype=torch.float64) for _ in range(world)]
+            lib.check(L.dram_peer_allreduce_f64(box_arr, arr(ins), arr(outs), n, 0, world, world, st), "peer_allreduce")
+            ref = ins[0].clone()
+            for t in ins[1:]:
+                ref = ref + t                                             # rank order, like the kernel
+            for r in range(world):
+                assert torch.equal(outs[r], ref), (call, r)
+        # in place
+        ins = [torch.randn(33, device="cuda", dtype=torch.float64) for _ in range(world)]
+        ref = torch.stack(ins).sum(0)
+        lib.check(L.dram_peer_allreduce_f64(box_arr, arr(ins), arr(ins), 33, 0, world, world, st), "peer_allreduce")
+        for r in range(world):
+            assert torch.allclose(ins[r], ref, rtol=0, atol=1e-12)
+        # fused BatchNorm finalize == bn_finalize on the summed statistics with the summed count
+        C = 96
+        sums = [torch.rand(2 * C, device="cuda", dtype=torch.float64) * 100 for _ in range(world)]
+        for s_ in sums:
+            s_[C:] += s_[:C] ** 2 / 50.0                                   # keep the variance positive
+        counts = [50.0 + r for r in range(world)]
+        gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+        rms = [torch.zeros(C, device="cuda") for _ in range(world)]
+        rvs = [torch.ones(C, device="cuda") for _ in range(world)]
+        gs = [torch.empty(2 * C + 1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        o4 = [torch.empty((4, C), device="cuda") for _ in range(world)]
+        cnt = (ctypes.c_double * world)(*counts)
+        lib.check(L.dram_bn_finalize_peer(box_arr, arr(sums), cnt, arr(gs), 0, world, world, arr([gamma] * world), arr([beta] * world),
+                                          arr(rms), arr(rvs), 0.1, 1e-5, 2, arr([t[0] for t in o4]), arr([t[1] for t in o4]),
+                                          arr([t[2] for t in o4]), arr([t[3] for t in o4]), C, st), "bn_finalize_peer")
+        total = sums[0].clone()
+        for t in sums[1:]:
+            total = total + t
+        rm_ref, rv_ref = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        mean, rstd, scale, shift = o.bn_finalize(total, sum(counts), gamma, beta, rm_ref, rv_ref, 0.1, 1e-5, 2)
+        for r in range(world):
+            assert torch.equal(gs[r][:2 * C], total) and gs[r][2 * C].item() == sum(counts)
+            for got, ref_ in zip(o4[r], (mean, rstd, scale, shift)):
+                assert torch.equal(got, ref_)
+            assert torch.equal(rms[r], rm_ref) and torch.equal(rvs[r], rv_ref)
+        torch.cuda.synchronize()
+    finally:
+        for b in boxes:
+            L.dram_peer_free(b)
