@@ -178,11 +178,14 @@ struct FwdParams {
   // loaded through a tensor map whose dimension order is (C,H,W,D,N), so shared-memory rows are ordered [w][h]: with
   // TH = 8 every w column is one 8-row / 1024-byte swizzle group and a kw shift is a 1024-byte-aligned descriptor offset.
   int w3, a_plane_bytes, taps_per_stage, b_tap_bytes, a_lo;
+  int cb_split;   // virtual concat (parts.py:153 without the copy): channel blocks [0, cb_split) come from the first activation
+                  // operand (tmA_*), blocks [cb_split, kblocks_c) from the second (tmA2_*); cb_split = kblocks_c: one operand
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
                 const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -241,12 +244,16 @@ k_conv_umma_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (elect_one()) {
               const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes, fb = full0 + 8 * s;
               mbar_expect_tx(fb, stage_tx);
+              const bool second = cb >= p.cb_split;       // virtual concat: which activation tensor owns this channel block
+              const CUtensorMap* mh = second ? &tmA2_hi : &tmA_hi;
+              const CUtensorMap* ml = second ? &tmA2_lo : &tmA_lo;
+              const int cc = (second ? cb - p.cb_split : cb) * 64;
               if (p.w3) {                                 // map dims (C,H,W,D,N); kw = 0 here, box starts at w0 - 1
-                tma_load_5d(sb, &tmA_hi, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
-                if (a_lo) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+                tma_load_5d(sb, mh, fb, cc, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
+                if (a_lo) tma_load_5d(sb + offAlo, ml, fb, cc, h0 + kh - 1, w0 - 1, d0 + kd - 1, n);
               } else {
-                tma_load_5d(sb, &tmA_hi, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
-                if (a_lo) tma_load_5d(sb + offAlo, &tmA_lo, fb, cb * 64, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+                tma_load_5d(sb, mh, fb, cc, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
+                if (a_lo) tma_load_5d(sb + offAlo, ml, fb, cc, w0 + kw - p.pad, h0 + kh - p.pad, d0 + kd - p.pad, n);
               }
               for (int t = 0; t < tps; ++t) {
                 const uint32_t bo = (uint32_t)t * (uint32_t)p.b_tap_bytes;
@@ -384,6 +391,7 @@ struct Fwd2Params {
   int SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes, acc_cols, tmem_cols;
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
   float* stat;       // training: BatchNorm partial sums of y, [n_mtiles * 4][2][Cout] (row = M tile x epilogue warp), or NULL
+  int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmA2_*)
 };
 
 // Column sums over the 32 lanes of a warp for 32 values per lane: after the five exchange rounds lane l holds the total
@@ -427,6 +435,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
                  const Fwd2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -486,11 +495,15 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
             const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes, fa = fullA0 + 8 * sA;
             mbar_expect_tx(fa, a_tx);
-            tma_load_5d(ab, &tmA_hi, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
-            if (a2) tma_load_5d(ab + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h00 + kh, d00 + kd, w00, n0);
+            const bool second = cb >= p.cb_split;         // virtual concat: which activation tensor owns this channel block
+            const CUtensorMap* mh = second ? &tmA2_hi : &tmA_hi;
+            const CUtensorMap* ml = second ? &tmA2_lo : &tmA_lo;
+            const int cc = (second ? cb - p.cb_split : cb) * 64;
+            tma_load_5d(ab, mh, fa, cc, h00 + kh, d00 + kd, w00, n0);
+            if (a2) tma_load_5d(ab + p.a_plane_bytes, ml, fa, cc, h00 + kh, d00 + kd, w00, n0);
             if (ntile == 2) {
-              tma_load_5d(ab + p.a_tile_bytes, &tmA_hi, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
-              if (a2) tma_load_5d(ab + p.a_tile_bytes + p.a_plane_bytes, &tmA_lo, fa, cb * 64, h01 + kh, d01 + kd, w01, n1);
+              tma_load_5d(ab + p.a_tile_bytes, mh, fa, cc, h01 + kh, d01 + kd, w01, n1);
+              if (a2) tma_load_5d(ab + p.a_tile_bytes + p.a_plane_bytes, ml, fa, cc, h01 + kh, d01 + kd, w01, n1);
             }
           }
           __syncwarp();
@@ -673,12 +686,14 @@ struct Fwd3Params {
   int SW, x_plane_bytes, x_stage_bytes, w_stage_bytes;
   long long* prof;   // DRAM_CONV_PROF diagnostics
   float* stat;       // training: BatchNorm partial sums of y, [rows][2][Cout]; rows = n_vtiles (x 2 warps in the stacked modes)
+  int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmX2_*)
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                 const __grid_constant__ CUtensorMap tmX2_hi, const __grid_constant__ CUtensorMap tmX2_lo,
                  const Fwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -729,8 +744,10 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
           if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
             const uint32_t xb = smemX_u + sX * (uint32_t)p.x_stage_bytes, fx = fullX0 + 8 * sX;
             mbar_expect_tx(fx, x_tx);
-            tma_load_5d(xb, &tmX_hi, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
-            if (x2) tma_load_5d(xb + p.x_plane_bytes, &tmX_lo, fx, cb * 64, h0 + kh, d0 + kd, w0, n);
+            const bool second = cb >= p.cb_split;         // virtual concat: which activation tensor owns this channel block
+            const int cc = (second ? cb - p.cb_split : cb) * 64;
+            tma_load_5d(xb, second ? &tmX2_hi : &tmX_hi, fx, cc, h0 + kh, d0 + kd, w0, n);
+            if (x2) tma_load_5d(xb + p.x_plane_bytes, second ? &tmX2_lo : &tmX_lo, fx, cc, h0 + kh, d0 + kd, w0, n);
           }
           __syncwarp();
 #pragma unroll
@@ -925,6 +942,7 @@ struct WgParams {
   int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles, n_ntiles, BN;
   int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, spg;
   int passes, stages, stage_bytes, tmem_cols, concat, y_lo;
+  int cb_split;   // virtual concat: input channel blocks >= cb_split are read from the second X operand (tmX2_*)
 };
 // slab -> chunks first, first + step, ... (count of them): the slabs of a group of `spg` consecutive slabs (about one wave of
 // CTAs) interleave over the group's contiguous chunk range, so that all CTAs in flight read neighbouring chunks (see Wg3Params)
@@ -942,6 +960,7 @@ __device__ __forceinline__ WgRange wg_range(int n_chunks, int n_slabs, int spg, 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                   const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                  const __grid_constant__ CUtensorMap tmX2_hi, const __grid_constant__ CUtensorMap tmX2_lo,
                   const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1000,11 +1019,13 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
           if (elect_one()) {
             const uint32_t sb = smem_u32(smem) + s * (uint32_t)p.stage_bytes, fb = full0 + 8 * s;
             mbar_expect_tx(fb, tx);
-            tma_load_5d(sb, &tmX_hi, fb, cb0 * 64, w0 + kw0, h0 + kh0, d0 + kd0, n0);
-            if (three) tma_load_5d(sb + offAlo, &tmX_lo, fb, cb0 * 64, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+            const bool s0 = cb0 >= p.cb_split, s1 = cb1 >= p.cb_split;       // virtual concat: second X operand
+            const int cc0 = (s0 ? cb0 - p.cb_split : cb0) * 64, cc1 = (s1 ? cb1 - p.cb_split : cb1) * 64;
+            tma_load_5d(sb, s0 ? &tmX2_hi : &tmX_hi, fb, cc0, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+            if (three) tma_load_5d(sb + offAlo, s0 ? &tmX2_lo : &tmX_lo, fb, cc0, w0 + kw0, h0 + kh0, d0 + kd0, n0);
             if (has1) {
-              tma_load_5d(sb + kWgBlkBytes, &tmX_hi, fb, cb1 * 64, w0 + kw1, h0 + kh1, d0 + kd1, n0);
-              if (three) tma_load_5d(sb + offAlo + kWgBlkBytes, &tmX_lo, fb, cb1 * 64, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+              tma_load_5d(sb + kWgBlkBytes, s1 ? &tmX2_hi : &tmX_hi, fb, cc1, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+              if (three) tma_load_5d(sb + offAlo + kWgBlkBytes, s1 ? &tmX2_lo : &tmX_lo, fb, cc1, w0 + kw1, h0 + kh1, d0 + kd1, n0);
             }
             for (int j = 0; j < nb; ++j) {
               tma_load_5d(sb + offBhi + j * kWgBlkBytes, &tmY_hi, fb, nt * p.BN + j * 64, w0, h0, d0, n0);
@@ -1112,6 +1133,7 @@ struct Wg3Params {
   float* ws;
   int* prog;      // [n_items] chunks issued so far per work item (pacing of the single-source items, see below)
   int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, spg, stages, dfast, y_lo;
+  int cb_split;   // virtual concat: input channel blocks >= cb_split are read from the second X operand (tmX2_*)
 };
 
 // Chunk schedule of the kw-reuse wgrad.  The voxel chunks are split over `n_slabs` slabs (split-K); a work item is
@@ -1128,6 +1150,7 @@ __device__ __forceinline__ Wg3Range wg3_range(const Wg3Params& p, int slab) { re
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                      const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                     const __grid_constant__ CUtensorMap tmX2_hi, const __grid_constant__ CUtensorMap tmX2_lo,
                      const Wg3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1203,11 +1226,13 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
           if (elect_one()) {                         // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
             const uint32_t sb = smem_u32(smem) + s * (uint32_t)kW3Stage, fb = full0 + 8 * s;
             mbar_expect_tx(fb, tx);
-            tma_load_5d(sb, &tmX_hi, fb, cb0 * 64, h0 + kh0, w0 - 1, d0 + kd0, n0);
-            tma_load_5d(sb + offXlo, &tmX_lo, fb, cb0 * 64, h0 + kh0, w0 - 1, d0 + kd0, n0);
+            const bool v0 = cb0 >= p.cb_split, v1 = cb1 >= p.cb_split;       // virtual concat: second X operand
+            const int cc0 = (v0 ? cb0 - p.cb_split : cb0) * 64, cc1 = (v1 ? cb1 - p.cb_split : cb1) * 64;
+            tma_load_5d(sb, v0 ? &tmX2_hi : &tmX_hi, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
+            tma_load_5d(sb + offXlo, v0 ? &tmX2_lo : &tmX_lo, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
             if (nsrc == 2) {
-              tma_load_5d(sb + kW3XBox, &tmX_hi, fb, cb1 * 64, h0 + kh1, w0 - 1, d0 + kd1, n0);
-              tma_load_5d(sb + offXlo + kW3XBox, &tmX_lo, fb, cb1 * 64, h0 + kh1, w0 - 1, d0 + kd1, n0);
+              tma_load_5d(sb + kW3XBox, v1 ? &tmX2_hi : &tmX_hi, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
+              tma_load_5d(sb + offXlo + kW3XBox, v1 ? &tmX2_lo : &tmX_lo, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
             }
             tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
             if (p.y_lo) tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
@@ -1617,8 +1642,14 @@ int dram_bn_stats_from_partials(const float* partials, long long rows, int C, do
 }
 
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* scale,
-                         const float* shift, float* y, void* out_hi, void* out_lo, float* bn_partials, int N, int D, int H,
-                         int W, int Cin, int Cin_pad, int Cout, int ksize, void* stream) {
+                         const float* shift, float* y, void* out_hi, void* out_lo, float* bn_partials, const void* x2_hi,
+                         const void* x2_lo, int Cin1_pad, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize,
+                         void* stream) {
+  // virtual concat (UpsampleConvBlock5d, parts.py:151-155, without materialising cat([up, skip])): x holds the first Cin1_pad
+  // channels (its own row pitch), x2 the remaining Cin_pad - Cin1_pad; the K loop switches tensor maps at the block boundary
+  const int C1p = x2_hi ? Cin1_pad : Cin_pad, C2p = Cin_pad - C1p;
+  DRAM_REQUIRE(!x2_hi || (Cin1_pad > 0 && Cin1_pad % 64 == 0 && C2p > 0 && (x2_lo != nullptr) == (x_lo != nullptr)),
+               "conv3d_umma_fwd: second operand needs 0 < Cin1_pad (%d, multiple of 64) < Cin_pad (%d) and the same planes as x", Cin1_pad, Cin_pad);
   DRAM_REQUIRE(x_hi && w_hi && (y || out_hi) && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_fwd: bad arguments");
   DRAM_REQUIRE(!out_hi || (scale && Cout % 64 == 0), "conv3d_umma_fwd: plane output needs scale/shift (eval mode) and Cout %% 64 == 0 (no channel padding)");
   DRAM_REQUIRE(out_hi || !out_lo, "conv3d_umma_fwd: out_lo without out_hi");
@@ -1654,9 +1685,14 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     DRAM_REQUIRE(q.SW >= 2, "conv3d_umma_fwd: channels-on-M pipeline does not fit in shared memory");
     CUtensorMap mX_hi, mX_lo, mW_hi, mW_lo;
     int rc3;
-    if ((rc3 = make_volume_map_hdw(&mX_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3;
-    if (x_lo) { if ((rc3 = make_volume_map_hdw(&mX_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc3; }
+    CUtensorMap mX2_hi, mX2_lo;
+    q.cb_split = C1p / 64;
+    if ((rc3 = make_volume_map_hdw(&mX_hi, x_hi, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc3;
+    if (x_lo) { if ((rc3 = make_volume_map_hdw(&mX_lo, x_lo, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc3; }
     else mX_lo = mX_hi;
+    mX2_hi = mX_hi; mX2_lo = mX_lo;
+    if (x2_hi && (rc3 = make_volume_map_hdw(&mX2_hi, x2_hi, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc3;
+    if (x2_lo && (rc3 = make_volume_map_hdw(&mX2_lo, x2_lo, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc3;
     if ((rc3 = make_weight_map(&mW_hi, w_hi, 27ll * Cout, Cin_pad, q.CT))) return rc3;
     if ((rc3 = make_weight_map(&mW_lo, w_lo, 27ll * Cout, Cin_pad, q.CT))) return rc3;
     const size_t smem3 = 2 * (size_t)q.x_stage_bytes + (size_t)q.SW * q.w_stage_bytes + xchg + 1024 + 512;
@@ -1672,10 +1708,10 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     static const bool want_prof3 = getenv("DRAM_CONV_PROF") != nullptr;
     if (want_prof3 && !prof_buf3) cudaMalloc(&prof_buf3, kNumSMs * 8 * sizeof(long long));
     q.prof = want_prof3 ? prof_buf3 : nullptr;
-    if (mode == 0) k_conv_umma_fwd3<0><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
-    else if (mode == 1) k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
-    else if (mode == 2) k_conv_umma_fwd3<2><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
-    else k_conv_umma_fwd3<3><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, q);
+    if (mode == 0) k_conv_umma_fwd3<0><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
+    else if (mode == 1) k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
+    else if (mode == 2) k_conv_umma_fwd3<2><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
+    else k_conv_umma_fwd3<3><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
     DRAM_LAUNCH_CHECK();
     if (want_prof3) {
       long long h[kNumSMs * 8];
@@ -1710,10 +1746,15 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     DRAM_REQUIRE(q.SB >= 2 && q.tmem_cols <= 512, "conv3d_umma_fwd: tile-pair pipeline does not fit (SB=%d, tmem=%d)", q.SB, q.tmem_cols);
     CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
     int rc2;
-    if ((rc2 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
+    CUtensorMap mA2_hi, mA2_lo;
+    q.cb_split = C1p / 64;
+    if ((rc2 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc2;
     if ((rc2 = make_weight_map(&mB_hi, w_hi, 27ll * Cout, Cin_pad, q.BN))) return rc2;
     mA_lo = mA_hi; mB_lo = mB_hi;
-    if (x_lo && (rc2 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, Cin_pad, q.TW + 2, q.TDD))) return rc2;
+    if (x_lo && (rc2 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc2;
+    mA2_hi = mA_hi; mA2_lo = mA_lo;
+    if (x2_hi && (rc2 = make_volume_map_hdw(&mA2_hi, x2_hi, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc2;
+    if (x2_lo && (rc2 = make_volume_map_hdw(&mA2_lo, x2_lo, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc2;
     if (w_lo && (rc2 = make_weight_map(&mB_lo, w_lo, 27ll * Cout, Cin_pad, q.BN))) return rc2;
     const size_t smem2 = 2 * (size_t)q.a_stage_bytes + (size_t)q.SB * q.b_stage_bytes + 1024 + 512;
     static std::once_flag once2;
@@ -1729,11 +1770,11 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     if (want_prof && !prof_buf) cudaMalloc(&prof_buf, kNumSMs * 8 * sizeof(long long));
     q.prof = want_prof ? prof_buf : nullptr;
     const int grid2 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
-    if (mode == 0) k_conv_umma_fwd2<0><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
-    else if (mode == 1) k_conv_umma_fwd2<1><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
-    else if (mode == 2) k_conv_umma_fwd2<2><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
-    else if (mode == 3) k_conv_umma_fwd2<3><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
-    else k_conv_umma_fwd2<4><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+    if (mode == 0) k_conv_umma_fwd2<0><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
+    else if (mode == 1) k_conv_umma_fwd2<1><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
+    else if (mode == 2) k_conv_umma_fwd2<2><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
+    else if (mode == 3) k_conv_umma_fwd2<3><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
+    else k_conv_umma_fwd2<4><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
     DRAM_LAUNCH_CHECK();
     if (want_prof) {                         // diagnostics: per-CTA averages of the MMA thread's and one epilogue warp's cycle split
       long long h[kNumSMs * 8];
@@ -1774,17 +1815,22 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc;
   const int abw = p.w3 ? p.TW + 2 : p.TW;
-  if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
+  CUtensorMap tmA2_hi, tmA2_lo;
+  p.cb_split = C1p / 64;
+  if ((rc = make_volume_map(&tmA_hi, x_hi, N, D, H, W, C1p, abw, p.TH, p.TD, 1, p.w3))) return rc;
   if ((rc = make_weight_map(&tmB_hi, w_hi, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
   tmA_lo = tmA_hi; tmB_lo = tmB_hi;
-  if (x_lo && (rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, Cin_pad, abw, p.TH, p.TD, 1, p.w3))) return rc;
+  if (x_lo && (rc = make_volume_map(&tmA_lo, x_lo, N, D, H, W, C1p, abw, p.TH, p.TD, 1, p.w3))) return rc;
   if (w_lo && (rc = make_weight_map(&tmB_lo, w_lo, (long long)p.taps * Cout, Cin_pad, p.BN))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(k_conv_umma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   const long long tiles = (long long)p.n_mtiles * p.n_ntiles;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_conv_umma_fwd<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  tmA2_hi = tmA_hi; tmA2_lo = tmA_lo;
+  if (x2_hi && (rc = make_volume_map(&tmA2_hi, x2_hi, N, D, H, W, C2p, abw, p.TH, p.TD, 1, p.w3))) return rc;
+  if (x2_lo && (rc = make_volume_map(&tmA2_lo, x2_lo, N, D, H, W, C2p, abw, p.TH, p.TD, 1, p.w3))) return rc;
+  k_conv_umma_fwd<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmA2_hi, tmA2_lo, p);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
@@ -1883,8 +1929,12 @@ size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Ci
 }
 
 int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* dw,
-                           void* workspace, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad,
-                           int ksize, void* stream) {
+                           void* workspace, const void* x2_hi, const void* x2_lo, int Cin1_pad, int N, int D, int H, int W,
+                           int Cin, int Cin_pad, int Cout, int Cout_pad, int ksize, void* stream) {
+  // virtual concat of the layer input, see dram_conv3d_umma_fwd
+  const int C1p = x2_hi ? Cin1_pad : Cin_pad, C2p = Cin_pad - C1p;
+  DRAM_REQUIRE(!x2_hi || (Cin1_pad > 0 && Cin1_pad % 64 == 0 && C2p > 0 && (x2_lo != nullptr) == (x_lo != nullptr)),
+               "conv3d_umma_wgrad: second operand needs 0 < Cin1_pad (%d, multiple of 64) < Cin_pad (%d) and the same planes as x", Cin1_pad, Cin_pad);
   DRAM_REQUIRE(dy_hi && x_hi && dw && workspace && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_wgrad: bad arguments");
   DRAM_REQUIRE(!(dy_lo != nullptr && x_lo == nullptr), "conv3d_umma_wgrad: dy_lo needs x_lo (modes: both = bf16x3, x_lo only = single-plane gradient x split input, neither = bf16)");
   DRAM_REQUIRE(ksize == 1 || ksize == 3, "conv3d_umma_wgrad: kernel size %d unsupported", ksize);
@@ -1898,8 +1948,13 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     q.y_lo = dy_lo ? 1 : 0;
     CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo;
     int rc3;
-    if ((rc3 = make_volume_map(&mX_hi, x_hi, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
-    if ((rc3 = make_volume_map(&mX_lo, x_lo, N, D, H, W, Cin_pad, 10, 8, 1, 1, true))) return rc3;
+    CUtensorMap mX2_hi, mX2_lo;
+    q.cb_split = C1p / 64;
+    if ((rc3 = make_volume_map(&mX_hi, x_hi, N, D, H, W, C1p, 10, 8, 1, 1, true))) return rc3;
+    if ((rc3 = make_volume_map(&mX_lo, x_lo, N, D, H, W, C1p, 10, 8, 1, 1, true))) return rc3;
+    mX2_hi = mX_hi; mX2_lo = mX_lo;
+    if (x2_hi && (rc3 = make_volume_map(&mX2_hi, x2_hi, N, D, H, W, C2p, 10, 8, 1, 1, true))) return rc3;
+    if (x2_lo && (rc3 = make_volume_map(&mX2_lo, x2_lo, N, D, H, W, C2p, 10, 8, 1, 1, true))) return rc3;
     if ((rc3 = make_volume_map(&mY_hi, dy_hi, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3;
     if (dy_lo) { if ((rc3 = make_volume_map(&mY_lo, dy_lo, N, D, H, W, Cout_pad, 8, 8, 1, 1, true))) return rc3; }
     else mY_lo = mY_hi;
@@ -1908,7 +1963,7 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     std::call_once(once3, [] { cudaFuncSetAttribute(k_conv_umma_wgrad_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     const int items3 = q.n_slabs * q.n_pairs;
     cudaStream_t st3 = (cudaStream_t)stream;
-    k_conv_umma_wgrad_w3<<<items3 < kNumSMs ? items3 : kNumSMs, kFwdThreads, smem3, st3>>>(mX_hi, mX_lo, mY_hi, mY_lo, q);
+    k_conv_umma_wgrad_w3<<<items3 < kNumSMs ? items3 : kNumSMs, kFwdThreads, smem3, st3>>>(mX_hi, mX_lo, mY_hi, mY_lo, mX2_hi, mX2_lo, q);
     DRAM_LAUNCH_CHECK();
     k_wgrad_w3_reduce<<<grid_for(27ll * Cin * Cout, 256), 256, 0, st3>>>(q.ws, dw, Cout, Cin, q.CB, q.n_pairs, q.n_slabs);
     DRAM_LAUNCH_CHECK();
@@ -1921,10 +1976,12 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
   p.ws = (float*)workspace;
   CUtensorMap tmX_hi, tmX_lo, tmY_hi, tmY_lo;
   int rc;
-  if ((rc = make_volume_map(&tmX_hi, x_hi, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  CUtensorMap tmX2_hi, tmX2_lo;
+  p.cb_split = C1p / 64;
+  if ((rc = make_volume_map(&tmX_hi, x_hi, N, D, H, W, C1p, p.TW, p.TH, p.TD, p.TN))) return rc;
   if ((rc = make_volume_map(&tmY_hi, dy_hi, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
   tmX_lo = tmX_hi; tmY_lo = tmY_hi;
-  if (x_lo && (rc = make_volume_map(&tmX_lo, x_lo, N, D, H, W, Cin_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
+  if (x_lo && (rc = make_volume_map(&tmX_lo, x_lo, N, D, H, W, C1p, p.TW, p.TH, p.TD, p.TN))) return rc;
   if (dy_lo && (rc = make_volume_map(&tmY_lo, dy_lo, N, D, H, W, Cout_pad, p.TW, p.TH, p.TD, p.TN))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   static std::once_flag once;
@@ -1932,7 +1989,10 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
   const int items = p.n_slabs * p.n_mtiles * p.n_ntiles;
   const int grid = items < kNumSMs ? items : kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
-  k_conv_umma_wgrad<<<grid, kFwdThreads, smem, st>>>(tmX_hi, tmX_lo, tmY_hi, tmY_lo, p);
+  tmX2_hi = tmX_hi; tmX2_lo = tmX_lo;
+  if (x2_hi && (rc = make_volume_map(&tmX2_hi, x2_hi, N, D, H, W, C2p, p.TW, p.TH, p.TD, p.TN))) return rc;
+  if (x2_lo && (rc = make_volume_map(&tmX2_lo, x2_lo, N, D, H, W, C2p, p.TW, p.TH, p.TD, p.TN))) return rc;
+  k_conv_umma_wgrad<<<grid, kFwdThreads, smem, st>>>(tmX_hi, tmX_lo, tmY_hi, tmY_lo, tmX2_hi, tmX2_lo, p);
   DRAM_LAUNCH_CHECK();
   k_wgrad_reduce<<<grid_for((long long)p.taps * Cin * Cout, 256), 256, 0, st>>>(p.ws, dw, Cout, Cin, p.taps, p.CB, p.n_mtiles,
                                                                                 p.n_ntiles, p.BN, p.n_slabs);

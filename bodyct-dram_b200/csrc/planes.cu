@@ -951,6 +951,27 @@ int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void
   return DRAM_OK;
 }
 
+int dram_upsample2x_planes(const void* x_hi, const void* x_lo, void* out_hi, void* out_lo, int N, int d, int h, int w, int C1,
+                           int P1, int Pout, void* stream) {
+  DRAM_REQUIRE(x_hi && out_hi && N > 0 && d > 0 && h > 0 && w > 0, "upsample2x_planes: bad arguments");
+  DRAM_REQUIRE((x_lo == nullptr) == (out_lo == nullptr), "upsample2x_planes: lo planes must be both set or both NULL");
+  DRAM_REQUIRE(C1 > 0 && C1 % 8 == 0 && P1 >= C1 && P1 % 8 == 0 && Pout == C1,
+               "upsample2x_planes: C1=%d must be a multiple of 8 and fill the output rows (Pout=%d)", C1, Pout);
+  DRAM_REQUIRE((long long)N * 8 * d * h * w < (1ll << 31), "upsample2x_planes: volume too large");
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const long long cols1 = (long long)N * h * w * (C1 / 8);
+  int nseg = (int)((4ll * kNumSMs * 8 * 128 + cols1 - 1) / cols1);
+  if (nseg > d / 8) nseg = d / 8;
+  if (nseg < 1) nseg = 1;
+  const int zseg = (d + nseg - 1) / nseg;
+  nseg = (d + zseg - 1) / zseg;
+  k_up2x_planes_zslide<<<grid_fixed_group((long long)N * nseg * h * w, C1 / 8, 128, 64), 128, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x_hi, (const uint4*)x_lo, (uint4*)out_hi, (uint4*)out_lo, N, d, h, w, C1, P1, Pout, ac_scale(d, D),
+      ac_scale(h, H), ac_scale(w, W), zseg, nseg);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
 int dram_merge_planes(const void* hi, const void* lo, float* out, long long rows, int C, int Cpad, void* stream) {
   DRAM_REQUIRE(hi && out && rows > 0 && C > 0 && C % 8 == 0 && Cpad >= C && Cpad % 8 == 0, "merge_planes: bad arguments (C=%d Cpad=%d)", C, Cpad);
   k_merge_planes<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)hi, (const uint4*)lo, out, rows, C, Cpad);

@@ -216,7 +216,8 @@ class ConvBnRelu(torch.autograd.Function):
         xs = x_real = None
         pointwise = False
         if x_hi is not None:
-            xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1])
+            second = getattr(x_hi, "_dram_second", None)       # virtual concat: the skip planes ride on the hi tensor (upsample_concat)
+            xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1] + (second.Cpad if second is not None else 0), second)
             pointwise = not umma and not ctx.needs_input_grad[0] and ops.pointwise8_ok(xs, Cout, k)
             if not umma and not pointwise:
                 x_real = ops.merge_planes(xs)
@@ -463,8 +464,14 @@ class UpsampleConcat(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.planes = x_hi is not None and s_hi is not None
         if ctx.planes:
-            cat = ops.upsample2x_concat_planes(ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1]),
-                                               ops.SplitPlanes(s_hi, s_lo, tuple(skip.shape), s_hi.shape[-1]))
+            xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1])
+            ss = ops.SplitPlanes(s_hi, s_lo, tuple(skip.shape), s_hi.shape[-1])
+            if ops.virtual_concat_ok(xs, ss):
+                # VIRTUAL concat: only the upsampled half is written; the skip planes are handed on as they are and the
+                # convolution reads both through two tensor maps (the caller re-attaches them, see upsample_concat)
+                cat = ops.upsample2x_virtual_concat(xs, ss)
+            else:
+                cat = ops.upsample2x_concat_planes(xs, ss)
             ctx.mark_non_differentiable(*[t for t in (cat.hi, cat.lo) if t is not None])
             return _handle(cat.shape, x_hi.device), cat.hi, cat.lo
         if x_hi is not None:
@@ -491,7 +498,13 @@ class UpsampleConcat(torch.autograd.Function):
 
 def upsample_concat(x, skip):
     t, hi, lo = UpsampleConcat.apply(*_unwrap(x), *_unwrap(skip))
-    return _wrap(t, hi, lo)
+    out = _wrap(t, hi, lo)
+    if isinstance(out, Act) and isinstance(skip, Act) and hi.shape[-1] < ops._pad64(t.shape[1]):
+        # the planes returned hold only the upsampled channels: virtual concat with the skip planes as second operand.  The
+        # autograd Functions take (handle, hi, lo) triples, so the second operand travels as an attribute of the hi tensor.
+        out.planes = ops.SplitPlanes(hi, lo, tuple(t.shape), hi.shape[-1] + skip.planes.Cpad, second=skip.planes)
+        hi._dram_second = skip.planes
+    return out
 
 
 class TrilinearResize(torch.autograd.Function):

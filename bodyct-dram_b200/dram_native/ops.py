@@ -129,11 +129,24 @@ def conv_simt_wgrad(x, dy, ksize):
 
 
 class SplitPlanes:
-    """bf16 split planes of a CL volume: hi (+ lo in bf16x3 mode), channels zero-padded to a multiple of 64."""
-    __slots__ = ("hi", "lo", "shape", "Cpad")
+    """bf16 split planes of a CL volume: hi (+ lo in bf16x3 mode), channels zero-padded to a multiple of 64.
+    `second`: a VIRTUAL channel concat — this object holds the first `C1` channels (pitch Cpad1 = hi.shape[-1]) and
+    `second` (another SplitPlanes of the same spatial size) the rest; `shape` / `Cpad` describe the concatenated volume.
+    The tensor-core convolutions read both through two tensor maps (parts.py:153 without the copy)."""
+    __slots__ = ("hi", "lo", "shape", "Cpad", "second")
 
-    def __init__(self, hi, lo, shape, Cpad):
-        self.hi, self.lo, self.shape, self.Cpad = hi, lo, shape, Cpad
+    def __init__(self, hi, lo, shape, Cpad, second=None):
+        self.hi, self.lo, self.shape, self.Cpad, self.second = hi, lo, shape, Cpad, second
+
+    @property
+    def Cpad1(self):
+        return self.hi.shape[-1]
+
+    def x2(self):
+        """(x2_hi ptr, x2_lo ptr, Cin1_pad) for the C ABI"""
+        if self.second is None:
+            return 0, 0, 0
+        return self.second.hi.data_ptr(), _p(self.second.lo), self.Cpad1
 
 
 def split_bf16(x, three=None):
@@ -172,8 +185,8 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
             raise _lib.DramLibraryError("conv_umma: plane output needs folded BatchNorm scale/shift and Cout % 64 == 0")
         out = alloc_planes((N, Cout, D, H, W), three=xs.lo is not None)
         _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), scale.data_ptr(),
-                                             shift.data_ptr(), None, out.hi.data_ptr(), _p(out.lo), None, N, D, H, W, Cin,
-                                             xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
+                                             shift.data_ptr(), None, out.hi.data_ptr(), _p(out.lo), None, *xs.x2(), N, D, H, W,
+                                             Cin, xs.Cpad, Cout, ksize, _stream()), "conv3d_umma_fwd")
         return out
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
     partials, rows = None, 0
@@ -182,8 +195,8 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
         if rows > 0:
             partials = torch.empty((rows, 2, Cout), device=xs.hi.device, dtype=torch.float32)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),
-                                         y.data_ptr(), None, None, _p(partials), N, D, H, W, Cin, xs.Cpad, Cout, ksize,
-                                         _stream()), "conv3d_umma_fwd")
+                                         y.data_ptr(), None, None, _p(partials), *xs.x2(), N, D, H, W, Cin, xs.Cpad, Cout,
+                                         ksize, _stream()), "conv3d_umma_fwd")
     if not want_stats:
         return y
     if partials is None:
@@ -207,7 +220,7 @@ def conv_umma_wgrad(dys, xs, Cin, Cout, ksize, stream=None, keep=None, out=None)
     dw = out if out is not None else torch.empty((Cout, Cin, ksize, ksize, ksize), device=xs.hi.device, dtype=torch.float32)
     _lib.PROFILE.note(flops=2.0 * N * D * H * W * Cin * Cout * ksize ** 3, tag=f"{Cin}->{Cout}@{D}")
     _lib.check(_L().dram_conv3d_umma_wgrad(dys.hi.data_ptr(), _p(dys.lo), xs.hi.data_ptr(), _p(xs.lo), dw.data_ptr(),
-                                           ws.data_ptr(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize,
+                                           ws.data_ptr(), *xs.x2(), N, D, H, W, Cin, xs.Cpad, Cout, dys.Cpad, ksize,
                                            _stream() if stream is None else stream), "conv3d_umma_wgrad")
     if keep is not None:
         keep.append(ws)
@@ -274,6 +287,11 @@ def bn_relu_apply_planes(y, scale, shift, pool=False):
 
 def merge_planes(xs):
     """split planes -> fp32 channels-last volume"""
+    if xs.second is not None:
+        N, C, D, H, W = xs.shape
+        C1 = xs.Cpad1
+        a = merge_planes(SplitPlanes(xs.hi, xs.lo, (N, C1, D, H, W), C1))
+        return torch.cat([a, merge_planes(xs.second)], dim=1).contiguous(memory_format=CL)
     N, C, D, H, W = xs.shape
     out = new_volume(N, C, D, H, W, xs.hi.device)
     _lib.check(_L().dram_merge_planes(xs.hi.data_ptr(), _p(xs.lo), out.data_ptr(), N * D * H * W, C, xs.Cpad, _stream()),
@@ -283,7 +301,7 @@ def merge_planes(xs):
 
 def pointwise8_ok(xs, Cout, k):
     """1x1x1 conv to 8 channels straight from planes (the attention reshape heads)"""
-    return k == 1 and isinstance(xs, SplitPlanes) and bool(_L().dram_pointwise8_planes_supported(int(xs.Cpad), int(Cout)))
+    return xs.second is None and k == 1 and isinstance(xs, SplitPlanes) and bool(_L().dram_pointwise8_planes_supported(int(xs.Cpad), int(Cout)))
 
 
 def pointwise8_planes(xs, w, bias):
@@ -384,6 +402,25 @@ def upsample2x_concat_planes(xs, skips):
                                                   cat.hi.data_ptr(), _p(cat.lo), N, d, h, w, C1, xs.Cpad, Ds, Hs, Ws, C2,
                                                   skips.Cpad, cat.Cpad, _stream()), "upsample2x_concat_planes")
     return cat
+
+
+def virtual_concat_ok(xs, skips):
+    """can cat([up2x(x), skip]) stay virtual?  exact x2 sizes (no crop), the upsampled half fills whole 64-channel blocks"""
+    N, C1, d, h, w = xs.shape
+    _, C2, Ds, Hs, Ws = skips.shape
+    return (os.environ.get("DRAM_VIRTUAL_CONCAT", "1") == "1" and (Ds, Hs, Ws) == (2 * d, 2 * h, 2 * w) and C1 % 64 == 0
+            and skips.second is None and xs.second is None and (xs.lo is None) == (skips.lo is None))
+
+
+def upsample2x_virtual_concat(xs, skips):
+    """planes of x [N,C1,d,h,w] and skip [N,C2,2d,2h,2w] -> SplitPlanes of cat [N,C1+C2,2d,2h,2w] whose first half is the freshly
+    upsampled tensor and whose `second` half IS the skip planes (no copy)"""
+    N, C1, d, h, w = xs.shape
+    C2 = skips.shape[1]
+    up = alloc_planes((N, C1, 2 * d, 2 * h, 2 * w), three=xs.lo is not None)
+    _lib.check(_L().dram_upsample2x_planes(xs.hi.data_ptr(), _p(xs.lo), up.hi.data_ptr(), _p(up.lo), N, d, h, w, C1, xs.Cpad,
+                                           up.Cpad, _stream()), "upsample2x_planes")
+    return SplitPlanes(up.hi, up.lo, (N, C1 + C2, 2 * d, 2 * h, 2 * w), up.Cpad + skips.Cpad, second=skips)
 
 
 def upsample2x_concat_bwd(dcat, x_shape, skip_shape, want_dskip=True):

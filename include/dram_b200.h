@@ -80,7 +80,12 @@ int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo /*nullable*/, i
 int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                          const float* scale /*nullable*/, const float* shift /*nullable*/, float* y /*nullable with out_hi*/,
                          void* out_hi /*nullable*/, void* out_lo /*nullable*/, float* bn_partials /*nullable*/,
+                         const void* x2_hi /*nullable*/, const void* x2_lo /*nullable*/, int Cin1_pad,
                          int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, void* stream);
+/* x2_hi != NULL: VIRTUAL channel concat of the input (UpsampleConvBlock5d: cat([upsampled, skip]), parts.py:151-155, without
+ * materialising the 768/384/192-channel tensor): x holds channels [0, Cin1_pad) with row pitch Cin1_pad (multiple of 64),
+ * x2 holds channels [Cin1_pad, Cin_pad) with row pitch Cin_pad - Cin1_pad; the weights are packed for the concatenated
+ * input as usual.  The K loop of every kernel switches tensor maps at the 64-channel block boundary. */
 /* Train-mode BatchNorm statistics (parts.py:19) as a by-product of the convolution's epilogue: with
  * bn_partials != NULL (raw output only) the epilogue also writes per-channel partial sums of y and y*y,
  * [rows][2][Cout] floats, rows = dram_conv3d_umma_fwd_stat_rows(...) (one row per output tile and epilogue warp; 0 = the
@@ -98,8 +103,9 @@ int dram_bn_stats_from_partials(const float* partials, long long rows, int C, do
  * deterministically into dw in nn.Parameter layout [Cout][Cin][taps]. */
 size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize);
 int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* dw,
-                           void* workspace, int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad,
-                           int ksize, void* stream);
+                           void* workspace, const void* x2_hi /*nullable*/, const void* x2_lo /*nullable*/, int Cin1_pad,
+                           int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int Cout_pad, int ksize, void* stream);
+/* (x2_*, Cin1_pad: virtual concat of the layer input, as in dram_conv3d_umma_fwd) */
 
 /* ------------------------------------------------------------------------------------------------ BatchNorm + ReLU (+ pool)
  * nn.BatchNorm3d (eps 1e-5, momentum 0.1) + nn.ReLU: parts.py:19,50,107-108.  rows = N*D*H*W, y is [rows][C]. */
@@ -159,6 +165,10 @@ int dram_bn_pool_bwd_apply_planes(const float* ga /*nullable*/, long long ga_pit
 int dram_upsample2x_concat_planes(const void* x_hi, const void* x_lo, const void* skip_hi, const void* skip_lo, void* cat_hi,
                                   void* cat_lo, int N, int d, int h, int w, int C1, int P1, int Ds, int Hs, int Ws, int C2,
                                   int P2, int Pc, void* stream);
+/* the upsampled half alone, planes -> planes [N][2d][2h][2w][Pout] (channels [C1, Pout) zeroed): the first operand of the
+ * virtual concat; the skip planes are the second operand as they are (no crop: skip size == 2x the input size) */
+int dram_upsample2x_planes(const void* x_hi, const void* x_lo, void* out_hi, void* out_lo, int N, int d, int h, int w, int C1,
+                           int P1, int Pout, void* stream);
 /* planes -> fp32 [rows][C]: materialises an activation for a consumer outside the tensor-core path */
 int dram_merge_planes(const void* hi, const void* lo /*nullable*/, float* out, long long rows, int C, int Cpad, void* stream);
 

@@ -155,6 +155,52 @@ def test_conv_umma_forward_bn_statistics_epilogue(N, Cin, Cout, S):
     assert torch.equal(sums, o.conv_umma(xs, w_hi, w_lo, Cout, 3, want_stats=True)[1]), "fixed summation order: deterministic"
 
 
+@pytest.mark.parametrize("N,C1,C2,Cout,S", [
+    (1, 128, 64, 64, (8, 8, 16)),       # us2.c0 shape class: weight-sharing tile pairs forward, kw-reuse wgrad
+    (1, 256, 128, 128, (4, 8, 8)),      # us1.c0 shape class: channels-on-M forward, generic wgrad
+    (2, 128, 64, 256, (5, 5, 5)),       # us0.c0 shape class: ragged tiles, generic forward and wgrad
+    (1, 64, 32, 64, (8, 8, 16)),        # second operand with channel padding (32 -> 64)
+])
+def test_conv_umma_virtual_concat_equals_materialised_concat(N, C1, C2, Cout, S):
+    """UpsampleConvBlock5d's cat([up, skip]) (parts.py:151-155) read through two tensor maps == the same convolution on the
+    materialised concat: forward, eval-mode plane epilogue and weight gradient, bit for bit"""
+    o = ops()
+    a, b = torch.randn(N, C1, *S), torch.randn(N, C2, *S)
+    w = torch.randn(Cout, C1 + C2, 3, 3, 3) * (2.0 / ((C1 + C2) * 27)) ** 0.5
+    dy = torch.randn(N, Cout, *S)
+    cat = o.split_bf16(cuda_cl(torch.cat([a, b], 1)), True)
+    xa, xb = o.split_bf16(cuda_cl(a), True), o.split_bf16(cuda_cl(b), True)
+    virt = o.SplitPlanes(xa.hi, xa.lo, (N, C1 + C2, *S), xa.Cpad + xb.Cpad, second=xb)
+    assert cat.Cpad == virt.Cpad
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    assert torch.equal(o.conv_umma(virt, w_hi, w_lo, Cout, 3), o.conv_umma(cat, w_hi, w_lo, Cout, 3))
+    y1, s1 = o.conv_umma(virt, w_hi, w_lo, Cout, 3, want_stats=True)
+    y2, s2 = o.conv_umma(cat, w_hi, w_lo, Cout, 3, want_stats=True)
+    assert (s1 is None) == (s2 is None) and (s1 is None or torch.equal(s1, s2))
+    if Cout % 64 == 0:
+        scale, shift = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda") * 0.1
+        p1 = o.conv_umma(virt, w_hi, w_lo, Cout, 3, scale, shift, out_planes=True)
+        p2 = o.conv_umma(cat, w_hi, w_lo, Cout, 3, scale, shift, out_planes=True)
+        assert torch.equal(p1.hi, p2.hi) and torch.equal(p1.lo, p2.lo)
+    dys = o.split_bf16(cuda_cl(dy), True)
+    assert torch.equal(o.conv_umma_wgrad(dys, virt, C1 + C2, Cout, 3), o.conv_umma_wgrad(dys, cat, C1 + C2, Cout, 3))
+    assert_close(o.merge_planes(virt), torch.cat([a, b], 1), 1e-4, "merge of a virtual concat")
+
+
+def test_upsample_virtual_concat_planes():
+    """the upsampled half written alone + the skip planes as second operand == the materialised upsample+concat planes"""
+    o = ops()
+    x, sk = torch.randn(2, 64, 3, 4, 5), torch.randn(2, 24, 6, 8, 10)
+    xs, ss = o.split_bf16(cuda_cl(x), True), o.split_bf16(cuda_cl(sk), True)
+    assert o.virtual_concat_ok(xs, ss)
+    v = o.upsample2x_virtual_concat(xs, ss)
+    m = o.upsample2x_concat_planes(xs, ss)
+    assert v.second is ss and v.shape == m.shape and v.Cpad == m.Cpad
+    assert torch.equal(v.hi, m.hi[:, :64]) and torch.equal(v.lo, m.lo[:, :64])
+    assert torch.equal(o.merge_planes(v), o.merge_planes(m))
+    assert not o.virtual_concat_ok(o.split_bf16(cuda_cl(torch.randn(1, 32, 2, 2, 2)), True), o.split_bf16(cuda_cl(torch.randn(1, 8, 4, 4, 4)), True))
+
+
 def test_conv_umma_forward_folded_bn_relu():
     o = ops()
     N, Cin, Cout, S = 1, 64, 64, (8, 8, 8)
