@@ -425,6 +425,47 @@ def measure_train(dist, args, att, peaks, clocks=True):
     }
 
 
+def measure_rank_spread(dist, args, sync_ms):
+    """N > 1: the same training step with the data-parallel exchanges SUSPENDED — every GPU free-running on its own replica,
+    all GPUs of the box loaded at the same time — gathered over the ranks.  The synchronised step cannot be faster than
+    the slowest GPU's free-running step (28 BatchNorm exchanges per step make all ranks move in lockstep), so
+    max(free-running) / synchronised is what the exchanges themselves cost; the spread between the GPUs (silicon and
+    cooling differ under the same 1 kW cap) is what weak scaling loses before any communication."""
+    import torch
+    import job_runner
+    from dram_native import dist as ddist
+    from utils import Settings
+    ddist.suspend(True)
+    try:
+        settings = Settings(os.path.join(ROOT, "bodyct-dram_b200", "exp_settings", "st_dram_ref.py"))
+        settings.OPTIMIZER['lr'] = 1e-3
+        settings.TRAIN_BATCH_SIZE = args.batch
+        torch.manual_seed(0)
+        runner = job_runner.LesionSegChunkTrain(settings_module=settings)
+        batch = {k: (v.to(dist.dev) if hasattr(v, "to") else v) for k, v in make_batch(args.batch, seed=dist.rank, pinned=False).items()}
+        for _ in range(max(args.warmup, 3)):
+            runner.train_step(batch)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            runner.train_step(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = e0.elapsed_time(e1) / args.steps
+        del runner
+        torch.cuda.empty_cache()
+    finally:
+        ddist.suspend(False)
+    per_rank = [None] * dist.world
+    dist.td.all_gather_object(per_rank, mine)
+    return {"free_running_ms_per_step_by_rank": [round(v, 3) for v in per_rank], "slowest_gpu_ms": max(per_rank),
+            "fastest_gpu_ms": min(per_rank), "synchronised_ms_per_step": sync_ms,
+            "exchange_cost_ms": sync_ms - max(per_rank),
+            "note": "free-running = same step, data-parallel exchanges suspended, all GPUs loaded simultaneously; the synchronised step "
+                    "is bounded below by the slowest GPU"}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm: inference
 def build_att_runner(head="sigmoid"):
     import torch
@@ -661,6 +702,8 @@ def run_b200(args):
         extra["scan"] = measure_scan(dist, runner, min(max(args.steps, 5), 10), min(args.warmup, 3), clocks=False)
         del runner
         torch.cuda.empty_cache()
+        if dist.world > 1:
+            extra["rank_spread"] = measure_rank_spread(dist, args, main["ms_per_step"])
         if dist.world == 1:
             extra["hbm_kernels"] = hbm_kernel_rooflines(peaks)
             if os.environ.get("DRAM_BWD_PRECISION", "bf16x3") != "bf16x2":

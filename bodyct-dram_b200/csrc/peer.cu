@@ -88,10 +88,16 @@ k_peer_allreduce(const PeerArgs a, const BnFinalizeArgs f) {
   if (threadIdx.x < a.world) {
     st_release_sys(&a.box[threadIdx.x]->flag[slot][me], seq);
     const unsigned long long* fl = &mine->flag[slot][threadIdx.x];
-    unsigned long long spins = 0;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
     while (ld_acquire_sys(fl) < seq) {
       __nanosleep(64);
-      if (++spins > (1ull << 28)) __trap();                // ~20 s: a rank died; fail the step instead of hanging the box
+      if ((++spins & 0x3ff) == 0) {                         // wall-clock bound: a rank died or the ranks' call sequences diverged
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20ull * 1000000000ull) __trap();   // 20 s: fail the step instead of hanging the box
+      }
     }
   }
   __syncthreads();

@@ -239,7 +239,7 @@ k_itk_resample_v4(const T* __restrict__ src, T* __restrict__ dst, int d, int h, 
 // Block = 32 (x) x 8 (y) threads, kScatterZ consecutive z per thread: a warp reads 32 consecutive labels and writes up to
 // 128 contiguous bytes of the heat map per z; the x / y interpolation set-up is shared by the thread's z steps; the eight
 // source taps come from the 2 MB chunk RAM (L1 / L2 resident).  Algorithmic HBM bytes: 1 (label) + 4 (heat) per crop voxel.
-constexpr int kScatterZ = 4;
+constexpr int kScatterZ = 8;
 __global__ void __launch_bounds__(256)
 k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __restrict__ labels, int label,
                              float* __restrict__ heat, int d, int h, int w, int cd, int ch, int cw, int SH, int SW, int oz,
@@ -249,15 +249,21 @@ k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __res
   const Lerp lx = lerp_setup(X, sx, w), ly = lerp_setup(Y, sy, h);
   const int o00 = ly.i0 * w + lx.i0, o01 = ly.i0 * w + lx.i1, o10 = ly.i1 * w + lx.i0, o11 = ly.i1 * w + lx.i1;
   const long long col = (long long)(Y + oy) * SW + (X + ox);
+  const long long plane = (long long)SH * SW;
+  // all label loads of the column first, then the source taps of ALL z steps unconditionally (clamped, L1/L2-resident 2 MB
+  // chunk): the loads of the eight steps are independent and in flight together instead of one dependent chain per step
   uint8_t lab[kScatterZ];
 #pragma unroll
   for (int k = 0; k < kScatterZ; ++k)
-    lab[k] = (Z0 + k < cd) ? labels[(long long)(Z0 + k + oz) * SH * SW + col] : (uint8_t)0;
+    lab[k] = (Z0 + k < cd) ? __ldg(labels + (long long)(Z0 + k + oz) * plane + col) : (uint8_t)0;
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < kScatterZ; ++k) any = any || (lab[k] == label);
+  if (!any) return;
+  float v[kScatterZ];
 #pragma unroll
   for (int k = 0; k < kScatterZ; ++k) {
-    const int Z = Z0 + k;
-    if (Z >= cd || lab[k] != label) continue;
-    const Lerp lz = lerp_setup(Z, sz, d);
+    const Lerp lz = lerp_setup(min(Z0 + k, cd - 1), sz, d);
     const float* p0 = ram + (long long)lz.i0 * h * w;
     const float* p1 = ram + (long long)lz.i1 * h * w;
     float a00 = __ldg(p0 + o00), b00 = __ldg(p0 + o01), a01 = __ldg(p0 + o10), b01 = __ldg(p0 + o11);
@@ -267,11 +273,14 @@ k_ram_upsample_label_scatter(const float* __restrict__ ram, const uint8_t* __res
       a10 = sigmoidf_(a10); b10 = sigmoidf_(b10); a11 = sigmoidf_(a11); b11 = sigmoidf_(b11);
     }
     // same nesting as ATen's upsample_trilinear3d: d(h(w))
-    float v = lz.w0 * (ly.w0 * (lx.w0 * a00 + lx.w1 * b00) + ly.w1 * (lx.w0 * a01 + lx.w1 * b01)) +
+    float t = lz.w0 * (ly.w0 * (lx.w0 * a00 + lx.w1 * b00) + ly.w1 * (lx.w0 * a01 + lx.w1 * b01)) +
               lz.w1 * (ly.w0 * (lx.w0 * a10 + lx.w1 * b10) + ly.w1 * (lx.w0 * a11 + lx.w1 * b11));
-    if (act == 2) v = fmaxf(v, 0.f);
-    heat[(long long)(Z + oz) * SH * SW + col] = v * gain;
+    if (act == 2) t = fmaxf(t, 0.f);
+    v[k] = t * gain;
   }
+#pragma unroll
+  for (int k = 0; k < kScatterZ; ++k)
+    if (lab[k] == label) heat[(long long)(Z0 + k + oz) * plane + col] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------ Otsu inputs / masks

@@ -27,7 +27,13 @@ def rank():
 
 
 def active():
-    return world_size() > 1
+    """data parallel exchanges on?  (`suspend()` turns them off inside an initialised process group: every rank then trains
+    on its own, which is how bench.py measures the per-GPU free-running step time next to the synchronised one)"""
+    return world_size() > 1 and not _STATE.get("suspended", False)
+
+
+def suspend(flag=True):
+    _STATE["suspended"] = bool(flag)
 
 
 def shard(items):

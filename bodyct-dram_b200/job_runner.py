@@ -356,6 +356,21 @@ class LesionSegChunkTrain(JobRunner, _ScanPipeline):
         _DF.WEIGHTS.invalidate()           # the replay changed the weights behind PyTorch's version counters
         return self._static_out
 
+    def close(self):
+        """Drop the captured step (a CUDA graph that holds NCCL work must be gone before the process group is destroyed, or
+        the teardown waits on it forever) and the gradient hooks.  The runner can keep training afterwards (it re-captures)."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self._graph = self._graph_key = self._static_in = self._static_labels = self._static_out = None
+        self._eager_steps = 0
+        if self.reducer is not None:
+            self.reducer.remove()
+            self.reducer = None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def train(self, loader=None):
         """One epoch over `loader` (default: self.tr_loader) — job_runner.py:649-681."""
         loader = self.tr_loader if loader is None else loader

@@ -82,4 +82,6 @@ if __name__ == "__main__":
                          epochs=args.epochs)
     print({"epoch": r.epoch_n, "iteration": r.current_iteration, **r.metrics})
     if torch.distributed.is_available() and torch.distributed.is_initialized():
+        r.close()                                   # the captured step holds NCCL work: drop it before the group goes away
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()

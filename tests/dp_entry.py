@@ -43,7 +43,8 @@ def main():
         ok = len(set(digests)) == 1 and runner.current_iteration == 8
         if rank == 0:
             ok = ok and os.path.exists(os.path.join(runner.exp_path, "1.pth"))
-            print("REPLICAS IDENTICAL" if ok else f"REPLICAS DIFFER {digests}")
+            print("REPLICAS IDENTICAL" if ok else f"REPLICAS DIFFER {digests}", flush=True)
+        runner.close()
     else:
         import process_pipeline
         import utils
@@ -70,7 +71,7 @@ def main():
         ok = flat == [f"case{i}" for i in range(5)] and all(len(part) >= 2 for part in allr)
         ok = ok and all(os.path.exists(os.path.join(out, "test", f"case{i}.mha")) for i in range(5))
         if rank == 0:
-            print("EACH SCAN ONCE" if ok else f"SHARDING WRONG {allr}")
+            print("EACH SCAN ONCE" if ok else f"SHARDING WRONG {allr}", flush=True)
     td.barrier()
     td.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -121,7 +121,7 @@ def test_pooling_global_max_and_avg():
     assert torch.allclose(models.pooling_dense_features(x, lungs, "avg"), ref, rtol=1e-5, atol=1e-6)
 
 
-def _torchrun(nproc, script, *args, env=None, timeout=600):
+def _torchrun(nproc, script, *args, env=None, timeout=240):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + os.getpid() % 300), script, *args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(env or {})})
