@@ -198,6 +198,157 @@ k_pcm_attend(const PcmGeom g, const float* __restrict__ qk, const float* __restr
   if (SAVE) stats[P.i] = make_float4(any ? m : 0.f, il, invT, o);
 }
 
+// ------------------------------------------------------------------------------------------------ fused forward (inference)
+// Projection + attention in ONE kernel for the no-grad forward (process_pipeline / evaluate_scan): nothing is kept for a
+// backward, so the theta|phi projections never go to global memory (k_pcm_project writes 64 B/voxel that k_pcm_attend reads
+// back; the two launches together moved 204 B/voxel for 76 algorithmic and were latency-bound on global gathers).
+// A block owns a (kPfYT x kPfXT) column of the grid and marches along z:
+//   * per new z-plane every thread projects ITS voxel (q for itself in registers, k and cam into shared memory) and the
+//     first 140 threads project the halo ring (k only): planes z-1, z, z+1 live in a 3-slot ring,
+//     kp[slot][F/4][halo voxel] as float4 (a warp = 32 consecutive x reads 512 contiguous bytes: conflict-free);
+//   * the 6/18/26(+1) neighbour dot products then read shared memory; all multiply-adds are packed fp32 pairs
+//     (fma.rn.f32x2, sm_100) — half the FMA issue slots of the scalar kernels;
+//   * same stencil macro, degree temperature and two-pass softmax as k_pcm_attend.
+constexpr int kPfYT = 4, kPfXT = 64, kPfHX = kPfXT + 2, kPfHV = (kPfYT + 2) * kPfHX, kPfRing = kPfHV - kPfYT * kPfXT;
+
+template <int F>
+__device__ __forceinline__ void pcm_project_voxel(const float* __restrict__ fp, int Cf, const float4* __restrict__ sw,
+                                                  const float4* __restrict__ sb, bool want_q, float2 (&q)[F / 2],
+                                                  float2 (&k)[F / 2]) {
+  constexpr int Q4 = F / 4;                       // float4 per projection
+#pragma unroll
+  for (int j = 0; j < Q4; ++j) {
+    const float4 bq = sb[j], bk = sb[Q4 + j];
+    q[2 * j] = make_float2(bq.x, bq.y); q[2 * j + 1] = make_float2(bq.z, bq.w);
+    k[2 * j] = make_float2(bk.x, bk.y); k[2 * j + 1] = make_float2(bk.z, bk.w);
+  }
+  for (int c = 0; c < Cf; ++c) {
+    const float v = __ldg(fp + c);
+    const float2 vv = make_float2(v, v);
+    const float4* wc = sw + c * 2 * Q4;
+#pragma unroll
+    for (int j = 0; j < Q4; ++j) {
+      const float4 wk = wc[Q4 + j];
+      k[2 * j] = __ffma2_rn(vv, make_float2(wk.x, wk.y), k[2 * j]);
+      k[2 * j + 1] = __ffma2_rn(vv, make_float2(wk.z, wk.w), k[2 * j + 1]);
+      if (want_q) {
+        const float4 wq = wc[j];
+        q[2 * j] = __ffma2_rn(vv, make_float2(wq.x, wq.y), q[2 * j]);
+        q[2 * j + 1] = __ffma2_rn(vv, make_float2(wq.z, wq.w), q[2 * j + 1]);
+      }
+    }
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kPfYT * kPfXT)
+k_pcm_fused(const PcmGeom g, const float* __restrict__ f, const float* __restrict__ cam, const float* __restrict__ tw,
+            const float* __restrict__ tb, const float* __restrict__ pw, const float* __restrict__ pb, float* __restrict__ out,
+            int zseg, int tiles_x) {
+  constexpr int Q4 = F / 4;
+  extern __shared__ float4 pf_sm[];
+  float4* sw = pf_sm;                                   // [Cf][2*Q4]: theta | phi weights of one input channel
+  float4* sb = sw + g.Cf * 2 * Q4;                      // [2*Q4] biases
+  float4* kp = sb + 2 * Q4;                             // [3][Q4][kPfHV]
+  float* cp = reinterpret_cast<float*>(kp + 3 * Q4 * kPfHV);   // [3][kPfHV]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < g.Cf * 2 * F; i += blockDim.x) {
+    const int c = i / (2 * F), j = i - c * 2 * F;
+    reinterpret_cast<float*>(sw)[i] = j < F ? tw[j * g.Cf + c] : pw[(j - F) * g.Cf + c];
+  }
+  for (int i = tid; i < 2 * F; i += blockDim.x) reinterpret_cast<float*>(sb)[i] = i < F ? tb[i] : pb[i - F];
+  __syncthreads();
+
+  const int W = g.W, H = g.H, D = g.D, flags = g.flags;
+  const bool relu = flags & 1;
+  const int x0 = (blockIdx.x % tiles_x) * kPfXT, y0 = (blockIdx.x / tiles_x) * kPfYT;
+  const int z0 = blockIdx.y * zseg, z1 = min(z0 + zseg, D), b = blockIdx.z;
+  const int tx = tid % kPfXT, ty = tid / kPfXT;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool live = x < W && y < H;
+  const int hv = (ty + 1) * kPfHX + tx + 1;
+  // halo ring element of this thread (tid < kPfRing): top row, bottom row, left column, right column
+  int rhy = 0, rhx = 0;
+  if (tid < kPfHX) { rhy = 0; rhx = tid; }
+  else if (tid < 2 * kPfHX) { rhy = kPfYT + 1; rhx = tid - kPfHX; }
+  else { const int r = tid - 2 * kPfHX; rhy = 1 + r % kPfYT; rhx = (r / kPfYT) ? kPfXT + 1 : 0; }
+  const int ry = y0 + rhy - 1, rx = x0 + rhx - 1;
+  const bool ring = tid < kPfRing && ry >= 0 && ry < H && rx >= 0 && rx < W;
+  const int rhv = rhy * kPfHX + rhx;
+  const long long HW = (long long)H * W, vol = HW * D;
+
+  float2 q[F / 2], qn[F / 2], kk[F / 2];
+  auto project_plane = [&](int z, bool keep_q) {
+    const int slot = z % 3;
+    float4* kps = kp + slot * Q4 * kPfHV;
+    float* cps = cp + slot * kPfHV;
+    const long long base = b * vol + z * HW;
+    if (live) {
+      const long long i = base + (long long)y * W + x;
+      pcm_project_voxel<F>(f + i * g.Cf, g.Cf, sw, sb, keep_q, qn, kk);
+#pragma unroll
+      for (int j = 0; j < Q4; ++j) kps[j * kPfHV + hv] = make_float4(kk[2 * j].x, kk[2 * j].y, kk[2 * j + 1].x, kk[2 * j + 1].y);
+      cps[hv] = __ldg(cam + i);
+    }
+    if (ring) {
+      const long long i = base + (long long)ry * W + rx;
+      float2 dummy[F / 2];
+      pcm_project_voxel<F>(f + i * g.Cf, g.Cf, sw, sb, false, dummy, kk);
+#pragma unroll
+      for (int j = 0; j < Q4; ++j) kps[j * kPfHV + rhv] = make_float4(kk[2 * j].x, kk[2 * j].y, kk[2 * j + 1].x, kk[2 * j + 1].y);
+      cps[rhv] = __ldg(cam + i);
+    }
+  };
+
+  if (z0 > 0) project_plane(z0 - 1, false);
+  project_plane(z0, true);
+#pragma unroll
+  for (int j = 0; j < F / 2; ++j) q[j] = qn[j];
+  const bool ym = y > 0, yp = y < H - 1, xm = x > 0, xp = x < W - 1;
+  for (int z = z0; z < z1; ++z) {
+    if (z + 1 < D) project_plane(z + 1, true);
+    __syncthreads();
+    if (live) {
+      const bool zm = z > 0, zp = z < D - 1;
+      const int deg = degree_from(flags, zm + zp, ym + yp, xm + xp);
+      const float invT = inv_temperature(flags, deg);
+      float s[27], c[27];
+      float m = -INFINITY;
+      PCM_FOR_EACH_OFFSET(flags) {
+        float d = -INFINITY, cv = 0.f;
+        const bool in = (dz < 0 ? zm : (dz > 0 ? zp : true)) && (dy < 0 ? ym : (dy > 0 ? yp : true)) && (dx < 0 ? xm : (dx > 0 ? xp : true));
+        if (in) {
+          const int slot = (z + dz + 3) % 3, n = hv + dy * kPfHX + dx;
+          const float4* kps = kp + slot * Q4 * kPfHV + n;
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < Q4; ++j) {
+            const float4 k4 = kps[j * kPfHV];
+            acc = __ffma2_rn(q[2 * j], make_float2(k4.x, k4.y), acc);
+            acc = __ffma2_rn(q[2 * j + 1], make_float2(k4.z, k4.w), acc);
+          }
+          d = acc.x + acc.y;
+          if (relu) d = fmaxf(d, 0.f);
+          d *= invT;
+          cv = cp[slot * kPfHV + n];
+        }
+        s[t_] = d; c[t_] = cv;
+        m = fmaxf(m, d);
+      }
+      float l = 0.f, acc = 0.f;
+      PCM_FOR_EACH_OFFSET(flags) {
+        const float e = __expf(s[t_] - m);                 // absent neighbour: exp(-inf) = 0
+        l += e;
+        acc = fmaf(e, c[t_], acc);
+      }
+      out[b * vol + z * HW + (long long)y * W + x] = deg > 0 ? acc / l : 0.f;
+    }
+    __syncthreads();                                       // plane z-1's slot is overwritten by the next projection
+#pragma unroll
+    for (int j = 0; j < F / 2; ++j) q[j] = qn[j];
+  }
+}
+
 // backward, one thread per voxel i in both of its roles, nothing but `stats` kept from the forward:
 //  node role   (i = x):  a_o = exp(s_o/T_x - m_x)/l_x,  ds_o = a_o (g_x cam_{x+o} - g_x s_x) / T_x [logit > 0],
 //                        dq_x = sum_o ds_o k_{x+o}
@@ -422,12 +573,36 @@ size_t dram_pcm_bwd_ws_floats(long long rows, int Cf, int F) {
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,
                  int connectivity, int self_loop, int flags, void* stream) {
-  DRAM_REQUIRE(f && cam && theta_w && theta_b && phi_w && phi_b && qk && out, "pcm_fwd: null pointer");
+  DRAM_REQUIRE(f && cam && theta_w && theta_b && phi_w && phi_b && out, "pcm_fwd: null pointer");
+  DRAM_REQUIRE(qk || (!stats && !getenv("DRAM_PCM_TWO_KERNELS")), "pcm_fwd: qk workspace is required whenever statistics are kept for the backward");
   PcmGeom g;
   int rc = pcm_geom(g, B, D, H, W, Cf, F, connectivity, self_loop, flags);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)B * D * H * W;
+  if (!stats && !getenv("DRAM_PCM_TWO_KERNELS")) {
+    // inference: nothing kept for a backward -> projection + attention in one kernel, projections stay on chip
+    const int tiles_x = (W + kPfXT - 1) / kPfXT, tiles_y = (H + kPfYT - 1) / kPfYT;
+    int zsegs = (2 * kNumSMs + B * tiles_x * tiles_y - 1) / (B * tiles_x * tiles_y);      // >= 2 blocks per SM when the grid allows
+    if (zsegs > D / 4) zsegs = D / 4;
+    if (zsegs < 1) zsegs = 1;
+    const int zseg = (D + zsegs - 1) / zsegs;
+    zsegs = (D + zseg - 1) / zseg;
+    const size_t sm = sizeof(float4) * ((size_t)Cf * 2 * (F / 4) + 2 * (F / 4) + 3 * (size_t)(F / 4) * kPfHV) + sizeof(float) * 3 * kPfHV;
+    const dim3 gridf((unsigned)(tiles_x * tiles_y), (unsigned)zsegs, (unsigned)B);
+    DRAM_REQUIRE(B <= 65535 && zsegs <= 65535, "pcm_fwd: batch too large for the fused kernel's grid");
+#define PCM_FUSED(FF)                                                                                              \
+  do {                                                                                                             \
+    if (sm > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_fused<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_pcm_fused<FF><<<gridf, kPfYT * kPfXT, sm, st>>>(g, f, cam, theta_w, theta_b, phi_w, phi_b, out, zseg, tiles_x);            \
+  } while (0)
+    if (F == 4) PCM_FUSED(4);
+    else if (F == 8) PCM_FUSED(8);
+    else PCM_FUSED(16);
+#undef PCM_FUSED
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
   const int J4 = (2 * F + 3) / 4;
   const size_t smem = sizeof(float) * ((size_t)Cf * 4 * J4 + 4 * J4 + (size_t)8 * 32 * (Cf | 1));
   if (smem > 48 * 1024) DRAM_CUDA(cudaFuncSetAttribute(k_pcm_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -544,12 +544,13 @@ def pcm_fwd(f, cam, tw, tb, pw, pb, connectivity, self_loop, flags, keep_stats=T
     B, Cf, D, H, W = f.shape
     F = tw.shape[0]
     V = D * H * W
-    qk = torch.empty(_L().dram_pcm_qk_floats(B * V, F), device=f.device, dtype=torch.float32)
+    two_kernels = keep_stats or bool(os.environ.get("DRAM_PCM_TWO_KERNELS"))
+    qk = torch.empty(_L().dram_pcm_qk_floats(B * V, F), device=f.device, dtype=torch.float32) if two_kernels else None
     stats = torch.empty((B * V, 4), device=f.device, dtype=torch.float32) if keep_stats else None
     out = torch.empty((B, 1, D, H, W), device=f.device, dtype=torch.float32)
     _lib.PROFILE.note(bytes=4.0 * B * V * (Cf + 2))
     _lib.check(_L().dram_pcm_fwd(f.data_ptr(), cam.data_ptr(), tw.data_ptr(), tb.data_ptr(), pw.data_ptr(), pb.data_ptr(),
-                                 qk.data_ptr(), _p(stats), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
+                                 _p(qk), _p(stats), out.data_ptr(), B, D, H, W, Cf, F, int(connectivity),
                                  int(bool(self_loop)), int(flags), _stream()), "pcm_fwd")
     return out, qk, stats
 

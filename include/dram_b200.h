@@ -252,7 +252,9 @@ int dram_pcm_num_offsets(int connectivity, int self_loop); /* O: 18 for (2, no s
 /* R = B*V rows.  qk (out, dram_pcm_qk_floats(R, F) floats): theta|phi projections in blocks of 32 consecutive voxels,
  * [ceil(R/32)][2F][32] (coalesced neighbour loads, compile-time feature offsets).  F: 4 | 8 | 16.
  * stats [R][4] (out, may be NULL at inference): (max, 1/normaliser, 1/T, output) of each node's softmax - what the backward
- * keeps instead of the [R][O] attention weights (they are recomputed from qk) */
+ * keeps instead of the [R][O] attention weights (they are recomputed from qk).
+ * stats == NULL (no-grad forward): projection and attention run as ONE kernel with the projections in shared memory (a block
+ * marches a 4 x 64 column of the grid along z, three z-planes of phi(f) and cam in a ring); qk may then be NULL. */
 size_t dram_pcm_qk_floats(long long rows, int F);
 int dram_pcm_fwd(const float* f, const float* cam, const float* theta_w, const float* theta_b, const float* phi_w,
                  const float* phi_b, float* qk, float* stats, float* out, int B, int D, int H, int W, int Cf, int F,

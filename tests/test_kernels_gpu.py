@@ -699,6 +699,8 @@ def test_reshape_head_unit_on_planes(training):
     ("scaled_dot_product", False, 3, (4, 6, 5), 8), ("smrelu", False, 2, (2, 1, 3), 8),
     ("scaled_dot_product_relu", False, 2, (3, 4, 64), 8), ("scaled_dot_product_relu", False, 2, (2, 3, 37), 8),
     ("scaled_dot_product_relu", False, 2, (3, 20, 20), 8),          # plane larger than one 256-thread block
+    ("scaled_dot_product_relu", False, 2, (9, 6, 70), 8),           # fused inference kernel: two x tiles, halo columns between them
+    ("scaled_dot_product_relu", False, 2, (40, 9, 8), 8),           # fused inference kernel: several z segments, ragged y tiles
     ("scaled_dot_product_relu", True, 3, (4, 5, 6), 4), ("smscaled", False, 2, (5, 4, 7), 16)])
 def test_pcm_attention(merge, self_loop, conn, grid, Fd):
     from oracle_import import O
