@@ -279,8 +279,16 @@ class GradReducer:
                 from . import functional as _F
                 _F.SIDE.join()
                 self.work.append(td.all_reduce(self._ensure(), op=td.ReduceOp.SUM, group=_STATE["group"], async_op=True))
+            from . import lib as _lib
+            prof = _lib.PROFILE.enabled                       # bench.py's per-kernel events: time the exposed part of the all-reduce
+            if prof:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             for w in self.work:
                 w.wait()
+            if prof:
+                e1.record()
+                _lib.PROFILE.records.append(("nccl_grad_allreduce_exposed", {"bytes": 4.0 * self.total}, e0, e1))
             if self.scale != 1.0:
                 self.flat.mul_(self.scale)
         self.reset()

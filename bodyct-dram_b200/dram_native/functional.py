@@ -216,8 +216,7 @@ class ConvBnRelu(torch.autograd.Function):
         xs = x_real = None
         pointwise = False
         if x_hi is not None:
-            second = getattr(x_hi, "_dram_second", None)       # virtual concat: the skip planes ride on the hi tensor (upsample_concat)
-            xs = ops.SplitPlanes(x_hi, x_lo, tuple(x.shape), x_hi.shape[-1] + (second.Cpad if second is not None else 0), second)
+            xs = _planes_of(x, x_hi, x_lo)                     # incl. the second operand of a virtual concat
             pointwise = not umma and not ctx.needs_input_grad[0] and ops.pointwise8_ok(xs, Cout, k)
             if not umma and not pointwise:
                 x_real = ops.merge_planes(xs)
@@ -368,12 +367,19 @@ def conv_bn_relu(x, w, bias, gamma, beta, running_mean, running_var, training, m
     return _wrap(a, a_hi, a_lo)
 
 
+def _planes_of(t, hi, lo):
+    """(handle, hi, lo) as they travel through the autograd Functions -> SplitPlanes; a virtual concat's second operand rides
+    on the hi tensor (upsample_concat)"""
+    second = getattr(hi, "_dram_second", None)
+    return ops.SplitPlanes(hi, lo, tuple(t.shape), hi.shape[-1] + (second.Cpad if second is not None else 0), second)
+
+
 class Materialize(torch.autograd.Function):
     """planes -> fp32 channels-last volume (for consumers outside the tensor-core path); gradient passes through."""
 
     @staticmethod
     def forward(ctx, t, hi, lo):
-        return ops.merge_planes(ops.SplitPlanes(hi, lo, tuple(t.shape), hi.shape[-1]))
+        return ops.merge_planes(_planes_of(t, hi, lo))
 
     @staticmethod
     def backward(ctx, g):
