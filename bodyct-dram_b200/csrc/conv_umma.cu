@@ -392,6 +392,7 @@ struct Fwd2Params {
   long long* prof;   // DRAM_CONV_PROF: per-CTA cycle counters [8] (diagnostics only)
   float* stat;       // training: BatchNorm partial sums of y, [n_mtiles * 4][2][Cout] (row = M tile x epilogue warp), or NULL
   int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmA2_*)
+  int dbg;           // DRAM_CONV_DBG (diagnostics, results are garbage): bit 0 = no activation loads after the first ring fill, bit 1 = no weight loads
 };
 
 // Column sums over the 32 lanes of a warp for 32 values per lane: after the five exchange rounds lane l holds the total
@@ -492,7 +493,9 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int cb = 0; cb < p.kblocks_c; ++cb, ++itA) {
           const uint32_t sA = itA & 1;
           mbar_wait(emptyA0 + 8 * sA, ((itA >> 1) & 1) ^ 1);
-          if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
+          if ((p.dbg & 1) && itA >= 2) {
+            if (elect_one()) mbar_arrive(fullA0 + 8 * sA);
+          } else if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
             const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes, fa = fullA0 + 8 * sA;
             mbar_expect_tx(fa, a_tx);
             const bool second = cb >= p.cb_split;         // virtual concat: which activation tensor owns this channel block
@@ -510,7 +513,9 @@ k_conv_umma_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             mbar_wait(emptyB0 + 8 * sB, phB ^ 1);
-            if (elect_one()) {
+            if ((p.dbg & 2) && (itA > 8 || item != (int)blockIdx.x)) {
+              if (elect_one()) mbar_arrive(fullB0 + 8 * sB);
+            } else if (elect_one()) {
               const uint32_t bb = smemB_u + sB * (uint32_t)p.b_stage_bytes, fb = fullB0 + 8 * sB;
               mbar_expect_tx(fb, b_tx);
               const int brow = (g * 3 + kw) * p.Cout + nt * p.BN;
@@ -687,6 +692,7 @@ struct Fwd3Params {
   long long* prof;   // DRAM_CONV_PROF diagnostics
   float* stat;       // training: BatchNorm partial sums of y, [rows][2][Cout]; rows = n_vtiles (x 2 warps in the stacked modes)
   int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmX2_*)
+  int dbg;           // DRAM_CONV_DBG (diagnostics, results are garbage): bit 0 = no activation loads after the first ring fill, bit 1 = no weight loads
 };
 
 template <int MODE>
@@ -741,7 +747,9 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         for (int cb = 0; cb < p.kblocks_c; ++cb, ++itX) {
           const uint32_t sX = itX & 1;
           mbar_wait(emptyX0 + 8 * sX, ((itX >> 1) & 1) ^ 1);
-          if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
+          if ((p.dbg & 1) && itX >= 2) {
+            if (elect_one()) mbar_arrive(fullX0 + 8 * sX);
+          } else if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
             const uint32_t xb = smemX_u + sX * (uint32_t)p.x_stage_bytes, fx = fullX0 + 8 * sX;
             mbar_expect_tx(fx, x_tx);
             const bool second = cb >= p.cb_split;         // virtual concat: which activation tensor owns this channel block
@@ -753,7 +761,9 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             mbar_wait(emptyW0 + 8 * sW, phW ^ 1);
-            if (elect_one()) {
+            if ((p.dbg & 2) && (itX > 8 || item != (int)blockIdx.x)) {
+              if (elect_one()) mbar_arrive(fullW0 + 8 * sW);
+            } else if (elect_one()) {
               const uint32_t wb = smemW_u + sW * (uint32_t)p.w_stage_bytes, fw = fullW0 + 8 * sW;
               mbar_expect_tx(fw, w_tx);
               const int wrow = (g * 3 + kw) * p.Cout + ct * p.CT;
@@ -931,6 +941,324 @@ k_conv_umma_fwd3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad, SM pairs (cta_group::2)
+// `DRAM_CONV_DBG=3 python tests/micro_conv.py 8 us2.c0` (profiles/r02b_dbg_skip.txt): with NO TMA traffic at all the tile-pair
+// kernel keeps its time (6.47 -> 6.32 ms) at 58 % tensor-pipe activity: k_conv_umma_fwd2 is bound by the shared-memory operand
+// reads of its own MMAs (an M=128 x N MMA reads (128 + N) x 32 B for N/2 tensor cycles: 128 B/cycle at N = 128, 192 at N = 64).
+// This kernel runs the same voxels-on-M GEMM on a PAIR of SMs (thread-block cluster of 2, tcgen05.mma.cta_group::2, M = 256):
+//   * each CTA supplies the activation rows of its own 128-voxel tile(s) and only HALF of the weight columns of every MMA, so
+//     the operand bytes per SM and MMA drop to (128 + N/2) x 32 B: 96 B/cycle for the N = 2*BN MMA below, and each weight tile
+//     is fetched from L2 once per pair instead of once per CTA;
+//   * split-bf16 with exactly three products for every BN: CTA r keeps the weight rows [W_hi[r*h, (r+1)*h) ; W_lo[r*h, (r+1)*h)]
+//     (h = BN/2) of the N tile, so   MMA1: X_hi x [W_hi a | W_lo a | W_hi b | W_lo b]  (N = 2*BN; a / b = lower / upper half
+//     of the tile's channels) fills accumulator columns [HH a | HL a | HH b | HL b], and   MMA2: X_lo x [W_hi a | W_hi b]
+//     (N = BN: the first h rows of each CTA's weight stage, the SAME shared-memory descriptor) accumulates at column offset h,
+//     i.e. LH a on top of HL a and LH b on top of HH b.  The epilogue adds column c and c + h of each half.
+//   * leader CTA (cluster rank 0): one elected thread issues every MMA of the pair; both CTAs run a TMA producer (2-SM loads
+//     that signal the LEADER's full barriers) and four epilogue warps on their own TMEM lanes; tcgen05.commit multicasts the
+//     stage-free / accumulator-full arrivals to both CTAs; the epilogues of both CTAs arrive on the leader's tmem-empty barrier.
+// Work item = 2*TPC M tiles (TPC per CTA, sharing every weight tile) x one N tile; accumulators 2 sets x TPC x 2*BN columns.
+struct Fwd4Params {
+  float* y;
+  uint16_t* o_hi;   // eval mode: folded BatchNorm + ReLU output written as bf16 split planes [rows][Cout] instead of y
+  uint16_t* o_lo;
+  const float* scale;
+  const float* shift;
+  int N, D, H, W, Cout, BN, kblocks_c, ksteps;
+  int co_base;       // this launch covers output channels [co_base, co_base + n_ntiles * BN) of the layer's Cout (Cout = 192 runs
+                     // as one launch of 128-channel tiles and one of a 64-channel tile)
+  int TW, TDD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles, n_items, TPC;
+  int SA, SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes;
+  long long* prof;   // DRAM_CONV_PROF: per-cluster cycle counters [8] (diagnostics only)
+  float* stat;       // training: BatchNorm partial sums of y, [n_mtiles * 4][2][Cout] (row = M tile x epilogue warp), or NULL
+  int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmA2_*)
+  int dbg;           // DRAM_CONV_DBG (diagnostics, results are garbage): bit 0 = no activation loads after the first ring fill, bit 1 = no weight loads
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA loads: the data lands in the executing CTA's shared memory, the transaction bytes are counted on `bar`, a
+// shared::cluster address that may belong to the peer CTA (the pair's leader)
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// collective over the pair: the same warp of both CTAs executes it with the same arguments
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// kind::f16 instruction descriptor of the pair: D=f32, A=B=bf16 K-major, M=256 (128 rows per CTA), N=n (a multiple of 16)
+__device__ __forceinline__ uint32_t umma_idesc_2sm(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
+                 const Fwd4Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int SA = p.SA, SB = p.SB, TPC = p.TPC;
+  uint8_t* smemB = smem + (size_t)SA * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)SB * p.b_stage_bytes);
+  // fullA / fullB / tempty are used in the leader only; emptyA / emptyB / tfull exist (and are signalled) in both CTAs
+  const uint32_t fullA0 = smem_u32(bars), emptyA0 = fullA0 + 8 * SA, fullB0 = emptyA0 + 8 * SA, emptyB0 = fullB0 + 8 * SB,
+                 tfull0 = emptyB0 + 8 * SB, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t smemA_u = smem_u32(smem), smemB_u = smem_u32(smemB);
+  const int h = p.BN >> 1, acc_cols = 2 * p.BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 8); }   // 4 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // barriers of both CTAs initialised before any remote arrive / 2-SM load / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_g = 9 * p.kblocks_c;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs: own tiles, own weight half)
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    }
+    const uint32_t a_tx = 2u * (uint32_t)TPC * 2u * (uint32_t)p.a_plane_bytes;     // both CTAs of the pair
+    const uint32_t b_tx = 2u * (uint32_t)p.b_stage_bytes;
+    uint32_t sA = 0, phA = 0, sB = 0, phB = 0;
+    for (int item = cid; item < p.n_items; item += n_clusters) {
+      const int nt = item % p.n_ntiles, grp = item / p.n_ntiles;
+      int w0[2], h0[2], d0[2], n0[2];
+      for (int j = 0; j < TPC; ++j) {
+        int mt = (grp * 2 + (int)rank) * TPC + j;
+        w0[j] = (mt % p.tiles_w) * p.TW - 1; mt /= p.tiles_w;
+        h0[j] = (mt % p.tiles_h) * 8 - 1; mt /= p.tiles_h;
+        d0[j] = (mt % p.tiles_d) * p.TDD - 1;
+        n0[j] = mt / p.tiles_d;
+      }
+      for (int g = 0; g < 9; ++g) {
+        const int kd = g / 3, kh = g - 3 * kd;
+        for (int cb = 0; cb < p.kblocks_c; ++cb) {
+          mbar_wait(emptyA0 + 8 * sA, phA ^ 1);
+          if ((p.dbg & 1) && (phA || item != cid)) {
+            if (leader && elect_one()) mbar_arrive(fullA0 + 8 * sA);
+          } else if (elect_one()) {                          // map dims (C,H,D,W,N); the box starts at w0 - 1 (kw = 0)
+            const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes, fa = mapa_u32(fullA0 + 8 * sA, 0);
+            if (leader) mbar_expect_tx(fullA0 + 8 * sA, a_tx);
+            const bool second = cb >= p.cb_split;         // virtual concat: which activation tensor owns this channel block
+            const CUtensorMap* mh = second ? &tmA2_hi : &tmA_hi;
+            const CUtensorMap* ml = second ? &tmA2_lo : &tmA_lo;
+            const int cc = (second ? cb - p.cb_split : cb) * 64;
+            for (int j = 0; j < TPC; ++j) {
+              tma_load_5d_2sm(ab + j * p.a_tile_bytes, mh, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
+              tma_load_5d_2sm(ab + j * p.a_tile_bytes + p.a_plane_bytes, ml, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
+            }
+          }
+          __syncwarp();
+          if (++sA == (uint32_t)SA) { sA = 0; phA ^= 1; }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(emptyB0 + 8 * sB, phB ^ 1);
+            if ((p.dbg & 2) && (phB || item != cid)) {
+              if (leader && elect_one()) mbar_arrive(fullB0 + 8 * sB);
+            } else if (elect_one()) {
+              const uint32_t bb = smemB_u + sB * (uint32_t)p.b_stage_bytes, fb = mapa_u32(fullB0 + 8 * sB, 0);
+              if (leader) mbar_expect_tx(fullB0 + 8 * sB, b_tx);
+              const int brow = (g * 3 + kw) * p.Cout + p.co_base + nt * p.BN + (int)rank * h;
+              tma_load_2d_2sm(bb, &tmB_hi, fb, cb * 64, brow);
+              tma_load_2d_2sm(bb + h * 128, &tmB_lo, fb, cb * 64, brow);
+            }
+            __syncwarp();
+            if (++sB == (uint32_t)SB) { sB = 0; phB ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------------------------------------------------------- MMA issuer of the pair (one elected lane issues)
+      // DRAM_CONV_DBG bit 2 (diagnostics, garbage results): issue the N = BN MMA with N = 2*BN at column 0 — does a pair MMA of
+      // N = 64 cost less than one of N = 128?
+      const uint32_t idesc1 = umma_idesc_2sm(2 * p.BN), idesc2 = umma_idesc_2sm((p.dbg & 4) ? 2 * p.BN : p.BN);
+      const uint32_t d2_off = (p.dbg & 4) ? 0u : (uint32_t)h;
+      const uint32_t kw_shift = (uint32_t)p.TDD * 1024u;
+      uint32_t sA = 0, phA = 0, sB = 0, phB = 0, icount = 0;
+      long long t_te = 0, t_fa = 0, t_fb = 0, t0 = 0, t_start = clock64();
+      const bool prof = p.prof != nullptr;
+      for (int item = cid; item < p.n_items; item += n_clusters, ++icount) {
+        const uint32_t set = icount & 1;
+        if (prof) t0 = clock64();
+        mbar_wait(tempty0 + 8 * set, ((icount >> 1) & 1) ^ 1);
+        if (prof) t_te += clock64() - t0;
+        tc_fence_after();
+        const uint32_t d_set = tmem_base + set * (uint32_t)(TPC * acc_cols);
+        for (int g = 0; g < n_g; ++g) {
+          if (prof) t0 = clock64();
+          mbar_wait(fullA0 + 8 * sA, phA);
+          if (prof) t_fa += clock64() - t0;
+          tc_fence_after();
+          const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            if (prof) t0 = clock64();
+            mbar_wait(fullB0 + 8 * sB, phB);
+            if (prof) t_fb += clock64() - t0;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t b_d = umma_desc(smemB_u + sB * (uint32_t)p.b_stage_bytes, 16, 1024);
+              for (int j = 0; j < TPC; ++j) {
+                const uint32_t aj = ab + (uint32_t)j * (uint32_t)p.a_tile_bytes + (uint32_t)kw * kw_shift;
+                const uint64_t a_hi = umma_desc(aj, 16, 1024), a_lo = umma_desc(aj + (uint32_t)p.a_plane_bytes, 16, 1024);
+                const uint32_t d_tmem = d_set + (uint32_t)(j * acc_cols);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                  if (k >= p.ksteps) break;            // all-zero padding channels: nothing to accumulate
+                  const uint64_t adv = (uint64_t)(k * 2);
+                  umma_bf16_2sm(d_tmem, a_hi + adv, b_d + adv, idesc1, (g | kw | k) ? 1u : 0u);
+                  umma_bf16_2sm(d_tmem + d2_off, a_lo + adv, b_d + adv, idesc2, 1u);
+                }
+              }
+              umma_commit_2sm(emptyB0 + 8 * sB);             // frees the weight stage of both CTAs when these MMAs retire
+              if (kw == 2) umma_commit_2sm(emptyA0 + 8 * sA);
+              if (kw == 2 && g == n_g - 1) umma_commit_2sm(tfull0 + 8 * set);   // accumulators complete -> both epilogues
+            }
+            __syncwarp();
+            if (++sB == (uint32_t)SB) { sB = 0; phB ^= 1; }
+          }
+          if (++sA == (uint32_t)SA) { sA = 0; phA ^= 1; }
+        }
+      }
+      if (prof && lane == 0) {
+        long long* o = p.prof + cid * 8;
+        o[0] = clock64() - t_start; o[1] = t_te; o[2] = t_fa; o[3] = t_fb;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs): own TMEM lanes -> fp32 channels-last
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row / (8 * p.TDD), tdd = (row >> 3) % p.TDD, th = row & 7;
+    const uint32_t tempty_leader = mapa_u32(tempty0, 0);
+    uint32_t icount = 0;
+    long long e_wait = 0, e_work = 0, e0 = 0;
+    const bool prof = p.prof != nullptr;
+    for (int item = cid; item < p.n_items; item += n_clusters, ++icount) {
+      const int nt = item % p.n_ntiles, grp = item / p.n_ntiles;
+      const uint32_t set = icount & 1;
+      if (prof) e0 = clock64();
+      mbar_wait(tfull0 + 8 * set, (icount >> 1) & 1);
+      if (prof) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
+      tc_fence_after();
+      for (int j = 0; j < TPC; ++j) {
+        const int mtile = (grp * 2 + (int)rank) * TPC + j;
+        int mt = mtile;
+        const int w = (mt % p.tiles_w) * p.TW + tw; mt /= p.tiles_w;
+        const int hh = (mt % p.tiles_h) * 8 + th; mt /= p.tiles_h;
+        const int d = (mt % p.tiles_d) * p.TDD + tdd;
+        const int n = mt / p.tiles_d;
+        const int cbase = p.co_base + nt * p.BN;
+        const long long oo = ((((long long)n * p.D + d) * p.H + hh) * p.W + w) * p.Cout + cbase;   // element offset in y / in the planes
+        float* out = p.y + oo;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * (uint32_t)TPC + (uint32_t)j) * (uint32_t)acc_cols;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          // channels [c0, c0 + 16) of the N tile: lower half -> columns [c0 | h + c0], upper half -> [2h + (c0 - h) | 3h + (c0 - h)]
+          const uint32_t col = (uint32_t)(c0 < h ? c0 : c0 + h);
+          uint32_t r[16], r2[16];
+          tmem_ld16(taddr + col, r);
+          tmem_ld16(taddr + col + (uint32_t)h, r2);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(r[jj]) + __uint_as_float(r2[jj]);
+          if (p.stat) {                              // BatchNorm batch statistics as in k_conv_umma_fwd2
+            float x[32];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) { x[jj] = v[jj]; x[jj + 16] = v[jj] * v[jj]; }
+            const float tot = warp_transpose_sum32(x, lane);
+            const long long srow = (long long)mtile * 4 + q;
+            p.stat[(srow * 2 + (lane >> 4)) * p.Cout + cbase + c0 + (lane & 15)] = tot;
+          }
+          if (p.scale) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = cbase + c0 + jj;
+              v[jj] = fmaxf(fmaf(v[jj], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
+            }
+          }
+          if (p.o_hi) {
+            const long long po = oo + c0;
+            store_planes16(p.o_hi + po, p.o_lo ? p.o_lo + po : nullptr, v);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4)
+              *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * set);
+      if (prof) e_work += clock64() - e0;
+    }
+    if (prof && leader && warp == 2 && lane == 0) { p.prof[cid * 8 + 4] = e_wait; p.prof[cid * 8 + 5] = e_work; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512u);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -1526,8 +1854,23 @@ static int pow2_cols(int c) { int v = 32; while (v < c) v *= 2; return v; }
 constexpr int kSmemBudget = 200 * 1024;
 
 // which forward / dgrad kernel runs a layer (shared by the launcher and by the query for the BatchNorm partial rows)
-enum { kFwdGeneric = 0, kFwdPairs = 2, kFwdChannelsOnM = 3 };
-static int fwd_kernel_kind(int D, int H, int W, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
+enum { kFwdGeneric = 0, kFwdPairs = 2, kFwdChannelsOnM = 3, kFwdSmPairs = 4 };
+// SM-pair kernel (k_conv_umma_fwd4): 128-channel N tiles plus a 64-channel tail tile
+static int fwd_kernel_kind(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
+  // DRAM_CONV_V4=0 switches it off.  It takes every split-bf16 3x3x3 layer whose volume tiles into 8(h) x TDD(d) x TW(w) boxes
+  // and whose Cout is a multiple of 64 (interleaved A/B on one box, profiles/r02c_pairs.txt: 11-18 % faster than the single-SM
+  // kernels on all of them), except a single short K block (Cin <= 32: ds0.c1, 2 K steps per tap — too little MMA time per
+  // halo box for its two activation stages)
+  {
+    const char* v4_env = getenv("DRAM_CONV_V4");
+    const bool allow_v4 = !(v4_env && atoi(v4_env) == 0);
+    if (allow_v4 && Cout % 64 == 0 && x_lo && w_lo && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) &&
+        !(Cin_pad == 64 && Cin <= 32)) {
+      const int TW = (W % 16 == 0) ? 16 : 8, TDD = (W % 16 == 0) ? 1 : 2;
+      const long long mt = (long long)N * (D / TDD) * (H / 8) * (W / TW);
+      if (mt % 2 == 0) return kFwdSmPairs;
+    }
+  }
   // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
   // DRAM_CONV_V3: 0 = never, 1 = wherever it applies, unset = where it measured faster in an interleaved A/B on one box
   // (profiles/r01b_conv_fwd2_vs_fwd3.txt): 128-channel tiles, or a single 64-channel tile with at most two K blocks per tap
@@ -1543,14 +1886,14 @@ static int fwd_kernel_kind(int D, int H, int W, int Cin_pad, int Cout, int ksize
   return kFwdGeneric;
 }
 // rows of the BatchNorm partial-sum buffer [rows][2][Cout] the kernel's epilogue fills (0: this kernel has no such epilogue)
-static long long fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
-  const int kind = fwd_kernel_kind(D, H, W, Cin_pad, Cout, ksize, x_lo, w_lo);
+static long long fwd_stat_rows(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
+  const int kind = fwd_kernel_kind(N, D, H, W, Cin, Cin_pad, Cout, ksize, x_lo, w_lo);
   if (kind == kFwdChannelsOnM) {
     const int TW = (W % 16 == 0 && D % 2 == 0) ? 16 : 8, TDD = (W % 16 == 0 && D % 2 == 0) ? 2 : 4;
     const long long vt = (long long)N * (D / TDD) * (H / 8) * (W / TW);
     return (Cout % 128 == 0) ? vt : 2 * vt;
   }
-  if (kind == kFwdPairs) {
+  if (kind == kFwdPairs || kind == kFwdSmPairs) {
     const int TW = (W % 16 == 0) ? 16 : 8, TDD = (W % 16 == 0) ? 1 : 2;
     return 4ll * N * (D / TDD) * (H / 8) * (W / TW);
   }
@@ -1623,9 +1966,9 @@ int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo, int Cout, int 
   return DRAM_OK;
 }
 
-long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo) {
-  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin_pad <= 0 || Cin_pad % 64 || Cout <= 0) return 0;
-  return fwd_stat_rows(N, D, H, W, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
+long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin_pad < Cin || Cin_pad % 64 || Cout <= 0) return 0;
+  return fwd_stat_rows(N, D, H, W, Cin, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
 }
 
 size_t dram_bn_stats_from_partials_workspace_bytes(int C) { return C > 0 ? sizeof(double) * 2 * (size_t)C * kStatChunks : 0; }
@@ -1661,10 +2004,79 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   // channels [Cin, Cin_pad) are zeros in x and w: with a single 64-channel block the K = 16 steps that would only multiply
   // padding are not issued (ds0.c1, Cin = 32: 2 of 4 steps)
   const int ksteps = (Cin_pad == 64 && !getenv("DRAM_CONV_FULL_K")) ? (Cin + 15) / 16 : 4;
-  const int kind = fwd_kernel_kind(D, H, W, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr);
-  DRAM_REQUIRE(!bn_partials || (!scale && fwd_stat_rows(N, D, H, W, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr) > 0),
+  const int kind = fwd_kernel_kind(N, D, H, W, Cin, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr);
+  DRAM_REQUIRE(!bn_partials || (!scale && fwd_stat_rows(N, D, H, W, Cin, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr) > 0),
                "conv3d_umma_fwd: bn_partials needs a raw (no scale/shift) output and a kernel with the statistics epilogue "
                "(dram_conv3d_umma_fwd_stat_rows > 0)");
+  if (kind == kFwdSmPairs) {
+    Fwd4Params q;
+    q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo; q.stat = bn_partials;
+    q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
+    if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
+    q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
+    q.n_mtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
+    q.a_plane_bytes = (q.TW + 2) * q.TDD * 1024;
+    q.a_tile_bytes = 2 * q.a_plane_bytes;
+    q.cb_split = C1p / 64;
+    CUtensorMap mA_hi, mA_lo, mA2_hi, mA2_lo;
+    int rc4;
+    if ((rc4 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
+    if ((rc4 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
+    mA2_hi = mA_hi; mA2_lo = mA_lo;
+    if (x2_hi && (rc4 = make_volume_map_hdw(&mA2_hi, x2_hi, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
+    if (x2_lo && (rc4 = make_volume_map_hdw(&mA2_lo, x2_lo, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
+    static int max_clusters = 0;
+    static std::once_flag once4;
+    std::call_once(once4, [&] {
+      cudaFuncSetAttribute(k_conv_umma_fwd4, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = 227 * 1024 - 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, k_conv_umma_fwd4, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = kNumSMs / 2; }
+      max_clusters = nc < kNumSMs / 2 ? nc : kNumSMs / 2;
+    });
+    static long long* prof_buf4 = nullptr;
+    static const bool want_prof4 = getenv("DRAM_CONV_PROF") != nullptr;
+    if (want_prof4 && !prof_buf4) cudaMalloc(&prof_buf4, kNumSMs * 8 * sizeof(long long));
+    q.prof = want_prof4 ? prof_buf4 : nullptr;
+    { const char* e = getenv("DRAM_CONV_DBG"); q.dbg = e ? atoi(e) : 0; }
+    // Cout = 128 * n128 (+ 64): one launch of 128-channel N tiles (both MMAs at N >= 128: the MMA pipe of the pair stays ~98 %
+    // busy), one launch for a 64-channel tail tile (its N = 64 MMA costs almost as much as an N = 128 one: ~77 %)
+    const int n128 = Cout / 128, tail = Cout % 128;
+    for (int part = 0; part < 2; ++part) {
+      if ((part == 0 && n128 == 0) || (part == 1 && tail == 0)) continue;
+      q.BN = part == 0 ? 128 : 64;
+      q.co_base = part == 0 ? 0 : 128 * n128;
+      q.n_ntiles = part == 0 ? n128 : 1;
+      q.TPC = (q.BN == 64 && q.n_mtiles % 4 == 0) ? 2 : 1;      // two M tiles per CTA share every weight tile (2 x 2 x 128 TMEM columns)
+      q.n_items = q.n_mtiles / (2 * q.TPC) * q.n_ntiles;
+      q.a_stage_bytes = q.TPC * q.a_tile_bytes;
+      q.b_stage_bytes = q.BN * 128;                        // this CTA's half of the N = 2*BN weight columns: BN/2 hi + BN/2 lo rows
+      q.SA = q.TPC == 2 ? 2 : 3;
+      q.SB = (227 * 1024 - 1024 - 512 - q.SA * q.a_stage_bytes) / q.b_stage_bytes;
+      if (q.SB > 8) q.SB = 8;
+      DRAM_REQUIRE(q.SB >= 3, "conv3d_umma_fwd: SM-pair pipeline does not fit in shared memory (SB=%d)", q.SB);
+      CUtensorMap mB_hi, mB_lo;
+      if ((rc4 = make_weight_map(&mB_hi, w_hi, 27ll * Cout, Cin_pad, q.BN / 2))) return rc4;
+      if ((rc4 = make_weight_map(&mB_lo, w_lo, 27ll * Cout, Cin_pad, q.BN / 2))) return rc4;
+      const size_t smem4 = (size_t)q.SA * q.a_stage_bytes + (size_t)q.SB * q.b_stage_bytes + 1024 + 512;
+      const int n_cl = q.n_items < max_clusters ? q.n_items : max_clusters;
+      k_conv_umma_fwd4<<<2 * n_cl, kFwdThreads, smem4, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
+      DRAM_LAUNCH_CHECK();
+      if (want_prof4) {
+        long long hbuf[kNumSMs * 8];
+        cudaMemcpy(hbuf, prof_buf4, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        for (int bi = 0; bi < n_cl; ++bi) for (int j = 0; j < 6; ++j) a[j] += (double)hbuf[bi * 8 + j] / n_cl;
+        fprintf(stderr, "[fwd4 prof] clusters %d items/cluster %.1f BN %d TPC %d cb %d SA %d SB %d | mma thread: total %.0f, wait tmem-empty %.0f, wait A %.0f, wait B %.0f | epilogue: wait %.0f, work %.0f (cycles)\n",
+                n_cl, (double)q.n_items / n_cl, q.BN, q.TPC, q.kblocks_c, q.SA, q.SB, a[0], a[1], a[2], a[3], a[4], a[5]);
+      }
+    }
+    return DRAM_OK;
+  }
   if (kind == kFwdChannelsOnM) {
     Fwd3Params q;
     const int plain = (Cout % 128 == 0) ? 1 : 0;
@@ -1708,6 +2120,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     static const bool want_prof3 = getenv("DRAM_CONV_PROF") != nullptr;
     if (want_prof3 && !prof_buf3) cudaMalloc(&prof_buf3, kNumSMs * 8 * sizeof(long long));
     q.prof = want_prof3 ? prof_buf3 : nullptr;
+    { const char* e = getenv("DRAM_CONV_DBG"); q.dbg = e ? atoi(e) : 0; }
     if (mode == 0) k_conv_umma_fwd3<0><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
     else if (mode == 1) k_conv_umma_fwd3<1><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
     else if (mode == 2) k_conv_umma_fwd3<2><<<grid3, kFwdThreads, smem3, (cudaStream_t)stream>>>(mX_hi, mX_lo, mW_hi, mW_lo, mX2_hi, mX2_lo, q);
@@ -1769,6 +2182,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     static const bool want_prof = getenv("DRAM_CONV_PROF") != nullptr;
     if (want_prof && !prof_buf) cudaMalloc(&prof_buf, kNumSMs * 8 * sizeof(long long));
     q.prof = want_prof ? prof_buf : nullptr;
+    { const char* e = getenv("DRAM_CONV_DBG"); q.dbg = e ? atoi(e) : 0; }
     const int grid2 = q.n_items < kNumSMs ? q.n_items : kNumSMs;
     if (mode == 0) k_conv_umma_fwd2<0><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);
     else if (mode == 1) k_conv_umma_fwd2<1><<<grid2, kFwdThreads, smem2, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mA2_hi, mA2_lo, q);

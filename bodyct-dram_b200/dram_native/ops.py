@@ -191,7 +191,7 @@ def conv_umma(xs, w_hi, w_lo, Cout, ksize, scale=None, shift=None, out_planes=Fa
     y = new_volume(N, Cout, D, H, W, xs.hi.device)
     partials, rows = None, 0
     if want_stats and scale is None and os.environ.get("DRAM_BN_EPILOGUE", "1") == "1":
-        rows = _L().dram_conv3d_umma_fwd_stat_rows(N, D, H, W, xs.Cpad, Cout, ksize, int(xs.lo is not None), int(w_lo is not None))
+        rows = _L().dram_conv3d_umma_fwd_stat_rows(N, D, H, W, Cin, xs.Cpad, Cout, ksize, int(xs.lo is not None), int(w_lo is not None))
         if rows > 0:
             partials = torch.empty((rows, 2, Cout), device=xs.hi.device, dtype=torch.float32)
     _lib.check(_L().dram_conv3d_umma_fwd(xs.hi.data_ptr(), _p(xs.lo), w_hi.data_ptr(), _p(w_lo), _p(scale), _p(shift),

@@ -92,7 +92,7 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
  * kernel that runs this shape has no such epilogue: use dram_bn_stats).  dram_bn_stats_from_partials adds the rows up in
  * double in a fixed order (two levels; workspace of dram_bn_stats_from_partials_workspace_bytes(C) bytes) ->
  * sums[0..C) = sum y, sums[C..2C) = sum y*y, what dram_bn_finalize takes. */
-long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo);
+long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo);
 size_t dram_bn_stats_from_partials_workspace_bytes(int C);
 int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* workspace, void* stream);
 /* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes
