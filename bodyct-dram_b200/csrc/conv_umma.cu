@@ -1440,6 +1440,174 @@ k_conv_umma_wgrad(const __grid_constant__ CUtensorMap tmX_hi, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, SM pairs (Cout tiles of 128)
+// The generic kernel above issues three M = 128, N = 128 MMAs per K step: 8 KB of shared-memory operands per 64 tensor cycles
+// (tensor pipe 78 % active, profiles/r01b_conv_umma_fwd2_ncu_full.md section 5) and every CTA streams the whole dY tile.
+// Pair version (cta_group::2, see k_conv_umma_fwd4): M = 256 = FOUR (tap, channel-block) blocks of X^T, two per CTA; the dY
+// tile of 128 channels is split across the pair — CTA r keeps the 64-channel block r as [dY_hi r | dY_lo r] — so that
+//   MMA1: X_hi^T x [dY_hi a | dY_lo a | dY_hi b | dY_lo b] (N = 256)  and  MMA2: X_lo^T x [dY_hi a | dY_hi b] (N = 128, the
+//   first block of each CTA's stage, accumulated at column offset 64: LH a on top of HL a, LH b on top of HH b)
+// give exactly the three split products with 64 / 96 B/cycle of operand reads per SM, and each CTA fetches half of dY.
+// Work item = (slab, group of four M blocks, N tile); the partial tiles land in the generic kernel's workspace layout
+// [slab][M tile = pair of blocks][N tile][128][128], so k_wgrad_reduce is shared.
+struct Wg2Params {
+  float* ws;
+  int N, D, H, W, taps, pad, CB /*Cin_pad/64*/, MB /*taps*CB*/, n_mtiles /*pairs of blocks*/, n_mt4 /*groups of four*/, n_ntiles;
+  int TW, TH, TD, TN, tiles_w, tiles_h, tiles_d, tiles_n, n_chunks, n_slabs, spg, stages;
+  int cb_split;   // virtual concat: input channel blocks >= cb_split are read from the second X operand (tmX2_*)
+};
+constexpr int kWg2Stage = 6 * kWgBlkBytes;      // X: 2 blocks x (hi, lo); dY: (hi, lo) of this CTA's 64-channel block
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+k_conv_umma_wgrad2(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                   const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                   const __grid_constant__ CUtensorMap tmX2_hi, const __grid_constant__ CUtensorMap tmX2_lo,
+                   const Wg2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * kWg2Stage);
+  // full / tempty are used in the leader only; empty / tfull exist (and are signalled) in both CTAs
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr uint32_t offXlo = 2 * kWgBlkBytes, offYhi = 4 * kWgBlkBytes, offYlo = 5 * kWgBlkBytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = p.n_slabs * p.n_mt4 * p.n_ntiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs: own X blocks, own dY block)
+    if (elect_one()) { tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo); }
+    uint32_t s = 0, ph = 0;
+    for (int item = cid; item < n_items; item += n_clusters) {
+      const int nt = item % p.n_ntiles;
+      const int mt4 = (item / p.n_ntiles) % p.n_mt4;
+      const int slab = item / (p.n_ntiles * p.n_mt4);
+      const int mb0 = 4 * mt4 + 2 * (int)rank, mb1 = mb0 + 1;
+      const bool has0 = mb0 < p.MB, has1 = mb1 < p.MB;
+      // blocks of the whole pair (the leader announces the bytes of both CTAs): 4 mt4 .. 4 mt4 + 3, cut at MB
+      const int nblk = min(4, p.MB - 4 * mt4);
+      const uint32_t tx = 2u * (uint32_t)nblk * kWgBlkBytes + 4u * kWgBlkBytes;
+      const int tap0 = has0 ? mb0 / p.CB : 0, cb0 = has0 ? mb0 % p.CB : 0, tap1 = has1 ? mb1 / p.CB : 0, cb1 = has1 ? mb1 % p.CB : 0;
+      const int kd0 = p.taps == 1 ? 0 : tap0 / 9 - p.pad, kh0 = p.taps == 1 ? 0 : (tap0 / 3) % 3 - p.pad, kw0 = p.taps == 1 ? 0 : tap0 % 3 - p.pad;
+      const int kd1 = p.taps == 1 ? 0 : tap1 / 9 - p.pad, kh1 = p.taps == 1 ? 0 : (tap1 / 3) % 3 - p.pad, kw1 = p.taps == 1 ? 0 : tap1 % 3 - p.pad;
+      const WgRange rg = wg_range(p.n_chunks, p.n_slabs, p.spg, slab);
+      for (int k = 0; k < rg.count; ++k) {
+        int t = rg.first + k * rg.step;            // depth fastest (see k_conv_umma_wgrad_w3)
+        const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
+        const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
+        const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
+        const int n0 = t * p.TN;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          const uint32_t sb = smem_u32(smem) + s * (uint32_t)kWg2Stage, fb = mapa_u32(full0 + 8 * s, 0);
+          if (leader) mbar_expect_tx(full0 + 8 * s, tx);
+          const bool s0 = cb0 >= p.cb_split, s1 = cb1 >= p.cb_split;       // virtual concat: second X operand
+          const int cc0 = (s0 ? cb0 - p.cb_split : cb0) * 64, cc1 = (s1 ? cb1 - p.cb_split : cb1) * 64;
+          if (has0) {
+            tma_load_5d_2sm(sb, s0 ? &tmX2_hi : &tmX_hi, fb, cc0, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+            tma_load_5d_2sm(sb + offXlo, s0 ? &tmX2_lo : &tmX_lo, fb, cc0, w0 + kw0, h0 + kh0, d0 + kd0, n0);
+          }
+          if (has1) {
+            tma_load_5d_2sm(sb + kWgBlkBytes, s1 ? &tmX2_hi : &tmX_hi, fb, cc1, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+            tma_load_5d_2sm(sb + offXlo + kWgBlkBytes, s1 ? &tmX2_lo : &tmX_lo, fb, cc1, w0 + kw1, h0 + kh1, d0 + kd1, n0);
+          }
+          tma_load_5d_2sm(sb + offYhi, &tmY_hi, fb, nt * 128 + (int)rank * 64, w0, h0, d0, n0);
+          tma_load_5d_2sm(sb + offYlo, &tmY_lo, fb, nt * 128 + (int)rank * 64, w0, h0, d0, n0);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------------------------------------------------------- MMA issuer of the pair
+      const uint32_t idesc1 = umma_idesc_2sm(256) | (1u << 15) | (1u << 16), idesc2 = umma_idesc_2sm(128) | (1u << 15) | (1u << 16);
+      uint32_t s = 0, ph = 0, tcount = 0;
+      for (int item = cid; item < n_items; item += n_clusters, ++tcount) {
+        const int slab = item / (p.n_ntiles * p.n_mt4);
+        const int c_end = wg_range(p.n_chunks, p.n_slabs, p.spg, slab).count;
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        for (int ch = 0; ch < c_end; ++ch) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem) + s * (uint32_t)kWg2Stage;
+            const uint64_t a_hi = umma_desc(sb, kWgBlkBytes, 1024), a_lo = umma_desc(sb + offXlo, kWgBlkBytes, 1024);
+            const uint64_t b_d = umma_desc(sb + offYhi, kWgBlkBytes, 1024);    // [dY_hi r | dY_lo r]: lo is LBO behind hi
+#pragma unroll
+            for (int k = 0; k < kWgKV / 16; ++k) {      // 16 voxel rows (2048 B) per MMA
+              const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+              umma_bf16_2sm(d_tmem, a_hi + adv, b_d + adv, idesc1, (ch | k) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem + 64u, a_lo + adv, b_d + adv, idesc2, 1u);
+            }
+            umma_commit_2sm(empty0 + 8 * s);
+            if (ch == c_end - 1) umma_commit_2sm(tfull0 + 8 * acc);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs): own 128 rows -> workspace
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tempty_leader = mapa_u32(tempty0, 0);
+    uint32_t tcount = 0;
+    for (int item = cid; item < n_items; item += n_clusters, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int nt = item % p.n_ntiles;
+      const int mt4 = (item / p.n_ntiles) % p.n_mt4;
+      const int slab = item / (p.n_ntiles * p.n_mt4);
+      const int mt = 2 * mt4 + (int)rank;                                  // this CTA's pair of blocks = one M tile of the workspace
+      const bool valid = mt < p.n_mtiles && (2 * mt + row / 64) < p.MB;
+      float* out = p.ws + ((((long long)slab * p.n_mtiles + mt) * p.n_ntiles + nt) * 128 + row) * 128;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        const uint32_t col = (uint32_t)(c0 < 64 ? c0 : c0 + 64);            // channels 0-63: [c | 64 + c]; 64-127: [128 + c' | 192 + c']
+        uint32_t r[16], r2[16];
+        tmem_ld16(taddr + col, r);
+        tmem_ld16(taddr + col + 64u, r2);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) =
+                make_float4(__uint_as_float(r[j]) + __uint_as_float(r2[j]), __uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]),
+                            __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512u);
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad, kw-reuse (Cout <= 64)
 // For the 64-channel layers of the 80^3 / 40^3 levels the generic kernel above is bound by the L2 -> shared-memory fill:
 // an N = 64 tile needs 48 KB of operands per 384 tensor-pipe cycles (125 B/cycle/SM).  Here one work item owns up to SIX
@@ -2286,6 +2454,40 @@ static int wgrad_plan(WgParams& p, int N, int D, int H, int W, int Cin_pad, int 
   return DRAM_OK;
 }
 
+// SM-pair wgrad (k_conv_umma_wgrad2): full split-bf16 layers whose Cout is a multiple of 128; DRAM_WGRAD_V2=0 switches it off
+static bool wgrad2_ok(int Cout_pad, int passes, int y_lo) {
+  const char* e = getenv("DRAM_WGRAD_V2");
+  return !(e && atoi(e) == 0) && passes == 3 && y_lo && Cout_pad % 128 == 0;
+}
+static void wgrad2_plan(Wg2Params& p, int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize) {
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.taps = ksize * ksize * ksize; p.pad = ksize / 2;
+  p.CB = Cin_pad / 64; p.MB = p.taps * p.CB; p.n_mtiles = cdiv(p.MB, 2); p.n_mt4 = cdiv(p.MB, 4);
+  p.n_ntiles = Cout_pad / 128;
+  pick_wgrad_chunk(N, D, H, W, p.TW, p.TH, p.TD, p.TN);
+  p.tiles_w = cdiv(W, p.TW); p.tiles_h = cdiv(H, p.TH); p.tiles_d = cdiv(D, p.TD); p.tiles_n = cdiv(N, p.TN);
+  p.n_chunks = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  // split-K over voxel slabs: whole waves of the 74 persistent clusters (as wgrad_plan does for 148 CTAs)
+  const int units = kNumSMs / 2, tiles = p.n_mt4 * p.n_ntiles;
+  const int max_slabs = cdiv(p.n_chunks, 8) < 48 ? cdiv(p.n_chunks, 8) : 48;    // >= 8 chunks per item
+  int best = 1;
+  double best_score = -1.0;
+  for (int sl = 1; sl <= (max_slabs > 1 ? max_slabs : 1); ++sl) {
+    const int cps = cdiv(p.n_chunks, sl), ns = cdiv(p.n_chunks, cps);
+    const long long items = (long long)ns * tiles;
+    const long long waves = (items + units - 1) / units;
+    const double lastslab = (double)(p.n_chunks - (ns - 1) * cps) / cps;
+    const double eff = ((double)items - tiles * (1.0 - lastslab)) / (double)(waves * units);
+    const double score = eff - 0.003 * sl;
+    if (score > best_score) { best_score = score; best = sl; }
+  }
+  p.n_slabs = cdiv(p.n_chunks, cdiv(p.n_chunks, best));
+  p.spg = cdiv(units, tiles);
+  { const char* e = getenv("DRAM_WGRAD_SPG"); if (e && atoi(e) > 0) p.spg = atoi(e); }
+  p.stages = (kSmemBudget - 1024) / kWg2Stage;
+  if (p.stages > 8) p.stages = 8;
+}
+
 // kw-reuse plan: slabs chosen so that the static round-robin schedule (item i -> CTA i % 148; a single-source item costs
 // 2 tiles, a full one 3) has the shortest makespan; more slabs cost workspace and reduction time.
 static bool wgrad_w3_ok(int H, int W, int Cout_pad, int ksize, int passes) {
@@ -2338,7 +2540,13 @@ size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Ci
   }
   WgParams p;
   wgrad_plan(p, N, D, H, W, Cin_pad, Cout_pad, ksize, 3);
-  const size_t generic = (size_t)p.n_slabs * p.n_mtiles * p.n_ntiles * 128 * p.BN * sizeof(float);
+  size_t generic = (size_t)p.n_slabs * p.n_mtiles * p.n_ntiles * 128 * p.BN * sizeof(float);
+  if (Cout_pad % 128 == 0) {                      // the SM-pair kernel plans its own slab count
+    Wg2Params q2;
+    wgrad2_plan(q2, N, D, H, W, Cin_pad, Cout_pad, ksize);
+    const size_t pairs = (size_t)q2.n_slabs * q2.n_mtiles * q2.n_ntiles * 128 * 128 * sizeof(float);
+    if (pairs > generic) generic = pairs;
+  }
   return generic > w3 ? generic : w3;
 }
 
@@ -2380,6 +2588,33 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     k_conv_umma_wgrad_w3<<<items3 < kNumSMs ? items3 : kNumSMs, kFwdThreads, smem3, st3>>>(mX_hi, mX_lo, mY_hi, mY_lo, mX2_hi, mX2_lo, q);
     DRAM_LAUNCH_CHECK();
     k_wgrad_w3_reduce<<<grid_for(27ll * Cin * Cout, 256), 256, 0, st3>>>(q.ws, dw, Cout, Cin, q.CB, q.n_pairs, q.n_slabs);
+    DRAM_LAUNCH_CHECK();
+    return DRAM_OK;
+  }
+  if (wgrad2_ok(Cout_pad, x_lo ? 3 : 1, dy_lo ? 1 : 0)) {
+    Wg2Params q;
+    wgrad2_plan(q, N, D, H, W, Cin_pad, Cout_pad, ksize);
+    q.ws = (float*)workspace;
+    q.cb_split = C1p / 64;
+    CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo, mX2_hi, mX2_lo;
+    int rc2;
+    if ((rc2 = make_volume_map(&mX_hi, x_hi, N, D, H, W, C1p, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    if ((rc2 = make_volume_map(&mX_lo, x_lo, N, D, H, W, C1p, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    if ((rc2 = make_volume_map(&mY_hi, dy_hi, N, D, H, W, Cout_pad, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    if ((rc2 = make_volume_map(&mY_lo, dy_lo, N, D, H, W, Cout_pad, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    mX2_hi = mX_hi; mX2_lo = mX_lo;
+    if (x2_hi && (rc2 = make_volume_map(&mX2_hi, x2_hi, N, D, H, W, C2p, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    if (x2_lo && (rc2 = make_volume_map(&mX2_lo, x2_lo, N, D, H, W, C2p, q.TW, q.TH, q.TD, q.TN))) return rc2;
+    const size_t smem2 = (size_t)q.stages * kWg2Stage + 1024 + 256;
+    static std::once_flag once2;
+    std::call_once(once2, [] { cudaFuncSetAttribute(k_conv_umma_wgrad2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const int items2 = q.n_slabs * q.n_mt4 * q.n_ntiles;
+    const int n_cl = items2 < kNumSMs / 2 ? items2 : kNumSMs / 2;
+    cudaStream_t st2 = (cudaStream_t)stream;
+    k_conv_umma_wgrad2<<<2 * n_cl, kFwdThreads, smem2, st2>>>(mX_hi, mX_lo, mY_hi, mY_lo, mX2_hi, mX2_lo, q);
+    DRAM_LAUNCH_CHECK();
+    k_wgrad_reduce<<<grid_for((long long)q.taps * Cin * Cout, 256), 256, 0, st2>>>(q.ws, dw, Cout, Cin, q.taps, q.CB, q.n_mtiles,
+                                                                                  q.n_ntiles, 128, q.n_slabs);
     DRAM_LAUNCH_CHECK();
     return DRAM_OK;
   }

@@ -260,6 +260,58 @@ def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
         assert_close(dw1, ref, TOL_X3, "conv_umma wgrad vs bf16-rounded dy")
 
 
+@pytest.mark.parametrize("N,Cin,Cout,S", [
+    (1, 64, 64, (16, 16, 16)),      # BN = 64, two M tiles per CTA
+    (1, 64, 64, (1, 8, 32)),        # BN = 64, 2 M tiles in all: one per CTA
+    (1, 192, 64, (8, 8, 8)),        # (TW,TDD) = (8,2), 3 K blocks per tap (us2.c0 shape class)
+    (1, 64, 192, (8, 8, 8)),        # Cout = 192: a launch of one 128-channel tile + a launch of the 64-channel tail (dgrad of us2.c0)
+    (2, 64, 128, (8, 8, 16)),       # BN = 128
+    (1, 128, 384, (2, 8, 16)),      # three 128-channel N tiles (dgrad of us1.c0 shape class)
+    (2, 64, 64, (16, 40, 40)),      # 40^3 tiling, more work items than clusters
+])
+def test_conv_umma_sm_pair_kernel_matches_single_sm_kernels(monkeypatch, N, Cin, Cout, S):
+    """k_conv_umma_fwd4 (cta_group::2) and the single-SM kernels it replaces (DRAM_CONV_V4=0: tile pairs / channels on M) compute
+    the same three split products; only the order of the fp32 additions differs.  Also keeps the single-SM kernels tested."""
+    o = ops()
+    x, w = torch.randn(N, Cin, *S), torch.randn(Cout, Cin, 3, 3, 3) * (2.0 / (Cin * 27)) ** 0.5
+    ref = F.conv3d(x, w, None, padding=1)
+    xs = o.split_bf16(cuda_cl(x), True)
+    w_hi, w_lo, _ = o.pack_weight_bf16(w.cuda(), 0, True)
+    y4, s4 = o.conv_umma(xs, w_hi, w_lo, Cout, 3, want_stats=True)
+    monkeypatch.setenv("DRAM_CONV_V4", "0")
+    y1, s1 = o.conv_umma(xs, w_hi, w_lo, Cout, 3, want_stats=True)
+    monkeypatch.delenv("DRAM_CONV_V4")
+    assert_close(y4, ref, TOL_X3, "conv_umma fwd, SM pairs")
+    assert_close(y1, ref, TOL_X3, "conv_umma fwd, single SM")
+    assert_close(y4, y1.cpu(), 2e-5, "SM pairs vs single SM")
+    assert s4 is not None and s1 is not None
+    yd = y4.double()
+    scale = torch.cat([yd.abs().sum(dim=(0, 2, 3, 4)), (yd * yd).sum(dim=(0, 2, 3, 4))])
+    assert ((s4 - s1).abs() <= 1e-5 * scale).all()
+    assert torch.equal(y4, o.conv_umma(xs, w_hi, w_lo, Cout, 3)), "deterministic, and the statistics epilogue does not change y"
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S", [(1, 64, 128, (6, 8, 24)), (2, 128, 256, (10, 10, 10)), (1, 384, 128, (4, 16, 8)),
+                                          (2, 96, 128, (5, 6, 7))])       # 96 channels: M blocks 54 = 13 groups of four + two
+def test_conv_umma_wgrad_sm_pair_kernel_matches_single_sm_kernel(monkeypatch, N, Cin, Cout, S):
+    """k_conv_umma_wgrad2 (cta_group::2) against the generic single-SM wgrad (DRAM_WGRAD_V2=0) and against torch"""
+    o = ops()
+    x = torch.randn(N, Cin, *S)
+    w = (torch.randn(Cout, Cin, 3, 3, 3) * 0.05).requires_grad_(True)
+    y = F.conv3d(x, w, None, padding=1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dys, xs = o.split_bf16(cuda_cl(dy), True), o.split_bf16(cuda_cl(x), True)
+    d2 = o.conv_umma_wgrad(dys, xs, Cin, Cout, 3)
+    monkeypatch.setenv("DRAM_WGRAD_V2", "0")
+    d1 = o.conv_umma_wgrad(dys, xs, Cin, Cout, 3)
+    monkeypatch.delenv("DRAM_WGRAD_V2")
+    assert_close(d2, w.grad, TOL_X3, "wgrad, SM pairs")
+    assert_close(d1, w.grad, TOL_X3, "wgrad, single SM")
+    assert_close(d2, d1.cpu(), 2e-5, "SM pairs vs single SM")
+    assert torch.equal(d2, o.conv_umma_wgrad(dys, xs, Cin, Cout, 3)), "deterministic"
+
+
 @pytest.mark.parametrize("Cin,Cout,S", [(32, 64, (16, 16, 16)), (24, 64, (8, 8, 16)), (32, 64, (5, 5, 5)), (16, 32, (8, 8, 8))])
 def test_conv_umma_skips_only_zero_padding(monkeypatch, Cin, Cout, S):
     """With one 64-channel K block the MMAs over the all-zero channel padding are not issued: same bits as issuing them"""
