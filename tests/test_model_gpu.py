@@ -217,6 +217,53 @@ def test_full_size_chunk_against_oracle(att):
     print("full-size gradient check: worst parameter", worst)
 
 
+def test_full_size_training_trajectory_against_oracle():
+    """BASELINE.json's full size, several optimizer steps: DC3D at the reference's widths on one 80^3 chunk, the reference's
+    optimizer (Adam, lr 1e-4, exp_settings OPTIMIZER), four steps on the GPU path and on the CPU oracle from the same
+    initialisation.  Every step's losses (train-mode forward of the weights trained so far) must stay inside the 1e-3 forward
+    bound: gradient rounding (split-bf16 in both directions) does not accumulate into the trajectory."""
+    from oracle_import import O
+    import metrics
+    g, cfg, m, images, lobes, lesions, ctsses = _full_width_case(False, (80, 80, 80), (64, 64, 64), 1, seed=41)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            params.append(v)
+    opt_ref = torch.optim.Adam(params, lr=1e-4)
+    m = m.cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    loss = metrics.IntRegRefineLoss(**g["loss_cfg"])
+    steps = 4
+    for it in range(steps):
+        opt_ref.zero_grad(set_to_none=True)
+        d_ref, r_ref = O.dc3d_forward(sd, images, cfg, True)
+        rl_ref, sl_ref = O.int_reg_refine_loss(d_ref, r_ref, lobes, lesions, ctsses, g["freq_map"])
+        (2.0 * rl_ref + sl_ref).backward()
+        opt_ref.step()
+        opt.zero_grad(set_to_none=True)
+        rl, sl = loss(m, images.cuda(), lobes.cuda(), lesions.cuda(), ctsses, obj=Host(g["freq_map"]), metas={})
+        (2.0 * rl + sl).backward()
+        opt.step()
+        assert_close(rl, rl_ref, 1e-3, f"reg loss, step {it}")
+        assert_close(sl, sl_ref, 1e-3, f"seg loss, step {it}")
+    # A convolution bias in front of a BatchNorm has an exactly zero gradient; both implementations produce rounding noise
+    # there, and Adam normalises noise to full +-lr steps.  The bias random-walks by up to steps * lr = 4e-4 in either
+    # implementation and the batch mean follows it one to one, so running means carry that (harmless: BatchNorm subtracts it
+    # again) difference; running variances do not see the bias.
+    worst_mean = max(rel_err(v, sd[k]) for k, v in m.state_dict().items() if "running_mean" in k)
+    worst_var = max(rel_err(v, sd[k]) for k, v in m.state_dict().items() if "running_var" in k)
+    m.eval()
+    with torch.no_grad():
+        d_ref, r_ref = O.dc3d_forward(sd, images, cfg, False)
+        d, r = m(images.cuda(), lobes.cuda())
+    print(f"trajectory after {steps} Adam steps: running_mean {worst_mean:.2e} running_var {worst_var:.2e} eval RAM {rel_err(d, d_ref):.2e}")
+    assert worst_var <= 1e-3 and worst_mean <= 1e-2, (worst_mean, worst_var)
+    assert rel_err(d, d_ref) <= 5e-3, rel_err(d, d_ref)      # eval mode: bias - running_mean, each with its own random walk
+    assert dice(d.cpu() > 0, d_ref > 0) >= 0.999
+
+
 @pytest.mark.parametrize("size", [(20, 18, 22), (9, 12, 10)])
 def test_ragged_chunk_sizes_against_oracle(size):
     """Sizes not divisible by 8: MaxPool3d floors odd extents and crop_concat_5d centre-crops the skip tensors with ceil
