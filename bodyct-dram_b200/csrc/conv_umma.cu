@@ -2099,13 +2099,17 @@ k_bn_partials_reduce(const float* __restrict__ partial, long long rows, int C, d
     ws[(long long)blockIdx.y * 2 * C + col] = t;
   }
 }
-__global__ void __launch_bounds__(128)
+// level 2: a warp per column, lanes stride the chunks, fixed shuffle tree (deterministic); the one-thread-per-column version
+// walked the 192 chunks serially: 21-24 us per layer for 6 KB of data
+__global__ void __launch_bounds__(256)
 k_bn_partials_finish(const double* __restrict__ ws, int chunks, int C, double* __restrict__ sums) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (col >= 2 * C) return;
   double t = 0.0;
-  for (int k = 0; k < chunks; ++k) t += ws[(long long)k * 2 * C + col];
-  sums[col] = t;
+  for (int k = lane; k < chunks; k += 32) t += ws[(long long)k * 2 * C + col];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) sums[col] = t;
 }
 
 }  // namespace dram
@@ -2147,7 +2151,7 @@ int dram_bn_stats_from_partials(const float* partials, long long rows, int C, do
   cudaStream_t st = (cudaStream_t)stream;
   k_bn_partials_reduce<<<dim3((2 * C + 31) / 32, chunks), 256, 0, st>>>(partials, rows, C, (double*)workspace);
   DRAM_LAUNCH_CHECK();
-  k_bn_partials_finish<<<(2 * C + 127) / 128, 128, 0, st>>>((const double*)workspace, chunks, C, sums);
+  k_bn_partials_finish<<<(2 * C + 7) / 8, 256, 0, st>>>((const double*)workspace, chunks, C, sums);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }
