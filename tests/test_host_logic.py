@@ -139,6 +139,46 @@ def test_metaimage_round_trip(tmp_path):
         assert np.array_equal(a, c)
 
 
+def test_metaimage_reader_on_a_file_assembled_from_the_format_description(tmp_path):
+    """A MetaImage put together byte by byte in this test from the published MetaIO format — the header ITK 4.13's MetaImageIO
+    writes for a 3-d image (key order, `True`/`False`, `CompressedDataSize`, x-fastest little-endian voxels, zlib stream) —
+    not by utils.write_mha: read_mha must return the voxels at [z, y, x], the element type and the geometry, and write_mha must
+    emit the same keys in the same order.  (No ITK in the image: the fixture restates the format, it is not an ITK-written file.)"""
+    import struct
+    import zlib
+    import utils
+    nx, ny, nz = 5, 4, 3
+    vox = [(x - 2) * 100 + y * 10 + z - 1000 for z in range(nz) for y in range(ny) for x in range(nx)]      # x runs fastest
+    cases = [("MET_SHORT", "<h", np.int16, True), ("MET_UCHAR", "<B", np.uint8, False), ("MET_FLOAT", "<f", np.float32, True)]
+    for met, fmt, dtype, compressed in cases:
+        vals = [v % 251 for v in vox] if dtype == np.uint8 else vox
+        payload = b"".join(struct.pack(fmt, v) for v in vals)
+        data = zlib.compress(payload) if compressed else payload
+        lines = ["ObjectType = Image", "NDims = 3", "BinaryData = True", "BinaryDataByteOrderMSB = False",
+                 f"CompressedData = {compressed}"] + ([f"CompressedDataSize = {len(data)}"] if compressed else []) + [
+                 "TransformMatrix = 1 0 0 0 1 0 0 0 1", "Offset = -170.5 -180.25 -300", "CenterOfRotation = 0 0 0",
+                 "AnatomicalOrientation = RAI", "ElementSpacing = 0.7 0.7 1.25", f"DimSize = {nx} {ny} {nz}",
+                 f"ElementType = {met}", "ElementDataFile = LOCAL"]
+        path = tmp_path / f"{met}.mha"
+        path.write_bytes(("\n".join(lines) + "\n").encode("ascii") + data)
+        arr, meta = utils.read_mha(str(path))
+        assert arr.dtype == dtype and arr.shape == (nz, ny, nx)
+        for z in range(nz):
+            for y in range(ny):
+                for x in range(nx):
+                    assert arr[z, y, x] == dtype(vals[(z * ny + y) * nx + x])
+        assert meta["spacing"] == [0.7, 0.7, 1.25] and meta["origin"] == [-170.5, -180.25, -300.0]
+        assert meta["direction"] == [1, 0, 0, 0, 1, 0, 0, 0, 1]
+        # the writer's header: the same keys in the same order, and the same bytes after it
+        utils.write_mha(str(tmp_path / "w.mha"), arr, spacing=meta["spacing"], origin=meta["origin"], direction=meta["direction"],
+                        compress=compressed)
+        raw = (tmp_path / "w.mha").read_bytes()
+        head = raw[:raw.index(b"ElementDataFile = LOCAL\n") + len(b"ElementDataFile = LOCAL\n")].decode("ascii")
+        assert [ln.split(" = ")[0] for ln in head.strip().split("\n")] == [ln.split(" = ")[0] for ln in lines]
+        body = raw[len(head):]
+        assert (zlib.decompress(body) if compressed else body) == payload
+
+
 @pytest.mark.parametrize("workload", ["train", "infer"])
 def test_bench_reference_arm_prints_one_json_line(workload):
     """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): exactly ONE stdout line, the contract's
