@@ -1630,6 +1630,7 @@ struct Wg3Params {
   int* prog;      // [n_items] chunks issued so far per work item (pacing of the single-source items, see below)
   int N, D, H, W, CB, n_src, n_pairs, tiles_w, tiles_h, n_chunks, n_slabs, spg, stages, dfast, y_lo;
   int cb_split;   // virtual concat: input channel blocks >= cb_split are read from the second X operand (tmX2_*)
+  int dbg;        // DRAM_CONV_DBG (diagnostics, garbage results): bit 0 = no X loads after the first ring fill, bit 1 = no dY loads
 };
 
 // Chunk schedule of the kw-reuse wgrad.  The voxel chunks are split over `n_slabs` slabs (split-K); a work item is
@@ -1721,17 +1722,23 @@ k_conv_umma_wgrad_w3(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           if (elect_one()) {                         // map dims (C,H,W,D,N): the box starts at w0 - 1 (kw = 0)
             const uint32_t sb = smem_u32(smem) + s * (uint32_t)kW3Stage, fb = full0 + 8 * s;
-            mbar_expect_tx(fb, tx);
+            const bool warm = ph || item != (int)blockIdx.x;                  // DRAM_CONV_DBG: the ring has been filled once
+            const bool skipx = (p.dbg & 1) && warm, skipy = (p.dbg & 2) && warm;
+            mbar_expect_tx(fb, (skipx ? 0u : 2u * (uint32_t)nsrc * kW3XBox) + (skipy ? 0u : (p.y_lo ? 2u : 1u) * kW3YBox));
             const bool v0 = cb0 >= p.cb_split, v1 = cb1 >= p.cb_split;       // virtual concat: second X operand
             const int cc0 = (v0 ? cb0 - p.cb_split : cb0) * 64, cc1 = (v1 ? cb1 - p.cb_split : cb1) * 64;
-            tma_load_5d(sb, v0 ? &tmX2_hi : &tmX_hi, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
-            tma_load_5d(sb + offXlo, v0 ? &tmX2_lo : &tmX_lo, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
-            if (nsrc == 2) {
-              tma_load_5d(sb + kW3XBox, v1 ? &tmX2_hi : &tmX_hi, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
-              tma_load_5d(sb + offXlo + kW3XBox, v1 ? &tmX2_lo : &tmX_lo, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
+            if (!skipx) {
+              tma_load_5d(sb, v0 ? &tmX2_hi : &tmX_hi, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
+              tma_load_5d(sb + offXlo, v0 ? &tmX2_lo : &tmX_lo, fb, cc0, h0 + kh0, w0 - 1, d0 + kd0, n0);
+              if (nsrc == 2) {
+                tma_load_5d(sb + kW3XBox, v1 ? &tmX2_hi : &tmX_hi, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
+                tma_load_5d(sb + offXlo + kW3XBox, v1 ? &tmX2_lo : &tmX_lo, fb, cc1, h0 + kh1, w0 - 1, d0 + kd1, n0);
+              }
             }
-            tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
-            if (p.y_lo) tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
+            if (!skipy) {
+              tma_load_5d(sb + offYhi, &tmY_hi, fb, 0, h0, w0, d0, n0);
+              if (p.y_lo) tma_load_5d(sb + offYlo, &tmY_lo, fb, 0, h0, w0, d0, n0);
+            }
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -2571,6 +2578,7 @@ int dram_conv3d_umma_wgrad(const void* dy_hi, const void* dy_lo, const void* x_h
     wgrad_w3_plan(q, N, D, H, W, Cin_pad);
     q.ws = (float*)workspace;
     q.prog = (int*)(q.ws + (size_t)q.n_slabs * q.n_pairs * 3 * 128 * 64);        // uninitialised on purpose (see the kernel)
+    { const char* e = getenv("DRAM_CONV_DBG"); q.dbg = e ? atoi(e) : 0; }
     q.y_lo = dy_lo ? 1 : 0;
     CUtensorMap mX_hi, mX_lo, mY_hi, mY_lo;
     int rc3;
