@@ -2,6 +2,8 @@
 // All of them are HBM-bound streaming kernels: float4 accesses along the contiguous channel dimension, grids sized
 // as multiples of the 148 SMs with grid-stride loops, per-block reductions finished with a few double atomics.
 #include <stdarg.h>
+#include <mutex>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dram {
@@ -574,6 +576,118 @@ k_up2x_adjoint(const float* __restrict__ ddst, float* __restrict__ dsrc, int N, 
   }
 }
 
+// Adjoint of the exact x2 upsample, shared-memory tiled, marching along z (round 2).  The register-blocked kernel above
+// pulls every destination value through L1/L2 27/8 times and ran at 0.37 of the HBM roofline.  Here a block owns an 8 x 8
+// (y, x) tile of SOURCE voxels x 32 channels (128 contiguous bytes per voxel) x a z segment and walks the destination planes
+// Z of that segment: the 18 x 18 destination patch of a plane is brought in ONCE with cp.async (double buffered), reduced
+// along x into [18][8] and along y into [8][8] through shared memory (4 taps each: source index i receives from destination
+// indices 2i-1 .. 2i+2 only), and the plane's result is scattered along z exactly as the forward gathered it
+// (lerp_setup(Z): out[Z] = w0 in[i0] + w1 in[i1]  =>  din[i0] += w0 u, din[i1] += w1 u) into two rolling accumulators per
+// thread; a source plane is written once its last contributing destination plane has passed.  Same weights as
+// k_trilinear_fwd, so this is its exact transpose; only the order of the additions differs from k_up2x_adjoint.
+constexpr int kAdjT = 8;                       // source tile edge
+constexpr int kAdjP = 2 * kAdjT + 2;           // destination patch edge (18)
+constexpr int kAdjC = 32;                      // channels per block
+constexpr int kAdjTileFloats = kAdjP * kAdjP * kAdjC;
+__global__ void __launch_bounds__(256, 2)
+k_up2x_adjoint_tiled(const float* __restrict__ ddst, float* __restrict__ dsrc, int N, int d, int h, int w, int C, int dstC,
+                     int dstOff, float sz, float sy, float sx, int zsegs) {
+  extern __shared__ __align__(16) float sm_adj[];
+  float* tile = sm_adj;                                        // [2][18][18][32]
+  float* tbuf = sm_adj + 2 * kAdjTileFloats;                   // [18][8][32]  (x-reduced)
+  float* wxs = tbuf + kAdjP * kAdjT * kAdjC;                   // [8][4]
+  float* wys = wxs + kAdjT * 4;                                // [8][4]
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const int tx_n = (w + kAdjT - 1) / kAdjT, ty_n = (h + kAdjT - 1) / kAdjT, cg_n = C / kAdjC;
+  unsigned r = blockIdx.x;
+  const int x0 = (int)(r % (unsigned)tx_n) * kAdjT; r /= (unsigned)tx_n;
+  const int y0 = (int)(r % (unsigned)ty_n) * kAdjT; r /= (unsigned)ty_n;
+  const int c0 = (int)(r % (unsigned)cg_n) * kAdjC; r /= (unsigned)cg_n;
+  const int seg = (int)(r % (unsigned)zsegs);
+  const int n = (int)(r / (unsigned)zsegs);
+  const int cz = (d + zsegs - 1) / zsegs, zc0 = seg * cz, zc1 = min(d, zc0 + cz);
+  if (zc0 >= zc1) return;
+  const int tid = threadIdx.x;
+  if (tid < 2 * kAdjT * 4) {                                   // per-axis tap weights of the tile (0 outside the volume)
+    const int axis = tid >> 5, i = (tid >> 2) & 7, t = tid & 3;
+    const int src = (axis ? y0 : x0) + i, O = 2 * src - 1 + t, in_size = axis ? h : w;
+    const float wgt = (src < in_size && O >= 0 && O < 2 * in_size) ? adj_weight(O, src, axis ? sy : sx, in_size) : 0.f;
+    (axis ? wys : wxs)[i * 4 + t] = wgt;
+  }
+  const int Zbeg = max(0, 2 * zc0 - 2), Zend = min(D - 1, 2 * zc1 + 1);
+  auto issue = [&](int Z, int buf) {                           // destination plane Z -> tile[buf], 16 bytes per cp.async
+    float* dstp = tile + buf * kAdjTileFloats;
+    const long long zbase = ((long long)n * D + Z) * H;
+    for (int it = tid; it < kAdjP * kAdjP * (kAdjC / 4); it += 256) {
+      const int g = it & 7, pos = it >> 3, lx = pos % kAdjP, ly = pos / kAdjP;
+      const int Y = min(max(2 * y0 - 1 + ly, 0), H - 1), X = min(max(2 * x0 - 1 + lx, 0), W - 1);
+      const float* src = ddst + ((zbase + Y) * W + X) * (long long)dstC + dstOff + c0 + g * 4;
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dstp + (pos * (kAdjC / 4) + g) * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // stage-2 items of this thread: (yc, xc, g) for item = tid and tid + 256
+  float4 accA[2], accB[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) accA[k] = accB[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int curA = lerp_setup(Zbeg, sz, d).i0;
+  auto flush_one = [&]() {                                     // source plane curA is complete: store it, roll the accumulators
+    if (curA >= zc0 && curA < zc1) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int item = tid + k * 256, g = item & 7, xc = (item >> 3) & 7, yc = item >> 6;
+        const int y = y0 + yc, x = x0 + xc;
+        if (y < h && x < w)
+          *reinterpret_cast<float4*>(dsrc + ((((long long)n * d + curA) * h + y) * w + x) * (long long)C + c0 + g * 4) = accA[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { accA[k] = accB[k]; accB[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    ++curA;
+  };
+  issue(Zbeg, 0);
+  for (int Z = Zbeg; Z <= Zend; ++Z) {
+    const int buf = (Z - Zbeg) & 1;
+    if (Z < Zend) issue(Z + 1, buf ^ 1);
+    if (Z < Zend) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                           // tile[buf] complete; the previous plane's tbuf reads are done
+    const float4* tp = reinterpret_cast<const float4*>(tile + buf * kAdjTileFloats);
+    for (int it = tid; it < kAdjP * kAdjT * (kAdjC / 4); it += 256) {          // reduce along x: [18][18] -> [18][8]
+      const int g = it & 7, xc = (it >> 3) & 7, ly = it >> 6;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float wv = wxs[xc * 4 + t];
+        const float4 v = tp[(ly * kAdjP + 2 * xc + t) * (kAdjC / 4) + g];
+        a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
+      }
+      reinterpret_cast<float4*>(tbuf)[it] = a;
+    }
+    __syncthreads();
+    const Lerp lz = lerp_setup(Z, sz, d);
+    while (curA < lz.i0) flush_one();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                                              // reduce along y, scatter along z
+      const int item = tid + k * 256, g = item & 7, xc = (item >> 3) & 7, yc = item >> 6;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float wv = wys[yc * 4 + t];
+        const float4 v = reinterpret_cast<const float4*>(tbuf)[((2 * yc + t) * kAdjT + xc) * (kAdjC / 4) + g];
+        u.x = fmaf(wv, v.x, u.x); u.y = fmaf(wv, v.y, u.y); u.z = fmaf(wv, v.z, u.z); u.w = fmaf(wv, v.w, u.w);
+      }
+      accA[k].x = fmaf(lz.w0, u.x, accA[k].x); accA[k].y = fmaf(lz.w0, u.y, accA[k].y);
+      accA[k].z = fmaf(lz.w0, u.z, accA[k].z); accA[k].w = fmaf(lz.w0, u.w, accA[k].w);
+      float4& b = (lz.i1 == lz.i0) ? accA[k] : accB[k];
+      b.x = fmaf(lz.w1, u.x, b.x); b.y = fmaf(lz.w1, u.y, b.y); b.z = fmaf(lz.w1, u.z, b.z); b.w = fmaf(lz.w1, u.w, b.w);
+    }
+  }
+  flush_one();
+  flush_one();
+}
+
 // copy the (centre-cropped) skip tensor into / out of channels [C1, C1+C2) of the concat buffer
 template <int VEC, bool BWD>
 __global__ void k_concat_skip(const float* __restrict__ in, float* __restrict__ out, int N, int D, int H, int W,
@@ -836,9 +950,23 @@ int dram_upsample2x_concat_bwd(const float* dcat, float* dx, float* dskip, int N
   DRAM_REQUIRE(Ds >= D && Hs >= H && Ws >= W, "upsample2x_concat_bwd: bad skip size");
   cudaStream_t st = (cudaStream_t)stream;
   if (C1 % 4 == 0 && C2 % 4 == 0 && (long long)N * d * h * w < (1ll << 31)) {
-    const long long blocks = (long long)N * ((d + 1) / 2) * ((h + 1) / 2) * ((w + 1) / 2);
-    k_up2x_adjoint<<<grid_fixed_group(blocks, C1 / 4, 128, 64), 128, 0, st>>>(dcat, dx, N, d, h, w, C1, C1 + C2, 0, ac_scale(d, D),
-                                                                           ac_scale(h, H), ac_scale(w, W));
+    const bool tiled_ok = getenv("DRAM_UP2X_ADJ_BLOCKED") == nullptr;
+    const long long tiles = (long long)N * ((h + kAdjT - 1) / kAdjT) * ((w + kAdjT - 1) / kAdjT) * (C1 / kAdjC);
+    if (tiled_ok && C1 % kAdjC == 0 && d >= 2 && tiles > 0) {
+      // z segments: a few waves of 2 blocks per SM, at least 4 source planes per block (each segment re-reads ~4 halo planes)
+      int zsegs = (int)((4ll * 2 * kNumSMs + tiles - 1) / tiles);
+      if (zsegs > d / 4) zsegs = d / 4;
+      if (zsegs < 1) zsegs = 1;
+      const size_t smem = (2 * kAdjTileFloats + kAdjP * kAdjT * kAdjC + 2 * kAdjT * 4) * sizeof(float);
+      static std::once_flag once;
+      std::call_once(once, [] { cudaFuncSetAttribute(k_up2x_adjoint_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); });
+      k_up2x_adjoint_tiled<<<(unsigned)(tiles * zsegs), 256, smem, st>>>(dcat, dx, N, d, h, w, C1, C1 + C2, 0, ac_scale(d, D),
+                                                                        ac_scale(h, H), ac_scale(w, W), zsegs);
+    } else {
+      const long long blocks = (long long)N * ((d + 1) / 2) * ((h + 1) / 2) * ((w + 1) / 2);
+      k_up2x_adjoint<<<grid_fixed_group(blocks, C1 / 4, 128, 64), 128, 0, st>>>(dcat, dx, N, d, h, w, C1, C1 + C2, 0, ac_scale(d, D),
+                                                                             ac_scale(h, H), ac_scale(w, W));
+    }
     DRAM_LAUNCH_CHECK();
   } else {
     int rc = launch_trilinear_bwd(dcat, dx, N, d, h, w, D, H, W, C1, C1 + C2, 0, st);

@@ -543,7 +543,10 @@ def test_maxpool_backward_first_max_on_ties():
 
 
 # ------------------------------------------------------------------------------------------------ decoder glue / resize
-@pytest.mark.parametrize("C1,C2,s,skip", [(8, 4, (4, 5, 6), (8, 10, 12)), (16, 8, (3, 3, 3), (7, 6, 8)), (3, 5, (4, 4, 4), (8, 8, 8))])
+@pytest.mark.parametrize("C1,C2,s,skip", [(8, 4, (4, 5, 6), (8, 10, 12)), (16, 8, (3, 3, 3), (7, 6, 8)), (3, 5, (4, 4, 4), (8, 8, 8)),
+                                          (32, 8, (4, 5, 6), (8, 10, 12)),          # tiled adjoint: one partial 8 x 8 tile
+                                          (64, 32, (10, 10, 10), (20, 20, 20)),     # tiled adjoint: 2 x 2 tiles, 2 channel chunks, z segments
+                                          (32, 4, (9, 3, 17), (18, 7, 34))])        # tiled adjoint: odd extents, cropped skip
 def test_upsample_concat(C1, C2, s, skip):
     from oracle_import import O
     x = torch.randn(2, C1, *s, requires_grad=True)
@@ -558,6 +561,26 @@ def test_upsample_concat(C1, C2, s, skip):
     got.backward(g.cuda())
     assert_close(xg.grad, x.grad, TOL_F32, "upsample+concat dx")
     assert torch.equal(skg.grad.cpu(), sk.grad), "skip gradient is a pure copy: bit-exact"
+
+
+@pytest.mark.parametrize("C1,C2,s", [(32, 8, (4, 5, 6)), (128, 64, (12, 16, 20)), (32, 32, (2, 8, 8))])
+def test_upsample_adjoint_tiled_kernel_matches_register_blocked_kernel(monkeypatch, C1, C2, s):
+    """k_up2x_adjoint_tiled (shared-memory tiles, marching along z) == k_up2x_adjoint (DRAM_UP2X_ADJ_BLOCKED=1) up to the order
+    of the fp32 additions, and both are the exact transpose of the forward: <up(x), g> == <x, adjoint(g)>"""
+    o = ops()
+    B = 2
+    D, H, W = (2 * v for v in s)
+    g = cuda_cl(torch.randn(B, C1 + C2, D, H, W))
+    dx_t, _ = o.upsample2x_concat_bwd(g, (B, C1, *s), (B, C2, D, H, W), want_dskip=False)
+    monkeypatch.setenv("DRAM_UP2X_ADJ_BLOCKED", "1")
+    dx_b, _ = o.upsample2x_concat_bwd(g, (B, C1, *s), (B, C2, D, H, W), want_dskip=False)
+    monkeypatch.delenv("DRAM_UP2X_ADJ_BLOCKED")
+    assert_close(dx_t, dx_b.cpu(), TOL_F32, "tiled vs register-blocked adjoint")
+    x = torch.randn(B, C1, *s)
+    up = F.interpolate(x, scale_factor=(2, 2, 2), mode="trilinear", align_corners=True)
+    lhs = (up.double() * g[:, :C1].cpu().double()).sum().item()
+    rhs = (x.double() * dx_t.cpu().double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * (up.double().abs() * g[:, :C1].cpu().double().abs()).sum().item(), (lhs, rhs)
 
 
 @pytest.mark.parametrize("C,src,dst", [(1, (20, 20, 20), (16, 16, 16)), (1, (16, 16, 16), (20, 20, 20)), (8, (10, 12, 9), (16, 16, 16)),
