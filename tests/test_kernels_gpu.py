@@ -312,6 +312,37 @@ def test_conv_umma_wgrad_sm_pair_kernel_matches_single_sm_kernel(monkeypatch, N,
     assert torch.equal(d2, o.conv_umma_wgrad(dys, xs, Cin, Cout, 3)), "deterministic"
 
 
+@pytest.mark.parametrize("name,Cin,Cout,S", [("us2.c0", 192, 64, 80), ("us2.c1", 64, 64, 80), ("ds0.c1", 32, 64, 80),
+                                             ("us1.c0", 384, 128, 40), ("ds1.c1", 64, 128, 40), ("us0.c1", 256, 256, 20)])
+def test_conv_umma_full_size_batch8_adjoint_identities(name, Cin, Cout, S):
+    """BASELINE's full size (batch 8, the benchmark's exact tile / cluster schedules), checked through size-independent
+    properties instead of a CPU oracle: forward, dgrad and wgrad of one layer are three views of ONE trilinear form,
+    <conv(x, w), g> == <x, dgrad(g, w)> == <w, wgrad(x, g)>, and the forward is linear in x."""
+    o = ops()
+    B = 8
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = o.new_volume(B, Cin, S, S, S, "cuda").normal_(generator=gen)
+    g = o.new_volume(B, Cout, S, S, S, "cuda").normal_(generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=gen) * (2.0 / (Cin * 27)) ** 0.5
+    xs, gs = o.split_bf16(x), o.split_bf16(g)
+    wf, wd = o.pack_weight_bf16(w, 0), o.pack_weight_bf16(w, 1)
+    y = o.conv_umma(xs, wf[0], wf[1], Cout, 3)
+    dx = o.conv_umma(gs, wd[0], wd[1], Cin, 3)
+    dw = o.conv_umma_wgrad(gs, xs, Cin, Cout, 3)
+    assert torch.isfinite(y).all() and torch.isfinite(dx).all() and torch.isfinite(dw).all()
+    a = (y.double() * g.double()).sum().item()
+    b = (x.double() * dx.double()).sum().item()
+    c = (w.double() * dw.double()).sum().item()
+    scale = (y.double().abs() * g.double().abs()).sum().item()          # sum of |terms|: the three sums agree to ~1e-6 of it
+    assert abs(a - b) <= 2e-6 * scale and abs(a - c) <= 2e-6 * scale, (name, a, b, c, scale)
+    # linearity of the forward in x (split-bf16 operands: each term is rounded to ~2^-16 on its own)
+    x2 = o.new_volume(B, Cin, S, S, S, "cuda").normal_(generator=gen)
+    y2 = o.conv_umma(o.split_bf16(x2), wf[0], wf[1], Cout, 3)
+    y12 = o.conv_umma(o.split_bf16(0.75 * x - 1.5 * x2), wf[0], wf[1], Cout, 3)
+    ref = 0.75 * y - 1.5 * y2
+    assert (y12 - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("Cin,Cout,S", [(32, 64, (16, 16, 16)), (24, 64, (8, 8, 16)), (32, 64, (5, 5, 5)), (16, 32, (8, 8, 8))])
 def test_conv_umma_skips_only_zero_padding(monkeypatch, Cin, Cout, S):
     """With one 64-channel K block the MMAs over the all-zero channel padding are not issued: same bits as issuing them"""
