@@ -228,8 +228,8 @@ def conv_roofline(prof, peaks, per_steps, note):
     achieved = rk["flops"] / (rk["ms"] / 1e3) / 1e12 if rk["ms"] > 0 else 0.0
     traffic, src, stale = ncu_traffic_per_launch(("dram::k_conv_umma_fwd",) if roof_k == "dram_conv3d_umma_fwd" else ("dram::k_conv_umma_wgrad",))
     return {"bound": "tensor",
-            "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd3 / k_conv_umma_fwd2 / k_conv_umma_fwd (forward + dgrad launches)",
-                       "dram_conv3d_umma_wgrad": "k_conv_umma_wgrad(_w3)"}[roof_k],
+            "kernel": {"dram_conv3d_umma_fwd": "k_conv_umma_fwd4 (SM pairs, cta_group::2) / k_conv_umma_fwd / _fwd2 / _fwd3 (forward + dgrad launches)",
+                       "dram_conv3d_umma_wgrad": "k_conv_umma_wgrad_w3 / k_conv_umma_wgrad2 (SM pairs)"}[roof_k],
             "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
             "traffic": traffic,
             "traffic_source": (f"bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), mean over this kernel family's launches "
@@ -240,7 +240,7 @@ def conv_roofline(prof, peaks, per_steps, note):
             "ms_per_step": rk["ms"] / per_steps, "launches_per_step": rk["calls"] / per_steps,
             "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
             "note": "achieved = algorithmic FLOPs (unpadded channels, one pass; the split-bf16 kernels issue 3 MMAs per algorithmic "
-                    "MAC, so 1/3 of the peak is the ceiling) / CUDA-event time of this family's launches on the launching stream; " + note}
+                    "MAC, so 1/3 of the tensor peak AT THE CLOCK THE KERNELS RUN AT is the ceiling; `peak` is the sustained cuBLAS figure measured at ~1.3 GHz, the pair kernels hold 1.5-1.6 GHz) / CUDA-event time of this family's launches on the launching stream; " + note}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
@@ -535,7 +535,7 @@ def measure_infer(dist, runner, steps, warmup, peaks, clocks=True):
         "e2e": {"value": dist.world * B * steps / e2e_s, "unit": "chunks/s", "h2d_bytes_per_step": 2 * img_h.numel() * 4,
                 "d2h_bytes_per_step": B * 4, "api": "DC3DATGeneric.forward + pooling_dense_features on pinned host chunks, scores read back"},
         "clocks": ck, "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd3 / _fwd2 / _fwd (13 forward launches, folded BN + ReLU epilogues)",
+        "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd4 (SM pairs) / _fwd / _fwd3 (13 forward launches, folded BN + ReLU epilogues)",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                      "traffic": None, "ms_per_step": k["ms"] / ev, "peak_source": peaks["source"] + ", sustained figure",
                      "note": "algorithmic FLOPs / CUDA-event time; 1/3 of the peak is the split-bf16 ceiling"},
@@ -599,7 +599,7 @@ def measure_scan(dist, runner, steps, warmup, small=False, clocks=True):
                 "d2h_bytes_per_step": int(2 * lobe_h.numel() + 4), "api": "LesionSegTest.run_scans (pinned host scans in, host masks out; "
                 "pipelined copies)", "single_scan_latency_s": single},
         "clocks": ck, "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd3 / _fwd2 / _fwd (13 launches per scan, the dominant kernels of a scan)",
+        "roofline": {"bound": "tensor", "kernel": "k_conv_umma_fwd4 (SM pairs) / _fwd / _fwd3 (13 launches per scan, the dominant kernels of a scan)",
                      "achieved": k["flops"] / (k["ms"] / 1e3) / 1e12 if k["ms"] else 0.0, "unit": "TFLOP/s",
                      "ms_per_scan": k["ms"], "share_of_kernel_time": k["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0),
                      "traffic": None},
