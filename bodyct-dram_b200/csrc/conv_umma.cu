@@ -971,6 +971,10 @@ struct Fwd4Params {
                      // as one launch of 128-channel tiles and one of a 64-channel tile)
   int TW, TDD, tiles_w, tiles_h, tiles_d, n_mtiles, n_ntiles, n_items, TPC;
   int SA, SB, a_plane_bytes, a_tile_bytes, a_stage_bytes, b_stage_bytes;
+  // generic-tile mode (gen = 1; the 20^3 / 10^3 levels, whose extents do not tile into 8-row boxes): the M tile is a
+  // (TW, TH, TD) box of <= 128 voxels (rows ordered [d][h][w], rows beyond TW*TH*TD unused), every tap loads its own
+  // shifted box through a (C,W,H,D,N) tensor map (no kw re-use) and the weights follow tap by tap
+  int gen, TH, TD, a_box_bytes;
   long long* prof;   // DRAM_CONV_PROF: per-cluster cycle counters [8] (diagnostics only)
   float* stat;       // training: BatchNorm partial sums of y, [n_mtiles * 4][2][Cout] (row = M tile x epilogue warp), or NULL
   int cb_split;      // virtual concat: channel blocks >= cb_split are read from the second activation operand (tmA2_*)
@@ -1069,15 +1073,16 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   cluster_sync_all();                 // barriers of both CTAs initialised before any remote arrive / 2-SM load / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_g = 9 * p.kblocks_c;
+  const int n_g = (p.gen ? 27 : 9) * p.kblocks_c;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs: own tiles, own weight half)
     if (elect_one()) {
       tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
     }
-    const uint32_t a_tx = 2u * (uint32_t)TPC * 2u * (uint32_t)p.a_plane_bytes;     // both CTAs of the pair
+    const uint32_t a_tx = 2u * (uint32_t)TPC * 2u * (uint32_t)(p.gen ? p.a_box_bytes : p.a_plane_bytes);     // both CTAs of the pair
     const uint32_t b_tx = 2u * (uint32_t)p.b_stage_bytes;
+    const int n_grp = p.gen ? 27 : 9, kw_n = p.gen ? 1 : 3;
     uint32_t sA = 0, phA = 0, sB = 0, phB = 0;
     for (int item = cid; item < p.n_items; item += n_clusters) {
       const int nt = item % p.n_ntiles, grp = item / p.n_ntiles;
@@ -1085,12 +1090,12 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int j = 0; j < TPC; ++j) {
         int mt = (grp * 2 + (int)rank) * TPC + j;
         w0[j] = (mt % p.tiles_w) * p.TW - 1; mt /= p.tiles_w;
-        h0[j] = (mt % p.tiles_h) * 8 - 1; mt /= p.tiles_h;
-        d0[j] = (mt % p.tiles_d) * p.TDD - 1;
+        h0[j] = (mt % p.tiles_h) * (p.gen ? p.TH : 8) - 1; mt /= p.tiles_h;
+        d0[j] = (mt % p.tiles_d) * (p.gen ? p.TD : p.TDD) - 1;
         n0[j] = mt / p.tiles_d;
       }
-      for (int g = 0; g < 9; ++g) {
-        const int kd = g / 3, kh = g - 3 * kd;
+      for (int g = 0; g < n_grp; ++g) {
+        const int kd = p.gen ? g / 9 : g / 3, kh = p.gen ? (g / 3) % 3 : g - 3 * kd, kwg = p.gen ? g % 3 : 0;
         for (int cb = 0; cb < p.kblocks_c; ++cb) {
           mbar_wait(emptyA0 + 8 * sA, phA ^ 1);
           if ((p.dbg & 1) && (phA || item != cid)) {
@@ -1103,21 +1108,27 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const CUtensorMap* ml = second ? &tmA2_lo : &tmA_lo;
             const int cc = (second ? cb - p.cb_split : cb) * 64;
             for (int j = 0; j < TPC; ++j) {
-              tma_load_5d_2sm(ab + j * p.a_tile_bytes, mh, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
-              tma_load_5d_2sm(ab + j * p.a_tile_bytes + p.a_plane_bytes, ml, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
+              if (p.gen) {                              // map dims (C,W,H,D,N): this tap's own shifted box
+                tma_load_5d_2sm(ab + j * p.a_tile_bytes, mh, fa, cc, w0[j] + kwg, h0[j] + kh, d0[j] + kd, n0[j]);
+                tma_load_5d_2sm(ab + j * p.a_tile_bytes + p.a_plane_bytes, ml, fa, cc, w0[j] + kwg, h0[j] + kh, d0[j] + kd, n0[j]);
+              } else {
+                tma_load_5d_2sm(ab + j * p.a_tile_bytes, mh, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
+                tma_load_5d_2sm(ab + j * p.a_tile_bytes + p.a_plane_bytes, ml, fa, cc, h0[j] + kh, d0[j] + kd, w0[j], n0[j]);
+              }
             }
           }
           __syncwarp();
           if (++sA == (uint32_t)SA) { sA = 0; phA ^= 1; }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
+            if (kw >= kw_n) break;
             mbar_wait(emptyB0 + 8 * sB, phB ^ 1);
             if ((p.dbg & 2) && (phB || item != cid)) {
               if (leader && elect_one()) mbar_arrive(fullB0 + 8 * sB);
             } else if (elect_one()) {
               const uint32_t bb = smemB_u + sB * (uint32_t)p.b_stage_bytes, fb = mapa_u32(fullB0 + 8 * sB, 0);
               if (leader) mbar_expect_tx(fullB0 + 8 * sB, b_tx);
-              const int brow = (g * 3 + kw) * p.Cout + p.co_base + nt * p.BN + (int)rank * h;
+              const int brow = (p.gen ? g : g * 3 + kw) * p.Cout + p.co_base + nt * p.BN + (int)rank * h;
               tma_load_2d_2sm(bb, &tmB_hi, fb, cb * 64, brow);
               tma_load_2d_2sm(bb + h * 128, &tmB_lo, fb, cb * 64, brow);
             }
@@ -1151,8 +1162,11 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (prof) t_fa += clock64() - t0;
           tc_fence_after();
           const uint32_t ab = smemA_u + sA * (uint32_t)p.a_stage_bytes;
+          const int kw_n = p.gen ? 1 : 3;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
+            if (kw >= kw_n) break;
+            const bool last_kw = kw == kw_n - 1;
             if (prof) t0 = clock64();
             mbar_wait(fullB0 + 8 * sB, phB);
             if (prof) t_fb += clock64() - t0;
@@ -1172,8 +1186,8 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
               }
               umma_commit_2sm(emptyB0 + 8 * sB);             // frees the weight stage of both CTAs when these MMAs retire
-              if (kw == 2) umma_commit_2sm(emptyA0 + 8 * sA);
-              if (kw == 2 && g == n_g - 1) umma_commit_2sm(tfull0 + 8 * set);   // accumulators complete -> both epilogues
+              if (last_kw) umma_commit_2sm(emptyA0 + 8 * sA);
+              if (last_kw && g == n_g - 1) umma_commit_2sm(tfull0 + 8 * set);   // accumulators complete -> both epilogues
             }
             __syncwarp();
             if (++sB == (uint32_t)SB) { sB = 0; phB ^= 1; }
@@ -1190,7 +1204,9 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ------------------------------------------------------------------ epilogue (both CTAs): own TMEM lanes -> fp32 channels-last
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int tw = row / (8 * p.TDD), tdd = (row >> 3) % p.TDD, th = row & 7;
+    // kw-reuse tiles: rows ordered [w][d][h]; generic tiles: [d][h][w] with rows >= TW*TH*TD unused
+    const int tw = p.gen ? row % p.TW : row / (8 * p.TDD), tdd = p.gen ? row / (p.TW * p.TH) : (row >> 3) % p.TDD,
+              th = p.gen ? (row / p.TW) % p.TH : row & 7;
     const uint32_t tempty_leader = mapa_u32(tempty0, 0);
     uint32_t icount = 0;
     long long e_wait = 0, e_work = 0, e0 = 0;
@@ -1206,9 +1222,10 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int mtile = (grp * 2 + (int)rank) * TPC + j;
         int mt = mtile;
         const int w = (mt % p.tiles_w) * p.TW + tw; mt /= p.tiles_w;
-        const int hh = (mt % p.tiles_h) * 8 + th; mt /= p.tiles_h;
-        const int d = (mt % p.tiles_d) * p.TDD + tdd;
+        const int hh = (mt % p.tiles_h) * (p.gen ? p.TH : 8) + th; mt /= p.tiles_h;
+        const int d = (mt % p.tiles_d) * (p.gen ? p.TD : p.TDD) + tdd;
         const int n = mt / p.tiles_d;
+        const bool valid = !p.gen || (tdd < p.TD && w < p.W && hh < p.H && d < p.D);    // ragged generic tiles: masked rows
         const int cbase = p.co_base + nt * p.BN;
         const long long oo = ((((long long)n * p.D + d) * p.H + hh) * p.W + w) * p.Cout + cbase;   // element offset in y / in the planes
         float* out = p.y + oo;
@@ -1238,13 +1255,15 @@ k_conv_umma_fwd4(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               v[jj] = fmaxf(fmaf(v[jj], __ldg(p.scale + c), __ldg(p.shift + c)), 0.f);
             }
           }
-          if (p.o_hi) {
-            const long long po = oo + c0;
-            store_planes16(p.o_hi + po, p.o_lo ? p.o_lo + po : nullptr, v);
-          } else {
+          if (valid) {
+            if (p.o_hi) {
+              const long long po = oo + c0;
+              store_planes16(p.o_hi + po, p.o_lo ? p.o_lo + po : nullptr, v);
+            } else {
 #pragma unroll
-            for (int jj = 0; jj < 16; jj += 4)
-              *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+              for (int jj = 0; jj < 16; jj += 4)
+                *reinterpret_cast<float4*>(out + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+            }
           }
         }
       }
@@ -2029,7 +2048,7 @@ static int pow2_cols(int c) { int v = 32; while (v < c) v *= 2; return v; }
 constexpr int kSmemBudget = 200 * 1024;
 
 // which forward / dgrad kernel runs a layer (shared by the launcher and by the query for the BatchNorm partial rows)
-enum { kFwdGeneric = 0, kFwdPairs = 2, kFwdChannelsOnM = 3, kFwdSmPairs = 4 };
+enum { kFwdGeneric = 0, kFwdPairs = 2, kFwdChannelsOnM = 3, kFwdSmPairs = 4, kFwdSmPairsGen = 5 };
 // SM-pair kernel (k_conv_umma_fwd4): 128-channel N tiles plus a 64-channel tail tile
 static int fwd_kernel_kind(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, bool x_lo, bool w_lo) {
   // DRAM_CONV_V4=0 switches it off.  It takes every split-bf16 3x3x3 layer whose volume tiles into 8(h) x TDD(d) x TW(w) boxes
@@ -2044,6 +2063,15 @@ static int fwd_kernel_kind(int N, int D, int H, int W, int Cin, int Cin_pad, int
       const int TW = (W % 16 == 0) ? 16 : 8, TDD = (W % 16 == 0) ? 1 : 2;
       const long long mt = (long long)N * (D / TDD) * (H / 8) * (W / TW);
       if (mt % 2 == 0) return kFwdSmPairs;
+    }
+    // the same kernel on generic (TW,TH,TD) tiles for volumes that do not tile into 8-row boxes (the 20^3 / 10^3 levels):
+    // Cout a multiple of 128 only (DRAM_CONV_V4=1 also allows a 64-channel tail)
+    if (allow_v4 && Cout % 64 == 0 && (Cout % 128 == 0 || (v4_env && atoi(v4_env) == 1)) && x_lo && w_lo && ksize == 3 &&
+        !(H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)))) {
+      int TW, TH, TD;
+      pick_fwd_tile(D, H, W, TW, TH, TD);
+      const long long mt = (long long)N * cdiv(D, TD) * cdiv(H, TH) * cdiv(W, TW);
+      if (mt % 2 == 0 && mt >= 2) return kFwdSmPairsGen;
     }
   }
   // channels-on-M kernel (k_conv_umma_fwd3) for split-bf16 layers with 64- or 128-channel output tiles
@@ -2187,23 +2215,39 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
   DRAM_REQUIRE(!bn_partials || (!scale && fwd_stat_rows(N, D, H, W, Cin, Cin_pad, Cout, ksize, x_lo != nullptr, w_lo != nullptr) > 0),
                "conv3d_umma_fwd: bn_partials needs a raw (no scale/shift) output and a kernel with the statistics epilogue "
                "(dram_conv3d_umma_fwd_stat_rows > 0)");
-  if (kind == kFwdSmPairs) {
+  if (kind == kFwdSmPairs || kind == kFwdSmPairsGen) {
     Fwd4Params q;
     q.y = y; q.scale = scale; q.shift = shift; q.o_hi = (uint16_t*)out_hi; q.o_lo = (uint16_t*)out_lo; q.stat = bn_partials;
     q.N = N; q.D = D; q.H = H; q.W = W; q.Cout = Cout; q.kblocks_c = Cin_pad / 64; q.ksteps = ksteps;
-    if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
-    q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
-    q.n_mtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
-    q.a_plane_bytes = (q.TW + 2) * q.TDD * 1024;
-    q.a_tile_bytes = 2 * q.a_plane_bytes;
+    q.gen = kind == kFwdSmPairsGen ? 1 : 0;
     q.cb_split = C1p / 64;
     CUtensorMap mA_hi, mA_lo, mA2_hi, mA2_lo;
     int rc4;
-    if ((rc4 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
-    if ((rc4 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
-    mA2_hi = mA_hi; mA2_lo = mA_lo;
-    if (x2_hi && (rc4 = make_volume_map_hdw(&mA2_hi, x2_hi, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
-    if (x2_lo && (rc4 = make_volume_map_hdw(&mA2_lo, x2_lo, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
+    if (q.gen) {
+      pick_fwd_tile(D, H, W, q.TW, q.TH, q.TD);
+      q.TDD = 1;
+      q.tiles_w = cdiv(W, q.TW); q.tiles_h = cdiv(H, q.TH); q.tiles_d = cdiv(D, q.TD);
+      q.a_plane_bytes = kATileBytes;                      // 128 rows reserved, TW*TH*TD of them written by TMA
+      q.a_box_bytes = q.TW * q.TH * q.TD * 128;
+      if ((rc4 = make_volume_map(&mA_hi, x_hi, N, D, H, W, C1p, q.TW, q.TH, q.TD, 1))) return rc4;
+      if ((rc4 = make_volume_map(&mA_lo, x_lo, N, D, H, W, C1p, q.TW, q.TH, q.TD, 1))) return rc4;
+      mA2_hi = mA_hi; mA2_lo = mA_lo;
+      if (x2_hi && (rc4 = make_volume_map(&mA2_hi, x2_hi, N, D, H, W, C2p, q.TW, q.TH, q.TD, 1))) return rc4;
+      if (x2_lo && (rc4 = make_volume_map(&mA2_lo, x2_lo, N, D, H, W, C2p, q.TW, q.TH, q.TD, 1))) return rc4;
+    } else {
+      if (W % 16 == 0) { q.TW = 16; q.TDD = 1; } else { q.TW = 8; q.TDD = 2; }
+      q.TH = 8; q.TD = q.TDD;
+      q.tiles_w = W / q.TW; q.tiles_h = H / 8; q.tiles_d = D / q.TDD;
+      q.a_plane_bytes = (q.TW + 2) * q.TDD * 1024;
+      q.a_box_bytes = q.a_plane_bytes;
+      if ((rc4 = make_volume_map_hdw(&mA_hi, x_hi, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
+      if ((rc4 = make_volume_map_hdw(&mA_lo, x_lo, N, D, H, W, C1p, q.TW + 2, q.TDD))) return rc4;
+      mA2_hi = mA_hi; mA2_lo = mA_lo;
+      if (x2_hi && (rc4 = make_volume_map_hdw(&mA2_hi, x2_hi, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
+      if (x2_lo && (rc4 = make_volume_map_hdw(&mA2_lo, x2_lo, N, D, H, W, C2p, q.TW + 2, q.TDD))) return rc4;
+    }
+    q.n_mtiles = N * q.tiles_d * q.tiles_h * q.tiles_w;
+    q.a_tile_bytes = 2 * q.a_plane_bytes;
     static int max_clusters = 0;
     static std::once_flag once4;
     std::call_once(once4, [&] {
