@@ -52,7 +52,7 @@ def main(src, out_md, out_json):
             f.write(f"| `{k[:70]}` | {n} | {a['ms']:.3f} | {100 * a['ms'] / total:.1f} % | {a['dram_read'] / n / 1e6:.1f} | {a['dram_write'] / n / 1e6:.1f} |\n")
     out = {k: {"launches": a["launches"], "ms": a["ms"], "share": a["ms"] / total,
                "dram_bytes_per_launch": (a["dram_read"] + a["dram_write"]) / a["launches"]} for k, a in rows}
-    json.dump({"source": src.split("/")[-1], "total_ms": total, "kernels": out}, open(out_json, "w"), indent=1)
+    json.dump({"source": src.split("/")[-1], "source_sha": source_sha(), "total_ms": total, "kernels": out}, open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
