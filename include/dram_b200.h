@@ -73,7 +73,12 @@ int dram_conv3d_simt_wgrad(const float* x, const float* dy, float* dpack,
  * Cin = real input channels; channels [Cin, Cin_pad) of x and w are zeros (with one 64-channel block the K = 16 steps that
  * would only multiply that padding are not issued).
  * Cout must be a multiple of 16.  K loop = taps x Cin_pad/64 stages of {A 128x64, B BNx64} fed by TMA (5-D tensor map
- * with zero fill for the padding halo), accumulators double-buffered in TMEM, persistent over output tiles. */
+ * with zero fill for the padding halo), accumulators double-buffered in TMEM, persistent over output tiles.
+ * Kernel choice is internal and shape-driven (no caller knob; environment overrides in INTEGRATION.md are diagnostics):
+ * full split-bf16 3x3x3 layers with Cout % 64 == 0 run on PAIRS of SMs (thread-block clusters of 2, tcgen05.mma
+ * cta_group::2, M = 256, weight columns split across the pair: k_conv_umma_fwd4; likewise k_conv_umma_wgrad2 for
+ * dram_conv3d_umma_wgrad with Cout_pad % 128 == 0); everything else runs on the single-SM kernels.  All variants compute
+ * the same products; results differ only in the order of the fp32 additions (2e-5 of max |y| in the tests). */
 int dram_split_bf16(const float* x, void* hi, void* lo /*nullable*/, long long rows, int C, int Cpad, void* stream);
 int dram_pack_weight_bf16(const float* w, void* w_hi, void* w_lo /*nullable*/, int Cout, int Cin, int Cin_pad,
                           int ksize, int mode, void* stream);
