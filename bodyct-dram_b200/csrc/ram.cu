@@ -175,6 +175,36 @@ __global__ void k_masked_pool_bwd(const float* __restrict__ x, const float* __re
   }
 }
 
+// interval-regression term from the pooled sums (metrics.py:121-137, 158-177): one thread per sample, thread 0 adds the B
+// terms in index order (deterministic); arithmetic follows the reference's dtypes step by step (fp32 tensors, the interval in
+// Python floats = double, rounded back to fp32)
+__global__ void k_int_reg_loss(const double* __restrict__ pp, const double* __restrict__ pr, const double* __restrict__ band,
+                               const float* __restrict__ w, double bw, float* __restrict__ loss, float* __restrict__ g, int B) {
+  extern __shared__ float terms[];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float pred = (float)(pp[2 * b] / pp[2 * b + 1]);
+    const double p = (double)(float)(pr[2 * b] / pr[2 * b + 1]);
+    const double clb = band[2 * b], cub = band[2 * b + 1];
+    const double lb = fmax(p - bw, 0.0), ub = fmin(p + bw, 1.0);
+    double lo = fmax(clb, lb), hi = fmin(cub, ub);
+    const bool empty = hi < lo, below = empty && (ub <= clb);
+    lo = below ? lb : (empty ? clb : lo);
+    hi = below ? ub : (empty ? cub : hi);
+    const float t0 = (float)lo, t1 = (float)hi;
+    const float half = 0.5f * (t1 - t0), K = half * half, mid = (t1 + t0) / 2.0f;
+    const float dlt = pred - mid, unh = dlt * dlt - K;
+    terms[b] = fmaxf(unh, 0.f) / w[b];
+    const float dpred = unh > 0.f ? 2.f * dlt / w[b] : 0.f;
+    g[b] = (float)((double)dpred / pp[2 * b + 1]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += terms[b];
+    loss[0] = acc;
+  }
+}
+
 __global__ void k_ram_activation(const float* __restrict__ in, float* __restrict__ out, long long n, int act) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = in[i];
@@ -364,6 +394,14 @@ int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, floa
   DRAM_REQUIRE(x && mask && g && dx && B > 0 && V > 0, "masked_pool_bwd: bad arguments");
   int gx = grid_for(V, 256 * 4, 4);
   k_masked_pool_bwd<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, mask, g, dx, V, use_sigmoid, mode_gt0);
+  DRAM_LAUNCH_CHECK();
+  return DRAM_OK;
+}
+
+int dram_int_reg_loss(const double* pool_pred, const double* pool_rub, const double* band, const float* w, double band_width,
+                      float* loss, float* g, int B, void* stream) {
+  DRAM_REQUIRE(pool_pred && pool_rub && band && w && loss && g && B > 0 && B <= 8192, "int_reg_loss: bad arguments (B=%d)", B);
+  k_int_reg_loss<<<1, 128, sizeof(float) * B, (cudaStream_t)stream>>>(pool_pred, pool_rub, band, w, band_width, loss, g, B);
   DRAM_LAUNCH_CHECK();
   return DRAM_OK;
 }

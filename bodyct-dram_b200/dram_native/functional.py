@@ -578,6 +578,33 @@ class MaskedMean(torch.autograd.Function):
         return dx.view(ctx.xshape), None, None, None
 
 
+class IntRegHinge(torch.autograd.Function):
+    """Interval-regression term of IntRegLoss (metrics.py:121-137, 158-177) on a batch: two masked-pool reductions (the
+    prediction with the sigmoid fused, the lesion-candidate ratio), ONE tiny kernel for the interval / hinge / weighting of
+    the B samples, and in the backward one small multiply + the masked-pool gradient kernel — instead of ~40 [B]-sized ATen
+    launches around the same two reductions."""
+
+    @staticmethod
+    def forward(ctx, values, lobes, lesion_candidates, band, w, band_width, use_sigmoid):
+        B = values.shape[0]
+        x2 = values.reshape(B, -1).contiguous()
+        m2 = lobes.reshape(B, -1).contiguous()
+        l2 = lesion_candidates.reshape(B, -1).contiguous()
+        pool_p = ops.masked_pool(x2, m2, use_sigmoid, True)         # mean of the probabilities over lobe > 0
+        pool_r = ops.masked_pool(l2, m2, False, False)              # sum(lesion * lobe) / sum(lobe)
+        loss, g = ops.int_reg_loss(pool_p, pool_r, band.contiguous(), w.contiguous(), band_width)
+        ctx.save_for_backward(x2, m2, g)
+        ctx.use_sigmoid = use_sigmoid
+        ctx.xshape = tuple(values.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        x2, m2, g = ctx.saved_tensors
+        dx = ops.masked_pool_bwd(x2, m2, (g * gout).contiguous(), ctx.use_sigmoid, True)
+        return dx.view(ctx.xshape), None, None, None, None, None, None
+
+
 class BootBce(torch.autograd.Function):
     """Segmentation term of IntRegRefineLoss — pseudo labels from the RAM (metrics.py:325-354) + BootBinCrossEntropy on
     the refined RAM (metrics.py:10-51) — as one reduction kernel and one gradient kernel.  Gradient flows to the refined

@@ -490,6 +490,16 @@ def masked_pool_bwd(x, mask, g, use_sigmoid=False, mode_gt0=False):
     return dx
 
 
+def int_reg_loss(pool_pred, pool_rub, band, w, band_width):
+    """pooled sums [B,2] double (x2), band [B,2] double, w [B] fp32 -> (loss [1] fp32, g [B] fp32 = d loss / d pool_pred[:,0])"""
+    B = pool_pred.shape[0]
+    loss = torch.empty(1, device=pool_pred.device, dtype=torch.float32)
+    g = torch.empty(B, device=pool_pred.device, dtype=torch.float32)
+    _lib.check(_L().dram_int_reg_loss(pool_pred.data_ptr(), pool_rub.data_ptr(), band.data_ptr(), w.data_ptr(),
+                                      float(band_width), loss.data_ptr(), g.data_ptr(), B, _stream()), "int_reg_loss")
+    return loss, g
+
+
 def boot_bce_sums(dense, refined, lobes, lesions, keep, eps=1e-7):
     """[B,V] fp32 logits / masks, keep [B] -> double [7] (see dram_boot_bce_fwd)"""
     B, V = refined.shape

@@ -102,6 +102,9 @@ class IntRegLoss:
 
     def _reg_loss(self, values, lobes, lesion_candidates, ctsses, use_sigmoid, **kwargs):
         labels = kwargs.get("label_tensors") or self.label_tensors(ctsses, kwargs.get('obj').ctss_frequency_map, values.device)
+        if os.environ.get("DRAM_FUSED_LOSS", "1") == "1":
+            return DF.IntRegHinge.apply(values, lobes, lesion_candidates, labels["band"], labels["w"], float(self.band_width),
+                                        bool(use_sigmoid))
         with torch.no_grad():
             rub, _ = DF.MaskedMean.apply(lesion_candidates, lobes, False, False)     # sum(lesion*lobe)/sum(lobe)
         pred_ratio, _ = DF.MaskedMean.apply(values, lobes, use_sigmoid, True)       # mean of probs over lobe > 0

@@ -223,6 +223,17 @@ int dram_masked_pool_fwd(const float* x, const float* mask, double* out, int B, 
 /* dx[b][v] = g[b] * f'(x) * m[b][v]   (g already divided by the mask count by the caller) */
 int dram_masked_pool_bwd(const float* x, const float* mask, const float* g, float* dx, int B, long long V,
                          int use_sigmoid, int mode_gt0, void* stream);
+/* Interval-regression term of IntRegLoss from the two masked-pool results of a batch (metrics.py:121-137 get_labels +
+ * :158-177 compute_reg_loss_with_probs), one tiny kernel instead of ~40 [B]-sized tensor ops:
+ *   pred[b] = pool_pred[b][0] / pool_pred[b][1] (mean probability over the lobe), rub[b] = pool_rub[b][0] / pool_rub[b][1]
+ *   (lesion-candidate ratio), both rounded to fp32 as the reference's tensors are; the target interval [lo, hi] =
+ *   band[b] = ctss_ratio_map[ctss] intersected with [rub - band_width, rub + band_width] clamped to [0, 1] (with the
+ *   reference's two fall-backs for an empty intersection), evaluated in double and rounded to fp32;
+ *   loss = sum_b max((pred - (hi + lo) / 2)^2 - (0.5 (hi - lo))^2, 0) / w[b]                 -> loss[0] (fp32)
+ *   g[b] = d loss / d pool_pred[b][0] = [hinge active] 2 (pred - mid) / w[b] / pool_pred[b][1]   -> g (fp32), which is what
+ *   dram_masked_pool_bwd takes.  band: double [B][2], w: fp32 [B] (already clamped), pools: double [B][2]. */
+int dram_int_reg_loss(const double* pool_pred, const double* pool_rub, const double* band, const float* w, double band_width,
+                      float* loss, float* g, int B, void* stream);
 /* Segmentation term of IntRegRefineLoss in two passes (metrics.py:10-51 BootBinCrossEntropy over the thresholded pseudo
  * labels of metrics.py:325-354): dense / refined are the RAM and refined-RAM logits [B][V], lobes / lesions the float
  * masks, keep[b] = 0 zeroes the pseudo labels of sample b (ctss == 0, metrics.py:327-328).

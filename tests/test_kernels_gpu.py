@@ -676,6 +676,48 @@ def test_masked_mean(use_sigmoid, gt0):
     assert_close(xg.grad, x.grad, TOL_F32, "masked mean bwd")
 
 
+def test_fused_interval_regression_loss_matches_tensor_op_form(monkeypatch):
+    """dram_int_reg_loss (IntRegHinge: two masked-pool reductions + one tiny kernel) against the tensor-op form of the same
+    loss (DRAM_FUSED_LOSS=0: metrics.py:121-137, 158-177 op by op) and against the CPU oracle: value and gradient w.r.t. the
+    RAM logits.  The samples cover every branch of get_labels: the ratio inside its band, the band cut by rub +- band_width on
+    either side, an empty intersection above and below the band, ctss 0, and an inactive hinge (zero gradient)."""
+    import metrics
+    from oracle_import import O
+    torch.manual_seed(11)
+    B, S = 8, (8, 8, 8)
+    lobes = O.ellipsoid_lobe(B, S, seed=5).cuda()
+    dense = (torch.randn(B, 1, *S) * 2).cuda()
+    dense[7] = -9.0                                              # mean probability ~1e-4: inside band 0 -> hinge inactive
+    lesions = torch.zeros(B, 1, *S)
+    for b, frac in enumerate([0.2, 0.02, 0.04, 0.6, 0.0, 0.3, 0.9, 0.0]):      # lesion-candidate ratio of each sample
+        lesions[b].view(-1)[: int(frac * S[0] * S[1] * S[2])] = 1.0
+    lesions = lesions.cuda()
+    ctsses = ["3", "2", "2", "5", "0", "1", "3", "0"]            # bands 0.05-0.35, 0.01-0.05, ..., 0-0.001
+    freq = {k: 0.1 + 0.12 * k for k in range(6)}
+
+    class Host:
+        ctss_frequency_map, debug_path, epoch_n = freq, "/tmp/x", 0
+
+    loss_obj = metrics.IntRegRefineLoss(band_width=1e-2)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DRAM_FUSED_LOSS", mode)
+        d = dense.clone().requires_grad_(True)
+        loss = loss_obj.compute_reg_loss_with_logits(d, lobes, lesions, ctsses, obj=Host())
+        loss.backward()
+        out[mode] = (loss.detach().cpu(), d.grad.cpu())
+    monkeypatch.delenv("DRAM_FUSED_LOSS")
+    assert out["1"][0].shape == out["0"][0].shape == ()
+    assert abs(out["1"][0].item() - out["0"][0].item()) <= 1e-6 * abs(out["0"][0].item())
+    assert_close(out["1"][1], out["0"][1], 1e-6, "d reg loss / d RAM, fused vs tensor ops")
+    assert out["1"][1][7].abs().max().item() == 0.0 and out["1"][1][0].abs().max().item() > 0.0
+    dc = dense.detach().cpu().requires_grad_(True)
+    ref = O.reg_loss(dc, lobes.cpu(), lesions.cpu(), ctsses, freq, band_width=1e-2)
+    ref.backward()
+    assert abs(out["1"][0].item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert_close(out["1"][1], dc.grad, TOL_F32, "d reg loss / d RAM vs oracle")
+
+
 def test_fused_boot_bce_matches_unfused_loss():
     """dram_boot_bce_fwd/_bwd against the tensor-op BootBinCrossEntropy + pseudo_labels of metrics.py (same arithmetic as
     the reference's metrics.py:10-51,325-354): value and gradient w.r.t. the refined logits, incl. a sample with
