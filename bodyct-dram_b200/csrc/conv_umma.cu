@@ -2178,6 +2178,11 @@ long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin, in
   return fwd_stat_rows(N, D, H, W, Cin, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
 }
 
+int dram_conv3d_umma_fwd_kernel(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin_pad < Cin || Cin_pad % 64 || Cout <= 0) return -1;
+  return fwd_kernel_kind(N, D, H, W, Cin, Cin_pad, Cout, ksize, has_x_lo != 0, has_w_lo != 0);
+}
+
 size_t dram_bn_stats_from_partials_workspace_bytes(int C) { return C > 0 ? sizeof(double) * 2 * (size_t)C * kStatChunks : 0; }
 
 int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* workspace, void* stream) {
@@ -2581,6 +2586,14 @@ static void wgrad_w3_plan(Wg3Params& p, int N, int D, int H, int W, int Cin_pad)
   { const char* e = getenv("DRAM_WGRAD_SPG"); if (e && atoi(e) > 0) p.spg = atoi(e); }
   p.stages = (kSmemBudget - 1024) / kW3Stage;
   { const char* e = getenv("DRAM_WGRAD_ORDER"); p.dfast = e ? atoi(e) : 1; }
+}
+
+int dram_conv3d_umma_wgrad_kernel(int H, int W, int Cout_pad, int ksize, int has_x_lo, int has_dy_lo) {
+  if (H <= 0 || W <= 0 || Cout_pad <= 0 || Cout_pad % 64) return -1;
+  const int passes = has_x_lo ? 3 : 1;
+  if (wgrad_w3_ok(H, W, Cout_pad, ksize, passes)) return 1;
+  if (wgrad2_ok(Cout_pad, passes, has_dy_lo ? 1 : 0)) return 2;
+  return 0;
 }
 
 size_t dram_conv3d_umma_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin_pad, int Cout_pad, int ksize) {

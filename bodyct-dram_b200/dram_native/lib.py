@@ -43,7 +43,7 @@ class DramLibraryError(RuntimeError):
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim); memsets are not counted
 KERNELS_PER_CALL = {"dram_peer_mailbox_bytes": 0, "dram_peer_max_doubles": 0, "dram_peer_max_ranks": 0, "dram_peer_alloc": 0,
                     "dram_peer_free": 0, "dram_peer_export": 0, "dram_peer_open": 0, "dram_peer_close": 0,
-                    "dram_conv3d_umma_fwd_stat_rows": 0, "dram_bn_stats_from_partials_workspace_bytes": 0,
+                    "dram_conv3d_umma_fwd_stat_rows": 0, "dram_conv3d_umma_fwd_kernel": 0, "dram_conv3d_umma_wgrad_kernel": 0, "dram_bn_stats_from_partials_workspace_bytes": 0,
                     "dram_bn_stats_from_partials": 2, "dram_version": 0, "dram_sm_arch": 0, "dram_last_error": 0, "dram_device_check": 0,
                     "dram_pcm_num_offsets": 0, "dram_pcm_qk_floats": 0, "dram_labelled_sum_workspace_bytes": 0, "dram_labelled_sum": 2, "dram_pcm_bwd_ws_floats": 0, "dram_conv3d_umma_wgrad_workspace_bytes": 0,
                     "dram_upsample2x_concat_fwd": 2, "dram_upsample2x_concat_planes": 2, "dram_upsample2x_concat_bwd": 1, "dram_conv3d_umma_wgrad": 2,

@@ -98,6 +98,13 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
  * double in a fixed order (two levels; workspace of dram_bn_stats_from_partials_workspace_bytes(C) bytes) ->
  * sums[0..C) = sum y, sums[C..2C) = sum y*y, what dram_bn_finalize takes. */
 long long dram_conv3d_umma_fwd_stat_rows(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo);
+/* Which kernel dram_conv3d_umma_fwd / _wgrad run for a shape (host logic only, no device work; for tests and diagnostics):
+ * fwd: 0 = generic single-SM tiles (k_conv_umma_fwd), 2 = weight-sharing tile pairs (k_conv_umma_fwd2), 3 = channels on M
+ * (k_conv_umma_fwd3), 4 = SM pairs with kw re-use (k_conv_umma_fwd4), 5 = SM pairs on generic tiles (k_conv_umma_fwd4);
+ * wgrad: 0 = generic (k_conv_umma_wgrad), 1 = kw re-use for Cout <= 64 (k_conv_umma_wgrad_w3), 2 = SM pairs
+ * (k_conv_umma_wgrad2).  -1 = invalid arguments. */
+int dram_conv3d_umma_fwd_kernel(int N, int D, int H, int W, int Cin, int Cin_pad, int Cout, int ksize, int has_x_lo, int has_w_lo);
+int dram_conv3d_umma_wgrad_kernel(int H, int W, int Cout_pad, int ksize, int has_x_lo, int has_dy_lo);
 size_t dram_bn_stats_from_partials_workspace_bytes(int C);
 int dram_bn_stats_from_partials(const float* partials, long long rows, int C, double* sums, void* workspace, void* stream);
 /* wgrad on tensor cores: dw[co][ci][tap] (+)= sum_m dy[m][co] * x[m+tap][ci]; operands as split planes

@@ -119,6 +119,40 @@ def test_utils_helpers():
     assert abs(utils.binary_cam(v)[1] - O.binary_cam(v)) < 1e-12
 
 
+def test_kernel_schedule_of_the_benchmark_layers(monkeypatch):
+    """Which tensor-core kernel runs each convolution of the DC3D training step at the benchmark size (batch 8, 80^3 chunks):
+    host logic of the library only (no device work), asserted here so that a change of the selection rules is a visible
+    change.  forward / dgrad: 4 = SM pairs (cta_group::2) with kw re-use, 5 = SM pairs on generic (5,5,5) tiles, 3 = channels
+    on M, 2 = single-SM tile pairs;  wgrad: 1 = kw re-use (Cout <= 64), 2 = SM pairs."""
+    from dram_native import lib
+    monkeypatch.delenv("DRAM_CONV_V4", raising=False)
+    monkeypatch.delenv("DRAM_WGRAD_V2", raising=False)
+    L = lib.load()
+    pad = lambda c: (c + 63) // 64 * 64
+    layers = [("ds0.c1", 32, 64, 80), ("ds1.c0", 64, 64, 40), ("ds1.c1", 64, 128, 40), ("ds2.c0", 128, 128, 20),
+              ("ds2.c1", 128, 256, 20), ("bg.c0", 256, 256, 10), ("bg.c1", 256, 512, 10), ("us0.c0", 768, 256, 20),
+              ("us0.c1", 256, 256, 20), ("us1.c0", 384, 128, 40), ("us1.c1", 128, 128, 40), ("us2.c0", 192, 64, 80),
+              ("us2.c1", 64, 64, 80)]
+    got = {}
+    for name, ci, co, s in layers:
+        fwd = L.dram_conv3d_umma_fwd_kernel(8, s, s, s, ci, pad(ci), co, 3, 1, 1)
+        dgrad = L.dram_conv3d_umma_fwd_kernel(8, s, s, s, co, pad(co), ci, 3, 1, 1)       # the same kernel on dy, channels swapped
+        wgrad = L.dram_conv3d_umma_wgrad_kernel(s, s, pad(co), 3, 1, 1)
+        got[name] = (fwd, dgrad, wgrad)
+    assert got == {"ds0.c1": (3, 2, 1), "ds1.c0": (4, 4, 1), "ds1.c1": (4, 4, 2), "ds2.c0": (5, 5, 2), "ds2.c1": (5, 5, 2),
+                   "bg.c0": (5, 5, 2), "bg.c1": (5, 5, 2), "us0.c0": (5, 5, 2), "us0.c1": (5, 5, 2), "us1.c0": (4, 4, 2),
+                   "us1.c1": (4, 4, 2), "us2.c0": (4, 4, 1), "us2.c1": (4, 4, 1)}, got
+    monkeypatch.setenv("DRAM_CONV_V4", "0")                    # the single-SM kernels the tests compare against
+    assert L.dram_conv3d_umma_fwd_kernel(8, 80, 80, 80, 192, 192, 64, 3, 1, 1) == 2
+    assert L.dram_conv3d_umma_fwd_kernel(8, 40, 40, 40, 384, 384, 128, 3, 1, 1) == 3
+    assert L.dram_conv3d_umma_fwd_kernel(8, 20, 20, 20, 256, 256, 256, 3, 1, 1) == 0
+    monkeypatch.delenv("DRAM_CONV_V4")
+    # the one-plane gradient backward (DRAM_BWD_PRECISION=bf16x2) stays on the single-SM kernels
+    assert L.dram_conv3d_umma_fwd_kernel(8, 80, 80, 80, 64, 64, 64, 3, 0, 1) == 3
+    assert L.dram_conv3d_umma_wgrad_kernel(40, 40, 128, 3, 1, 0) == 0
+    assert L.dram_conv3d_umma_fwd_kernel(0, 1, 1, 1, 1, 64, 64, 3, 1, 1) == -1
+
+
 def test_metaimage_round_trip(tmp_path):
     """utils.write_array_to_mha_itk (utils.py:142-159) / read_mha: voxels, element type and geometry survive, compressed
     and uncompressed; the header is what ITK's MetaImageIO writes for a 3-d image."""
