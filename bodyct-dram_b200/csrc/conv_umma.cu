@@ -2058,7 +2058,7 @@ static int fwd_kernel_kind(int N, int D, int H, int W, int Cin, int Cin_pad, int
   {
     const char* v4_env = getenv("DRAM_CONV_V4");
     const bool allow_v4 = !(v4_env && atoi(v4_env) == 0);
-    if (allow_v4 && Cout % 64 == 0 && x_lo && w_lo && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) &&
+    if (allow_v4 && Cout % 32 == 0 && x_lo && w_lo && ksize == 3 && H % 8 == 0 && (W % 16 == 0 || (W % 8 == 0 && D % 2 == 0)) &&
         !(Cin_pad == 64 && Cin <= 32)) {
       const int TW = (W % 16 == 0) ? 16 : 8, TDD = (W % 16 == 0) ? 1 : 2;
       const long long mt = (long long)N * (D / TDD) * (H / 8) * (W / TW);
@@ -2273,13 +2273,17 @@ int dram_conv3d_umma_fwd(const void* x_hi, const void* x_lo, const void* w_hi, c
     { const char* e = getenv("DRAM_CONV_DBG"); q.dbg = e ? atoi(e) : 0; }
     // Cout = 128 * n128 (+ 64): one launch of 128-channel N tiles (both MMAs at N >= 128: the MMA pipe of the pair stays ~98 %
     // busy), one launch for a 64-channel tail tile (its N = 64 MMA costs almost as much as an N = 128 one: ~77 %)
+    // a 32-channel tail (ds0.c1's dgrad, 64 -> 32) runs the same scheme at BN = 32 (N = 64 / 32 MMAs: ~48 % MMA efficiency, against
+    // 33 % tensor-pipe activity of the single-SM tile-pair kernel on that layer, profiles/r02u_all_conv_launches.md #39)
     const int n128 = Cout / 128, tail = Cout % 128;
-    for (int part = 0; part < 2; ++part) {
-      if ((part == 0 && n128 == 0) || (part == 1 && tail == 0)) continue;
-      q.BN = part == 0 ? 128 : 64;
-      q.co_base = part == 0 ? 0 : 128 * n128;
+    for (int part = 0; part < 3; ++part) {
+      const int bn = part == 0 ? 128 : (part == 1 ? 64 : 32);
+      const bool run = part == 0 ? n128 > 0 : (part == 1 ? (tail & 64) != 0 : (tail & 32) != 0);
+      if (!run) continue;
+      q.BN = bn;
+      q.co_base = part == 0 ? 0 : (part == 1 ? 128 * n128 : 128 * n128 + (tail & 64));
       q.n_ntiles = part == 0 ? n128 : 1;
-      q.TPC = (q.BN == 64 && q.n_mtiles % 4 == 0) ? 2 : 1;      // two M tiles per CTA share every weight tile (2 x 2 x 128 TMEM columns)
+      q.TPC = (q.BN <= 64 && q.n_mtiles % 4 == 0) ? 2 : 1;      // two M tiles per CTA share every weight tile (2 x 2 x 128 TMEM columns)
       q.n_items = q.n_mtiles / (2 * q.TPC) * q.n_ntiles;
       q.a_stage_bytes = q.TPC * q.a_tile_bytes;
       q.b_stage_bytes = q.BN * 128;                        // this CTA's half of the N = 2*BN weight columns: BN/2 hi + BN/2 lo rows

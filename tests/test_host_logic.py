@@ -123,7 +123,7 @@ def test_kernel_schedule_of_the_benchmark_layers(monkeypatch):
     """Which tensor-core kernel runs each convolution of the DC3D training step at the benchmark size (batch 8, 80^3 chunks):
     host logic of the library only (no device work), asserted here so that a change of the selection rules is a visible
     change.  forward / dgrad: 4 = SM pairs (cta_group::2) with kw re-use, 5 = SM pairs on generic (5,5,5) tiles, 3 = channels
-    on M, 2 = single-SM tile pairs;  wgrad: 1 = kw re-use (Cout <= 64), 2 = SM pairs."""
+    on M (ds0.c1's forward: Cin = 32, two K steps per tap);  wgrad: 1 = kw re-use (Cout <= 64), 2 = SM pairs."""
     from dram_native import lib
     monkeypatch.delenv("DRAM_CONV_V4", raising=False)
     monkeypatch.delenv("DRAM_WGRAD_V2", raising=False)
@@ -139,7 +139,7 @@ def test_kernel_schedule_of_the_benchmark_layers(monkeypatch):
         dgrad = L.dram_conv3d_umma_fwd_kernel(8, s, s, s, co, pad(co), ci, 3, 1, 1)       # the same kernel on dy, channels swapped
         wgrad = L.dram_conv3d_umma_wgrad_kernel(s, s, pad(co), 3, 1, 1)
         got[name] = (fwd, dgrad, wgrad)
-    assert got == {"ds0.c1": (3, 2, 1), "ds1.c0": (4, 4, 1), "ds1.c1": (4, 4, 2), "ds2.c0": (5, 5, 2), "ds2.c1": (5, 5, 2),
+    assert got == {"ds0.c1": (3, 4, 1), "ds1.c0": (4, 4, 1), "ds1.c1": (4, 4, 2), "ds2.c0": (5, 5, 2), "ds2.c1": (5, 5, 2),
                    "bg.c0": (5, 5, 2), "bg.c1": (5, 5, 2), "us0.c0": (5, 5, 2), "us0.c1": (5, 5, 2), "us1.c0": (4, 4, 2),
                    "us1.c1": (4, 4, 2), "us2.c0": (4, 4, 1), "us2.c1": (4, 4, 1)}, got
     monkeypatch.setenv("DRAM_CONV_V4", "0")                    # the single-SM kernels the tests compare against

@@ -268,6 +268,9 @@ def test_conv_umma_wgrad(N, Cin, Cout, S, k, three):
     (2, 64, 128, (8, 8, 16)),       # BN = 128
     (1, 128, 384, (2, 8, 16)),      # three 128-channel N tiles (dgrad of us1.c0 shape class)
     (2, 64, 64, (16, 40, 40)),      # 40^3 tiling, more work items than clusters
+    (2, 64, 32, (8, 8, 16)),        # 32-channel tile (dgrad of ds0.c1): N = 64 / 32 MMAs
+    (1, 64, 96, (4, 8, 16)),        # 64-channel + 32-channel tail tiles
+    (1, 64, 224, (2, 8, 16)),       # 128 + 64 + 32
 ])
 def test_conv_umma_sm_pair_kernel_matches_single_sm_kernels(monkeypatch, N, Cin, Cout, S):
     """k_conv_umma_fwd4 (cta_group::2) and the single-SM kernels it replaces (DRAM_CONV_V4=0: tile pairs / channels on M) compute
