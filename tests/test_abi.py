@@ -56,3 +56,6 @@ def test_sass_contains_blackwell_instructions():
     sass = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+    # the SM-pair kernels: cta_group::2 MMAs, 2-SM TMA loads, multicast commits, cluster barriers
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.5D.2CTA", "UTCBAR.2CTA.MULTICAST", "UCGABAR_ARV"):
+        assert mnemonic in sass, mnemonic
