@@ -348,32 +348,32 @@ k_conv_c1_fwd_q(const float* __restrict__ x, const float* __restrict__ pack, con
 #pragma unroll
   for (int j = 0; j < 8; ++j) b8[j] = bias ? bias[g * 8 + j] : 0.f;
   for (long long qd = tid / groups; qd < quads; qd += dq) {
-    float xv[9][6], acc[4][8];
-    long long m0;
+    float xv[9][6];
+    float2 acc[4][4];                                   // packed fp32 pairs (fma.rn.f32x2, sm_100): half the FMA issue slots,
+    long long m0;                                       // the same roundings as 864 scalar FMAs per quad
     c1_window(x, (unsigned)qd, D, H, W4, xv, m0);
 #pragma unroll
     for (int v = 0; v < 4; ++v)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[v][j] = b8[j];
+      for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(b8[2 * j], b8[2 * j + 1]);
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
       const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8]);
       const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * Cout + g * 8 + 4]);
+      const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w), wc = make_float2(w1.x, w1.y), wd = make_float2(w1.z, w1.w);
       const int r9 = t / 3, dx = t % 3;                 // tap t = (dz,dy) row r9, column dx: voxel v reads xv[r9][v + dx]
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const float xs = xv[r9][v + dx];
-        acc[v][0] = fmaf(xs, w0.x, acc[v][0]); acc[v][1] = fmaf(xs, w0.y, acc[v][1]);
-        acc[v][2] = fmaf(xs, w0.z, acc[v][2]); acc[v][3] = fmaf(xs, w0.w, acc[v][3]);
-        acc[v][4] = fmaf(xs, w1.x, acc[v][4]); acc[v][5] = fmaf(xs, w1.y, acc[v][5]);
-        acc[v][6] = fmaf(xs, w1.z, acc[v][6]); acc[v][7] = fmaf(xs, w1.w, acc[v][7]);
+        const float2 xs = make_float2(xv[r9][v + dx], xv[r9][v + dx]);
+        acc[v][0] = __ffma2_rn(xs, wa, acc[v][0]); acc[v][1] = __ffma2_rn(xs, wb, acc[v][1]);
+        acc[v][2] = __ffma2_rn(xs, wc, acc[v][2]); acc[v][3] = __ffma2_rn(xs, wd, acc[v][3]);
       }
     }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       float4* o = reinterpret_cast<float4*>(y + (m0 + v) * Cout + g * 8);
-      o[0] = make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
-      o[1] = make_float4(acc[v][4], acc[v][5], acc[v][6], acc[v][7]);
+      o[0] = make_float4(acc[v][0].x, acc[v][0].y, acc[v][1].x, acc[v][1].y);
+      o[1] = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
     }
   }
 }
@@ -387,11 +387,9 @@ k_conv_c1_wgrad_q(const float* __restrict__ x, const float* __restrict__ dy, flo
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long dq = ((long long)gridDim.x * blockDim.x) / groups;
   const int g = (int)(tid % groups);
-  float acc[27][4];
+  float2 acc2[27][2];                                   // packed fp32 pairs (fma.rn.f32x2): same roundings, half the issue slots
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  for (int t = 0; t < 27; ++t) acc2[t][0] = acc2[t][1] = make_float2(0.f, 0.f);
   for (long long qd = tid / groups; qd < quads; qd += dq) {
     float xv[9][6];
     long long m0;
@@ -404,9 +402,9 @@ k_conv_c1_wgrad_q(const float* __restrict__ x, const float* __restrict__ dy, flo
       const int r9 = t / 3, dx = t % 3;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const float xs = xv[r9][v + dx];
-        acc[t][0] = fmaf(xs, d4[v].x, acc[t][0]); acc[t][1] = fmaf(xs, d4[v].y, acc[t][1]);
-        acc[t][2] = fmaf(xs, d4[v].z, acc[t][2]); acc[t][3] = fmaf(xs, d4[v].w, acc[t][3]);
+        const float2 xs = make_float2(xv[r9][v + dx], xv[r9][v + dx]);
+        acc2[t][0] = __ffma2_rn(xs, make_float2(d4[v].x, d4[v].y), acc2[t][0]);
+        acc2[t][1] = __ffma2_rn(xs, make_float2(d4[v].z, d4[v].w), acc2[t][1]);
       }
     }
   }
@@ -415,7 +413,7 @@ k_conv_c1_wgrad_q(const float* __restrict__ x, const float* __restrict__ dy, flo
   for (int t = 0; t < 27; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float v = acc[t][j];
+      float v = (j & 1) ? acc2[t][j >> 1].y : acc2[t][j >> 1].x;
       for (int o = 16; o >= groups; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane < groups) red[warp][t * Cout + lane * 4 + j] = v;
     }
