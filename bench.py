@@ -654,6 +654,18 @@ def hbm_kernel_rooflines(peaks):
     with torch.no_grad():
         ms = timed(lambda: pcm(cam, f))
     out["pcm_fwd"] = row(76.0 * Bp * G ** 3, ms, note="algorithmic 76 B/voxel (f 17x4 + cam 4 in, 4 out), inference form (nothing kept for a backward)")
+    # x2 trilinear upsample of the decoder (parts.py:149-153) at the us2 level: 128 channels, 40^3 -> 80^3, batch 8
+    del feat, ram, mask, labels, heat, f, cam
+    C1, C2, d = 128, 64, 40
+    xs = ops.split_bf16(ops.new_volume(B, C1, d, d, d, "cuda").normal_())
+    sk = ops.split_bf16(ops.new_volume(B, C2, 2 * d, 2 * d, 2 * d, "cuda").normal_())
+    vin, vout = B * d ** 3, B * (2 * d) ** 3
+    out["upsample2x_planes_fwd"] = row(4.0 * C1 * (vin + vout), timed(lambda: ops.upsample2x_virtual_concat(xs, sk)),
+                                       note="bf16 split planes in (4 B/element) and out; the skip half of the concat is never copied")
+    g = ops.new_volume(B, C1 + C2, 2 * d, 2 * d, 2 * d, "cuda").normal_()
+    out["upsample2x_adjoint"] = row(4.0 * C1 * (vin + vout),
+                                    timed(lambda: ops.upsample2x_concat_bwd(g, (B, C1, d, d, d), (B, C2, 2 * d, 2 * d, 2 * d), want_dskip=False)),
+                                    note="reads the C1 channels of the fp32 concat gradient once, writes the source gradient")
     return out
 
 
