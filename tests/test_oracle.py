@@ -138,3 +138,65 @@ def test_itk_resample_known_answers_from_the_itk_definitions():
     d = np.arange(5, dtype=np.float32).reshape(5, 1, 1)
     r = O.resample_to_spacing(d, (1.5, 1.0, 1.0), (1.0, 1.0, 1.0), "linear")
     assert r.shape == (8, 1, 1) and np.allclose(r.ravel()[:7], np.arange(7) / 1.5, atol=1e-12) and r.ravel()[7] == 0.0   # 7/1.5 = 4.67 >= 4.5
+
+
+def test_otsu_restatements_match_opencv():
+    """scikit-image is not in the image, so `threshold_otsu` (utils.py:239) cannot be called; OpenCV's THRESH_OTSU is an
+    independent third-party implementation of the same published algorithm on 8-bit data (first maximum of the between-class
+    variance over the 256-bin histogram; threshold t: values > t are foreground = skimage's bin centre for integer images).
+    The oracle's restatement and the product's histogram form must both return exactly OpenCV's threshold."""
+    cv2 = pytest.importorskip("cv2")
+    import utils
+    rs = np.random.RandomState(0)
+    checked = 0
+    for trial in range(200):
+        n = int(rs.randint(50, 20000))
+        kind = trial % 5
+        if kind == 0:
+            v = rs.randint(0, 256, n)
+        elif kind == 1:
+            v = np.concatenate([rs.normal(60, 15, n // 2), rs.normal(180, 25, n - n // 2)])
+        elif kind == 2:
+            v = rs.exponential(20, n)
+        elif kind == 3:
+            v = np.concatenate([rs.normal(10, 3, n * 9 // 10), rs.normal(240, 5, n - n * 9 // 10)])
+        else:
+            v = rs.randint(rs.randint(0, 100), rs.randint(101, 256), n)
+        v = np.clip(v, 0, 255).astype(np.uint8)
+        if len(np.unique(v)) < 2:
+            continue
+        t_cv, _ = cv2.threshold(v.reshape(-1, 1), 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        assert O.threshold_otsu_u8(v) == t_cv, (trial, O.threshold_otsu_u8(v), t_cv)
+        assert utils.otsu_threshold_from_histogram(np.bincount(v, minlength=256)) == t_cv, trial
+        checked += 1
+    assert checked > 150
+
+
+def test_itk_resample_interpolation_against_scipy():
+    """No SimpleITK in the image.  The INTERPOLATION part of the float64 restatement (trilinear weights, edge clamping inside the
+    half-voxel border, default value 0 outside the buffer) is checked against an independent implementation of linear / nearest
+    interpolation, scipy.ndimage.map_coordinates, evaluated at the same ITK continuous indices; the coordinate convention itself
+    is covered by the known-answer test above."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    rs = np.random.RandomState(2)
+    for shape, new_size, in_sp in [((10, 12, 9), (20, 24, 18), None), ((23, 17, 31), (16, 16, 16), (1.0, 0.7, 0.7)),
+                                   ((8, 8, 8), (11, 5, 13), (2.5, 1.0, 0.5))]:
+        a = rs.randn(*shape).astype(np.float32)
+        in_sp = [1.0, 1.0, 1.0] if in_sp is None else list(in_sp)
+        out_sp = O.fixed_size_spacing(shape, new_size, in_sp)
+        cz, cy, cx = O.itk_continuous_indices(shape, new_size, in_sp, out_sp)
+        zz, yy, xx = np.meshgrid(cz, cy, cx, indexing="ij")
+        inside = ((zz >= -0.5) & (zz < shape[0] - 0.5) & (yy >= -0.5) & (yy < shape[1] - 0.5) & (xx >= -0.5) & (xx < shape[2] - 0.5))
+        clip = lambda c, n: np.clip(c, 0.0, n - 1.0)              # ITK: no interpolation beyond the first / last sample
+        ref = ndi.map_coordinates(a.astype(np.float64), [clip(zz, shape[0]), clip(yy, shape[1]), clip(xx, shape[2])], order=1,
+                                  mode="nearest")
+        ref[~inside] = 0.0
+        got = O.itk_resample(a, new_size, "linear", in_spacing=in_sp)
+        assert got.shape == tuple(new_size) and got.dtype == np.float32
+        assert np.abs(got.astype(np.float64) - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+        m = (rs.rand(*shape) > 0.5).astype(np.uint8)
+        nn = ndi.map_coordinates(m, [np.floor(clip(zz, shape[0]) + 0.5), np.floor(clip(yy, shape[1]) + 0.5),
+                                     np.floor(clip(xx, shape[2]) + 0.5)], order=0, mode="nearest")
+        nn[~inside] = 0
+        assert np.array_equal(O.itk_resample(m, new_size, "nearest", in_spacing=in_sp), nn)
+
